@@ -1,0 +1,209 @@
+/*
+ * mrb_b200.h -- C ABI of libmrb_b200.so: the Blackwell (sm_100a) replacement for the
+ * native surface of facebookresearch/maskrcnn-benchmark (`maskrcnn_benchmark._C`,
+ * reference csrc/vision.cpp:9-25) plus the dense-conv engine behind
+ * `maskrcnn_benchmark.layers.Conv2d` / `FrozenBatchNorm2d`.
+ *
+ * Conventions (all entry points):
+ *   - extern "C", plain pointers and sizes, no C++/torch types.
+ *   - every pointer is a DEVICE pointer unless the name ends in `_host`.
+ *   - returns 0 (MRB_OK), a positive cudaError_t, or a negative MRB_ERR_* code.
+ *     Never throws, never prints (the reference DCN kernels printf-and-continue,
+ *     csrc/cuda/deform_conv_kernel_cuda.cu:279-283; here the binding raises).
+ *   - explicit stream parameter (the reference launches NMS / DCN on the legacy
+ *     default stream: csrc/cuda/nms.cu:94, deform_conv_kernel_cuda.cu:272).
+ *   - no allocation and no host synchronisation inside; scratch is supplied by the
+ *     caller and sized by the matching mrb_*_workspace_bytes() query.
+ *   - there is NO CPU path.  On a machine without a Blackwell GPU every compute
+ *     entry point fails with a CUDA error; nothing falls back.
+ *
+ * The reference-side binding (ctypes `_C` module) is
+ * maskrcnn-benchmark_b200/maskrcnn_benchmark/_C.py; see INTEGRATION.md.
+ */
+#ifndef MRB_B200_H_
+#define MRB_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* mrb_stream_t; /* cudaStream_t */
+
+#define MRB_OK 0
+#define MRB_ERR_BAD_ARG (-1)
+#define MRB_ERR_UNSUPPORTED (-2)
+#define MRB_ERR_WORKSPACE (-3)
+#define MRB_ERR_DRIVER (-4)
+
+/* memory layouts of a logical [N,C,H,W] activation */
+#define MRB_LAYOUT_NCHW 0
+#define MRB_LAYOUT_NHWC 1 /* torch.channels_last */
+
+/* element types */
+#define MRB_F32 0
+#define MRB_BF16 1
+
+int mrb_version(void);
+/* static string for MRB_ERR_* and cudaError_t values */
+const char* mrb_error_string(int code);
+
+/* ------------------------------------------------------------------ ROIAlign
+ * replaces ROIAlign_forward / ROIAlign_backward (csrc/ROIAlign.h:11-45;
+ * CUDA csrc/cuda/ROIAlign_cuda.cu:257-346; CPU csrc/cpu/ROIAlign_cpu.cpp:221-257).
+ * input  : logical [batch, channels, height, width] in `layout`, fp32
+ * rois   : [num_rois, 5] fp32 (batch_idx, x1, y1, x2, y2) image coordinates
+ * output : [num_rois, channels, pooled_h, pooled_w] fp32, contiguous (NCHW order)
+ * Semantics: aligned=False, ROI coords not rounded, min ROI size 1, sampling_ratio<=0
+ * => ceil(roi/pooled) adaptive grid.  Forward is bit-identical to the reference CPU
+ * kernel (no FMA contraction, same operation order). */
+int mrb_roi_align_fwd(const float* input, const float* rois, float* output, int num_rois, int batch,
+                      int channels, int height, int width, int pooled_h, int pooled_w,
+                      float spatial_scale, int sampling_ratio, int layout, mrb_stream_t stream);
+/* grad_input : logical [batch, channels, height, width] in `layout`; fully overwritten
+ * (zero-filled inside, as at::zeros at ROIAlign_cuda.cu:316). */
+int mrb_roi_align_bwd(const float* grad_output, const float* rois, float* grad_input, int num_rois,
+                      int batch, int channels, int height, int width, int pooled_h, int pooled_w,
+                      float spatial_scale, int sampling_ratio, int layout, mrb_stream_t stream);
+
+/* Multi-level (FPN) ROIAlign: the whole `Pooler.forward` loop
+ * (modeling/poolers.py:91-121: LevelMapper + per-level ROIAlign + index scatter) in one
+ * launch.  levels[l] is the NHWC bf16/fp32 feature map of level l; level assignment is
+ * floor(k0 + log2(sqrt(area)/s0 + eps)) clamped to [k_min,k_max] (poolers.py:31-42).
+ * feats        : host array of num_levels device pointers
+ * heights/widths/scales : host arrays, one entry per level
+ * output       : [num_rois, channels, P, P] fp32 or bf16 (dtype) NCHW-order */
+int mrb_roi_align_fpn_fwd(const void* const* feats_host, const int* heights_host, const int* widths_host,
+                          const float* scales_host, int num_levels, const float* rois, void* output,
+                          int num_rois, int batch, int channels, int pooled, int sampling_ratio,
+                          int k_min, int k_max, float canonical_scale, int canonical_level, int dtype,
+                          mrb_stream_t stream);
+int mrb_roi_align_fpn_bwd(const void* grad_output, void* const* grad_feats_host, const int* heights_host,
+                          const int* widths_host, const float* scales_host, int num_levels,
+                          const float* rois, int num_rois, int batch, int channels, int pooled,
+                          int sampling_ratio, int k_min, int k_max, float canonical_scale,
+                          int canonical_level, int dtype, mrb_stream_t stream);
+
+/* ------------------------------------------------------------------- ROIPool
+ * replaces ROIPool_forward / ROIPool_backward (csrc/ROIPool.h:11-45;
+ * csrc/cuda/ROIPool_cuda.cu:16-202).  NCHW fp32.  argmax: int32 offset in the H*W
+ * plane, -1 for an empty bin. */
+int mrb_roi_pool_fwd(const float* input, const float* rois, float* output, int32_t* argmax,
+                     int num_rois, int batch, int channels, int height, int width, int pooled_h,
+                     int pooled_w, float spatial_scale, mrb_stream_t stream);
+int mrb_roi_pool_bwd(const float* grad_output, const float* rois, const int32_t* argmax,
+                     float* grad_input, int num_rois, int batch, int channels, int height, int width,
+                     int pooled_h, int pooled_w, mrb_stream_t stream);
+
+/* ----------------------------------------------------------------------- NMS
+ * replaces nms (csrc/nms.h:10-28; CPU csrc/cpu/nms_cpu.cpp:5-75; CUDA csrc/cuda/nms.cu:70-131).
+ * Parity target is the CPU path: legacy "+1" areas, suppress when IoU >= threshold
+ * (nms_cpu.cpp:60), kept indices returned ASCENDING BY INDEX (nms_cpu.cpp:64).
+ * IoU is evaluated with round-to-nearest mul/add/sub/div and no FMA, so indices are
+ * bit-exact with the reference for distinct scores; equal scores are ordered by
+ * ascending index (the reference's non-stable sort leaves tie order unspecified).
+ * Fully on device: no D2H mask copy, no host scan (cf. nms.cu:100-123).
+ *   boxes [n,4] fp32 xyxy, scores [n] fp32
+ *   keep  [n]   int64, first *num_keep entries valid
+ *   num_keep    int32 (device)
+ *   workspace   >= mrb_nms_workspace_bytes(n) bytes, 16-byte aligned */
+size_t mrb_nms_workspace_bytes(int n);
+int mrb_nms(const float* boxes, const float* scores, int n, float threshold, int64_t* keep,
+            int32_t* num_keep, void* workspace, size_t workspace_bytes, mrb_stream_t stream);
+/* Batched NMS over `num_problems` independent box sets stored back to back:
+ * problem p owns rows [offsets_host[p], offsets_host[p+1]); keep rows are written at the
+ * same offsets (indices relative to the problem), num_keep[p] per problem.  One
+ * launch sequence for all (image, level) pairs of an RPN step
+ * (modeling/rpn/inference.py:116-121 calls nms once per pair). */
+size_t mrb_nms_batched_workspace_bytes(const int* offsets_host, int num_problems);
+int mrb_nms_batched(const float* boxes, const float* scores, const int* offsets_host, int num_problems,
+                    float threshold, int64_t* keep, int32_t* num_keep, void* workspace,
+                    size_t workspace_bytes, mrb_stream_t stream);
+
+/* ----------------------------------------------------------- SigmoidFocalLoss
+ * replaces SigmoidFocalLoss_forward / _backward (csrc/SigmoidFocalLoss.h:10-41;
+ * csrc/cuda/SigmoidFocalLoss_cuda.cu:20-188).  logits [A,num_classes] fp32, targets [A]
+ * int32 (1..num_classes positive, 0 background, -1 ignore). */
+int mrb_sigmoid_focal_fwd(const float* logits, const int32_t* targets, float* losses, int64_t num_anchors,
+                          int num_classes, float gamma, float alpha, mrb_stream_t stream);
+int mrb_sigmoid_focal_bwd(const float* logits, const int32_t* targets, const float* d_losses,
+                          float* d_logits, int64_t num_anchors, int num_classes, float gamma,
+                          float alpha, mrb_stream_t stream);
+
+/* --------------------------------------------------- deformable convolution
+ * replaces deform_conv_forward / _backward_input / _backward_parameters and
+ * modulated_deform_conv_forward / _backward (csrc/deform_conv.h:11-191;
+ * csrc/cuda/deform_conv_cuda.cu:158-691, deform_conv_kernel_cuda.cu:197-874).
+ * All tensors NCHW fp32 contiguous.  `mask` == NULL selects DCNv1 (no modulation);
+ * `bias` may be NULL.  No `columns` tensor is materialised in HBM beyond the caller's
+ * workspace.  offset [N, dg*2*kh*kw, Ho, Wo]; mask [N, dg*kh*kw, Ho, Wo];
+ * weight [Cout, Cin/groups, kh, kw]. */
+typedef struct mrb_dcn_params {
+  int batch, cin, height, width, cout, kh, kw, stride_h, stride_w, pad_h, pad_w, dil_h, dil_w;
+  int groups, deformable_groups;
+} mrb_dcn_params;
+size_t mrb_deform_conv_workspace_bytes(const mrb_dcn_params* p);
+int mrb_deform_conv_fwd(const mrb_dcn_params* p, const float* input, const float* offset,
+                        const float* mask, const float* weight, const float* bias, float* output,
+                        void* workspace, size_t workspace_bytes, mrb_stream_t stream);
+/* grad_input / grad_offset / grad_mask are overwritten; grad_weight / grad_bias are
+ * ACCUMULATED into (+= scale * dW), matching deform_conv_backward_parameters' `scale`
+ * and the modulated backward's accumulate-into-zeroed-buffers behaviour
+ * (layers/dcn/deform_conv_func.py:97-104,218-224).  Any grad pointer may be NULL to skip. */
+int mrb_deform_conv_bwd(const mrb_dcn_params* p, const float* input, const float* offset,
+                        const float* mask, const float* weight, const float* grad_output,
+                        float* grad_input, float* grad_offset, float* grad_mask, float* grad_weight,
+                        float* grad_bias, float scale, void* workspace, size_t workspace_bytes,
+                        mrb_stream_t stream);
+
+/* ---------------------------------------------- deformable PS-ROI pooling
+ * replaces deform_psroi_pooling_forward / _backward (csrc/deform_pool.h:11-70;
+ * csrc/cuda/deform_pool_kernel_cuda.cu:53-365). NCHW fp32.  channels_trans = trans.size(1)
+ * (2 * num_classes; ignored when no_trans).  The backward ACCUMULATES into in_grad /
+ * trans_grad (the reference uses atomicAdd into caller-zeroed tensors). */
+int mrb_deform_psroi_fwd(const float* data, const float* rois, const float* trans, float* out,
+                         float* top_count, int batch, int channels, int height, int width, int num_rois,
+                         int no_trans, int channels_trans, float spatial_scale, int output_dim,
+                         int group_size, int pooled_size, int part_size, int sample_per_part,
+                         float trans_std, mrb_stream_t stream);
+int mrb_deform_psroi_bwd(const float* out_grad, const float* data, const float* rois, const float* trans,
+                         const float* top_count, float* in_grad, float* trans_grad, int batch,
+                         int channels, int height, int width, int num_rois, int no_trans,
+                         int channels_trans, float spatial_scale, int output_dim, int group_size,
+                         int pooled_size, int part_size, int sample_per_part, float trans_std,
+                         mrb_stream_t stream);
+
+/* --------------------------------------------------------- dense conv engine
+ * replaces the ATen/cuDNN convolution behind layers.Conv2d (layers/misc.py:30-43) and the
+ * FrozenBatchNorm2d / ReLU / residual-add elementwise passes that follow it in
+ * Bottleneck.forward (modeling/backbone/resnet.py:324-344; layers/batch_norm.py:27-31).
+ * Implicit GEMM on tcgen05 tensor cores: NHWC bf16 activations, KRSC bf16 weights
+ * ([Cout, kh, kw, Cin]), fp32 accumulation in TMEM, fused epilogue
+ *     y = act( acc * scale[c] + bias[c] + residual )        (scale/bias/residual optional)
+ * TMA feeds shared memory directly from the NHWC tensor (im2col is folded into the TMA
+ * box coordinates; no column matrix exists anywhere). */
+typedef struct mrb_conv_params {
+  int batch, height, width, cin;   /* input  NHWC */
+  int cout, kh, kw;                /* filter KRSC */
+  int stride, pad;                 /* symmetric; dilation 1; groups 1 */
+  int relu;                        /* fused ReLU in the epilogue */
+  int out_dtype;                   /* MRB_BF16 or MRB_F32 */
+} mrb_conv_params;
+int mrb_conv2d_fwd(const mrb_conv_params* p, const void* input_bf16, const void* weight_bf16,
+                   const float* scale, const float* bias, const void* residual, void* output,
+                   mrb_stream_t stream);
+/* dgrad: grad_input[N,H,W,Cin] = conv_transpose(grad_output, weight); optional fused
+ * ReLU-backward mask (zero where `relu_input_mask` <= 0, same shape as grad_input). */
+int mrb_conv2d_dgrad(const mrb_conv_params* p, const void* grad_output_bf16, const void* weight_bf16,
+                     void* grad_input, mrb_stream_t stream);
+/* wgrad: grad_weight[Cout,kh,kw,Cin] (fp32) = sum over N,Ho,Wo; split-K with fp32 atomics into a
+ * zero-initialised buffer (zeroed inside). */
+int mrb_conv2d_wgrad(const mrb_conv_params* p, const void* input_bf16, const void* grad_output_bf16,
+                     float* grad_weight, mrb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MRB_B200_H_ */
