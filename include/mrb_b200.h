@@ -68,24 +68,6 @@ int mrb_roi_align_bwd(const float* grad_output, const float* rois, float* grad_i
                       int batch, int channels, int height, int width, int pooled_h, int pooled_w,
                       float spatial_scale, int sampling_ratio, int layout, mrb_stream_t stream);
 
-/* Multi-level (FPN) ROIAlign: the whole `Pooler.forward` loop
- * (modeling/poolers.py:91-121: LevelMapper + per-level ROIAlign + index scatter) in one
- * launch.  levels[l] is the NHWC bf16/fp32 feature map of level l; level assignment is
- * floor(k0 + log2(sqrt(area)/s0 + eps)) clamped to [k_min,k_max] (poolers.py:31-42).
- * feats        : host array of num_levels device pointers
- * heights/widths/scales : host arrays, one entry per level
- * output       : [num_rois, channels, P, P] fp32 or bf16 (dtype) NCHW-order */
-int mrb_roi_align_fpn_fwd(const void* const* feats_host, const int* heights_host, const int* widths_host,
-                          const float* scales_host, int num_levels, const float* rois, void* output,
-                          int num_rois, int batch, int channels, int pooled, int sampling_ratio,
-                          int k_min, int k_max, float canonical_scale, int canonical_level, int dtype,
-                          mrb_stream_t stream);
-int mrb_roi_align_fpn_bwd(const void* grad_output, void* const* grad_feats_host, const int* heights_host,
-                          const int* widths_host, const float* scales_host, int num_levels,
-                          const float* rois, int num_rois, int batch, int channels, int pooled,
-                          int sampling_ratio, int k_min, int k_max, float canonical_scale,
-                          int canonical_level, int dtype, mrb_stream_t stream);
-
 /* ------------------------------------------------------------------- ROIPool
  * replaces ROIPool_forward / ROIPool_backward (csrc/ROIPool.h:11-45;
  * csrc/cuda/ROIPool_cuda.cu:16-202).  NCHW fp32.  argmax: int32 offset in the H*W
@@ -187,21 +169,25 @@ int mrb_deform_psroi_bwd(const float* out_grad, const float* data, const float* 
 typedef struct mrb_conv_params {
   int batch, height, width, cin;   /* input  NHWC */
   int cout, kh, kw;                /* filter KRSC */
-  int stride, pad;                 /* symmetric; dilation 1; groups 1 */
+  int stride, pad;                 /* symmetric; dilation 1; groups 1; stride 2 only for 1x1 */
   int relu;                        /* fused ReLU in the epilogue */
   int out_dtype;                   /* MRB_BF16 or MRB_F32 */
 } mrb_conv_params;
 int mrb_conv2d_fwd(const mrb_conv_params* p, const void* input_bf16, const void* weight_bf16,
                    const float* scale, const float* bias, const void* residual, void* output,
                    mrb_stream_t stream);
-/* dgrad: grad_input[N,H,W,Cin] = conv_transpose(grad_output, weight); optional fused
- * ReLU-backward mask (zero where `relu_input_mask` <= 0, same shape as grad_input). */
+/* dgrad: grad_input[N,H,W,Cin] = conv_transpose(grad_output[N,Ho,Wo,Cout] (bf16), weight) computed by the
+ * same implicit-GEMM kernel on flipped/transposed weights that are prepared into `workspace`
+ * (>= mrb_conv2d_dgrad_workspace_bytes).  `scale` (optional, per Cout) folds the frozen-BN scale of the
+ * forward epilogue into the weights; `add` (optional, bf16, shaped like grad_input) is summed in (the
+ * other branch of a residual join); `relu_mask` (optional, bf16, shaped like grad_input) zeroes the
+ * result where the saved forward activation is <= 0 (ReLU backward of the producer layer).
+ * p->out_dtype selects the grad_input element type.  stride 2 is supported for 1x1 kernels only
+ * (grad_input is zero-filled, then written at even positions) and without add / relu_mask. */
+size_t mrb_conv2d_dgrad_workspace_bytes(const mrb_conv_params* p);
 int mrb_conv2d_dgrad(const mrb_conv_params* p, const void* grad_output_bf16, const void* weight_bf16,
-                     void* grad_input, mrb_stream_t stream);
-/* wgrad: grad_weight[Cout,kh,kw,Cin] (fp32) = sum over N,Ho,Wo; split-K with fp32 atomics into a
- * zero-initialised buffer (zeroed inside). */
-int mrb_conv2d_wgrad(const mrb_conv_params* p, const void* input_bf16, const void* grad_output_bf16,
-                     float* grad_weight, mrb_stream_t stream);
+                     const float* scale, const void* add, const void* relu_mask, void* grad_input,
+                     void* workspace, size_t workspace_bytes, mrb_stream_t stream);
 
 #ifdef __cplusplus
 }

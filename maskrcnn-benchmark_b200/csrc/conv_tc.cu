@@ -1,0 +1,545 @@
+// conv_tc.cu -- dense convolution as implicit GEMM on the 5th-generation tensor cores (sm_100a).
+//
+// Replaces the ATen/cuDNN convolution behind layers.Conv2d (reference layers/misc.py:30-43, call
+// sites modeling/backbone/resnet.py:258-353, fpn.py:35-36, rpn/rpn.py:87-93, make_layers.py:53,99) and
+// the FrozenBatchNorm2d / ReLU / residual-add passes that follow it (layers/batch_norm.py:27-31,
+// resnet.py:324-344), fused into the epilogue.
+//
+//   D[pixel, cout] = sum_{tap, cin} X[pixel + tap, cin] * W[cout, tap, cin]
+//
+// GEMM view: M = output pixels (tile = th x tw = 128 pixels of one image), N = Cout tile (<= 256),
+// K = taps x Cin in blocks of 64 channels of one filter tap.
+//   * A (activations, NHWC bf16): one 4-D TMA box {64 ch, tw, th, 1} per (tap, channel block), its
+//     (w, h) corner shifted by the tap offset.  Out-of-image rows/columns are zero-filled by the TMA
+//     unit, so padding and partial tiles cost nothing and no im2col matrix exists anywhere.
+//     The box lands in shared memory as 128 rows x 128 B with the 128-byte swizzle == the canonical
+//     K-major SWIZZLE_128B operand layout of tcgen05.mma.
+//   * B (weights, [Cout, taps, Cin] bf16): 3-D TMA box {64 ch, 1 tap, BN}.
+//   * accumulators: fp32 in TMEM, two stages of BN columns, so the epilogue of tile i overlaps the
+//     main loop of tile i+1.
+//   * warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread
+//     tcgen05.mma issuer, warps 2..5 = epilogue (tcgen05.ld 32x32b -> scale/bias/residual/ReLU/mask
+//     -> bf16/fp32 -> 128-bit global stores).  smem ring of 4-8 stages guarded by mbarriers;
+//     tcgen05.commit releases ring slots and publishes accumulators.
+//   * persistent: grid = min(#tiles, 148 SMs), static round-robin tile order with the Cout tile
+//     fastest so co-resident CTAs share activation tiles through L2.
+// The same kernel serves forward, data-gradient (flipped/transposed weights prepared by
+// conv_prepare_dgrad_weights_kernel, output optionally strided for stride-2 1x1 layers) and, through
+// the degenerate H = 1 view, the fully-connected layers of the ROI heads.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include <mutex>
+
+#include "common.cuh"
+
+namespace mrb {
+
+// ------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], bf16 x bf16 -> fp32
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
+//   [0,14) start>>4 | [16,30) LBO>>4 (unused for swizzled K-major, 1) | [32,46) SBO>>4 = 1024 B (8 rows x 128 B)
+//   [46,48) version = 1 (Blackwell) | [61,64) layout = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+
+// ------------------------------------------------------------------------------- kernel
+constexpr int kConvThreads = 192;
+constexpr int kTileM = 128;
+constexpr int kBlockK = 64;                 // channels per k-block (128 B of bf16)
+constexpr int kABytes = kTileM * kBlockK * 2;  // 16 KB
+
+struct ConvArgs {
+  int tiles_total, tiles_n, tiles_w, tiles_h;  // tiles_total = batch * tiles_h * tiles_w * tiles_n
+  int th, tw, Ho, Wo;
+  int cin_blocks, kh, kw, pad;
+  int cout, bn, stages, relu, out_f32;
+  long long out_n, out_h, out_w;  // output strides in elements (channel stride 1)
+  const float* scale;
+  const float* bias;
+  const __nv_bfloat16* residual;   // same indexing as out (bf16)
+  const __nv_bfloat16* relu_mask;  // same indexing as out: result zeroed where mask <= 0
+  void* out;
+};
+
+__device__ __forceinline__ void tile_coords(const ConvArgs& a, int tile, int& n_tile, int& img, int& h0, int& w0) {
+  n_tile = tile % a.tiles_n;
+  int m = tile / a.tiles_n;
+  const int wt = m % a.tiles_w; m /= a.tiles_w;
+  const int ht = m % a.tiles_h;
+  img = m / a.tiles_h;
+  h0 = ht * a.th;
+  w0 = wt * a.tw;
+}
+
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const ConvArgs a) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t stage_bytes = kABytes + (uint32_t)a.bn * 128u;
+  const uint32_t bar_base = smem_base + (uint32_t)a.stages * stage_bytes;
+  // barriers: full[stages], empty[stages], tmem_full[2], tmem_empty[2]; then the TMEM base slot
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (a.stages + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * a.stages + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * a.stages + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * a.stages + 4);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int k_blocks = a.kh * a.kw * a.cin_blocks;
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < 2u * a.bn) tmem_cols <<= 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < a.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 128); }
+    fence_barrier_init();
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      int s = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < a.tiles_total; tile += gridDim.x) {
+        int n_tile, img, h0, w0;
+        tile_coords(a, tile, n_tile, img, h0, w0);
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          const int tap = kb / a.cin_blocks, cb = kb - tap * a.cin_blocks;
+          const int r = tap / a.kw, q = tap - r * a.kw;
+          mbar_wait(empty_bar(s), phase ^ 1u);
+          mbar_expect_tx(full_bar(s), stage_bytes);
+          const uint32_t sa = smem_base + (uint32_t)s * stage_bytes;
+          tma_load_4d(sa, &map_a, full_bar(s), cb * kBlockK, w0 + q - a.pad, h0 + r - a.pad, img);
+          tma_load_3d(sa + kABytes, &map_b, full_bar(s), cb * kBlockK, tap, n_tile * a.bn);
+          if (++s == a.stages) { s = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    if (lane == 0) {
+      // instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6)=1, a=BF16 [7,10)=1, b=BF16 [10,13)=1,
+      // a,b K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29)
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.bn >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+      int s = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < a.tiles_total; tile += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * a.bn);
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(full_bar(s), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + (uint32_t)s * stage_bytes;
+          const uint64_t da = umma_desc_k_sw128(sa), db = umma_desc_k_sw128(sa + kABytes);
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k)  // +32 B per K=16 step inside the 128 B swizzle span
+            umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+          umma_commit(empty_bar(s));
+          if (kb == k_blocks - 1) umma_commit(tfull_bar(acc));
+          if (++s == a.stages) { s = 0; phase ^= 1u; }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else {
+    // ================================ epilogue ================================
+    const int quad = warp & 3;                 // TMEM lane quadrant this warp may read
+    const int row = quad * 32 + lane;          // accumulator row == pixel within the tile
+    const int hh = row / a.tw, ww = row - hh * a.tw;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < a.tiles_total; tile += gridDim.x) {
+      int n_tile, img, h0, w0;
+      tile_coords(a, tile, n_tile, img, h0, w0);
+      const int h = h0 + hh, w = w0 + ww;
+      const bool valid = (h < a.Ho) && (w < a.Wo);
+      const long long pix = (long long)img * a.out_n + (long long)h * a.out_h + (long long)w * a.out_w;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * a.bn);
+      for (int col = 0; col < a.bn; col += 32) {
+        const int c0 = n_tile * a.bn + col;
+        if (c0 >= a.cout) break;  // warp-uniform
+        uint32_t v[32];
+        __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge lanes that skipped the stores of the last chunk
+        tmem_ld32(t_row + (uint32_t)col, v);
+        tmem_ld_wait();
+        if (!valid) continue;
+        const int nvalid = min(32, a.cout - c0);
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float x = __uint_as_float(v[j]);
+          if (j < nvalid) {
+            if (a.scale) x *= __ldg(a.scale + c0 + j);
+            if (a.bias) x += __ldg(a.bias + c0 + j);
+          }
+          f[j] = x;
+        }
+        const long long o = pix + c0;
+        const bool vec = (nvalid == 32) && ((a.cout & 7) == 0);
+        if (a.residual) {
+          if (vec) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint4 rr = __ldg(reinterpret_cast<const uint4*>(a.residual + o + q * 8));
+              const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rr);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 t = __bfloat1622float2(r2[j]);
+                f[q * 8 + 2 * j] += t.x; f[q * 8 + 2 * j + 1] += t.y;
+              }
+            }
+          } else {
+            for (int j = 0; j < nvalid; ++j) f[j] += __bfloat162float(a.residual[o + j]);
+          }
+        }
+        if (a.relu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+        }
+        if (a.relu_mask) {
+          if (vec) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint4 rr = __ldg(reinterpret_cast<const uint4*>(a.relu_mask + o + q * 8));
+              const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rr);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 t = __bfloat1622float2(r2[j]);
+                if (!(t.x > 0.f)) f[q * 8 + 2 * j] = 0.f;
+                if (!(t.y > 0.f)) f[q * 8 + 2 * j + 1] = 0.f;
+              }
+            }
+          } else {
+            for (int j = 0; j < nvalid; ++j) if (!(__bfloat162float(a.relu_mask[o + j]) > 0.f)) f[j] = 0.f;
+          }
+        }
+        if (a.out_f32) {
+          float* dst = reinterpret_cast<float*>(a.out) + o;
+          if (vec && ((a.cout & 3) == 0)) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              *reinterpret_cast<float4*>(dst + q * 4) = make_float4(f[q * 4], f[q * 4 + 1], f[q * 4 + 2], f[q * 4 + 3]);
+          } else {
+            for (int j = 0; j < nvalid; ++j) dst[j] = f[j];
+          }
+        } else {
+          __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(a.out) + o;
+          if (vec) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint4 pk;
+              __nv_bfloat162* p2 = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) p2[j] = __floats2bfloat162_rn(f[q * 8 + 2 * j], f[q * 8 + 2 * j + 1]);
+              *reinterpret_cast<uint4*>(dst + q * 8) = pk;
+            }
+          } else {
+            for (int j = 0; j < nvalid; ++j) dst[j] = __float2bfloat16_rn(f[j]);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+// ------------------------------------------------------------------------------- weight prep
+// dgrad weights: Wd[cin][kh-1-r][kw-1-q][cout] = W[cout][r][q][cin] * (scale ? scale[cout] : 1)
+__global__ void conv_prepare_dgrad_weights_kernel(const __nv_bfloat16* __restrict__ w, const float* __restrict__ scale,
+                                                  __nv_bfloat16* __restrict__ wd, int cout, int taps, int cin) {
+  const int total = cout * taps * cin;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    // i indexes the destination [cin][tap'][cout] so that writes are coalesced
+    const int co = i % cout;
+    const int tp = (i / cout) % taps;
+    const int ci = i / cout / taps;
+    float v = __bfloat162float(w[((size_t)co * taps + (taps - 1 - tp)) * cin + ci]);
+    if (scale) v *= scale[co];
+    wd[i] = __float2bfloat16_rn(v);
+  }
+}
+
+// ------------------------------------------------------------------------------- host side
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_tmapEncodeTiled get_encode() {
+  static PFN_tmapEncodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (PFN_tmapEncodeTiled)p;
+  });
+  return fn;
+}
+
+static int encode_bf16(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                       const cuuint32_t* box) {
+  PFN_tmapEncodeTiled enc = get_encode();
+  if (!enc) return MRB_ERR_DRIVER;
+  cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? MRB_OK : MRB_ERR_BAD_ARG;
+}
+
+struct ConvPlan {
+  // logical GEMM-side geometry after the 1x1 flattening
+  int batch, Hin, Win;        // TMA view of the input (already subsampled for stride 2)
+  long long in_w, in_h, in_n; // input strides in elements
+  int Ho, Wo;
+  long long out_n, out_h, out_w;
+};
+
+// Launch one implicit-GEMM convolution.  `x` is the TMA-visible input [batch][Hin][Win][cin] with the
+// given element strides; `w` is [cout][taps][cin].
+static int conv_launch(const ConvPlan& pl, const void* x, const void* w, int cin, int cout, int kh, int kw, int pad,
+                       const float* scale, const float* bias, const void* residual, const void* relu_mask, void* out,
+                       int relu, int out_f32, cudaStream_t stream) {
+  if (cin % 8 || ((uintptr_t)x & 15) || ((uintptr_t)w & 15) || ((uintptr_t)out & 15)) return MRB_ERR_UNSUPPORTED;
+  if ((pl.in_w * 2) % 16 || (pl.in_h * 2) % 16 || (pl.in_n * 2) % 16) return MRB_ERR_UNSUPPORTED;
+  if (residual && ((uintptr_t)residual & 15)) return MRB_ERR_UNSUPPORTED;
+  if (relu_mask && ((uintptr_t)relu_mask & 15)) return MRB_ERR_UNSUPPORTED;
+  // tile shape: th * tw == 128, minimise padded work
+  int best_th = 1, best_tw = 128;
+  long long best = -1;
+  const int th_order[8] = {8, 4, 16, 2, 32, 1, 64, 128};  // squarer tiles first: better halo reuse in L2
+  for (int i = 0; i < 8; ++i) {
+    const int th = th_order[i], tw = 128 / th;
+    const long long cost = (long long)ceil_div(pl.Ho, th) * th * ceil_div(pl.Wo, tw) * tw;
+    if (best < 0 || cost < best) { best = cost; best_th = th; best_tw = tw; }
+  }
+  const int th = best_th, tw = best_tw;
+  int bn = (cout + 15) / 16 * 16;
+  if (bn > 256) bn = 256;
+  ConvArgs a;
+  a.th = th; a.tw = tw; a.Ho = pl.Ho; a.Wo = pl.Wo;
+  a.tiles_h = ceil_div(pl.Ho, th); a.tiles_w = ceil_div(pl.Wo, tw); a.tiles_n = ceil_div(cout, bn);
+  const long long tiles = (long long)pl.batch * a.tiles_h * a.tiles_w * a.tiles_n;
+  if (tiles <= 0 || tiles >= (1ll << 31)) return tiles == 0 ? MRB_OK : MRB_ERR_UNSUPPORTED;
+  a.tiles_total = (int)tiles;
+  a.cin_blocks = ceil_div(cin, kBlockK); a.kh = kh; a.kw = kw; a.pad = pad;
+  a.cout = cout; a.bn = bn; a.relu = relu; a.out_f32 = out_f32;
+  a.out_n = pl.out_n; a.out_h = pl.out_h; a.out_w = pl.out_w;
+  a.scale = scale; a.bias = bias; a.residual = (const __nv_bfloat16*)residual; a.relu_mask = (const __nv_bfloat16*)relu_mask;
+  a.out = out;
+  const uint32_t stage_bytes = kABytes + bn * 128;
+  int stages = (int)((200 * 1024) / stage_bytes);
+  if (stages > 8) stages = 8;
+  a.stages = stages;
+  const size_t smem = (size_t)stages * stage_bytes + 8 * (2 * stages + 4) + 16 + 1024;
+
+  CUtensorMap map_a, map_b;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)pl.Win, (cuuint64_t)pl.Hin, (cuuint64_t)pl.batch};
+    cuuint64_t strides[3] = {(cuuint64_t)pl.in_w * 2, (cuuint64_t)pl.in_h * 2, (cuuint64_t)pl.in_n * 2};
+    cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)tw, (cuuint32_t)th, 1};
+    int rc = encode_bf16(&map_a, x, 4, dims, strides, box);
+    if (rc) return rc;
+  }
+  {
+    const int taps = kh * kw;
+    cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)taps, (cuuint64_t)cout};
+    cuuint64_t strides[2] = {(cuuint64_t)cin * 2, (cuuint64_t)taps * cin * 2};
+    cuuint32_t box[3] = {(cuuint32_t)kBlockK, 1, (cuuint32_t)bn};
+    int rc = encode_bf16(&map_b, w, 3, dims, strides, box);
+    if (rc) return rc;
+  }
+  static std::once_flag attr_once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(attr_once, [] {
+    attr_err = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  });
+  if (attr_err != cudaSuccess) return (int)attr_err;
+  const int grid = a.tiles_total < kNumSMs ? a.tiles_total : kNumSMs;
+  conv_tc_kernel<<<grid, kConvThreads, smem, stream>>>(map_a, map_b, a);
+  MRB_LAUNCH_CHECK();
+  return MRB_OK;
+}
+
+static int conv_check(const mrb_conv_params* p) {
+  if (!p) return MRB_ERR_BAD_ARG;
+  if (p->batch < 0 || p->height <= 0 || p->width <= 0 || p->cin <= 0 || p->cout <= 0 || p->kh <= 0 || p->kw <= 0 ||
+      p->stride <= 0 || p->pad < 0)
+    return MRB_ERR_BAD_ARG;
+  if (p->kh != p->kw) return MRB_ERR_UNSUPPORTED;
+  if (p->stride != 1 && !(p->stride == 2 && p->kh == 1 && p->pad == 0)) return MRB_ERR_UNSUPPORTED;
+  return MRB_OK;
+}
+
+}  // namespace mrb
+using namespace mrb;
+
+MRB_API int mrb_conv2d_fwd(const mrb_conv_params* p, const void* input, const void* weight, const float* scale,
+                           const float* bias, const void* residual, void* output, mrb_stream_t stream) {
+  int rc = conv_check(p);
+  if (rc) return rc;
+  if (p->batch == 0) return MRB_OK;
+  if (!input || !weight || !output) return MRB_ERR_BAD_ARG;
+  const int Ho = (p->height + 2 * p->pad - p->kh) / p->stride + 1, Wo = (p->width + 2 * p->pad - p->kw) / p->stride + 1;
+  if (Ho <= 0 || Wo <= 0) return MRB_ERR_BAD_ARG;
+  ConvPlan pl;
+  const long long C = p->cin, Co = p->cout;
+  if (p->kh == 1 && p->stride == 1 && p->pad == 0) {
+    // pure GEMM: all pixels of the batch on one axis, zero tile waste
+    pl.batch = 1; pl.Hin = 1; pl.Win = p->batch * p->height * p->width;
+    pl.in_w = C; pl.in_h = (long long)pl.Win * C; pl.in_n = pl.in_h;
+    pl.Ho = 1; pl.Wo = pl.Win;
+    pl.out_w = Co; pl.out_h = (long long)pl.Wo * Co; pl.out_n = pl.out_h;
+  } else {
+    pl.batch = p->batch; pl.Hin = (p->stride == 2 ? Ho : p->height); pl.Win = (p->stride == 2 ? Wo : p->width);
+    pl.in_w = C * p->stride; pl.in_h = (long long)p->width * C * p->stride; pl.in_n = (long long)p->height * p->width * C;
+    pl.Ho = Ho; pl.Wo = Wo;
+    pl.out_w = Co; pl.out_h = (long long)Wo * Co; pl.out_n = (long long)Ho * Wo * Co;
+  }
+  return conv_launch(pl, input, weight, p->cin, p->cout, p->kh, p->kw, p->pad, scale, bias, residual, nullptr, output,
+                     p->relu, p->out_dtype == MRB_F32, (cudaStream_t)stream);
+}
+
+MRB_API size_t mrb_conv2d_dgrad_workspace_bytes(const mrb_conv_params* p) {
+  if (conv_check(p)) return 0;
+  return ((size_t)p->cout * p->kh * p->kw * p->cin * 2 + 255) & ~(size_t)255;
+}
+
+MRB_API int mrb_conv2d_dgrad(const mrb_conv_params* p, const void* grad_output, const void* weight, const float* scale,
+                             const void* add, const void* relu_mask, void* grad_input, void* workspace,
+                             size_t workspace_bytes, mrb_stream_t stream_) {
+  int rc = conv_check(p);
+  if (rc) return rc;
+  if (p->batch == 0) return MRB_OK;
+  if (!grad_output || !weight || !grad_input || !workspace) return MRB_ERR_BAD_ARG;
+  if (workspace_bytes < mrb_conv2d_dgrad_workspace_bytes(p)) return MRB_ERR_WORKSPACE;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int Ho = (p->height + 2 * p->pad - p->kh) / p->stride + 1, Wo = (p->width + 2 * p->pad - p->kw) / p->stride + 1;
+  const int taps = p->kh * p->kw;
+  __nv_bfloat16* wd = (__nv_bfloat16*)workspace;
+  {
+    const int total = p->cout * taps * p->cin;
+    conv_prepare_dgrad_weights_kernel<<<grid_for(total, 256, 8, 4), 256, 0, stream>>>((const __nv_bfloat16*)weight, scale, wd,
+                                                                                     p->cout, taps, p->cin);
+    MRB_LAUNCH_CHECK();
+  }
+  // dgrad == forward conv of grad_output [N,Ho,Wo,Cout] with Wd [Cin][taps][Cout], pad' = k - 1 - pad
+  ConvPlan pl;
+  const long long Ci = p->cin, Co = p->cout;
+  if (p->stride == 2) {
+    // 1x1 stride 2: grad_input[2h, 2w] = Wd . grad_output[h, w]; every other position is zero
+    if (add || relu_mask) return MRB_ERR_UNSUPPORTED;
+    const size_t bytes = (size_t)p->batch * p->height * p->width * p->cin * (p->out_dtype == MRB_F32 ? 4 : 2);
+    MRB_CUDA_TRY(cudaMemsetAsync(grad_input, 0, bytes, stream));
+    pl.batch = p->batch; pl.Hin = Ho; pl.Win = Wo;
+    pl.in_w = Co; pl.in_h = (long long)Wo * Co; pl.in_n = (long long)Ho * Wo * Co;
+    pl.Ho = Ho; pl.Wo = Wo;
+    pl.out_w = 2 * Ci; pl.out_h = 2ll * p->width * Ci; pl.out_n = (long long)p->height * p->width * Ci;
+    return conv_launch(pl, grad_output, wd, p->cout, p->cin, 1, 1, 0, nullptr, nullptr, nullptr, nullptr, grad_input, 0,
+                       p->out_dtype == MRB_F32, stream);
+  }
+  if (p->kh == 1 && p->pad == 0) {
+    pl.batch = 1; pl.Hin = 1; pl.Win = p->batch * Ho * Wo;
+    pl.in_w = Co; pl.in_h = (long long)pl.Win * Co; pl.in_n = pl.in_h;
+    pl.Ho = 1; pl.Wo = pl.Win;
+    pl.out_w = Ci; pl.out_h = (long long)pl.Wo * Ci; pl.out_n = pl.out_h;
+  } else {
+    pl.batch = p->batch; pl.Hin = Ho; pl.Win = Wo;
+    pl.in_w = Co; pl.in_h = (long long)Wo * Co; pl.in_n = (long long)Ho * Wo * Co;
+    pl.Ho = p->height; pl.Wo = p->width;
+    pl.out_w = Ci; pl.out_h = (long long)p->width * Ci; pl.out_n = (long long)p->height * p->width * Ci;
+  }
+  return conv_launch(pl, grad_output, wd, p->cout, p->cin, p->kh, p->kw, p->kh - 1 - p->pad, nullptr, nullptr, add, relu_mask,
+                     grad_input, 0, p->out_dtype == MRB_F32, stream);
+}
