@@ -1,0 +1,148 @@
+"""Box arithmetic shared by RPN and ROI heads (legacy "+1" pixel convention throughout)."""
+import math
+
+import numpy as np
+import torch
+
+
+def box_area(b):
+    """structures/bounding_box.py:214-226 (xyxy, TO_REMOVE = 1)"""
+    return (b[:, 2] - b[:, 0] + 1) * (b[:, 3] - b[:, 1] + 1)
+
+
+def box_iou(a, b):
+    """structures/boxlist_ops.py:53-89: [len(a), len(b)] IoU with +1 areas."""
+    area_a, area_b = box_area(a), box_area(b)
+    lt = torch.max(a[:, None, :2], b[None, :, :2])
+    rb = torch.min(a[:, None, 2:], b[None, :, 2:])
+    wh = (rb - lt + 1).clamp(min=0)
+    inter = wh[..., 0] * wh[..., 1]
+    return inter / (area_a[:, None] + area_b[None, :] - inter)
+
+
+class BoxCoder:
+    """modeling/box_coder.py:7-95"""
+
+    def __init__(self, weights, bbox_xform_clip=math.log(1000.0 / 16)):
+        self.weights = weights
+        self.clip = bbox_xform_clip
+
+    def encode(self, reference_boxes, proposals):
+        ew = proposals[:, 2] - proposals[:, 0] + 1
+        eh = proposals[:, 3] - proposals[:, 1] + 1
+        ex = proposals[:, 0] + 0.5 * ew
+        ey = proposals[:, 1] + 0.5 * eh
+        gw = reference_boxes[:, 2] - reference_boxes[:, 0] + 1
+        gh = reference_boxes[:, 3] - reference_boxes[:, 1] + 1
+        gx = reference_boxes[:, 0] + 0.5 * gw
+        gy = reference_boxes[:, 1] + 0.5 * gh
+        wx, wy, ww, wh = self.weights
+        return torch.stack((wx * (gx - ex) / ew, wy * (gy - ey) / eh, ww * torch.log(gw / ew), wh * torch.log(gh / eh)), 1)
+
+    def decode(self, rel_codes, boxes):
+        boxes = boxes.to(rel_codes.dtype)
+        w = boxes[:, 2] - boxes[:, 0] + 1
+        h = boxes[:, 3] - boxes[:, 1] + 1
+        cx = boxes[:, 0] + 0.5 * w
+        cy = boxes[:, 1] + 0.5 * h
+        wx, wy, ww, wh = self.weights
+        dx, dy = rel_codes[:, 0::4] / wx, rel_codes[:, 1::4] / wy
+        dw = torch.clamp(rel_codes[:, 2::4] / ww, max=self.clip)
+        dh = torch.clamp(rel_codes[:, 3::4] / wh, max=self.clip)
+        pcx, pcy = dx * w[:, None] + cx[:, None], dy * h[:, None] + cy[:, None]
+        pw, ph = torch.exp(dw) * w[:, None], torch.exp(dh) * h[:, None]
+        out = torch.zeros_like(rel_codes)
+        out[:, 0::4] = pcx - 0.5 * pw
+        out[:, 1::4] = pcy - 0.5 * ph
+        out[:, 2::4] = pcx + 0.5 * pw - 1
+        out[:, 3::4] = pcy + 0.5 * ph - 1
+        return out
+
+
+def clip_boxes(boxes, width, height):
+    """BoxList.clip_to_image(remove_empty=False), structures/bounding_box.py:198-212"""
+    boxes = boxes.clone()
+    boxes[..., 0].clamp_(min=0, max=width - 1)
+    boxes[..., 1].clamp_(min=0, max=height - 1)
+    boxes[..., 2].clamp_(min=0, max=width - 1)
+    boxes[..., 3].clamp_(min=0, max=height - 1)
+    return boxes
+
+
+class Matcher:
+    """modeling/matcher.py:5-112.  -1 = below low threshold, -2 = between thresholds."""
+    BELOW_LOW, BETWEEN = -1, -2
+
+    def __init__(self, high, low, allow_low_quality_matches=False):
+        assert low <= high
+        self.high, self.low, self.allow_low = high, low, allow_low_quality_matches
+
+    def __call__(self, quality):  # [num_gt, num_pred]
+        if quality.numel() == 0:
+            raise ValueError("No ground-truth / proposal boxes available for one of the images during training")
+        vals, matches = quality.max(dim=0)
+        all_matches = matches.clone() if self.allow_low else None
+        below = vals < self.low
+        between = (vals >= self.low) & (vals < self.high)
+        matches = torch.where(below, torch.full_like(matches, self.BELOW_LOW), matches)
+        matches = torch.where(between, torch.full_like(matches, self.BETWEEN), matches)
+        if self.allow_low:
+            best_per_gt = quality.max(dim=1)[0]
+            is_best = (quality == best_per_gt[:, None]).any(dim=0)  # predictions that are some gt's best (ties incl.)
+            matches = torch.where(is_best, all_matches, matches)
+        return matches
+
+
+def sample_pos_neg(labels, batch_size, positive_fraction, generator=None):
+    """modeling/balanced_positive_negative_sampler.py:19-68 for one image.
+    labels: -1 ignore, 0 negative, >0 positive.  Returns boolean masks (pos, neg).  Sync-free: a random
+    key per element, top-k by key among the candidates == a uniform random subset."""
+    n = labels.numel()
+    num_pos_cap = int(batch_size * positive_fraction)
+    pos, neg = labels >= 1, labels == 0
+    key = torch.rand(n, device=labels.device, generator=generator)
+    # rank of each positive among positives by random key
+    pos_rank = torch.argsort(torch.argsort(torch.where(pos, key, key.new_full((), 2.0))))
+    num_pos = torch.clamp(pos.sum(), max=num_pos_cap)
+    pos_sel = pos & (pos_rank < num_pos)
+    neg_rank = torch.argsort(torch.argsort(torch.where(neg, key, key.new_full((), 2.0))))
+    num_neg = torch.minimum(neg.sum(), batch_size - num_pos)
+    neg_sel = neg & (neg_rank < num_neg)
+    return pos_sel, neg_sel
+
+
+# ---------------------------------------------------------------------------------- anchors
+def _whctrs(a):
+    w, h = a[2] - a[0] + 1, a[3] - a[1] + 1
+    return w, h, a[0] + 0.5 * (w - 1), a[1] + 0.5 * (h - 1)
+
+
+def _mk(ws, hs, cx, cy):
+    ws, hs = ws[:, None], hs[:, None]
+    return np.hstack((cx - 0.5 * (ws - 1), cy - 0.5 * (hs - 1), cx + 0.5 * (ws - 1), cy + 0.5 * (hs - 1)))
+
+
+def cell_anchors(stride, sizes, aspect_ratios):
+    """The Detectron anchor enumeration (modeling/rpn/anchor_generator.py:211-289): ratios on the
+    stride-sized base window with rounded widths/heights, then scales = size / stride."""
+    base = np.array([1, 1, stride, stride], dtype=np.float64) - 1
+    ratios = np.array(aspect_ratios, dtype=np.float64)
+    scales = np.array(sizes, dtype=np.float64) / stride
+    w, h, cx, cy = _whctrs(base)
+    ws = np.round(np.sqrt(w * h / ratios))
+    hs = np.round(ws * ratios)
+    ratio_anchors = _mk(ws, hs, cx, cy)
+    out = []
+    for a in ratio_anchors:
+        w, h, cx, cy = _whctrs(a)
+        out.append(_mk(w * scales, h * scales, cx, cy))
+    return torch.from_numpy(np.vstack(out)).float()
+
+
+def grid_anchors(cell, stride, gh, gw, device):
+    """anchor_generator.py:72-98: [(gh*gw*A), 4], location-major, anchor-minor."""
+    sx = torch.arange(0, gw * stride, step=stride, dtype=torch.float32, device=device)
+    sy = torch.arange(0, gh * stride, step=stride, dtype=torch.float32, device=device)
+    yy, xx = torch.meshgrid(sy, sx, indexing="ij")
+    shifts = torch.stack((xx.reshape(-1), yy.reshape(-1), xx.reshape(-1), yy.reshape(-1)), 1)
+    return (shifts.view(-1, 1, 4) + cell.to(device).view(1, -1, 4)).reshape(-1, 4)
