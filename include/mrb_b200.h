@@ -68,6 +68,26 @@ int mrb_roi_align_bwd(const float* grad_output, const float* rois, float* grad_i
                       int batch, int channels, int height, int width, int pooled_h, int pooled_w,
                       float spatial_scale, int sampling_ratio, int layout, mrb_stream_t stream);
 
+/* Multi-level (FPN) ROIAlign: the whole `Pooler.forward` loop (modeling/poolers.py:91-121:
+ * LevelMapper + per-level nonzero/ROIAlign/index-scatter) in one launch.  Feature maps are NHWC,
+ * bf16 or fp32 (`dtype`, also the output element type); each ROI picks its level in the kernel:
+ * floor(canonical_level + log2(sqrt(area)/canonical_scale + 1e-6)) clamped to [k_min,k_max]
+ * (poolers.py:31-42), levels[l] <-> k_min + l.
+ *   feats_host / heights_host / widths_host / scales_host : HOST arrays, one entry per level
+ *                  (the device pointers inside feats_host are device pointers)
+ *   output       : [num_rois, channels, P, P] (out_nhwc == 0) or [num_rois, P, P, channels]
+ * Backward accumulates (red.add.v4.f32) into caller-zeroed fp32 NHWC gradient maps. */
+int mrb_roi_align_fpn_fwd(const void* const* feats_host, const int* heights_host, const int* widths_host,
+                          const float* scales_host, int num_levels, const float* rois, void* output,
+                          int num_rois, int batch, int channels, int pooled, int sampling_ratio,
+                          int k_min, int k_max, float canonical_scale, int canonical_level, int dtype,
+                          int out_nhwc, mrb_stream_t stream);
+int mrb_roi_align_fpn_bwd(const void* grad_output, float* const* grad_feats_host, const int* heights_host,
+                          const int* widths_host, const float* scales_host, int num_levels,
+                          const float* rois, int num_rois, int batch, int channels, int pooled,
+                          int sampling_ratio, int k_min, int k_max, float canonical_scale,
+                          int canonical_level, int dtype, int out_nhwc, mrb_stream_t stream);
+
 /* ------------------------------------------------------------------- ROIPool
  * replaces ROIPool_forward / ROIPool_backward (csrc/ROIPool.h:11-45;
  * csrc/cuda/ROIPool_cuda.cu:16-202).  NCHW fp32.  argmax: int32 offset in the H*W
@@ -172,6 +192,9 @@ typedef struct mrb_conv_params {
   int stride, pad;                 /* symmetric; dilation 1; groups 1; stride 2 only for 1x1 */
   int relu;                        /* fused ReLU in the epilogue */
   int out_dtype;                   /* MRB_BF16 or MRB_F32 */
+  int out_h, out_w;                /* 0 = (in + 2*pad - k)/stride + 1; a smaller explicit size computes only the
+                                      top-left out_h x out_w outputs (used by the space-to-depth stem, whose 4x4
+                                      kernel needs padding 2 on the left/top but 1 on the right/bottom) */
 } mrb_conv_params;
 int mrb_conv2d_fwd(const mrb_conv_params* p, const void* input_bf16, const void* weight_bf16,
                    const float* scale, const float* bias, const void* residual, void* output,

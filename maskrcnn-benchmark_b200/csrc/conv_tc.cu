@@ -471,11 +471,15 @@ MRB_API int mrb_conv2d_fwd(const mrb_conv_params* p, const void* input, const vo
   if (rc) return rc;
   if (p->batch == 0) return MRB_OK;
   if (!input || !weight || !output) return MRB_ERR_BAD_ARG;
-  const int Ho = (p->height + 2 * p->pad - p->kh) / p->stride + 1, Wo = (p->width + 2 * p->pad - p->kw) / p->stride + 1;
+  int Ho = (p->height + 2 * p->pad - p->kh) / p->stride + 1, Wo = (p->width + 2 * p->pad - p->kw) / p->stride + 1;
   if (Ho <= 0 || Wo <= 0) return MRB_ERR_BAD_ARG;
+  if (p->out_h > 0 || p->out_w > 0) {
+    if (p->out_h <= 0 || p->out_w <= 0 || p->out_h > Ho || p->out_w > Wo || p->stride != 1) return MRB_ERR_BAD_ARG;
+    Ho = p->out_h; Wo = p->out_w;
+  }
   ConvPlan pl;
   const long long C = p->cin, Co = p->cout;
-  if (p->kh == 1 && p->stride == 1 && p->pad == 0) {
+  if (p->kh == 1 && p->stride == 1 && p->pad == 0 && p->out_h == 0) {
     // pure GEMM: all pixels of the batch on one axis, zero tile waste
     pl.batch = 1; pl.Hin = 1; pl.Win = p->batch * p->height * p->width;
     pl.in_w = C; pl.in_h = (long long)pl.Win * C; pl.in_n = pl.in_h;
@@ -503,6 +507,7 @@ MRB_API int mrb_conv2d_dgrad(const mrb_conv_params* p, const void* grad_output, 
   if (rc) return rc;
   if (p->batch == 0) return MRB_OK;
   if (!grad_output || !weight || !grad_input || !workspace) return MRB_ERR_BAD_ARG;
+  if (p->out_h || p->out_w) return MRB_ERR_UNSUPPORTED;
   if (workspace_bytes < mrb_conv2d_dgrad_workspace_bytes(p)) return MRB_ERR_WORKSPACE;
   cudaStream_t stream = (cudaStream_t)stream_;
   const int Ho = (p->height + 2 * p->pad - p->kh) / p->stride + 1, Wo = (p->width + 2 * p->pad - p->kw) / p->stride + 1;

@@ -34,7 +34,7 @@ class DcnParams(ctypes.Structure):
 class ConvParams(ctypes.Structure):
     """struct mrb_conv_params (include/mrb_b200.h)"""
     _fields_ = [(n, _c_int) for n in (
-        "batch", "height", "width", "cin", "cout", "kh", "kw", "stride", "pad", "relu", "out_dtype")]
+        "batch", "height", "width", "cin", "cout", "kh", "kw", "stride", "pad", "relu", "out_dtype", "out_h", "out_w")]
 
 
 def _load():

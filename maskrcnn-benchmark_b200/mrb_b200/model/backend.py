@@ -106,8 +106,57 @@ class B200Backend(Backend):
         return _ConvFn.apply(x, weight, bias, residual, self._weight16(weight), scale, shift, stride, pad, relu,
                              out_fp32, self.wgrad_fn)
 
+    def stem(self, images, weight, scale, shift):
+        """7x7/2 conv on 3 channels == 4x4/1 conv on the 2x2 space-to-depth image (12 -> 16 channels):
+        out(o) = sum_t w[t] in(2o-3+t); with a leading zero tap t' = t+1 the taps pair up as
+        in(2(o-2+a)+i), a = 0..3, i = 0..1 -> s2d block o-2+a, phase i: a 4-tap conv with 2 blocks of
+        padding on the left/top, computed only for the Ho x Wo valid outputs."""
+        from mrb_b200 import ops
+        n, c, h, w = images.shape
+        if (h | w) & 1:
+            images = F.pad(images, (0, w & 1, 0, h & 1))
+        x = F.pixel_unshuffle(images, 2)
+        x = F.pad(x, (0, 0, 0, 0, 0, 16 - x.shape[1])).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        key = ("stem", id(weight))
+        ent = self._w16.get(key)
+        if ent is None or ent[0] != weight._version or ent[1].device != weight.device:
+            co = weight.shape[0]
+            w8 = F.pad(weight.detach(), (1, 0, 1, 0))                                   # [co, 3, 8, 8]
+            w4 = w8.view(co, c, 4, 2, 4, 2).permute(0, 1, 3, 5, 2, 4).reshape(co, c * 4, 4, 4)
+            w4 = F.pad(w4, (0, 0, 0, 0, 0, 16 - c * 4)).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+            self._w16[key] = (weight._version, w4)
+        else:
+            w4 = ent[1]
+        return ops.conv2d_fwd(x, w4, scale, shift, None, 1, 2, True, out_hw=((h + 1) // 2, (w + 1) // 2))
+
     def max_pool(self, x, k, s, p):
         return F.max_pool2d(x, k, s, p)
 
     def upsample2x(self, x):
         return F.interpolate(x, scale_factor=2, mode="nearest")
+
+    def linear(self, x, weight, bias, relu=False, out_fp32=False):
+        """Fully connected layer on the conv engine: [R, K] x [Cout, K]^T as a 1x1 conv over R "pixels"."""
+        r, k = x.shape
+        y = self.conv(x.to(torch.bfloat16).reshape(r, k, 1, 1), weight.view(weight.shape[0], k, 1, 1), bias=bias,
+                      relu=relu, out_fp32=out_fp32)
+        return y.reshape(r, weight.shape[0])
+
+    def deconv2x2(self, x, weight, bias, relu=False):
+        """ConvTranspose2d(k=2, s=2): four independent 1x1 convs (one per output sub-pixel) run as ONE
+        1x1 conv with 4*Cout outputs on the conv engine, then a pixel shuffle.  weight [Cin, Cout, 2, 2]."""
+        cin, cout = weight.shape[:2]
+        w4 = weight.permute(2, 3, 1, 0).reshape(4 * cout, cin, 1, 1)       # ((i, j, co), ci)
+        b4 = bias.repeat(4) if bias is not None else None
+        y = self.conv(x, w4, bias=b4, relu=relu)                            # [N, 4*Cout, H, W]
+        n, _, h, w = y.shape
+        y = y.view(n, 2, 2, cout, h, w).permute(0, 3, 4, 1, 5, 2).reshape(n, cout, 2 * h, 2 * w)
+        return y.contiguous(memory_format=torch.channels_last)
+
+    def roi_align_fpn(self, feats, rois, scales, pooled, sampling_ratio, nhwc):
+        from mrb_b200 import ops
+        return ops.roi_align_fpn(list(feats), rois, scales, pooled, sampling_ratio, out_nhwc=nhwc)
+
+    def nms_batched(self, boxes, scores, sizes, thr):
+        from mrb_b200 import ops
+        return ops.nms_batched(boxes, scores, sizes, thr)

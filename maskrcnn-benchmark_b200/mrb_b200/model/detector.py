@@ -1,0 +1,78 @@
+"""GeneralizedRCNN for the R-50-FPN configs (reference modeling/detector/generalized_rcnn.py:16-65)."""
+import torch
+from torch import nn
+
+from .backbone import Backbone
+from .config import RCNNConfig
+from .roi_heads import BoxHead, MaskHead, _to_rois
+from .rpn import RPN
+
+
+class _Heads(nn.Module):
+    pass
+
+
+class GeneralizedRCNN(nn.Module):
+    def __init__(self, cfg, backend):
+        super().__init__()
+        self.cfg = cfg
+        self.be = backend
+        self.backbone = Backbone(cfg)
+        self.rpn = RPN(cfg, self.backbone.out_channels)
+        self.roi_heads = _Heads()
+        self.roi_heads.box = BoxHead(cfg, self.backbone.out_channels)
+        if cfg.mask_on:
+            self.roi_heads.mask = MaskHead(cfg, self.backbone.out_channels)
+
+    def pad_images(self, images):
+        """to_image_list(size_divisible=32): zero-pad a list of [3,H,W] to a common divisible size
+        (structures/image_list.py:29-72)."""
+        d = self.cfg.size_divisibility
+        sizes = [tuple(im.shape[-2:]) for im in images]
+        h = -(-max(s[0] for s in sizes) // d) * d
+        w = -(-max(s[1] for s in sizes) // d) * d
+        batch = images[0].new_zeros((len(images), 3, h, w))
+        for i, im in enumerate(images):
+            batch[i, :, :im.shape[1], :im.shape[2]] = im
+        return batch, sizes
+
+    def forward(self, images, image_sizes, targets=None, generator=None):
+        """images: [N,3,H,W] fp32 already padded; image_sizes: [(h, w)]; targets: list of dicts with
+        'boxes' [G,4] xyxy fp32 and 'labels' [G] int64 (masks == box rectangles)."""
+        be = self.be
+        if self.training and targets is None:
+            raise ValueError("In training mode, targets should be passed")
+        feats = self.backbone.run(be, images)
+        proposals, losses = self.rpn.run(be, feats, image_sizes, targets, self.training, generator)
+        box = self.roi_heads.box
+        if self.training:
+            boxes, labels, reg_t, gidx = box.subsample(proposals, targets, generator)
+            rois = _to_rois(boxes)
+            x = box.features(be, feats, rois)
+            cls, reg = box.predict(be, x)
+            lc, lb = box.loss(cls, reg, labels, reg_t)
+            losses.update({"loss_classifier": lc, "loss_box_reg": lb})
+            if self.cfg.mask_on:
+                mask = self.roi_heads.mask
+                lab = labels.reshape(-1)
+                pos = (lab > 0).nonzero().squeeze(1)                 # keep_only_positive_boxes (mask_head.py:11-32)
+                rois_pos = rois[pos]
+                logits = mask.run(be, feats, rois_pos)
+                n, s = labels.shape
+                gt_all = torch.stack([t["boxes"][gidx[i]] for i, t in enumerate(targets)]).reshape(n * s, 4)
+                tgt = mask.mask_targets(gt_all[pos], rois_pos[:, 1:], self.cfg.mask_resolution)
+                losses["loss_mask"] = mask.loss(logits, lab[pos], tgt)
+            return losses
+        boxes, _, valid = proposals
+        rois = _to_rois(boxes)
+        x = box.features(be, feats, rois)
+        cls, reg = box.predict(be, x)
+        return box.postprocess(be, cls, reg, proposals, image_sizes)
+
+
+def build_model(cfg=None, backend=None, device="cuda"):
+    cfg = cfg or RCNNConfig()
+    if backend is None:
+        from .backend import B200Backend
+        backend = B200Backend()
+    return GeneralizedRCNN(cfg, backend).to(device)

@@ -1,0 +1,221 @@
+"""RPN: head, anchors, proposal selection, loss (reference modeling/rpn/rpn.py:73-205,
+rpn/inference.py:14-201, rpn/loss.py:23-157, rpn/anchor_generator.py:34-148).
+
+Differences from the reference, all on the host-logic side and none in the arithmetic of a proposal:
+the per-(image, level) Python loops are batched (one top-k / decode / clip per level for the whole
+batch, ONE batched NMS launch sequence for all image x level problems) and kept fixed-shape with
+validity masks, so the step has no host synchronisation here (the reference syncs in every NMS call,
+csrc/cuda/nms.cu:100, and in every `nonzero`)."""
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from maskrcnn_benchmark.layers import Conv2d, smooth_l1_loss
+
+from . import box_ops
+
+
+class BufferList(nn.Module):
+    """rpn/anchor_generator.py:13-31: keeps cell anchors in the state_dict under cell_anchors.<i>"""
+
+    def __init__(self, buffers):
+        super().__init__()
+        for i, b in enumerate(buffers):
+            self.register_buffer(str(i), b)
+
+    def __iter__(self):
+        return iter(self._buffers.values())
+
+    def __len__(self):
+        return len(self._buffers)
+
+
+class AnchorGenerator(nn.Module):
+    def __init__(self, cfg):
+        super().__init__()
+        self.strides = cfg.anchor_strides
+        self.straddle_thresh = cfg.straddle_thresh
+        self.cell_anchors = BufferList([box_ops.cell_anchors(s, (sz,), cfg.aspect_ratios)
+                                        for s, sz in zip(cfg.anchor_strides, cfg.anchor_sizes)])
+        self._cache = {}
+
+    def num_anchors_per_location(self):
+        return [len(c) for c in self.cell_anchors]
+
+    def grid(self, grid_sizes, device):
+        key = (tuple(grid_sizes), str(device))
+        if key not in self._cache:
+            self._cache[key] = [box_ops.grid_anchors(c, s, gh, gw, device)
+                                for (gh, gw), s, c in zip(grid_sizes, self.strides, self.cell_anchors)]
+        return self._cache[key]
+
+    def visibility(self, anchors, width, height):
+        t = self.straddle_thresh
+        if t < 0:
+            return torch.ones(anchors.shape[0], dtype=torch.bool, device=anchors.device)
+        return (anchors[:, 0] >= -t) & (anchors[:, 1] >= -t) & (anchors[:, 2] < width + t) & (anchors[:, 3] < height + t)
+
+
+class RPNHead(nn.Module):
+    """rpn.py:73-106"""
+
+    def __init__(self, in_channels, num_anchors):
+        super().__init__()
+        self.conv = Conv2d(in_channels, in_channels, 3, 1, 1)
+        self.cls_logits = Conv2d(in_channels, num_anchors, 1)
+        self.bbox_pred = Conv2d(in_channels, num_anchors * 4, 1)
+        for l in (self.conv, self.cls_logits, self.bbox_pred):
+            nn.init.normal_(l.weight, std=0.01)
+            nn.init.constant_(l.bias, 0)
+        self.num_anchors = num_anchors
+
+    def run(self, be, feats):
+        # cls and bbox 1x1 heads run as ONE conv with Cout = A + 4A over the shared 3x3 output
+        w = torch.cat([self.cls_logits.weight, self.bbox_pred.weight], 0)
+        b = torch.cat([self.cls_logits.bias, self.bbox_pred.bias], 0)
+        logits, deltas = [], []
+        for f in feats:
+            t = be.conv(f, self.conv.weight, bias=self.conv.bias, pad=1, relu=True)
+            o = be.conv(t, w, bias=b, out_fp32=True)              # [N, 5A, H, W]
+            o = o.permute(0, 2, 3, 1)                             # [N, H, W, 5A] (a view for channels_last)
+            n, h, ww, _ = o.shape
+            a = self.num_anchors
+            logits.append(o[..., :a].reshape(n, h * ww * a))      # (h, w, a) order == permute_and_flatten
+            deltas.append(o[..., a:].reshape(n, h * ww * a, 4))
+        return logits, deltas
+
+
+class RPN(nn.Module):
+    def __init__(self, cfg, in_channels):
+        super().__init__()
+        self.cfg = cfg
+        self.anchor_generator = AnchorGenerator(cfg)
+        self.head = RPNHead(in_channels, self.anchor_generator.num_anchors_per_location()[0])
+        self.box_coder = box_ops.BoxCoder((1.0, 1.0, 1.0, 1.0))
+        self.matcher = box_ops.Matcher(cfg.rpn_fg_iou, cfg.rpn_bg_iou, allow_low_quality_matches=True)
+
+    # ------------------------------------------------------------------ proposals (no_grad)
+    @torch.no_grad()
+    def select_proposals(self, be, anchors, logits, deltas, image_sizes, targets, training):
+        """-> (boxes [N, P, 4], scores [N, P], valid [N, P] bool).  P is fixed; invalid rows hold
+        zero boxes / -1 scores."""
+        cfg = self.cfg
+        n = logits[0].shape[0]
+        dev = logits[0].device
+        pre_n = cfg.pre_nms_top_n_train if training else cfg.pre_nms_top_n_test
+        post_n = cfg.post_nms_top_n_train if training else cfg.post_nms_top_n_test
+        fpn_post_n = cfg.fpn_post_nms_top_n_train if training else cfg.fpn_post_nms_top_n_test
+        widths = torch.tensor([s[1] for s in image_sizes], device=dev, dtype=torch.float32)
+        heights = torch.tensor([s[0] for s in image_sizes], device=dev, dtype=torch.float32)
+        all_boxes, all_scores, ks = [], [], []
+        for anc, lg, dl in zip(anchors, logits, deltas):
+            k = min(pre_n, lg.shape[1])
+            sc, idx = lg.sigmoid().topk(k, dim=1, sorted=True)                       # inference.py:91-95
+            d = torch.gather(dl, 1, idx[..., None].expand(-1, -1, 4))
+            bx = self.box_coder.decode(d.reshape(-1, 4).float(), anc[idx.reshape(-1)]).view(n, k, 4)
+            # clip_to_image(remove_empty=False); remove_small_boxes(min_size=0) keeps everything
+            bx = torch.stack([bx[..., 0].clamp(min=0).minimum(widths[:, None] - 1),
+                              bx[..., 1].clamp(min=0).minimum(heights[:, None] - 1),
+                              bx[..., 2].clamp(min=0).minimum(widths[:, None] - 1),
+                              bx[..., 3].clamp(min=0).minimum(heights[:, None] - 1)], -1)
+            all_boxes.append(bx)
+            all_scores.append(sc)
+            ks.append(k)
+        # one batched NMS over the N x L problems, problem order = (level, image)
+        boxes = torch.cat([b.reshape(-1, 4) for b in all_boxes]).contiguous()
+        scores = torch.cat([s.reshape(-1) for s in all_scores]).contiguous()
+        sizes = [k for k in ks for _ in range(n)]
+        keep, counts = be.nms_batched(boxes, scores, sizes, cfg.rpn_nms_thresh)       # keep: relative, ascending
+        # per problem: first min(count, post_n) kept rows (scores are sorted, so ascending index == by score)
+        out_b, out_s, out_v = [], [], []
+        off = 0
+        for li, k in enumerate(ks):
+            kk = keep[off:off + n * k].view(n, k)
+            cnt = counts[li * n:(li + 1) * n].clamp(max=post_n)
+            m = min(k, post_n)
+            pos = torch.arange(m, device=dev)[None, :]
+            valid = pos < cnt[:, None]
+            idx = kk[:, :m].clamp(min=0, max=k - 1)
+            out_b.append(torch.gather(all_boxes[li], 1, idx[..., None].expand(-1, -1, 4)))
+            out_s.append(torch.where(valid, torch.gather(all_scores[li], 1, idx), all_scores[li].new_full((), -1.0)))
+            out_v.append(valid)
+            off += n * k
+        b = torch.cat(out_b, 1)
+        s = torch.cat(out_s, 1)
+        v = torch.cat(out_v, 1)
+        # select_over_all_levels (inference.py:154-181)
+        if training and cfg.fpn_post_nms_per_batch:
+            flat = s.reshape(-1)
+            topn = min(fpn_post_n, flat.numel())
+            _, sel = flat.topk(topn, sorted=True)
+            m = torch.zeros_like(flat, dtype=torch.bool)
+            m[sel] = True
+            v = v & m.view_as(v)
+            # compact every image to a fixed width of `topn` columns, valid rows first (stable)
+            order = torch.sort((~v).to(torch.int8), dim=1, stable=True)[1][:, :topn]
+        else:
+            topn = min(fpn_post_n, s.shape[1])
+            order = s.topk(topn, dim=1, sorted=True)[1]
+        b = torch.gather(b, 1, order[..., None].expand(-1, -1, 4))
+        s = torch.gather(s, 1, order)
+        v = torch.gather(v, 1, order)
+        if training and targets is not None:
+            # add_gt_proposals (inference.py:53-74)
+            gmax = max(t["boxes"].shape[0] for t in targets)
+            gb = b.new_zeros((n, gmax, 4))
+            gv = torch.zeros((n, gmax), dtype=torch.bool, device=dev)
+            for i, t in enumerate(targets):
+                g = t["boxes"].shape[0]
+                gb[i, :g] = t["boxes"]
+                gv[i, :g] = True
+            b = torch.cat([b, gb], 1)
+            s = torch.cat([s, gv.float()], 1)
+            v = torch.cat([v, gv], 1)
+        b = torch.where(v[..., None], b, torch.zeros((), device=dev))
+        return b, s, v
+
+    # ------------------------------------------------------------------ loss
+    def loss(self, anchors_all, visibility, logits, deltas, targets, generator=None):
+        cfg = self.cfg
+        obj = torch.cat(logits, 1)            # [N, A_total]
+        reg = torch.cat(deltas, 1)            # [N, A_total, 4]
+        labels, reg_targets, pos_m, neg_m = [], [], [], []
+        with torch.no_grad():
+            for i, t in enumerate(targets):
+                q = box_ops.box_iou(t["boxes"], anchors_all)                           # loss.py:40-52
+                midx = self.matcher(q)
+                lab = (midx >= 0).float()
+                lab = torch.where(midx == box_ops.Matcher.BELOW_LOW, torch.zeros_like(lab), lab)
+                lab = torch.where(~visibility[i], -torch.ones_like(lab), lab)          # not_visibility
+                lab = torch.where(midx == box_ops.Matcher.BETWEEN, -torch.ones_like(lab), lab)
+                reg_targets.append(self.box_coder.encode(t["boxes"][midx.clamp(min=0)], anchors_all))
+                labels.append(lab)
+                p, ng = box_ops.sample_pos_neg(lab, cfg.rpn_batch_size, cfg.rpn_positive_fraction, generator)
+                pos_m.append(p)
+                neg_m.append(ng)
+            labels, reg_targets = torch.stack(labels), torch.stack(reg_targets)
+            pos_m, neg_m = torch.stack(pos_m), torch.stack(neg_m)
+            sampled = pos_m | neg_m
+            num_sampled = sampled.sum().clamp(min=1).float()
+        # loss.py:117-131, written with masks instead of index gathers (no nonzero sync)
+        diff = torch.abs(reg.float() - reg_targets)
+        beta = 1.0 / 9
+        l1 = torch.where(diff < beta, 0.5 * diff * diff / beta, diff - 0.5 * beta)
+        box_loss = (l1 * pos_m[..., None]).sum() / num_sampled
+        bce = F.binary_cross_entropy_with_logits(obj.float(), labels.clamp(min=0), reduction="none")
+        objectness_loss = (bce * sampled).sum() / num_sampled
+        return objectness_loss, box_loss
+
+    def run(self, be, feats, image_sizes, targets, training, generator=None):
+        logits, deltas = self.head.run(be, feats)
+        grid_sizes = [f.shape[-2:] for f in feats]
+        anchors = self.anchor_generator.grid(grid_sizes, feats[0].device)
+        proposals = self.select_proposals(be, anchors, [l.detach() for l in logits], [d.detach() for d in deltas],
+                                          image_sizes, targets, training)
+        losses = {}
+        if training:
+            anchors_all = torch.cat(anchors, 0)
+            vis = torch.stack([self.anchor_generator.visibility(anchors_all, w, h) for (h, w) in image_sizes])
+            lo, lb = self.loss(anchors_all, vis, logits, deltas, targets, generator)
+            losses = {"loss_objectness": lo, "loss_rpn_box_reg": lb}
+        return proposals, losses

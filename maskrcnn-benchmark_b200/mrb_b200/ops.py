@@ -26,7 +26,7 @@ def _nhwc(t, name):
     return t
 
 
-def _params(x_shape, w_shape, stride, pad, relu, out_dtype):
+def _params(x_shape, w_shape, stride, pad, relu, out_dtype, out_hw=None):
     n, c, h, w = x_shape
     co, ci, kh, kw = w_shape
     if ci != c:
@@ -37,17 +37,19 @@ def _params(x_shape, w_shape, stride, pad, relu, out_dtype):
     p.stride, p.pad, p.relu, p.out_dtype = stride, pad, int(bool(relu)), _DT[out_dtype]
     ho = (h + 2 * pad - kh) // stride + 1
     wo = (w + 2 * pad - kw) // stride + 1
+    if out_hw is not None:
+        p.out_h, p.out_w = ho, wo = int(out_hw[0]), int(out_hw[1])
     return p, ho, wo
 
 
 def conv2d_fwd(x, weight, scale=None, bias=None, residual=None, stride=1, pad=0, relu=False,
-               out_dtype=torch.bfloat16):
+               out_dtype=torch.bfloat16, out_hw=None):
     """y = act(conv(x, weight) * scale[c] + bias[c] + residual).  x, weight bf16 channels_last."""
     x = _nhwc(x, "conv2d_fwd(x)")
     weight = _nhwc(weight, "conv2d_fwd(weight)")
     if x.dtype != torch.bfloat16 or weight.dtype != torch.bfloat16:
         raise RuntimeError("conv2d_fwd: bf16 operands required")
-    p, ho, wo = _params(x.shape, weight.shape, stride, pad, relu, out_dtype)
+    p, ho, wo = _params(x.shape, weight.shape, stride, pad, relu, out_dtype, out_hw)
     out = torch.empty((p.batch, p.cout, ho, wo), dtype=out_dtype, device=x.device,
                       memory_format=torch.channels_last)
     if residual is not None:
@@ -86,3 +88,94 @@ def conv2d_dgrad(grad_out, weight, x_shape, scale=None, add=None, relu_mask=None
                                       _c._ptr(relu_mask), _c._ptr(gx), _c._ptr(ws), ctypes.c_size_t(nbytes),
                                       _c._stream()), "mrb_conv2d_dgrad")
     return gx
+
+
+# ------------------------------------------------------------------------- fused FPN ROIAlign
+class _RoiAlignFpn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, rois, scales, pooled, sampling_ratio, out_nhwc, k_min, k_max, s0, lvl0, *feats):
+        feats = [_nhwc(f, "roi_align_fpn(feat)") for f in feats]
+        dt = feats[0].dtype
+        if dt not in _DT or any(f.dtype != dt for f in feats):
+            raise RuntimeError("roi_align_fpn: feature maps must all be bf16 or all fp32")
+        n, c = feats[0].shape[:2]
+        r = rois.shape[0]
+        rois = rois.float().contiguous()
+        L = len(feats)
+        out = torch.empty((r, pooled, pooled, c) if out_nhwc else (r, c, pooled, pooled), dtype=dt, device=rois.device)
+        hs = (ctypes.c_int * L)(*[f.shape[2] for f in feats])
+        ws = (ctypes.c_int * L)(*[f.shape[3] for f in feats])
+        sc = (ctypes.c_float * L)(*[float(s) for s in scales])
+        ptrs = (ctypes.c_void_p * L)(*[f.data_ptr() for f in feats])
+        geom = (L, n, c, pooled, sampling_ratio, k_min, k_max, float(s0), lvl0, _DT[dt], int(bool(out_nhwc)))
+        if r > 0:
+            with torch.cuda.device(rois.device):
+                _c.check(lib.mrb_roi_align_fpn_fwd(ptrs, hs, ws, sc, L, _c._ptr(rois), _c._ptr(out), r, n, c, pooled,
+                                                   sampling_ratio, k_min, k_max, ctypes.c_float(s0), lvl0, _DT[dt],
+                                                   int(bool(out_nhwc)), _c._stream()), "mrb_roi_align_fpn_fwd")
+        ctx.save_for_backward(rois)
+        ctx.geom = geom
+        ctx.shapes = [tuple(f.shape) for f in feats]
+        ctx.scales = [float(s) for s in scales]
+        ctx.dt = dt
+        if out_nhwc:
+            out = out.permute(0, 3, 1, 2)  # logical [R, C, P, P], channels_last memory
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        (rois,) = ctx.saved_tensors
+        L, n, c, pooled, sr, k_min, k_max, s0, lvl0, dtc, out_nhwc = ctx.geom
+        dt = ctx.dt
+        if out_nhwc:
+            gout = gout.permute(0, 2, 3, 1)
+        gout = gout.to(dt).contiguous()
+        grads = [torch.zeros((s[0], s[2], s[3], s[1]), dtype=torch.float32, device=rois.device) for s in ctx.shapes]
+        r = rois.shape[0]
+        if r > 0:
+            hs = (ctypes.c_int * L)(*[s[2] for s in ctx.shapes])
+            ws = (ctypes.c_int * L)(*[s[3] for s in ctx.shapes])
+            sc = (ctypes.c_float * L)(*ctx.scales)
+            ptrs = (ctypes.c_void_p * L)(*[g.data_ptr() for g in grads])
+            with torch.cuda.device(rois.device):
+                _c.check(lib.mrb_roi_align_fpn_bwd(_c._ptr(gout), ptrs, hs, ws, sc, L, _c._ptr(rois), r, n, c, pooled, sr,
+                                                   k_min, k_max, ctypes.c_float(s0), lvl0, dtc, out_nhwc, _c._stream()),
+                         "mrb_roi_align_fpn_bwd")
+        outs = [g.permute(0, 3, 1, 2).to(dt) for g in grads]  # logical NCHW, channels_last memory
+        return (None,) * 9 + tuple(outs)
+
+
+def roi_align_fpn(feats, rois, scales, pooled, sampling_ratio, out_nhwc=False, k_min=2, k_max=5, canonical_scale=224.0,
+                  canonical_level=4):
+    """Multi-level ROIAlign == the reference `Pooler` (modeling/poolers.py:45-121) in one launch."""
+    if k_max - k_min + 1 != len(feats):
+        raise RuntimeError("roi_align_fpn: need one feature map per level k_min..k_max")
+    return _RoiAlignFpn.apply(rois, tuple(scales), pooled, sampling_ratio, out_nhwc, k_min, k_max, canonical_scale,
+                              canonical_level, *feats)
+
+
+# --------------------------------------------------------------------------------- batched NMS
+def nms_batched(boxes, scores, sizes, threshold):
+    """Independent NMS problems stored back to back (sizes[p] rows each).
+    -> (keep int64 [sum sizes]: per problem, kept indices relative to the problem, ascending, first
+    counts[p] entries valid; counts int32 [len(sizes)] on device).  No host synchronisation."""
+    if not boxes.is_cuda:
+        raise RuntimeError("nms_batched: expected CUDA tensors (no CPU path)")
+    boxes = boxes.float().contiguous()
+    scores = scores.float().contiguous()
+    p = len(sizes)
+    offs = [0]
+    for s in sizes:
+        offs.append(offs[-1] + int(s))
+    if offs[-1] != boxes.shape[0] or scores.numel() != boxes.shape[0]:
+        raise RuntimeError("nms_batched: sizes do not add up to the number of boxes")
+    offs_c = (ctypes.c_int * (p + 1))(*offs)
+    keep = torch.empty(max(offs[-1], 1), dtype=torch.int64, device=boxes.device)
+    counts = torch.zeros(max(p, 1), dtype=torch.int32, device=boxes.device)
+    with torch.cuda.device(boxes.device):
+        nbytes = lib.mrb_nms_batched_workspace_bytes(offs_c, p)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=boxes.device)
+        _c.check(lib.mrb_nms_batched(_c._ptr(boxes), _c._ptr(scores), offs_c, p, ctypes.c_float(threshold), _c._ptr(keep),
+                                     _c._ptr(counts), _c._ptr(ws), ctypes.c_size_t(nbytes), _c._stream()),
+                 "mrb_nms_batched")
+    return keep[:offs[-1]], counts[:p]

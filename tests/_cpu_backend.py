@@ -1,0 +1,87 @@
+"""CPU *checker* backend for the harness model: plain PyTorch fp32 for dense math + the oracle for
+ROIAlign / NMS.  Test infrastructure only (it imports `oracle`); the product backend is
+mrb_b200.model.backend.B200Backend and has no CPU path."""
+import torch
+import torch.nn.functional as F
+from torch.autograd import Function
+
+import oracle
+from mrb_b200.model.backend import Backend
+
+
+class _OracleRoiAlign(Function):
+    @staticmethod
+    def forward(ctx, feat, rois, scale, p, s):
+        ctx.save_for_backward(rois)
+        ctx.cfg = (scale, p, s, tuple(feat.shape))
+        return oracle.roi_align_forward(feat.detach().contiguous(), rois, scale, p, p, s)
+
+    @staticmethod
+    def backward(ctx, g):
+        (rois,) = ctx.saved_tensors
+        scale, p, s, shape = ctx.cfg
+        return oracle.roi_align_backward(g.contiguous(), rois, scale, p, p, *shape, s), None, None, None, None
+
+
+class CpuCheckerBackend(Backend):
+    name = "cpu-checker"
+    act_dtype = torch.float32
+
+    def prepare_input(self, images):
+        return images
+
+    @staticmethod
+    def _affine(y, scale, shift, bias, residual, relu):
+        if scale is not None:
+            y = y * scale[None, :, None, None]
+        add = shift if shift is not None else bias
+        if add is not None:
+            y = y + add[None, :, None, None]
+        if residual is not None:
+            y = y + residual
+        return F.relu(y) if relu else y
+
+    def conv(self, x, weight, scale=None, shift=None, bias=None, residual=None, stride=1, pad=0, relu=False,
+             out_fp32=False):
+        return self._affine(F.conv2d(x, weight, None, stride, pad), scale, shift, bias, residual, relu)
+
+    def stem(self, images, weight, scale, shift):
+        return self._affine(F.conv2d(images, weight, None, 2, 3), scale, shift, None, None, True)
+
+    def max_pool(self, x, k, s, p):
+        return F.max_pool2d(x, k, s, p)
+
+    def upsample2x(self, x):
+        return F.interpolate(x, scale_factor=2, mode="nearest")
+
+    def linear(self, x, weight, bias, relu=False, out_fp32=False):
+        y = F.linear(x, weight, bias)
+        return F.relu(y) if relu else y
+
+    def deconv2x2(self, x, weight, bias, relu=False):
+        y = F.conv_transpose2d(x, weight, bias, 2, 0)
+        return F.relu(y) if relu else y
+
+    def roi_align_fpn(self, feats, rois, scales, pooled, sampling_ratio, nhwc):
+        # LevelMapper, modeling/poolers.py:31-42
+        area = (rois[:, 3] - rois[:, 1] + 1) * (rois[:, 4] - rois[:, 2] + 1)
+        lv = torch.floor(4 + torch.log2(torch.sqrt(area) / 224 + 1e-6)).clamp(2, 5).long() - 2
+        out = feats[0].new_zeros((rois.shape[0], feats[0].shape[1], pooled, pooled))
+        for l, (f, sc) in enumerate(zip(feats, scales)):
+            idx = (lv == l).nonzero().squeeze(1)
+            if idx.numel():
+                out = out.index_put((idx,), _OracleRoiAlign.apply(f, rois[idx].contiguous(), sc, pooled, sampling_ratio))
+        return out
+
+    def nms_batched(self, boxes, scores, sizes, thr):
+        keep = torch.zeros(max(int(sum(sizes)), 1), dtype=torch.int64)
+        counts = torch.zeros(max(len(sizes), 1), dtype=torch.int32)
+        off = 0
+        for p, n in enumerate(sizes):
+            if n:
+                order = torch.sort(scores[off:off + n], stable=True, descending=True)[1]
+                k = oracle.nms(boxes[off:off + n].contiguous(), scores[off:off + n].contiguous(), thr, order=order)
+                keep[off:off + len(k)] = k
+                counts[p] = len(k)
+            off += n
+        return keep[:off], counts[:len(sizes)]
