@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""bench.py -- images/sec of the Mask R-CNN R-50-FPN training step (forward + backward + SGD update) on
+synthetic 800x1333 (padded to 800x1344) batches, 2 images per GPU, through the Blackwell hot path.
+
+  python bench.py --gpus 1 --steps 10 --warmup 3            # this repo's sm_100a path
+  python bench.py --impl reference --gpus 1 --steps 1       # the CPU path timed on the host cores
+  torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...   (one rank per GPU, NCCL)
+
+Prints ONE JSON line (rank 0).  `value` = whole-job images/s with inputs resident in HBM; `e2e` = the
+same step through the public API with pinned-host inputs (H2D of images + targets, D2H of the loss,
+inside the timed region); `roofline` = tcgen05 conv kernel, algorithmic FLOPs / CUDA-event time per
+launch, summed over the launches of one step; `cpu_baseline` = the same train step on the host cores
+(PyTorch CPU convs + the oracle / reference CPU kernels), bounded to one image.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "maskrcnn-benchmark_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+IMG_H, IMG_W, PAD_W = 800, 1333, 1344
+IMGS_PER_GPU = 2
+GT_PER_IMAGE = 8
+METRIC = "images/sec Mask R-CNN R-50-FPN fwd+bwd @1333x800"
+
+
+def synth_batch(n, seed, device="cpu", pin=False):
+    """images ~ N(0,1)*50 at 800x1333 zero-padded to 800x1344; 8 boxes per image with
+    w,h ~ U[32,400], labels 1..80; masks are the box rectangles."""
+    g = torch.Generator().manual_seed(seed)
+    images = torch.zeros(n, 3, IMG_H, PAD_W)
+    images[..., :IMG_W] = torch.randn(n, 3, IMG_H, IMG_W, generator=g) * 50
+    boxes, labels = [], []
+    for i in range(n):
+        wh = torch.rand(GT_PER_IMAGE, 2, generator=g) * (400 - 32) + 32
+        x1 = torch.rand(GT_PER_IMAGE, generator=g) * (IMG_W - 33)
+        y1 = torch.rand(GT_PER_IMAGE, generator=g) * (IMG_H - 33)
+        x2 = (x1 + wh[:, 0]).clamp(max=IMG_W - 1)
+        y2 = (y1 + wh[:, 1]).clamp(max=IMG_H - 1)
+        boxes.append(torch.stack([x1, y1, x2, y2], 1))
+        labels.append(torch.randint(1, 81, (GT_PER_IMAGE,), generator=g))
+    boxes, labels = torch.stack(boxes), torch.stack(labels)
+    if pin:
+        images, boxes, labels = images.pin_memory(), boxes.pin_memory(), labels.pin_memory()
+    return images.to(device), boxes.to(device), labels.to(device)
+
+
+def targets_of(boxes, labels):
+    return [{"boxes": boxes[i], "labels": labels[i]} for i in range(boxes.shape[0])]
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = str(index)
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", self.index], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm = sorted(float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def conv_roofline(calls, peaks, device):
+    """Time every distinct tcgen05 conv launch of one step in isolation (CUDA events on the launching
+    stream, L2 flushed between launches) and aggregate: achieved = sum(algorithmic FLOPs) / sum(time)."""
+    from mrb_b200 import ops
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)
+    shapes = {}
+    for c in calls:
+        shapes.setdefault(c, 0)
+        shapes[c] += 1
+    tot_flops = tot_time = 0.0
+    rows = []
+    for key, count in sorted(shapes.items()):
+        kind, n, cin, h, w, cout, k, stride, pad = key
+        x = torch.randn(n, cin, h, w, device=device).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        wt = torch.randn(cout, cin, k, k, device=device).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        ho, wo = (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
+        if kind == "dgrad":
+            go = torch.randn(n, cout, ho, wo, device=device).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+            fn = lambda: ops.conv2d_dgrad(go, wt, (n, cin, h, w), None, None, None, stride, pad)  # noqa: E731
+        else:
+            fn = lambda: ops.conv2d_fwd(x, wt, None, None, None, stride, pad, True)  # noqa: E731
+        fn()
+        ts = []
+        for _ in range(3):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            e1.synchronize()
+            ts.append(e0.elapsed_time(e1) * 1e-3)
+        t = sorted(ts)[1]
+        flops = 2.0 * n * ho * wo * cout * cin * k * k
+        tot_flops += flops * count
+        tot_time += t * count
+        rows.append({"kind": kind, "n": n, "cin": cin, "h": h, "w": w, "cout": cout, "k": k, "stride": stride, "count": count,
+                     "us": round(t * 1e6, 1), "tflops": round(flops / t / 1e12, 1)})
+    peak = peaks.get("bf16_tflops", 1590.0)
+    ach = tot_flops / max(tot_time, 1e-12) / 1e12
+    return {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit GEMM, fwd+dgrad launches of one step)",
+            "achieved": round(ach, 1), "peak": peak, "peak_source": peaks.get("_source", "fallback"), "unit": "TFLOP/s",
+            "frac": round(ach / peak, 4), "traffic": None, "launches_per_step": len(calls),
+            "algorithmic_gflop_per_step": round(tot_flops / 1e9, 1), "kernel_ms_per_step": round(tot_time * 1e3, 2)}, rows
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        d["_source"] = "measured (MEASURED_PEAKS.json)"
+        return d
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "_source": "fallback (B200_PROFILING.md)"}
+
+
+def cpu_train_step(n_images, use_ref, threads=None):
+    """The same train step on the host cores: PyTorch CPU fp32 convs + oracle (or oracle/_ref) kernels."""
+    from oracle.cpu_backend import CpuCheckerBackend
+    from mrb_b200.model import GeneralizedRCNN, RCNNConfig
+    if threads:
+        torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    model = GeneralizedRCNN(RCNNConfig(), CpuCheckerBackend(use_ref=use_ref)).train()
+    images, boxes, labels = synth_batch(n_images, 0)
+    sizes = [(IMG_H, IMG_W)] * n_images
+    t0 = time.perf_counter()
+    losses = model(images, sizes, targets_of(boxes, labels))
+    sum(losses.values()).backward()
+    dt = time.perf_counter() - t0
+    return n_images / dt, dt
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the CPU implementation of the path on the box's host cores (rank 0 only)."""
+    if rank != 0:
+        return
+    import oracle
+    oracle.build()
+    use_ref = oracle.ref() is not None
+    cores = torch.get_num_threads()
+    vals = []
+    for i in range(args.warmup + args.steps):
+        v, dt = cpu_train_step(1, use_ref)
+        if i >= args.warmup:
+            vals.append((v, dt))
+    v = sum(x for x, _ in vals) / len(vals)
+    ms = sum(d for _, d in vals) / len(vals) * 1e3
+    kind = "port"
+    sample = ("1 image (800x1333 padded to 800x1344) per step: full Mask R-CNN R-50-FPN train forward+backward, fp32, "
+              "PyTorch CPU convs + %s ROIAlign/NMS" % ("reference csrc/cpu kernels (oracle/_ref)" if use_ref else "oracle C port"))
+    out = {"impl": "reference", "metric": METRIC, "value": round(v, 4), "unit": "images/s", "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 1), "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": workload_config(args.gpus),
+           "cpu_baseline": {"value": round(v, 4), "unit": "images/s", "cores": cores, "kind": kind, "sample": sample},
+           "e2e": {"value": round(v, 4), "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+def workload_config(n_gpus):
+    return {"workload": "e2e_mask_rcnn_R_50_FPN_1x train step (fwd + bwd + SGD), synthetic 800x1333 images zero-padded to "
+                        "800x1344 NCHW, 8 GT boxes/image, random-init weights",
+            "global_batch": IMGS_PER_GPU * n_gpus, "images_per_gpu": IMGS_PER_GPU, "parallelism": "dp%d" % n_gpus,
+            "l2": "per-step working set (activations + gradients, several GB) exceeds the 126 MB L2; no explicit flush"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--dump-shapes", default=None, help="write the per-shape conv table (JSON) here")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+    assert torch.cuda.is_available(), "bench.py --impl b200 needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    from mrb_b200 import ops
+    from mrb_b200.model import build_model
+
+    torch.manual_seed(0)
+    model = build_model(device=device).train()
+    step_model = model
+    if world > 1:
+        step_model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], broadcast_buffers=False)
+    params = [p for p in model.parameters() if p.requires_grad]
+    opt = torch.optim.SGD(params, lr=1e-4, momentum=0.9, weight_decay=1e-4)
+    sizes = [(IMG_H, IMG_W)] * IMGS_PER_GPU
+    # distinct synthetic batches, pinned on the host (e2e) and resident in HBM (value)
+    n_batches = 4
+    host = [synth_batch(IMGS_PER_GPU, 100 * rank + i, pin=True) for i in range(n_batches)]
+    dev = [tuple(t.to(device) for t in b) for b in host]
+
+    def step(batch):
+        images, boxes, labels = batch
+        losses = step_model(images, sizes, targets_of(boxes, labels))
+        loss = sum(losses.values())
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        return loss
+
+    def step_e2e(hbatch):
+        batch = tuple(t.to(device, non_blocking=True) for t in hbatch)
+        loss = step(batch)
+        return loss.detach().float().cpu()  # D2H of the step's result
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(dev[i % n_batches])
+    # ---- timed: device-resident inputs
+    ops.STATS["launches"] = 0
+    ops.STATS["conv_calls"] = []
+    barrier()
+    sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step(dev[i % n_batches])
+    e1.record()
+    barrier()
+    t_dev = e0.elapsed_time(e1) * 1e-3
+    launches = ops.STATS["launches"]
+    conv_calls = list(ops.STATS["conv_calls"])
+    ops.STATS["conv_calls"] = None
+    # ---- timed: end to end from pinned host memory
+    step_e2e(host[0])
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        step_e2e(host[i % n_batches])
+    e1.record()
+    barrier()
+    t_e2e = e0.elapsed_time(e1) * 1e-3
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([t_dev, t_e2e], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_dev, t_e2e = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    imgs = IMGS_PER_GPU * world * args.steps
+    h2d = sum(t.numel() * t.element_size() for t in host[0])
+    peaks = load_peaks()
+    out = {"metric": METRIC, "value": round(imgs / t_dev, 3), "unit": "images/s", "n_gpus": world, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": round(t_dev / args.steps * 1e3, 2), "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+           "config": workload_config(world), "clocks": clocks,
+           "e2e": {"value": round(imgs / t_e2e, 3), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+           "gpu_launches": launches,
+           "library_ops": {"wgrad": model.be.wgrad_impl, "note": "conv forward and data-gradient run on the in-house tcgen05 "
+                           "kernel; weight-gradient, max-pool, nearest-upsample, topk/sort and the optimizer are PyTorch"}}
+    if not args.no_roofline and conv_calls:
+        per_step = conv_calls[:len(conv_calls) // args.steps]
+        rf, rows = conv_roofline(per_step, peaks, device)
+        # conv-FLOP roofline of the whole step (~1631 GFLOP/image fwd+bwd upper bound)
+        rf["step_conv_flop_roofline_frac"] = round((imgs / t_dev) / (peaks.get("bf16_tflops", 1590.0) * 1e3 / 1631.0) / world, 4)
+        out["roofline"] = rf
+        if args.dump_shapes:
+            json.dump(rows, open(args.dump_shapes, "w"), indent=1)
+    if not args.no_cpu_baseline:
+        try:
+            import oracle
+            oracle.lib()
+            use_ref = oracle.ref() is not None
+            v, dt = cpu_train_step(1, use_ref)
+            out["cpu_baseline"] = {"value": round(v, 4), "unit": "images/s", "cores": torch.get_num_threads(),
+                                   "kind": "port", "seconds": round(dt, 1),
+                                   "sample": "1 image, full train fwd+bwd, fp32 PyTorch CPU convs + %s ROIAlign/NMS"
+                                             % ("reference csrc/cpu (oracle/_ref)" if use_ref else "oracle C port")}
+        except Exception as e:  # the baseline must never break the bench line
+            out["cpu_baseline"] = {"value": None, "error": repr(e)[:200]}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -2,7 +2,7 @@
 
 B200Backend is the product: every hot op goes through libmrb_b200.so (tcgen05 convs in bf16 NHWC,
 fused multi-level ROIAlign, on-device batched NMS).  The model code is written against the small
-`Backend` interface so that tests can substitute a CPU checker backend (tests/_cpu_backend.py, built
+`Backend` interface so that tests can substitute a CPU checker backend (oracle/cpu_backend.py, built
 on plain PyTorch + the oracle) to validate the harness logic without a GPU; the product never does."""
 import torch
 import torch.nn.functional as F

@@ -15,6 +15,16 @@ lib.mrb_conv2d_dgrad_workspace_bytes.argtypes = [ctypes.POINTER(_c.ConvParams)]
 
 _DT = {torch.float32: 0, torch.bfloat16: 1}
 
+# launch accounting for bench.py: number of kernels of libmrb_b200.so launched through this module, and
+# (when a list is installed) the geometry of every tcgen05 conv launch
+STATS = {"launches": 0, "conv_calls": None}
+
+
+def _count(n, conv_key=None):
+    STATS["launches"] += n
+    if conv_key is not None and STATS["conv_calls"] is not None:
+        STATS["conv_calls"].append(conv_key)
+
 
 def _nhwc(t, name):
     if not t.is_cuda:
@@ -62,6 +72,7 @@ def conv2d_fwd(x, weight, scale=None, bias=None, residual=None, stride=1, pad=0,
     with torch.cuda.device(x.device):
         _c.check(lib.mrb_conv2d_fwd(ctypes.byref(p), _c._ptr(x), _c._ptr(weight), _c._ptr(scale), _c._ptr(bias),
                                     _c._ptr(residual), _c._ptr(out), _c._stream()), "mrb_conv2d_fwd")
+    _count(1, ("fwd", p.batch, p.cin, p.height, p.width, p.cout, p.kh, p.stride, p.pad))
     return out
 
 
@@ -87,6 +98,7 @@ def conv2d_dgrad(grad_out, weight, x_shape, scale=None, add=None, relu_mask=None
         _c.check(lib.mrb_conv2d_dgrad(ctypes.byref(p), _c._ptr(grad_out), _c._ptr(weight), _c._ptr(scale), _c._ptr(add),
                                       _c._ptr(relu_mask), _c._ptr(gx), _c._ptr(ws), ctypes.c_size_t(nbytes),
                                       _c._stream()), "mrb_conv2d_dgrad")
+    _count(2, ("dgrad", p.batch, p.cin, p.height, p.width, p.cout, p.kh, p.stride, p.pad))
     return gx
 
 
@@ -113,6 +125,7 @@ class _RoiAlignFpn(torch.autograd.Function):
                 _c.check(lib.mrb_roi_align_fpn_fwd(ptrs, hs, ws, sc, L, _c._ptr(rois), _c._ptr(out), r, n, c, pooled,
                                                    sampling_ratio, k_min, k_max, ctypes.c_float(s0), lvl0, _DT[dt],
                                                    int(bool(out_nhwc)), _c._stream()), "mrb_roi_align_fpn_fwd")
+            _count(1)
         ctx.save_for_backward(rois)
         ctx.geom = geom
         ctx.shapes = [tuple(f.shape) for f in feats]
@@ -141,6 +154,7 @@ class _RoiAlignFpn(torch.autograd.Function):
                 _c.check(lib.mrb_roi_align_fpn_bwd(_c._ptr(gout), ptrs, hs, ws, sc, L, _c._ptr(rois), r, n, c, pooled, sr,
                                                    k_min, k_max, ctypes.c_float(s0), lvl0, dtc, out_nhwc, _c._stream()),
                          "mrb_roi_align_fpn_bwd")
+            _count(1)
         outs = [g.permute(0, 3, 1, 2).to(dt) for g in grads]  # logical NCHW, channels_last memory
         return (None,) * 9 + tuple(outs)
 
@@ -178,4 +192,5 @@ def nms_batched(boxes, scores, sizes, threshold):
         _c.check(lib.mrb_nms_batched(_c._ptr(boxes), _c._ptr(scores), offs_c, p, ctypes.c_float(threshold), _c._ptr(keep),
                                      _c._ptr(counts), _c._ptr(ws), ctypes.c_size_t(nbytes), _c._stream()),
                  "mrb_nms_batched")
+    _count(3)
     return keep[:offs[-1]], counts[:p]

@@ -1,6 +1,7 @@
 """CPU *checker* backend for the harness model: plain PyTorch fp32 for dense math + the oracle for
-ROIAlign / NMS.  Test infrastructure only (it imports `oracle`); the product backend is
-mrb_b200.model.backend.B200Backend and has no CPU path."""
+ROIAlign / NMS (the reference's own compiled CPU kernels, oracle/_ref, when `use_ref` and they exist).
+Test / baseline infrastructure only: used by tests/ and by bench.py's cpu_baseline and
+`--impl reference` legs.  The product backend is mrb_b200.model.backend.B200Backend (no CPU path)."""
 import torch
 import torch.nn.functional as F
 from torch.autograd import Function
@@ -11,21 +12,26 @@ from mrb_b200.model.backend import Backend
 
 class _OracleRoiAlign(Function):
     @staticmethod
-    def forward(ctx, feat, rois, scale, p, s):
+    def forward(ctx, feat, rois, scale, p, s, ref=None):
         ctx.save_for_backward(rois)
         ctx.cfg = (scale, p, s, tuple(feat.shape))
+        if ref is not None:  # the reference's own ROIAlign_forward_cpu
+            return ref.roi_align_forward(feat.detach().contiguous(), rois, scale, p, p, s)
         return oracle.roi_align_forward(feat.detach().contiguous(), rois, scale, p, p, s)
 
     @staticmethod
     def backward(ctx, g):
         (rois,) = ctx.saved_tensors
         scale, p, s, shape = ctx.cfg
-        return oracle.roi_align_backward(g.contiguous(), rois, scale, p, p, *shape, s), None, None, None, None
+        return oracle.roi_align_backward(g.contiguous(), rois, scale, p, p, *shape, s), None, None, None, None, None
 
 
 class CpuCheckerBackend(Backend):
     name = "cpu-checker"
     act_dtype = torch.float32
+
+    def __init__(self, use_ref=False):
+        self.ref = oracle.ref() if use_ref else None
 
     def prepare_input(self, images):
         return images
@@ -70,7 +76,7 @@ class CpuCheckerBackend(Backend):
         for l, (f, sc) in enumerate(zip(feats, scales)):
             idx = (lv == l).nonzero().squeeze(1)
             if idx.numel():
-                out = out.index_put((idx,), _OracleRoiAlign.apply(f, rois[idx].contiguous(), sc, pooled, sampling_ratio))
+                out = out.index_put((idx,), _OracleRoiAlign.apply(f, rois[idx].contiguous(), sc, pooled, sampling_ratio, self.ref))
         return out
 
     def nms_batched(self, boxes, scores, sizes, thr):
@@ -79,8 +85,11 @@ class CpuCheckerBackend(Backend):
         off = 0
         for p, n in enumerate(sizes):
             if n:
-                order = torch.sort(scores[off:off + n], stable=True, descending=True)[1]
-                k = oracle.nms(boxes[off:off + n].contiguous(), scores[off:off + n].contiguous(), thr, order=order)
+                b, sc = boxes[off:off + n].contiguous(), scores[off:off + n].contiguous()
+                if self.ref is not None:  # the reference's own nms_cpu
+                    k = self.ref.nms(b, sc, float(thr))
+                else:
+                    k = oracle.nms(b, sc, thr, order=torch.sort(sc, stable=True, descending=True)[1])
                 keep[off:off + len(k)] = k
                 counts[p] = len(k)
             off += n

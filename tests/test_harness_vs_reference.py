@@ -36,7 +36,7 @@ def ref_dump(tmp_path_factory, built_lib):
 
 
 def test_state_dict_keys_and_outputs_match_reference(ref_dump):
-    from _cpu_backend import CpuCheckerBackend
+    from oracle.cpu_backend import CpuCheckerBackend
     from mrb_b200.model import GeneralizedRCNN
     d = ref_dump
     model = GeneralizedRCNN(tiny_cfg(), CpuCheckerBackend()).eval()
