@@ -114,9 +114,12 @@ def conv_roofline(calls, peaks, device):
         x = torch.randn(n, cin, h, w, device=device).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
         wt = torch.randn(cout, cin, k, k, device=device).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
         ho, wo = (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
-        if kind == "dgrad":
+        if kind in ("dgrad", "wgrad"):
             go = torch.randn(n, cout, ho, wo, device=device).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
-            fn = lambda: ops.conv2d_dgrad(go, wt, (n, cin, h, w), None, None, None, stride, pad)  # noqa: E731
+            if kind == "dgrad":
+                fn = lambda: ops.conv2d_dgrad(go, wt, (n, cin, h, w), None, None, None, stride, pad)  # noqa: E731
+            else:
+                fn = lambda: ops.conv2d_wgrad(x, go, wt.shape, stride, pad)  # noqa: E731
         else:
             fn = lambda: ops.conv2d_fwd(x, wt, None, None, None, stride, pad, True)  # noqa: E731
         fn()
@@ -212,6 +215,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--dump-shapes", default=None, help="write the per-shape conv table (JSON) here")
+    ap.add_argument("--wgrad", default="tc", choices=["tc", "cudnn"], help="weight-gradient kernel (A/B switch)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -231,7 +235,8 @@ def main():
     from mrb_b200.model import build_model
 
     torch.manual_seed(0)
-    model = build_model(device=device).train()
+    from mrb_b200.model.backend import B200Backend
+    model = build_model(backend=B200Backend(wgrad=args.wgrad), device=device).train()
     step_model = model
     if world > 1:
         step_model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], broadcast_buffers=False)
@@ -308,8 +313,9 @@ def main():
            "config": workload_config(world), "clocks": clocks,
            "e2e": {"value": round(imgs / t_e2e, 3), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
            "gpu_launches": launches,
-           "library_ops": {"wgrad": model.be.wgrad_impl, "note": "conv forward and data-gradient run on the in-house tcgen05 "
-                           "kernel; weight-gradient, max-pool, nearest-upsample, topk/sort and the optimizer are PyTorch"}}
+           "library_ops": {"wgrad": model.be.wgrad_impl, "note": "conv forward, data-gradient and weight-gradient run on the "
+                           "in-house tcgen05 kernels; max-pool, nearest-upsample, ReLU-mask, topk/sort, losses and the "
+                           "optimizer are PyTorch"}}
     if not args.no_roofline and conv_calls:
         per_step = conv_calls[:len(conv_calls) // args.steps]
         rf, rows = conv_roofline(per_step, peaks, device)

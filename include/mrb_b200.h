@@ -212,6 +212,13 @@ int mrb_conv2d_dgrad(const mrb_conv_params* p, const void* grad_output_bf16, con
                      const float* scale, const void* add, const void* relu_mask, void* grad_input,
                      void* workspace, size_t workspace_bytes, mrb_stream_t stream);
 
+/* wgrad: grad_weight[Cout][kh][kw][Cin] (fp32, KRSC == torch channels_last of [Cout,Cin,kh,kw]) =
+ * sum over N,Ho,Wo of grad_output (x) input, on tcgen05 with MN-major operands; the pixel axis is split
+ * across CTAs and reduced with red.global.add.f32 into the buffer, which is zeroed inside.  input and
+ * grad_output are NHWC bf16. */
+int mrb_conv2d_wgrad(const mrb_conv_params* p, const void* input_bf16, const void* grad_output_bf16,
+                     float* grad_weight, mrb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -333,6 +333,172 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
 }
 
+// ------------------------------------------------------------------------------- weight gradient
+// dW[co][tap][ci] = sum over pixels G[pixel, co] * X[pixel + tap, ci]      (fp32 result, split-K + red.add)
+// GEMM view: M = Cout tile (128), N = Cin tile (<= 256), K = output pixels in blocks of 64 (a th x tw
+// rectangle of one image).  Both operands are "MN-major" for the tensor core (channels are contiguous,
+// pixels are the reduction axis):
+//   A = G^T : two TMA boxes {64 co, tw, th, 1}  -> 2 x [64 pixel rows x 128 B], SWIZZLE_128B
+//   B = X^T : BN/64 boxes   {64 ci, tw, th, 1}, corner shifted by the tap (zero-filled outside the image)
+// UMMA descriptors: MN-major SWIZZLE_128B, LBO = 8 KB (distance between 64-channel groups),
+// SBO = 1 KB (8 pixel rows); one K=16 step advances the start address by 16 rows = 2 KB.
+// Work item = (co tile, ci tile, tap, K split); CTAs walk items round-robin; the accumulator tile is
+// flushed with red.global.add.f32 (the reduction over splits) into the zero-initialised dW.
+constexpr int kWgBlockK = 64;                       // pixels per k-block
+constexpr int kWgGroupBytes = kWgBlockK * 128;      // one 64-channel group of one k-block: 8 KB
+
+struct WgradArgs {
+  int items_total, co_tiles, ci_tiles, taps, splits;
+  int kh, kw, pad;
+  int th, tw, tiles_w, tiles_h, batch;   // pixel tiling of the OUTPUT (G) plane
+  int kblocks_total, kblocks_per_split;
+  int cin, cout, bn, stages;
+  float* dw;
+};
+
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr) {
+  // [0,14) start>>4 | [16,30) LBO>>4 = 8 KB | [32,46) SBO>>4 = 1 KB | version 1 | SWIZZLE_128B
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)(kWgGroupBytes >> 4) << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+
+__device__ __forceinline__ void wg_item(const WgradArgs& a, int item, int& co_t, int& ci_t, int& tap, int& split) {
+  split = item % a.splits; item /= a.splits;
+  ci_t = item % a.ci_tiles; item /= a.ci_tiles;
+  tap = item % a.taps;
+  co_t = item / a.taps;
+}
+
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant__ CUtensorMap map_x, const WgradArgs a) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int b_groups = a.bn / 64;
+  const uint32_t a_bytes = 2u * kWgGroupBytes;
+  const uint32_t stage_bytes = a_bytes + (uint32_t)b_groups * kWgGroupBytes;
+  const uint32_t bar_base = smem_base + (uint32_t)a.stages * stage_bytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (a.stages + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * a.stages + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * a.stages + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * a.stages + 4);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < 2u * a.bn) tmem_cols <<= 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < a.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 128); }
+    fence_barrier_init();
+    tma_prefetch_desc(&map_g);
+    tma_prefetch_desc(&map_x);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0; uint32_t phase = 0;
+      for (int item = blockIdx.x; item < a.items_total; item += gridDim.x) {
+        int co_t, ci_t, tap, split;
+        wg_item(a, item, co_t, ci_t, tap, split);
+        const int r = tap / a.kw, q = tap - r * a.kw;
+        const int kb0 = split * a.kblocks_per_split, kb1 = min(a.kblocks_total, kb0 + a.kblocks_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          int m = kb;
+          const int wt = m % a.tiles_w; m /= a.tiles_w;
+          const int ht = m % a.tiles_h;
+          const int img = m / a.tiles_h;
+          const int h0 = ht * a.th, w0 = wt * a.tw;
+          mbar_wait(empty_bar(s), phase ^ 1u);
+          mbar_expect_tx(full_bar(s), stage_bytes);
+          const uint32_t sa = smem_base + (uint32_t)s * stage_bytes;
+          tma_load_4d(sa, &map_g, full_bar(s), co_t * 128, w0, h0, img);
+          tma_load_4d(sa + kWgGroupBytes, &map_g, full_bar(s), co_t * 128 + 64, w0, h0, img);
+          for (int gi = 0; gi < b_groups; ++gi)
+            tma_load_4d(sa + a_bytes + (uint32_t)gi * kWgGroupBytes, &map_x, full_bar(s), ci_t * a.bn + gi * 64,
+                        w0 + q - a.pad, h0 + r - a.pad, img);
+          if (++s == a.stages) { s = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // a_major = b_major = 1 (MN-major): bits 15 and 16
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(a.bn >> 3) << 17) |
+                             ((uint32_t)(kTileM >> 4) << 24);
+      int s = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int item = blockIdx.x; item < a.items_total; item += gridDim.x) {
+        int co_t, ci_t, tap, split;
+        wg_item(a, item, co_t, ci_t, tap, split);
+        const int kb0 = split * a.kblocks_per_split, kb1 = min(a.kblocks_total, kb0 + a.kblocks_per_split);
+        if (kb1 <= kb0) continue;
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * a.bn);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(full_bar(s), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + (uint32_t)s * stage_bytes;
+          const uint64_t da = umma_desc_mn_sw128(sa), db = umma_desc_mn_sw128(sa + a_bytes);
+#pragma unroll
+          for (int k = 0; k < kWgBlockK / 16; ++k)  // 16 pixel rows = 2 KB per step
+            umma_bf16(d_tmem, da + (uint64_t)(128 * k), db + (uint64_t)(128 * k), idesc, (kb > kb0 || k) ? 1u : 0u);
+          umma_commit(empty_bar(s));
+          if (kb == kb1 - 1) umma_commit(tfull_bar(acc));
+          if (++s == a.stages) { s = 0; phase ^= 1u; }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else {
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int item = blockIdx.x; item < a.items_total; item += gridDim.x) {
+      int co_t, ci_t, tap, split;
+      wg_item(a, item, co_t, ci_t, tap, split);
+      const int kb0 = split * a.kblocks_per_split, kb1 = min(a.kblocks_total, kb0 + a.kblocks_per_split);
+      if (kb1 <= kb0) continue;
+      const int co = co_t * 128 + row;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * a.bn);
+      float* __restrict__ dst = a.dw + ((size_t)co * a.taps + tap) * a.cin;
+      for (int col = 0; col < a.bn; col += 32) {
+        const int c0 = ci_t * a.bn + col;
+        if (c0 >= a.cin) break;
+        uint32_t v[32];
+        __syncwarp();
+        tmem_ld32(t_row + (uint32_t)col, v);
+        tmem_ld_wait();
+        if (co >= a.cout) continue;
+        const int nvalid = min(32, a.cin - c0);
+        if (nvalid == 32 && (a.cin & 3) == 0) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            atomicAdd(reinterpret_cast<float4*>(dst + c0 + 4 * j),
+                      make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                                  __uint_as_float(v[4 * j + 3])));
+        } else {
+          for (int j = 0; j < nvalid; ++j) atomicAdd(dst + c0 + j, __uint_as_float(v[j]));
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+}
+
 // ------------------------------------------------------------------------------- weight prep
 // dgrad weights: Wd[cin][kh-1-r][kw-1-q][cout] = W[cout][r][q][cin] * (scale ? scale[cout] : 1)
 __global__ void conv_prepare_dgrad_weights_kernel(const __nv_bfloat16* __restrict__ w, const float* __restrict__ scale,
@@ -547,4 +713,87 @@ MRB_API int mrb_conv2d_dgrad(const mrb_conv_params* p, const void* grad_output, 
   }
   return conv_launch(pl, grad_output, wd, p->cout, p->cin, p->kh, p->kw, p->kh - 1 - p->pad, nullptr, nullptr, add, relu_mask,
                      grad_input, 0, p->out_dtype == MRB_F32, stream);
+}
+
+MRB_API int mrb_conv2d_wgrad(const mrb_conv_params* p, const void* input, const void* grad_output, float* grad_weight,
+                             mrb_stream_t stream_) {
+  int rc = conv_check(p);
+  if (rc) return rc;
+  if (p->out_h || p->out_w) return MRB_ERR_UNSUPPORTED;
+  if (!grad_weight) return MRB_ERR_BAD_ARG;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int taps = p->kh * p->kw;
+  MRB_CUDA_TRY(cudaMemsetAsync(grad_weight, 0, (size_t)p->cout * taps * p->cin * sizeof(float), stream));
+  if (p->batch == 0) return MRB_OK;
+  if (!input || !grad_output) return MRB_ERR_BAD_ARG;
+  if (p->cin % 8 || p->cout % 8 || ((uintptr_t)input & 15) || ((uintptr_t)grad_output & 15) || ((uintptr_t)grad_weight & 15))
+    return MRB_ERR_UNSUPPORTED;
+  const int Ho = (p->height + 2 * p->pad - p->kh) / p->stride + 1, Wo = (p->width + 2 * p->pad - p->kw) / p->stride + 1;
+  if (Ho <= 0 || Wo <= 0) return MRB_ERR_BAD_ARG;
+  // geometry of the pixel (reduction) axis; 1x1 stride-1 layers flatten the batch onto one axis
+  int batch = p->batch, gh = Ho, gw = Wo, xh = p->stride == 2 ? Ho : p->height, xw = p->stride == 2 ? Wo : p->width;
+  long long g_w = p->cout, g_h = (long long)Wo * p->cout, g_n = (long long)Ho * Wo * p->cout;
+  long long x_w = (long long)p->cin * p->stride, x_h = (long long)p->width * p->cin * p->stride,
+            x_n = (long long)p->height * p->width * p->cin;
+  if (p->kh == 1 && p->stride == 1 && p->pad == 0) {
+    gw = xw = p->batch * Ho * Wo; gh = xh = 1; batch = 1;
+    g_h = g_n = (long long)gw * p->cout; x_h = x_n = (long long)xw * p->cin;
+  }
+  WgradArgs a;
+  int best_th = 1, best_tw = 64;
+  long long best = -1;
+  const int th_order[7] = {8, 4, 16, 2, 32, 1, 64};
+  for (int i = 0; i < 7; ++i) {
+    const int th = th_order[i], tw = 64 / th;
+    const long long cost = (long long)ceil_div(gh, th) * th * ceil_div(gw, tw) * tw;
+    if (best < 0 || cost < best) { best = cost; best_th = th; best_tw = tw; }
+  }
+  a.th = best_th; a.tw = best_tw; a.tiles_h = ceil_div(gh, a.th); a.tiles_w = ceil_div(gw, a.tw); a.batch = batch;
+  const long long kblocks = (long long)batch * a.tiles_h * a.tiles_w;
+  if (kblocks >= (1ll << 31)) return MRB_ERR_UNSUPPORTED;
+  a.kblocks_total = (int)kblocks;
+  a.kh = p->kh; a.kw = p->kw; a.pad = p->pad; a.taps = taps;
+  a.cin = p->cin; a.cout = p->cout;
+  a.bn = ceil_div(p->cin, 64) * 64;
+  if (a.bn > 256) a.bn = 256;
+  a.co_tiles = ceil_div(p->cout, 128); a.ci_tiles = ceil_div(p->cin, a.bn);
+  const int out_tiles = a.co_tiles * a.ci_tiles * taps;
+  int splits = ceil_div(2 * kNumSMs, out_tiles);          // ~2 work items per SM
+  const int max_splits = ceil_div(a.kblocks_total, 8);     // at least 8 k-blocks per item
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  a.kblocks_per_split = ceil_div(a.kblocks_total, splits);
+  a.splits = ceil_div(a.kblocks_total, a.kblocks_per_split);
+  a.items_total = out_tiles * a.splits;
+  a.dw = grad_weight;
+  const uint32_t stage_bytes = (2 + a.bn / 64) * kWgGroupBytes;
+  int stages = (int)((200 * 1024) / stage_bytes);
+  if (stages > 8) stages = 8;
+  a.stages = stages;
+  const size_t smem = (size_t)stages * stage_bytes + 8 * (2 * stages + 4) + 16 + 1024;
+  CUtensorMap map_g, map_x;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)p->cout, (cuuint64_t)gw, (cuuint64_t)gh, (cuuint64_t)batch};
+    cuuint64_t strides[3] = {(cuuint64_t)g_w * 2, (cuuint64_t)g_h * 2, (cuuint64_t)g_n * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)a.tw, (cuuint32_t)a.th, 1};
+    rc = encode_bf16(&map_g, grad_output, 4, dims, strides, box);
+    if (rc) return rc;
+  }
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)p->cin, (cuuint64_t)xw, (cuuint64_t)xh, (cuuint64_t)batch};
+    cuuint64_t strides[3] = {(cuuint64_t)x_w * 2, (cuuint64_t)x_h * 2, (cuuint64_t)x_n * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)a.tw, (cuuint32_t)a.th, 1};
+    rc = encode_bf16(&map_x, input, 4, dims, strides, box);
+    if (rc) return rc;
+  }
+  static std::once_flag attr_once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(attr_once, [] {
+    attr_err = cudaFuncSetAttribute(conv_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  });
+  if (attr_err != cudaSuccess) return (int)attr_err;
+  const int grid = a.items_total < kNumSMs ? a.items_total : kNumSMs;
+  conv_wgrad_tc_kernel<<<grid, kConvThreads, smem, stream>>>(map_g, map_x, a);
+  MRB_LAUNCH_CHECK();
+  return MRB_OK;
 }

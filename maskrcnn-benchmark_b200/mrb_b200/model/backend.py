@@ -67,11 +67,16 @@ class _ConvFn(Function):
 
 
 def _wgrad_cudnn(x, g, w16, stride, pad):
-    """Weight gradient.  TODO(round 2): tcgen05 MN-major split-K wgrad kernel; until then this one
-    GEMM family is borrowed from the library (ATen/cuDNN) and reported as such in bench.py."""
+    """Library weight gradient (ATen/cuDNN): kept only as an A/B switch for bench.py --wgrad cudnn."""
     gw = torch.ops.aten.convolution_backward(g, x, w16, None, [stride, stride], [pad, pad], [1, 1], False, [0, 0], 1,
                                              [False, True, False])[1]
     return gw.float()
+
+
+def _wgrad_tc(x, g, w16, stride, pad):
+    """Weight gradient on the tcgen05 engine (MN-major operands, split-K, fp32 red.add)."""
+    from mrb_b200 import ops
+    return ops.conv2d_wgrad(x, g, w16.shape, stride, pad)
 
 
 class B200Backend(Backend):
@@ -79,10 +84,12 @@ class B200Backend(Backend):
     act_dtype = torch.bfloat16
     channels_last = True
 
-    def __init__(self):
+    def __init__(self, wgrad="tc"):
         self._w16 = {}
-        self.wgrad_fn = _wgrad_cudnn
-        self.wgrad_impl = "aten.convolution_backward (cuDNN)"
+        if wgrad == "tc":
+            self.wgrad_fn, self.wgrad_impl = _wgrad_tc, "mrb_conv2d_wgrad (tcgen05, in-house)"
+        else:
+            self.wgrad_fn, self.wgrad_impl = _wgrad_cudnn, "aten.convolution_backward (cuDNN)"
 
     def _weight16(self, w):
         key = id(w)

@@ -102,6 +102,23 @@ def conv2d_dgrad(grad_out, weight, x_shape, scale=None, add=None, relu_mask=None
     return gx
 
 
+def conv2d_wgrad(x, grad_out, w_shape, stride=1, pad=0):
+    """grad_weight (fp32, logical [Cout, Cin, kh, kw], channels_last memory == KRSC) on the tcgen05 engine."""
+    x = _nhwc(x, "conv2d_wgrad(x)")
+    grad_out = _nhwc(grad_out, "conv2d_wgrad(grad_out)")
+    if x.dtype != torch.bfloat16 or grad_out.dtype != torch.bfloat16:
+        raise RuntimeError("conv2d_wgrad: bf16 operands required")
+    p, ho, wo = _params(x.shape, tuple(w_shape), stride, pad, False, torch.float32)
+    if tuple(grad_out.shape) != (p.batch, p.cout, ho, wo):
+        raise RuntimeError("conv2d_wgrad: grad_out shape mismatch")
+    gw = torch.empty(tuple(w_shape), dtype=torch.float32, device=x.device).contiguous(memory_format=torch.channels_last)
+    with torch.cuda.device(x.device):
+        _c.check(lib.mrb_conv2d_wgrad(ctypes.byref(p), _c._ptr(x), _c._ptr(grad_out), _c._ptr(gw), _c._stream()),
+                 "mrb_conv2d_wgrad")
+    _count(1, ("wgrad", p.batch, p.cin, p.height, p.width, p.cout, p.kh, p.stride, p.pad))
+    return gw
+
+
 # ------------------------------------------------------------------------- fused FPN ROIAlign
 class _RoiAlignFpn(torch.autograd.Function):
     @staticmethod

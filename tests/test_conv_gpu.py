@@ -105,6 +105,27 @@ def test_conv_dgrad_fused(ops):
     _assert_close(got, want)
 
 
+WG_CASES = [
+    (2, 64, 40, 56, 256, 1, 1, 0), (2, 256, 40, 56, 128, 1, 1, 0), (1, 128, 24, 40, 128, 3, 1, 1),
+    (2, 128, 25, 42, 256, 3, 1, 1), (2, 256, 50, 84, 512, 1, 2, 0), (1, 128, 25, 41, 256, 1, 2, 0),
+    (1, 24, 20, 30, 48, 3, 1, 1), (1, 256, 30, 40, 81 + 7, 1, 1, 0), (1, 512, 14, 14, 2048, 1, 1, 0),
+    (300, 512, 1, 1, 1024, 1, 1, 0), (2, 256, 13, 21, 16, 1, 1, 0),
+]
+
+
+@pytest.mark.parametrize("n,c,h,w,co,k,stride,pad", WG_CASES)
+def test_conv_wgrad(ops, n, c, h, w, co, k, stride, pad):
+    x, wt = _mk(n, c, h, w, co, k, 9)
+    g = torch.Generator().manual_seed(10)
+    ho, wo = (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
+    go = torch.randn(n, co, ho, wo, generator=g).to(torch.bfloat16)
+    wf = wt.float().requires_grad_(True)
+    F.conv2d(x.float(), wf, stride=stride, padding=pad).backward(go.float())
+    got = ops.conv2d_wgrad(x.to(DEV), go.to(DEV), wt.shape, stride, pad)
+    assert got.shape == wf.grad.shape
+    _assert_close(got, wf.grad, tol=2e-4)   # split-K fp32 atomics: order differs
+
+
 def test_conv_rejects_unsupported(ops):
     x, wt = _mk(1, 64, 16, 16, 64, 3, 8)
     with pytest.raises(RuntimeError, match="unsupported"):
