@@ -92,26 +92,33 @@ class B200Backend(Backend):
             self.wgrad_fn, self.wgrad_impl = _wgrad_cudnn, "aten.convolution_backward (cuDNN)"
 
     def _weight16(self, w):
+        """bf16 KRSC copy of a weight.  Cached per nn.Parameter (refreshed when the optimizer bumps its
+        version); derived tensors (views, concatenations) are temporaries whose id/address can be recycled,
+        so they are converted on every call."""
+        def conv(t):
+            t = t.detach().to(torch.bfloat16)
+            return t.contiguous(memory_format=torch.channels_last) if t.dim() == 4 else t.contiguous()
+        if not isinstance(w, torch.nn.Parameter):
+            return conv(w)
         key = id(w)
         ent = self._w16.get(key)
-        if ent is None or ent[0] != w._version or ent[1].device != w.device:
-            w16 = w.detach().to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
-            self._w16[key] = (w._version, w16)
-            return w16
-        return ent[1]
+        if ent is None or ent[0] is not w or ent[1] != w._version or ent[2].device != w.device:
+            self._w16[key] = (w, w._version, conv(w))   # holding `w` keeps its id from being recycled
+        return self._w16[key][2]
 
     def prepare_input(self, images):
         return images.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
 
     def conv(self, x, weight, scale=None, shift=None, bias=None, residual=None, stride=1, pad=0, relu=False,
-             out_fp32=False):
+             out_fp32=False, w16=None):
         if x.numel() == 0:
             n, _, h, w = x.shape
             kh, kw = weight.shape[2:]
             return x.new_zeros((n, weight.shape[0], (h + 2 * pad - kh) // stride + 1, (w + 2 * pad - kw) // stride + 1),
                                dtype=torch.float32 if out_fp32 else torch.bfloat16)
-        return _ConvFn.apply(x, weight, bias, residual, self._weight16(weight), scale, shift, stride, pad, relu,
-                             out_fp32, self.wgrad_fn)
+        if w16 is None:
+            w16 = self._weight16(weight)
+        return _ConvFn.apply(x, weight, bias, residual, w16, scale, shift, stride, pad, relu, out_fp32, self.wgrad_fn)
 
     def stem(self, images, weight, scale, shift):
         """7x7/2 conv on 3 channels == 4x4/1 conv on the 2x2 space-to-depth image (12 -> 16 channels):
@@ -126,14 +133,14 @@ class B200Backend(Backend):
         x = F.pad(x, (0, 0, 0, 0, 0, 16 - x.shape[1])).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
         key = ("stem", id(weight))
         ent = self._w16.get(key)
-        if ent is None or ent[0] != weight._version or ent[1].device != weight.device:
+        if ent is None or ent[0] is not weight or ent[1] != weight._version or ent[2].device != weight.device:
             co = weight.shape[0]
             w8 = F.pad(weight.detach(), (1, 0, 1, 0))                                   # [co, 3, 8, 8]
             w4 = w8.view(co, c, 4, 2, 4, 2).permute(0, 1, 3, 5, 2, 4).reshape(co, c * 4, 4, 4)
             w4 = F.pad(w4, (0, 0, 0, 0, 0, 16 - c * 4)).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
-            self._w16[key] = (weight._version, w4)
+            self._w16[key] = (weight, weight._version, w4)
         else:
-            w4 = ent[1]
+            w4 = ent[2]
         return ops.conv2d_fwd(x, w4, scale, shift, None, 1, 2, True, out_hw=((h + 1) // 2, (w + 1) // 2))
 
     def max_pool(self, x, k, s, p):
@@ -145,9 +152,11 @@ class B200Backend(Backend):
     def linear(self, x, weight, bias, relu=False, out_fp32=False):
         """Fully connected layer on the conv engine: [R, K] x [Cout, K]^T as a 1x1 conv over R "pixels"."""
         r, k = x.shape
-        y = self.conv(x.to(torch.bfloat16).reshape(r, k, 1, 1), weight.view(weight.shape[0], k, 1, 1), bias=bias,
-                      relu=relu, out_fp32=out_fp32)
-        return y.reshape(r, weight.shape[0])
+        co = weight.shape[0]
+        w16 = self._weight16(weight).view(co, k, 1, 1)
+        y = self.conv(x.to(torch.bfloat16).reshape(r, k, 1, 1), weight.view(co, k, 1, 1), bias=bias, relu=relu,
+                      out_fp32=out_fp32, w16=w16)
+        return y.reshape(r, co)
 
     def deconv2x2(self, x, weight, bias, relu=False):
         """ConvTranspose2d(k=2, s=2): four independent 1x1 convs (one per output sub-pixel) run as ONE

@@ -33,9 +33,9 @@ def test_roi_align_fpn_vs_oracle(built_lib, oracle_mod, nhwc, dtype, p):
     feats = [f.to(dtype) for f in _inputs.fpn_features(2, 5, channels=64)]
     rois = _inputs.rois_for_level(300, 2, 21)
     scales = (0.25, 0.125, 0.0625, 0.03125)
-    cpu_feats = [f.float().requires_grad_(True) for f in feats]
+    cpu_feats = [f.float().clone().requires_grad_(True) for f in feats]
     want = CpuCheckerBackend().roi_align_fpn(cpu_feats, rois, scales, p, 2, False)
-    dfe = [f.to(DEV).contiguous(memory_format=torch.channels_last).requires_grad_(True) for f in feats]
+    dfe = [f.detach().to(DEV).contiguous(memory_format=torch.channels_last).clone().requires_grad_(True) for f in feats]
     got = ops.roi_align_fpn(dfe, rois.to(DEV), scales, p, 2, out_nhwc=nhwc)
     assert got.shape == want.shape
     if dtype == torch.float32:
