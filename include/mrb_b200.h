@@ -205,8 +205,9 @@ int mrb_conv2d_fwd(const mrb_conv_params* p, const void* input_bf16, const void*
  * forward epilogue into the weights; `add` (optional, bf16, shaped like grad_input) is summed in (the
  * other branch of a residual join); `relu_mask` (optional, bf16, shaped like grad_input) zeroes the
  * result where the saved forward activation is <= 0 (ReLU backward of the producer layer).
- * p->out_dtype selects the grad_input element type.  stride 2 is supported for 1x1 kernels only
- * (grad_input is zero-filled, then written at even positions) and without add / relu_mask. */
+ * p->out_dtype selects the grad_input element type.  stride 2 is supported for 1x1 kernels only:
+ * grad_input is zero-filled, then written at the even positions; there `add` must be grad_input itself
+ * (in-place accumulation of a second stride-2 branch, no zero fill). */
 size_t mrb_conv2d_dgrad_workspace_bytes(const mrb_conv_params* p);
 int mrb_conv2d_dgrad(const mrb_conv_params* p, const void* grad_output_bf16, const void* weight_bf16,
                      const float* scale, const void* add, const void* relu_mask, void* grad_input,

@@ -690,14 +690,19 @@ MRB_API int mrb_conv2d_dgrad(const mrb_conv_params* p, const void* grad_output, 
   const long long Ci = p->cin, Co = p->cout;
   if (p->stride == 2) {
     // 1x1 stride 2: grad_input[2h, 2w] = Wd . grad_output[h, w]; every other position is zero
-    if (add || relu_mask) return MRB_ERR_UNSUPPORTED;
-    const size_t bytes = (size_t)p->batch * p->height * p->width * p->cin * (p->out_dtype == MRB_F32 ? 4 : 2);
-    MRB_CUDA_TRY(cudaMemsetAsync(grad_input, 0, bytes, stream));
+    // `add` must be grad_input itself (accumulate a second stride-2 branch in place, e.g. conv1 + downsample of a
+    // stage's first bottleneck): then the zero fill is skipped.  The mask only needs the even positions.
+    if (add && add != grad_input) return MRB_ERR_UNSUPPORTED;
+    if (add && p->out_dtype == MRB_F32) return MRB_ERR_UNSUPPORTED;
+    if (!add) {
+      const size_t bytes = (size_t)p->batch * p->height * p->width * p->cin * (p->out_dtype == MRB_F32 ? 4 : 2);
+      MRB_CUDA_TRY(cudaMemsetAsync(grad_input, 0, bytes, stream));
+    }
     pl.batch = p->batch; pl.Hin = Ho; pl.Win = Wo;
     pl.in_w = Co; pl.in_h = (long long)Wo * Co; pl.in_n = (long long)Ho * Wo * Co;
     pl.Ho = Ho; pl.Wo = Wo;
     pl.out_w = 2 * Ci; pl.out_h = 2ll * p->width * Ci; pl.out_n = (long long)p->height * p->width * Ci;
-    return conv_launch(pl, grad_output, wd, p->cout, p->cin, 1, 1, 0, nullptr, nullptr, nullptr, nullptr, grad_input, 0,
+    return conv_launch(pl, grad_output, wd, p->cout, p->cin, 1, 1, 0, nullptr, nullptr, add, relu_mask, grad_input, 0,
                        p->out_dtype == MRB_F32, stream);
   }
   if (p->kh == 1 && p->pad == 0) {

@@ -180,16 +180,17 @@ nms_scan_kernel(NmsBatch nb, unsigned char* __restrict__ ws_base, long long* __r
     __syncthreads();
     const unsigned long long kept = s_kept;
     if (tid < rows && ((kept >> tid) & 1ull)) w.flags[w.order[b * 64 + tid]] = 1;
-    for (int t = b + 1 + tid; t < col_blocks; t += kScanThreads) {
-      unsigned long long acc = remv[t];
-      unsigned long long k = kept;
-      const unsigned long long* col = w.mask + (size_t)(b * 64) * col_blocks + t;
-      while (k) {
-        const int i = __ffsll((long long)k) - 1;
-        k &= k - 1;
-        acc |= col[(size_t)i * col_blocks];
-      }
-      remv[t] = acc;
+    // OR the kept rows of block b into the running "removed" words of the later column blocks.
+    // One warp per column block; lane l fetches rows l and l+32 (all 64 loads of a column in flight
+    // at once -- a per-thread loop over the kept rows serialises on L2 latency), OR-reduced with redux.
+    const unsigned long long* base = w.mask + (size_t)(b * 64) * col_blocks;
+    for (int t = b + 1 + warp; t < col_blocks; t += kScanThreads / 32) {
+      unsigned long long v = 0;
+      if ((kept >> lane) & 1ull) v = base[(size_t)lane * col_blocks + t];
+      if ((kept >> (lane + 32)) & 1ull) v |= base[(size_t)(lane + 32) * col_blocks + t];
+      const unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)v);
+      const unsigned hi = __reduce_or_sync(0xffffffffu, (unsigned)(v >> 32));
+      if (lane == 0) remv[t] |= ((unsigned long long)hi << 32) | lo;
     }
     __syncthreads();
   }

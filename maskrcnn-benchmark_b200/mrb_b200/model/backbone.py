@@ -54,6 +54,9 @@ class Bottleneck(nn.Module):
         self._aff_d = FrozenAffine(self.downsample[1]) if self.downsample is not None else None
 
     def run(self, be, x):
+        if hasattr(be, "bottleneck") and self.strides[1] == 1:
+            # every consumer of a bottleneck output (next block, FPN lateral) pre-masks the gradient it returns
+            return be.bottleneck(self, x, g_premasked=True)
         s1, s3, sd = self.strides
         (a1, b1), (a2, b2), (a3, b3) = (a.get() for a in self._aff)
         y = be.conv(x, self.conv1.weight, a1, b1, stride=s1, relu=True)
@@ -138,7 +141,8 @@ class FPN(nn.Module):
         for feat, inner, layer in zip(feats[::-1], self.inner_blocks[::-1], self.layer_blocks[::-1]):
             ib, lb = getattr(self, inner), getattr(self, layer)
             top_down = be.upsample2x(last) if last is not None else None
-            last = be.conv(feat, ib.weight, bias=ib.bias, residual=top_down)  # lateral + top-down add, fused
+            # lateral + top-down add, fused; `feat` is a bottleneck (ReLU) output: hand back a pre-masked gradient
+            last = be.conv(feat, ib.weight, bias=ib.bias, residual=top_down, premask_x=True)
             results.insert(0, be.conv(last, lb.weight, bias=lb.bias, pad=1))
         results.append(be.max_pool(results[-1], 1, 2, 0))  # P6 (fpn.py:77-79)
         return results

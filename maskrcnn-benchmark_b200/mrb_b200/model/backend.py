@@ -18,9 +18,12 @@ class Backend:
         raise NotImplementedError
 
     def conv(self, x, weight, scale=None, shift=None, bias=None, residual=None, stride=1, pad=0, relu=False,
-             out_fp32=False):
+             out_fp32=False, premask_x=False, gy_premasked=False):
         """y = act(conv(x, weight) * scale + shift|bias + residual).  `shift` is a frozen per-channel
-        constant (FrozenBatchNorm2d), `bias` a trainable conv bias; at most one of them is given."""
+        constant (FrozenBatchNorm2d), `bias` a trainable conv bias; at most one of them is given.
+        Backward-fusion hints (pure optimisation, ignored by backends that use plain autograd):
+        premask_x   -- x is the ReLU output of its producer: return grad_x already multiplied by [x > 0];
+        gy_premasked -- every consumer of y does that, so this op skips its own ReLU mask."""
         raise NotImplementedError
 
 
@@ -30,12 +33,14 @@ class _ConvFn(Function):
     backward: ReLU mask -> dgrad on the same engine (BN scale folded into the flipped weights) -> wgrad."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, residual, w16, scale, shift, stride, pad, relu, out_fp32, wgrad_fn):
+    def forward(ctx, x, weight, bias, residual, w16, scale, shift, stride, pad, relu, out_fp32, wgrad_fn,
+                premask_x=False, gy_premasked=False):
         from mrb_b200 import ops
         add = shift if shift is not None else (bias.detach().float() if bias is not None else None)
         y = ops.conv2d_fwd(x, w16, scale, add, residual, stride, pad, relu,
                            torch.float32 if out_fp32 else torch.bfloat16)
-        ctx.cfg = (stride, pad, relu, tuple(x.shape), wgrad_fn)
+        ctx.cfg = (stride, pad, relu and not gy_premasked, tuple(x.shape), wgrad_fn)
+        ctx.premask_x = premask_x
         ctx.has_bias = bias is not None
         ctx.has_res = residual is not None
         ctx.save_for_backward(x, w16, scale, y if relu else None)
@@ -54,7 +59,8 @@ class _ConvFn(Function):
         g = g.contiguous(memory_format=torch.channels_last)
         gx = gw = gb = gres = None
         if ctx.needs_input_grad[0]:
-            gx = ops.conv2d_dgrad(g, w16, x_shape, scale, None, None, stride, pad)
+            # premask_x: x is the ReLU output of its producer, whose backward then skips its own mask pass
+            gx = ops.conv2d_dgrad(g, w16, x_shape, scale, None, x if ctx.premask_x else None, stride, pad)
         if ctx.needs_input_grad[1]:
             gw = wgrad_fn(x, g, w16, stride, pad)
             if scale is not None:
@@ -63,7 +69,70 @@ class _ConvFn(Function):
             gb = g.float().sum((0, 2, 3))
         if ctx.has_res and ctx.needs_input_grad[3]:
             gres = g
-        return gx, gw, gb, gres, None, None, None, None, None, None, None, None
+        return gx, gw, gb, gres, None, None, None, None, None, None, None, None, None, None
+
+
+class _BottleneckFn(Function):
+    """One ResNet bottleneck (reference modeling/backbone/resnet.py:324-344) as a single autograd node:
+    4 fused forward convs and a hand-scheduled backward in which every ReLU mask, the frozen-BN scale and
+    the residual join ride in the epilogue of a dgrad launch -- no standalone elementwise pass:
+        g  (grad of out, already masked by out > 0 by its consumers)
+        g2 = dgrad3(g)   * [y2 > 0]        dW3 = wgrad(y2, g) * s3
+        g1 = dgrad2(g2)  * [y1 > 0]        dW2 = wgrad(y1, g2) * s2
+        gx = (dgrad1(g1) + identity-branch grad) * [x > 0]      dW1 = wgrad(x, g1) * s1, dWd = wgrad(x, g) * sd
+    The returned gx is therefore pre-masked for the producer of x (the previous bottleneck)."""
+
+    @staticmethod
+    def forward(ctx, x, w1, w2, w3, wd, be, blk, g_premasked):
+        from mrb_b200 import ops
+        s1, s3, sd = blk.strides
+        (a1, b1), (a2, b2), (a3, b3) = (a.get() for a in blk._aff)
+        w16 = [be._weight16(w) for w in (w1, w2, w3)]
+        y1 = ops.conv2d_fwd(x, w16[0], a1, b1, None, s1, 0, True)
+        y2 = ops.conv2d_fwd(y1, w16[1], a2, b2, None, s3, 1, True)
+        if wd is not None:
+            ad, bd = blk._aff_d.get()
+            wd16 = be._weight16(wd)
+            idn = ops.conv2d_fwd(x, wd16, ad, bd, None, sd, 0, False)
+        else:
+            ad, wd16, idn = None, None, x
+        out = ops.conv2d_fwd(y2, w16[2], a3, b3, idn, 1, 0, True)
+        ctx.be, ctx.strides, ctx.g_premasked = be, (s1, s3, sd), g_premasked
+        ctx.has_d = wd is not None
+        ctx.save_for_backward(x, y1, y2, out, w16[0], w16[1], w16[2], wd16, a1, a2, a3, ad)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        from mrb_b200 import ops
+        x, y1, y2, out, w1, w2, w3, wd, a1, a2, a3, ad = ctx.saved_tensors
+        s1, s3, sd = ctx.strides
+        wg = ctx.be.wgrad_fn
+        if not ctx.g_premasked:
+            g = torch.where(out > 0, g, torch.zeros((), dtype=g.dtype, device=g.device))
+        g = g.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        need = ctx.needs_input_grad
+        gw1 = gw2 = gw3 = gwd = gx = None
+        if need[3]:
+            gw3 = wg(y2, g, w3, 1, 0) * a3[:, None, None, None]
+        g2 = ops.conv2d_dgrad(g, w3, y2.shape, a3, None, y2, 1, 0)
+        if need[2]:
+            gw2 = wg(y1, g2, w2, s3, 1) * a2[:, None, None, None]
+        g1 = ops.conv2d_dgrad(g2, w2, y1.shape, a2, None, y1, s3, 1)
+        if need[1]:
+            gw1 = wg(x, g1, w1, s1, 0) * a1[:, None, None, None]
+        if ctx.has_d and need[4]:
+            gwd = wg(x, g, wd, sd, 0) * ad[:, None, None, None]
+        if need[0]:
+            if not ctx.has_d:
+                gx = ops.conv2d_dgrad(g1, w1, x.shape, a1, g, x, s1, 0)
+            elif sd == 1:
+                gi = ops.conv2d_dgrad(g, wd, x.shape, ad, None, None, 1, 0)
+                gx = ops.conv2d_dgrad(g1, w1, x.shape, a1, gi, x, s1, 0)
+            else:
+                gx = ops.conv2d_dgrad(g, wd, x.shape, ad, None, None, sd, 0)
+                gx = ops.conv2d_dgrad(g1, w1, x.shape, a1, None, x, s1, 0, accumulate_into=gx)
+        return gx, gw1, gw2, gw3, gwd, None, None, None
 
 
 def _wgrad_cudnn(x, g, w16, stride, pad):
@@ -110,15 +179,38 @@ class B200Backend(Backend):
         return images.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
 
     def conv(self, x, weight, scale=None, shift=None, bias=None, residual=None, stride=1, pad=0, relu=False,
-             out_fp32=False, w16=None):
+             out_fp32=False, w16=None, premask_x=False, gy_premasked=False):
         if x.numel() == 0:
             n, _, h, w = x.shape
             kh, kw = weight.shape[2:]
             return x.new_zeros((n, weight.shape[0], (h + 2 * pad - kh) // stride + 1, (w + 2 * pad - kw) // stride + 1),
                                dtype=torch.float32 if out_fp32 else torch.bfloat16)
+        co = weight.shape[0]
+        if co % 8:
+            # the data-gradient GEMM reduces over Cout, whose row pitch must be a multiple of 16 B for TMA:
+            # pad the (few, small) odd-sized heads -- RPN 3+12, predictor 81+324, mask logits 81 -- with zero
+            # output channels and slice them off again
+            if residual is not None:
+                raise RuntimeError("conv: residual with Cout % 8 != 0 is not supported")
+            padn = 8 - co % 8
+            weight = torch.cat([weight, weight.new_zeros((padn,) + tuple(weight.shape[1:]))], 0)
+            if bias is not None:
+                bias = torch.cat([bias, bias.new_zeros(padn)])
+            if shift is not None:
+                shift = torch.cat([shift, shift.new_zeros(padn)])
+            if scale is not None:
+                scale = torch.cat([scale, scale.new_ones(padn)])
+            w16 = None
         if w16 is None:
             w16 = self._weight16(weight)
-        return _ConvFn.apply(x, weight, bias, residual, w16, scale, shift, stride, pad, relu, out_fp32, self.wgrad_fn)
+        y = _ConvFn.apply(x, weight, bias, residual, w16, scale, shift, stride, pad, relu, out_fp32, self.wgrad_fn,
+                          premask_x, gy_premasked)
+        return y[:, :co] if co % 8 else y
+
+    def bottleneck(self, blk, x, g_premasked):
+        """Whole bottleneck as one autograd node (see _BottleneckFn).  Requires STRIDE_IN_1X1 geometry."""
+        wd = blk.downsample[0].weight if blk.downsample is not None else None
+        return _BottleneckFn.apply(x, blk.conv1.weight, blk.conv2.weight, blk.conv3.weight, wd, self, blk, g_premasked)
 
     def stem(self, images, weight, scale, shift):
         """7x7/2 conv on 3 channels == 4x4/1 conv on the 2x2 space-to-depth image (12 -> 16 channels):
@@ -149,22 +241,22 @@ class B200Backend(Backend):
     def upsample2x(self, x):
         return F.interpolate(x, scale_factor=2, mode="nearest")
 
-    def linear(self, x, weight, bias, relu=False, out_fp32=False):
+    def linear(self, x, weight, bias, relu=False, out_fp32=False, premask_x=False, gy_premasked=False):
         """Fully connected layer on the conv engine: [R, K] x [Cout, K]^T as a 1x1 conv over R "pixels"."""
         r, k = x.shape
         co = weight.shape[0]
         w16 = self._weight16(weight).view(co, k, 1, 1)
         y = self.conv(x.to(torch.bfloat16).reshape(r, k, 1, 1), weight.view(co, k, 1, 1), bias=bias, relu=relu,
-                      out_fp32=out_fp32, w16=w16)
+                      out_fp32=out_fp32, w16=w16, premask_x=premask_x, gy_premasked=gy_premasked)
         return y.reshape(r, co)
 
-    def deconv2x2(self, x, weight, bias, relu=False):
+    def deconv2x2(self, x, weight, bias, relu=False, premask_x=False, gy_premasked=False):
         """ConvTranspose2d(k=2, s=2): four independent 1x1 convs (one per output sub-pixel) run as ONE
         1x1 conv with 4*Cout outputs on the conv engine, then a pixel shuffle.  weight [Cin, Cout, 2, 2]."""
         cin, cout = weight.shape[:2]
         w4 = weight.permute(2, 3, 1, 0).reshape(4 * cout, cin, 1, 1)       # ((i, j, co), ci)
         b4 = bias.repeat(4) if bias is not None else None
-        y = self.conv(x, w4, bias=b4, relu=relu)                            # [N, 4*Cout, H, W]
+        y = self.conv(x, w4, bias=b4, relu=relu, premask_x=premask_x, gy_premasked=gy_premasked)  # [N, 4*Cout, H, W]
         n, _, h, w = y.shape
         y = y.view(n, 2, 2, cout, h, w).permute(0, 3, 4, 1, 5, 2).reshape(n, cout, 2 * h, 2 * w)
         return y.contiguous(memory_format=torch.channels_last)

@@ -77,14 +77,14 @@ class BoxHead(nn.Module):
         x = be.roi_align_fpn(feats[:4], rois, cfg.pooler_scales, cfg.box_resolution, cfg.box_sampling_ratio, nhwc=False)
         x = x.flatten(1)
         fe = self.feature_extractor
-        x = be.linear(x, fe.fc6.weight, fe.fc6.bias, relu=True)
-        return be.linear(x, fe.fc7.weight, fe.fc7.bias, relu=True)
+        x = be.linear(x, fe.fc6.weight, fe.fc6.bias, relu=True, gy_premasked=True)
+        return be.linear(x, fe.fc7.weight, fe.fc7.bias, relu=True, premask_x=True, gy_premasked=True)
 
     def predict(self, be, x):
         pr = self.predictor
         w = torch.cat([pr.cls_score.weight, pr.bbox_pred.weight], 0)
         b = torch.cat([pr.cls_score.bias, pr.bbox_pred.bias], 0)
-        o = be.linear(x, w, b, relu=False, out_fp32=True)
+        o = be.linear(x, w, b, relu=False, out_fp32=True, premask_x=True)
         nc = self.cfg.num_classes
         return o[:, :nc], o[:, nc:]
 
@@ -171,11 +171,11 @@ class MaskHead(nn.Module):
         x = be.roi_align_fpn(feats[:4], rois, cfg.pooler_scales, cfg.mask_resolution_pool, cfg.mask_sampling_ratio,
                              nhwc=True)
         fe, pr = self.feature_extractor, self.predictor
-        for name in self.blocks:
+        for i, name in enumerate(self.blocks):
             c = getattr(fe, name)
-            x = be.conv(x, c.weight, bias=c.bias, pad=1, relu=True)
-        x = be.deconv2x2(x, pr.conv5_mask.weight, pr.conv5_mask.bias, relu=True)
-        return be.conv(x, pr.mask_fcn_logits.weight, bias=pr.mask_fcn_logits.bias, out_fp32=True)
+            x = be.conv(x, c.weight, bias=c.bias, pad=1, relu=True, premask_x=i > 0, gy_premasked=True)
+        x = be.deconv2x2(x, pr.conv5_mask.weight, pr.conv5_mask.bias, relu=True, premask_x=True, gy_premasked=True)
+        return be.conv(x, pr.mask_fcn_logits.weight, bias=pr.mask_fcn_logits.bias, out_fp32=True, premask_x=True)
 
     @staticmethod
     @torch.no_grad()

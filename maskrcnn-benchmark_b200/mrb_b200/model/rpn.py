@@ -75,8 +75,8 @@ class RPNHead(nn.Module):
         b = torch.cat([self.cls_logits.bias, self.bbox_pred.bias], 0)
         logits, deltas = [], []
         for f in feats:
-            t = be.conv(f, self.conv.weight, bias=self.conv.bias, pad=1, relu=True)
-            o = be.conv(t, w, bias=b, out_fp32=True)              # [N, 5A, H, W]
+            t = be.conv(f, self.conv.weight, bias=self.conv.bias, pad=1, relu=True, gy_premasked=True)
+            o = be.conv(t, w, bias=b, out_fp32=True, premask_x=True)   # [N, 5A, H, W]
             o = o.permute(0, 2, 3, 1)                             # [N, H, W, 5A] (a view for channels_last)
             n, h, ww, _ = o.shape
             a = self.num_anchors

@@ -77,8 +77,10 @@ def conv2d_fwd(x, weight, scale=None, bias=None, residual=None, stride=1, pad=0,
 
 
 def conv2d_dgrad(grad_out, weight, x_shape, scale=None, add=None, relu_mask=None, stride=1, pad=0,
-                 out_dtype=torch.bfloat16):
-    """grad_x = conv_transpose(grad_out, weight * scale[cout]) (+ add) masked by (relu_mask > 0)."""
+                 out_dtype=torch.bfloat16, accumulate_into=None):
+    """grad_x = conv_transpose(grad_out, weight * scale[cout]) (+ add) masked by (relu_mask > 0).
+    `accumulate_into` (bf16, shaped like x) makes the call in-place: result = accumulate_into + dgrad,
+    written back into it (the only form of `add` the stride-2 path supports)."""
     grad_out = _nhwc(grad_out, "conv2d_dgrad(grad_out)")
     weight = _nhwc(weight, "conv2d_dgrad(weight)")
     if grad_out.dtype != torch.bfloat16 or weight.dtype != torch.bfloat16:
@@ -86,11 +88,21 @@ def conv2d_dgrad(grad_out, weight, x_shape, scale=None, add=None, relu_mask=None
     p, ho, wo = _params(tuple(x_shape), weight.shape, stride, pad, False, out_dtype)
     if tuple(grad_out.shape) != (p.batch, p.cout, ho, wo):
         raise RuntimeError("conv2d_dgrad: grad_out shape %s != %s" % (tuple(grad_out.shape), (p.batch, p.cout, ho, wo)))
-    gx = torch.empty(tuple(x_shape), dtype=out_dtype, device=grad_out.device, memory_format=torch.channels_last)
+    if accumulate_into is not None:
+        if add is not None:
+            raise RuntimeError("conv2d_dgrad: pass either add or accumulate_into")
+        gx = accumulate_into
+        if gx.dtype != torch.bfloat16 or tuple(gx.shape) != tuple(x_shape) or \
+                not gx.is_contiguous(memory_format=torch.channels_last):
+            raise RuntimeError("conv2d_dgrad: accumulate_into must be bf16 channels_last shaped like x")
+        add = gx
+    else:
+        gx = torch.empty(tuple(x_shape), dtype=out_dtype, device=grad_out.device, memory_format=torch.channels_last)
     for t in (add, relu_mask):
         if t is not None and (t.dtype != torch.bfloat16 or tuple(t.shape) != tuple(x_shape)):
             raise RuntimeError("conv2d_dgrad: add/relu_mask must be bf16 and shaped like x")
-    add = _nhwc(add, "add") if add is not None else None
+    if add is not None and add is not gx:
+        add = _nhwc(add, "add")
     relu_mask = _nhwc(relu_mask, "relu_mask") if relu_mask is not None else None
     with torch.cuda.device(grad_out.device):
         nbytes = lib.mrb_conv2d_dgrad_workspace_bytes(ctypes.byref(p))

@@ -48,7 +48,7 @@ class CpuCheckerBackend(Backend):
         return F.relu(y) if relu else y
 
     def conv(self, x, weight, scale=None, shift=None, bias=None, residual=None, stride=1, pad=0, relu=False,
-             out_fp32=False):
+             out_fp32=False, premask_x=False, gy_premasked=False):
         return self._affine(F.conv2d(x, weight, None, stride, pad), scale, shift, bias, residual, relu)
 
     def stem(self, images, weight, scale, shift):
@@ -60,11 +60,11 @@ class CpuCheckerBackend(Backend):
     def upsample2x(self, x):
         return F.interpolate(x, scale_factor=2, mode="nearest")
 
-    def linear(self, x, weight, bias, relu=False, out_fp32=False):
+    def linear(self, x, weight, bias, relu=False, out_fp32=False, premask_x=False, gy_premasked=False):
         y = F.linear(x, weight, bias)
         return F.relu(y) if relu else y
 
-    def deconv2x2(self, x, weight, bias, relu=False):
+    def deconv2x2(self, x, weight, bias, relu=False, premask_x=False, gy_premasked=False):
         y = F.conv_transpose2d(x, weight, bias, 2, 0)
         return F.relu(y) if relu else y
 

@@ -126,6 +126,26 @@ def test_conv_wgrad(ops, n, c, h, w, co, k, stride, pad):
     _assert_close(got, wf.grad, tol=2e-4)   # split-K fp32 atomics: order differs
 
 
+def test_conv_dgrad_stride2_accumulate_and_mask(ops):
+    """First bottleneck of a stage: grad_x = dgrad(conv1, s=2) + dgrad(downsample, s=2), masked by x > 0."""
+    n, c, h, w, co1, co2 = 2, 256, 26, 42, 128, 512
+    x, w1 = _mk(n, c, h, w, co1, 1, 11)
+    _, w2 = _mk(n, c, h, w, co2, 1, 12)
+    g = torch.Generator().manual_seed(13)
+    ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+    g1 = torch.randn(n, co1, ho, wo, generator=g).to(torch.bfloat16)
+    g2 = torch.randn(n, co2, ho, wo, generator=g).to(torch.bfloat16)
+    xf = x.float().requires_grad_(True)
+    (F.conv2d(xf, w1.float(), stride=2) * 1.0).backward(g1.float())
+    a = xf.grad.clone().to(torch.bfloat16).float()   # first branch is rounded to bf16 before the second accumulates
+    xf.grad = None
+    F.conv2d(xf, w2.float(), stride=2).backward(g2.float())
+    want = (a + xf.grad) * (x.float() > 0)
+    gx = ops.conv2d_dgrad(g1.to(DEV), w1.to(DEV), x.shape, stride=2)
+    gx = ops.conv2d_dgrad(g2.to(DEV), w2.to(DEV), x.shape, relu_mask=x.to(DEV), stride=2, accumulate_into=gx)
+    _assert_close(gx, want, tol=1e-2)
+
+
 def test_conv_rejects_unsupported(ops):
     x, wt = _mk(1, 64, 16, 16, 64, 3, 8)
     with pytest.raises(RuntimeError, match="unsupported"):
