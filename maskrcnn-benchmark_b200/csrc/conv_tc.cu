@@ -226,9 +226,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
   } else {
     // ================================ epilogue ================================
+    // Everything below indexes registers with compile-time constants only: the 32-column chunk must never
+    // spill to local memory (with ~200 KB of shared memory carved out, L1 is tiny and local traffic runs at
+    // L2 latency).  Per-channel scale/bias of the tile are staged in shared memory once per tile.
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may read
     const int row = quad * 32 + lane;          // accumulator row == pixel within the tile
+    const int et = threadIdx.x - 64;           // 0..127 among the epilogue threads
     const int hh = row / a.tw, ww = row - hh * a.tw;
+    float* s_aff = reinterpret_cast<float*>(smem_raw + (tmem_slot - smem_u32(smem_raw)) + 16);  // [2 acc][2][256]
+    const bool has_scale = a.scale != nullptr, has_bias = a.bias != nullptr;
+    const bool cout8 = (a.cout & 7) == 0;
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < a.tiles_total; tile += gridDim.x) {
       int n_tile, img, h0, w0;
@@ -236,6 +243,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int h = h0 + hh, w = w0 + ww;
       const bool valid = (h < a.Ho) && (w < a.Wo);
       const long long pix = (long long)img * a.out_n + (long long)h * a.out_h + (long long)w * a.out_w;
+      float* sc = s_aff + acc * 512;
+      float* bi = sc + 256;
+      if (has_scale || has_bias) {
+        for (int c = et; c < a.bn; c += 128) {
+          const int cg = n_tile * a.bn + c;
+          sc[c] = (has_scale && cg < a.cout) ? __ldg(a.scale + cg) : 1.f;
+          bi[c] = (has_bias && cg < a.cout) ? __ldg(a.bias + cg) : 0.f;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * a.bn);
@@ -247,78 +264,66 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         tmem_ld32(t_row + (uint32_t)col, v);
         tmem_ld_wait();
         if (!valid) continue;
-        const int nvalid = min(32, a.cout - c0);
-        float f[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float x = __uint_as_float(v[j]);
-          if (j < nvalid) {
-            if (a.scale) x *= __ldg(a.scale + c0 + j);
-            if (a.bias) x += __ldg(a.bias + c0 + j);
-          }
-          f[j] = x;
-        }
         const long long o = pix + c0;
-        const bool vec = (nvalid == 32) && ((a.cout & 7) == 0);
-        if (a.residual) {
-          if (vec) {
+        const bool full = (c0 + 32 <= a.cout) && cout8;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < 4; ++q) {          // 8 channels per step, all indices static
+          float f[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[q * 8 + j]);
+          if (has_scale || has_bias) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], sc[col + q * 8 + j], bi[col + q * 8 + j]);
+          }
+          if (full) {
+            if (a.residual) {
               const uint4 rr = __ldg(reinterpret_cast<const uint4*>(a.residual + o + q * 8));
               const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rr);
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 const float2 t = __bfloat1622float2(r2[j]);
-                f[q * 8 + 2 * j] += t.x; f[q * 8 + 2 * j + 1] += t.y;
+                f[2 * j] += t.x; f[2 * j + 1] += t.y;
               }
             }
-          } else {
-            for (int j = 0; j < nvalid; ++j) f[j] += __bfloat162float(a.residual[o + j]);
-          }
-        }
-        if (a.relu) {
+            if (a.relu) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
-        }
-        if (a.relu_mask) {
-          if (vec) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
+              for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+            }
+            if (a.relu_mask) {
               const uint4 rr = __ldg(reinterpret_cast<const uint4*>(a.relu_mask + o + q * 8));
               const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rr);
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 const float2 t = __bfloat1622float2(r2[j]);
-                if (!(t.x > 0.f)) f[q * 8 + 2 * j] = 0.f;
-                if (!(t.y > 0.f)) f[q * 8 + 2 * j + 1] = 0.f;
+                if (!(t.x > 0.f)) f[2 * j] = 0.f;
+                if (!(t.y > 0.f)) f[2 * j + 1] = 0.f;
               }
             }
-          } else {
-            for (int j = 0; j < nvalid; ++j) if (!(__bfloat162float(a.relu_mask[o + j]) > 0.f)) f[j] = 0.f;
-          }
-        }
-        if (a.out_f32) {
-          float* dst = reinterpret_cast<float*>(a.out) + o;
-          if (vec && ((a.cout & 3) == 0)) {
-#pragma unroll
-            for (int q = 0; q < 8; ++q)
-              *reinterpret_cast<float4*>(dst + q * 4) = make_float4(f[q * 4], f[q * 4 + 1], f[q * 4 + 2], f[q * 4 + 3]);
-          } else {
-            for (int j = 0; j < nvalid; ++j) dst[j] = f[j];
-          }
-        } else {
-          __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(a.out) + o;
-          if (vec) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
+            if (a.out_f32) {
+              float* dst = reinterpret_cast<float*>(a.out) + o + q * 8;
+              *reinterpret_cast<float4*>(dst) = make_float4(f[0], f[1], f[2], f[3]);
+              *reinterpret_cast<float4*>(dst + 4) = make_float4(f[4], f[5], f[6], f[7]);
+            } else {
               uint4 pk;
               __nv_bfloat162* p2 = reinterpret_cast<__nv_bfloat162*>(&pk);
 #pragma unroll
-              for (int j = 0; j < 4; ++j) p2[j] = __floats2bfloat162_rn(f[q * 8 + 2 * j], f[q * 8 + 2 * j + 1]);
-              *reinterpret_cast<uint4*>(dst + q * 8) = pk;
+              for (int j = 0; j < 4; ++j) p2[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+              *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.out) + o + q * 8) = pk;
             }
           } else {
-            for (int j = 0; j < nvalid; ++j) dst[j] = __float2bfloat16_rn(f[j]);
+            // ragged tail (Cout not a multiple of 8 / of the chunk): predicated scalar path, static indices
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int c = c0 + q * 8 + j;
+              if (c < a.cout) {
+                float x = f[j];
+                if (a.residual) x += __bfloat162float(a.residual[o + q * 8 + j]);
+                if (a.relu) x = fmaxf(x, 0.f);
+                if (a.relu_mask && !(__bfloat162float(a.relu_mask[o + q * 8 + j]) > 0.f)) x = 0.f;
+                if (a.out_f32) reinterpret_cast<float*>(a.out)[o + q * 8 + j] = x;
+                else reinterpret_cast<__nv_bfloat16*>(a.out)[o + q * 8 + j] = __float2bfloat16_rn(x);
+              }
+            }
           }
         }
       }
@@ -485,7 +490,9 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_con
                       make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
                                   __uint_as_float(v[4 * j + 3])));
         } else {
-          for (int j = 0; j < nvalid; ++j) atomicAdd(dst + c0 + j, __uint_as_float(v[j]));
+#pragma unroll
+          for (int j = 0; j < 32; ++j)  // static indices only: v[] must stay in registers
+            if (j < nvalid) atomicAdd(dst + c0 + j, __uint_as_float(v[j]));
         }
       }
       tc_fence_before();
@@ -585,10 +592,10 @@ static int conv_launch(const ConvPlan& pl, const void* x, const void* w, int cin
   a.scale = scale; a.bias = bias; a.residual = (const __nv_bfloat16*)residual; a.relu_mask = (const __nv_bfloat16*)relu_mask;
   a.out = out;
   const uint32_t stage_bytes = kABytes + bn * 128;
-  int stages = (int)((200 * 1024) / stage_bytes);
+  int stages = (int)((196 * 1024) / stage_bytes);
   if (stages > 8) stages = 8;
   a.stages = stages;
-  const size_t smem = (size_t)stages * stage_bytes + 8 * (2 * stages + 4) + 16 + 1024;
+  const size_t smem = (size_t)stages * stage_bytes + 8 * (2 * stages + 4) + 16 + 4096 + 1024;  // + scale/bias staging
 
   CUtensorMap map_a, map_b;
   {
