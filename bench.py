@@ -255,6 +255,7 @@ def main():
         opt.zero_grad(set_to_none=True)
         loss.backward()
         opt.step()
+        model.be.refresh_weights(params)   # bf16 operand copies of the updated weights: one multi-tensor cast
         return loss
 
     def step_e2e(hbatch):

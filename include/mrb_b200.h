@@ -218,7 +218,16 @@ int mrb_conv2d_dgrad(const mrb_conv_params* p, const void* grad_output_bf16, con
  * across CTAs and reduced with red.global.add.f32 into the buffer, which is zeroed inside.  input and
  * grad_output are NHWC bf16. */
 int mrb_conv2d_wgrad(const mrb_conv_params* p, const void* input_bf16, const void* grad_output_bf16,
-                     float* grad_weight, mrb_stream_t stream);
+                     const float* scale /* optional [Cout] */, float* grad_weight, mrb_stream_t stream);
+/* Forward with the residual given at HALF resolution [N, ceil(Ho/2), ceil(Wo/2), Cout]: the epilogue reads it at
+ * (h>>1, w>>1), i.e. FPN's `lateral(C_i) + nearest_upsample_2x(P_{i+1})` (modeling/backbone/fpn.py:59-64)
+ * without materialising the upsampled map. */
+int mrb_conv2d_fwd_up2(const mrb_conv_params* p, const void* input_bf16, const void* weight_bf16,
+                       const float* scale, const float* bias, const void* residual_half, void* output,
+                       mrb_stream_t stream);
+/* grad_bias[c] = sum over pixels of an NHWC bf16 gradient [pixels, channels] (fp32, zeroed inside). */
+int mrb_bias_grad(const void* grad_bf16_nhwc, float* grad_bias, long long pixels, int channels,
+                  mrb_stream_t stream);
 
 #ifdef __cplusplus
 }

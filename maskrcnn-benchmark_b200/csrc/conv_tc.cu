@@ -132,7 +132,9 @@ struct ConvArgs {
   long long out_n, out_h, out_w;  // output strides in elements (channel stride 1)
   const float* scale;
   const float* bias;
-  const __nv_bfloat16* residual;   // same indexing as out (bf16)
+  const __nv_bfloat16* residual;   // same indexing as out (bf16) unless res_up2
+  int res_up2;                     // residual is [N, ceil(Ho/2), ceil(Wo/2), Cout]: read at (h>>1, w>>1) == nearest 2x upsample
+  long long res_n, res_h, res_w;   // its strides in elements
   const __nv_bfloat16* relu_mask;  // same indexing as out: result zeroed where mask <= 0
   void* out;
 };
@@ -243,6 +245,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int h = h0 + hh, w = w0 + ww;
       const bool valid = (h < a.Ho) && (w < a.Wo);
       const long long pix = (long long)img * a.out_n + (long long)h * a.out_h + (long long)w * a.out_w;
+      const long long rpix = a.res_up2 ? (long long)img * a.res_n + (long long)(h >> 1) * a.res_h + (long long)(w >> 1) * a.res_w : pix;
       float* sc = s_aff + acc * 512;
       float* bi = sc + 256;
       if (has_scale || has_bias) {
@@ -265,6 +268,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         tmem_ld_wait();
         if (!valid) continue;
         const long long o = pix + c0;
+        const long long ro = rpix + c0;
         const bool full = (c0 + 32 <= a.cout) && cout8;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {          // 8 channels per step, all indices static
@@ -277,7 +281,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           }
           if (full) {
             if (a.residual) {
-              const uint4 rr = __ldg(reinterpret_cast<const uint4*>(a.residual + o + q * 8));
+              const uint4 rr = __ldg(reinterpret_cast<const uint4*>(a.residual + ro + q * 8));
               const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rr);
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
@@ -317,7 +321,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               const int c = c0 + q * 8 + j;
               if (c < a.cout) {
                 float x = f[j];
-                if (a.residual) x += __bfloat162float(a.residual[o + q * 8 + j]);
+                if (a.residual) x += __bfloat162float(a.residual[ro + q * 8 + j]);
                 if (a.relu) x = fmaxf(x, 0.f);
                 if (a.relu_mask && !(__bfloat162float(a.relu_mask[o + q * 8 + j]) > 0.f)) x = 0.f;
                 if (a.out_f32) reinterpret_cast<float*>(a.out)[o + q * 8 + j] = x;
@@ -359,6 +363,7 @@ struct WgradArgs {
   int kblocks_total, kblocks_per_split;
   int cin, cout, bn, stages;
   float* dw;
+  const float* scale;  // optional per-Cout factor (frozen-BN scale of the forward epilogue)
 };
 
 __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr) {
@@ -483,16 +488,17 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_con
         tmem_ld_wait();
         if (co >= a.cout) continue;
         const int nvalid = min(32, a.cin - c0);
+        const float sco = a.scale ? __ldg(a.scale + co) : 1.f;
         if (nvalid == 32 && (a.cin & 3) == 0) {
 #pragma unroll
           for (int j = 0; j < 8; ++j)
             atomicAdd(reinterpret_cast<float4*>(dst + c0 + 4 * j),
-                      make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
-                                  __uint_as_float(v[4 * j + 3])));
+                      make_float4(sco * __uint_as_float(v[4 * j]), sco * __uint_as_float(v[4 * j + 1]),
+                                  sco * __uint_as_float(v[4 * j + 2]), sco * __uint_as_float(v[4 * j + 3])));
         } else {
 #pragma unroll
           for (int j = 0; j < 32; ++j)  // static indices only: v[] must stay in registers
-            if (j < nvalid) atomicAdd(dst + c0 + j, __uint_as_float(v[j]));
+            if (j < nvalid) atomicAdd(dst + c0 + j, sco * __uint_as_float(v[j]));
         }
       }
       tc_fence_before();
@@ -563,7 +569,7 @@ struct ConvPlan {
 // given element strides; `w` is [cout][taps][cin].
 static int conv_launch(const ConvPlan& pl, const void* x, const void* w, int cin, int cout, int kh, int kw, int pad,
                        const float* scale, const float* bias, const void* residual, const void* relu_mask, void* out,
-                       int relu, int out_f32, cudaStream_t stream) {
+                       int relu, int out_f32, cudaStream_t stream, int res_up2 = 0, int res_hh = 0, int res_ww = 0) {
   if (cin % 8 || ((uintptr_t)x & 15) || ((uintptr_t)w & 15) || ((uintptr_t)out & 15)) return MRB_ERR_UNSUPPORTED;
   if ((pl.in_w * 2) % 16 || (pl.in_h * 2) % 16 || (pl.in_n * 2) % 16) return MRB_ERR_UNSUPPORTED;
   if (residual && ((uintptr_t)residual & 15)) return MRB_ERR_UNSUPPORTED;
@@ -591,6 +597,8 @@ static int conv_launch(const ConvPlan& pl, const void* x, const void* w, int cin
   a.out_n = pl.out_n; a.out_h = pl.out_h; a.out_w = pl.out_w;
   a.scale = scale; a.bias = bias; a.residual = (const __nv_bfloat16*)residual; a.relu_mask = (const __nv_bfloat16*)relu_mask;
   a.out = out;
+  a.res_up2 = res_up2;
+  a.res_w = cout; a.res_h = (long long)res_ww * cout; a.res_n = (long long)res_hh * res_ww * cout;
   const uint32_t stage_bytes = kABytes + bn * 128;
   int stages = (int)((196 * 1024) / stage_bytes);
   if (stages > 8) stages = 8;
@@ -638,8 +646,21 @@ static int conv_check(const mrb_conv_params* p) {
 }  // namespace mrb
 using namespace mrb;
 
+static int conv2d_fwd_impl(const mrb_conv_params* p, const void* input, const void* weight, const float* scale,
+                           const float* bias, const void* residual, int residual_up2, void* output, mrb_stream_t stream);
+
 MRB_API int mrb_conv2d_fwd(const mrb_conv_params* p, const void* input, const void* weight, const float* scale,
                            const float* bias, const void* residual, void* output, mrb_stream_t stream) {
+  return conv2d_fwd_impl(p, input, weight, scale, bias, residual, 0, output, stream);
+}
+
+MRB_API int mrb_conv2d_fwd_up2(const mrb_conv_params* p, const void* input, const void* weight, const float* scale,
+                               const float* bias, const void* residual_half, void* output, mrb_stream_t stream) {
+  return conv2d_fwd_impl(p, input, weight, scale, bias, residual_half, 1, output, stream);
+}
+
+static int conv2d_fwd_impl(const mrb_conv_params* p, const void* input, const void* weight, const float* scale,
+                           const float* bias, const void* residual, int residual_up2, void* output, mrb_stream_t stream) {
   int rc = conv_check(p);
   if (rc) return rc;
   if (p->batch == 0) return MRB_OK;
@@ -652,7 +673,8 @@ MRB_API int mrb_conv2d_fwd(const mrb_conv_params* p, const void* input, const vo
   }
   ConvPlan pl;
   const long long C = p->cin, Co = p->cout;
-  if (p->kh == 1 && p->stride == 1 && p->pad == 0 && p->out_h == 0) {
+  if (residual_up2 && (!residual || p->stride != 1)) return MRB_ERR_BAD_ARG;
+  if (p->kh == 1 && p->stride == 1 && p->pad == 0 && p->out_h == 0 && !residual_up2) {
     // pure GEMM: all pixels of the batch on one axis, zero tile waste
     pl.batch = 1; pl.Hin = 1; pl.Win = p->batch * p->height * p->width;
     pl.in_w = C; pl.in_h = (long long)pl.Win * C; pl.in_n = pl.in_h;
@@ -665,7 +687,7 @@ MRB_API int mrb_conv2d_fwd(const mrb_conv_params* p, const void* input, const vo
     pl.out_w = Co; pl.out_h = (long long)Wo * Co; pl.out_n = (long long)Ho * Wo * Co;
   }
   return conv_launch(pl, input, weight, p->cin, p->cout, p->kh, p->kw, p->pad, scale, bias, residual, nullptr, output,
-                     p->relu, p->out_dtype == MRB_F32, (cudaStream_t)stream);
+                     p->relu, p->out_dtype == MRB_F32, (cudaStream_t)stream, residual_up2, (Ho + 1) / 2, (Wo + 1) / 2);
 }
 
 MRB_API size_t mrb_conv2d_dgrad_workspace_bytes(const mrb_conv_params* p) {
@@ -727,8 +749,8 @@ MRB_API int mrb_conv2d_dgrad(const mrb_conv_params* p, const void* grad_output, 
                      grad_input, 0, p->out_dtype == MRB_F32, stream);
 }
 
-MRB_API int mrb_conv2d_wgrad(const mrb_conv_params* p, const void* input, const void* grad_output, float* grad_weight,
-                             mrb_stream_t stream_) {
+MRB_API int mrb_conv2d_wgrad(const mrb_conv_params* p, const void* input, const void* grad_output, const float* scale,
+                             float* grad_weight, mrb_stream_t stream_) {
   int rc = conv_check(p);
   if (rc) return rc;
   if (p->out_h || p->out_w) return MRB_ERR_UNSUPPORTED;
@@ -778,6 +800,7 @@ MRB_API int mrb_conv2d_wgrad(const mrb_conv_params* p, const void* input, const 
   a.splits = ceil_div(a.kblocks_total, a.kblocks_per_split);
   a.items_total = out_tiles * a.splits;
   a.dw = grad_weight;
+  a.scale = scale;
   const uint32_t stage_bytes = (2 + a.bn / 64) * kWgGroupBytes;
   int stages = (int)((200 * 1024) / stage_bytes);
   if (stages > 8) stages = 8;
@@ -806,6 +829,44 @@ MRB_API int mrb_conv2d_wgrad(const mrb_conv_params* p, const void* input, const 
   if (attr_err != cudaSuccess) return (int)attr_err;
   const int grid = a.items_total < kNumSMs ? a.items_total : kNumSMs;
   conv_wgrad_tc_kernel<<<grid, kConvThreads, smem, stream>>>(map_g, map_x, a);
+  MRB_LAUNCH_CHECK();
+  return MRB_OK;
+}
+
+// ------------------------------------------------------------------------------- bias gradient
+// db[c] = sum over pixels of g[pixel, c] for an NHWC bf16 gradient: each thread owns 2 adjacent channels
+// (one bf16x2 word), a CTA walks a slab of pixels with fully coalesced rows, one red.add per channel pair.
+__global__ void __launch_bounds__(256)
+bias_grad_kernel(const __nv_bfloat16* __restrict__ g, float* __restrict__ db, long long pixels, int C, int rows_per_cta) {
+  const int pairs = C >> 1;
+  const long long p0 = (long long)blockIdx.x * rows_per_cta;
+  const long long p1 = p0 + rows_per_cta < pixels ? p0 + rows_per_cta : pixels;
+  for (int c2 = threadIdx.x; c2 < pairs; c2 += 256) {
+    float sx = 0.f, sy = 0.f;
+    const __nv_bfloat162* col = reinterpret_cast<const __nv_bfloat162*>(g) + c2;
+#pragma unroll 4
+    for (long long p = p0; p < p1; ++p) {
+      const float2 t = __bfloat1622float2(col[p * pairs]);
+      sx += t.x; sy += t.y;
+    }
+    atomicAdd(db + 2 * c2, sx);
+    atomicAdd(db + 2 * c2 + 1, sy);
+  }
+}
+
+MRB_API int mrb_bias_grad(const void* grad_bf16_nhwc, float* grad_bias, long long pixels, int channels, mrb_stream_t stream_) {
+  if (pixels < 0 || channels <= 0 || (channels & 1)) return MRB_ERR_BAD_ARG;
+  if (!grad_bias) return MRB_ERR_BAD_ARG;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MRB_CUDA_TRY(cudaMemsetAsync(grad_bias, 0, sizeof(float) * channels, stream));
+  if (pixels == 0) return MRB_OK;
+  if (!grad_bf16_nhwc || ((uintptr_t)grad_bf16_nhwc & 3)) return MRB_ERR_BAD_ARG;
+  long long ctas = (pixels + 63) / 64;
+  const long long cap = (long long)kNumSMs * 8;
+  if (ctas > cap) ctas = cap;
+  const int rows = (int)((pixels + ctas - 1) / ctas);
+  ctas = (pixels + rows - 1) / rows;
+  bias_grad_kernel<<<(unsigned)ctas, 256, 0, stream>>>((const __nv_bfloat16*)grad_bf16_nhwc, grad_bias, pixels, channels, rows);
   MRB_LAUNCH_CHECK();
   return MRB_OK;
 }

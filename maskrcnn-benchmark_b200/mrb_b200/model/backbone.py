@@ -140,9 +140,8 @@ class FPN(nn.Module):
         results = []
         for feat, inner, layer in zip(feats[::-1], self.inner_blocks[::-1], self.layer_blocks[::-1]):
             ib, lb = getattr(self, inner), getattr(self, layer)
-            top_down = be.upsample2x(last) if last is not None else None
             # lateral + top-down add, fused; `feat` is a bottleneck (ReLU) output: hand back a pre-masked gradient
-            last = be.conv(feat, ib.weight, bias=ib.bias, residual=top_down, premask_x=True)
+            last = be.lateral_topdown(feat, ib.weight, ib.bias, last)
             results.insert(0, be.conv(last, lb.weight, bias=lb.bias, pad=1))
         results.append(be.max_pool(results[-1], 1, 2, 0))  # P6 (fpn.py:77-79)
         return results

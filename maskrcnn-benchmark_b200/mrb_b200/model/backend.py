@@ -14,6 +14,11 @@ class Backend:
     act_dtype = torch.float32
     channels_last = False
 
+    def lateral_topdown(self, feat, weight, bias, top):
+        """FPN inner block (fpn.py:51-64): conv1x1(feat) + nearest_upsample_2x(top) (top may be None)."""
+        top_down = self.upsample2x(top) if top is not None else None
+        return self.conv(feat, weight, bias=bias, residual=top_down, premask_x=True)
+
     def prepare_input(self, images):
         raise NotImplementedError
 
@@ -34,11 +39,12 @@ class _ConvFn(Function):
 
     @staticmethod
     def forward(ctx, x, weight, bias, residual, w16, scale, shift, stride, pad, relu, out_fp32, wgrad_fn,
-                premask_x=False, gy_premasked=False):
+                premask_x=False, gy_premasked=False, residual_up2=False):
         from mrb_b200 import ops
         add = shift if shift is not None else (bias.detach().float() if bias is not None else None)
         y = ops.conv2d_fwd(x, w16, scale, add, residual, stride, pad, relu,
-                           torch.float32 if out_fp32 else torch.bfloat16)
+                           torch.float32 if out_fp32 else torch.bfloat16, residual_up2=residual_up2)
+        ctx.residual_up2 = residual_up2
         ctx.cfg = (stride, pad, relu and not gy_premasked, tuple(x.shape), wgrad_fn)
         ctx.premask_x = premask_x
         ctx.has_bias = bias is not None
@@ -62,14 +68,13 @@ class _ConvFn(Function):
             # premask_x: x is the ReLU output of its producer, whose backward then skips its own mask pass
             gx = ops.conv2d_dgrad(g, w16, x_shape, scale, None, x if ctx.premask_x else None, stride, pad)
         if ctx.needs_input_grad[1]:
-            gw = wgrad_fn(x, g, w16, stride, pad)
-            if scale is not None:
-                gw = gw * scale[:, None, None, None]
+            gw = wgrad_fn(x, g, w16, stride, pad, scale)
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            gb = g.float().sum((0, 2, 3))
+            gb = ops.bias_grad(g)
         if ctx.has_res and ctx.needs_input_grad[3]:
-            gres = g
-        return gx, gw, gb, gres, None, None, None, None, None, None, None, None, None, None
+            # nearest-2x upsample backward == sum over each 2x2 block
+            gres = F.avg_pool2d(g, 2).mul_(4) if ctx.residual_up2 else g
+        return gx, gw, gb, gres, None, None, None, None, None, None, None, None, None, None, None
 
 
 class _BottleneckFn(Function):
@@ -114,15 +119,15 @@ class _BottleneckFn(Function):
         need = ctx.needs_input_grad
         gw1 = gw2 = gw3 = gwd = gx = None
         if need[3]:
-            gw3 = wg(y2, g, w3, 1, 0) * a3[:, None, None, None]
+            gw3 = wg(y2, g, w3, 1, 0, a3)
         g2 = ops.conv2d_dgrad(g, w3, y2.shape, a3, None, y2, 1, 0)
         if need[2]:
-            gw2 = wg(y1, g2, w2, s3, 1) * a2[:, None, None, None]
+            gw2 = wg(y1, g2, w2, s3, 1, a2)
         g1 = ops.conv2d_dgrad(g2, w2, y1.shape, a2, None, y1, s3, 1)
         if need[1]:
-            gw1 = wg(x, g1, w1, s1, 0) * a1[:, None, None, None]
+            gw1 = wg(x, g1, w1, s1, 0, a1)
         if ctx.has_d and need[4]:
-            gwd = wg(x, g, wd, sd, 0) * ad[:, None, None, None]
+            gwd = wg(x, g, wd, sd, 0, ad)
         if need[0]:
             if not ctx.has_d:
                 gx = ops.conv2d_dgrad(g1, w1, x.shape, a1, g, x, s1, 0)
@@ -135,17 +140,17 @@ class _BottleneckFn(Function):
         return gx, gw1, gw2, gw3, gwd, None, None, None
 
 
-def _wgrad_cudnn(x, g, w16, stride, pad):
+def _wgrad_cudnn(x, g, w16, stride, pad, scale=None):
     """Library weight gradient (ATen/cuDNN): kept only as an A/B switch for bench.py --wgrad cudnn."""
     gw = torch.ops.aten.convolution_backward(g, x, w16, None, [stride, stride], [pad, pad], [1, 1], False, [0, 0], 1,
-                                             [False, True, False])[1]
-    return gw.float()
+                                             [False, True, False])[1].float()
+    return gw * scale[:, None, None, None] if scale is not None else gw
 
 
-def _wgrad_tc(x, g, w16, stride, pad):
-    """Weight gradient on the tcgen05 engine (MN-major operands, split-K, fp32 red.add)."""
+def _wgrad_tc(x, g, w16, stride, pad, scale=None):
+    """Weight gradient on the tcgen05 engine (MN-major operands, split-K, fp32 red.add, BN scale fused)."""
     from mrb_b200 import ops
-    return ops.conv2d_wgrad(x, g, w16.shape, stride, pad)
+    return ops.conv2d_wgrad(x, g, w16.shape, stride, pad, scale)
 
 
 class B200Backend(Backend):
@@ -179,7 +184,7 @@ class B200Backend(Backend):
         return images.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
 
     def conv(self, x, weight, scale=None, shift=None, bias=None, residual=None, stride=1, pad=0, relu=False,
-             out_fp32=False, w16=None, premask_x=False, gy_premasked=False):
+             out_fp32=False, w16=None, premask_x=False, gy_premasked=False, residual_up2=False):
         if x.numel() == 0:
             n, _, h, w = x.shape
             kh, kw = weight.shape[2:]
@@ -204,7 +209,7 @@ class B200Backend(Backend):
         if w16 is None:
             w16 = self._weight16(weight)
         y = _ConvFn.apply(x, weight, bias, residual, w16, scale, shift, stride, pad, relu, out_fp32, self.wgrad_fn,
-                          premask_x, gy_premasked)
+                          premask_x, gy_premasked, residual_up2)
         return y[:, :co] if co % 8 else y
 
     def bottleneck(self, blk, x, g_premasked):
@@ -240,6 +245,27 @@ class B200Backend(Backend):
 
     def upsample2x(self, x):
         return F.interpolate(x, scale_factor=2, mode="nearest")
+
+    def lateral_topdown(self, feat, weight, bias, top):
+        # the 2x nearest upsample is folded into the epilogue's residual read: no upsampled map in HBM
+        return self.conv(feat, weight, bias=bias, residual=top, premask_x=True, residual_up2=top is not None)
+
+    def refresh_weights(self, params):
+        """Re-derive the bf16 operand copies of all (changed) parameters with one multi-tensor copy instead of
+        one cast kernel per layer; call once per step after the optimizer update."""
+        src, dst = [], []
+        for w in params:
+            if not isinstance(w, torch.nn.Parameter) or w.dim() not in (2, 4):
+                continue
+            ent = self._w16.get(id(w))
+            if ent is None or ent[0] is not w or ent[2].device != w.device or ent[2].stride() != w.stride():
+                continue   # first use goes through _weight16
+            if ent[1] != w._version:
+                src.append(w.detach())
+                dst.append(ent[2])
+                self._w16[id(w)] = (w, w._version, ent[2])
+        if src:
+            torch._foreach_copy_(dst, src)
 
     def linear(self, x, weight, bias, relu=False, out_fp32=False, premask_x=False, gy_premasked=False):
         """Fully connected layer on the conv engine: [R, K] x [Cout, K]^T as a 1x1 conv over R "pixels"."""

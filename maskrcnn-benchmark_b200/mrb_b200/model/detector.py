@@ -75,4 +75,12 @@ def build_model(cfg=None, backend=None, device="cuda"):
     if backend is None:
         from .backend import B200Backend
         backend = B200Backend()
-    return GeneralizedRCNN(cfg, backend).to(device)
+    model = GeneralizedRCNN(cfg, backend).to(device)
+    if getattr(backend, "channels_last", False):
+        # keep the fp32 master weights of every conv in KRSC memory (torch.channels_last): same logical shape and
+        # state_dict, but the tcgen05 wgrad output, the optimizer state and the bf16 operand copies then all share
+        # one layout (no per-step transposes, foreach optimizer fast path)
+        for p in model.parameters():
+            if p.dim() == 4:
+                p.data = p.data.contiguous(memory_format=torch.channels_last)
+    return model

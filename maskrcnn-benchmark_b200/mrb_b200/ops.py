@@ -53,8 +53,9 @@ def _params(x_shape, w_shape, stride, pad, relu, out_dtype, out_hw=None):
 
 
 def conv2d_fwd(x, weight, scale=None, bias=None, residual=None, stride=1, pad=0, relu=False,
-               out_dtype=torch.bfloat16, out_hw=None):
-    """y = act(conv(x, weight) * scale[c] + bias[c] + residual).  x, weight bf16 channels_last."""
+               out_dtype=torch.bfloat16, out_hw=None, residual_up2=False):
+    """y = act(conv(x, weight) * scale[c] + bias[c] + residual).  x, weight bf16 channels_last.
+    residual_up2: `residual` has half the output resolution and is read through a nearest 2x upsample."""
     x = _nhwc(x, "conv2d_fwd(x)")
     weight = _nhwc(weight, "conv2d_fwd(weight)")
     if x.dtype != torch.bfloat16 or weight.dtype != torch.bfloat16:
@@ -64,14 +65,16 @@ def conv2d_fwd(x, weight, scale=None, bias=None, residual=None, stride=1, pad=0,
                       memory_format=torch.channels_last)
     if residual is not None:
         residual = _nhwc(residual, "conv2d_fwd(residual)")
-        if residual.dtype != torch.bfloat16 or residual.shape != out.shape:
-            raise RuntimeError("conv2d_fwd: residual must be bf16 and shaped like the output")
+        want = (p.batch, p.cout, (ho + 1) // 2, (wo + 1) // 2) if residual_up2 else tuple(out.shape)
+        if residual.dtype != torch.bfloat16 or tuple(residual.shape) != want:
+            raise RuntimeError("conv2d_fwd: residual must be bf16 and shaped %s" % (want,))
     for v in (scale, bias):
         if v is not None and (v.dtype != torch.float32 or v.numel() != p.cout or not v.is_contiguous()):
             raise RuntimeError("conv2d_fwd: scale/bias must be contiguous fp32 [Cout]")
     with torch.cuda.device(x.device):
-        _c.check(lib.mrb_conv2d_fwd(ctypes.byref(p), _c._ptr(x), _c._ptr(weight), _c._ptr(scale), _c._ptr(bias),
-                                    _c._ptr(residual), _c._ptr(out), _c._stream()), "mrb_conv2d_fwd")
+        fn = lib.mrb_conv2d_fwd_up2 if residual_up2 else lib.mrb_conv2d_fwd
+        _c.check(fn(ctypes.byref(p), _c._ptr(x), _c._ptr(weight), _c._ptr(scale), _c._ptr(bias),
+                    _c._ptr(residual), _c._ptr(out), _c._stream()), "mrb_conv2d_fwd")
     _count(1, ("fwd", p.batch, p.cin, p.height, p.width, p.cout, p.kh, p.stride, p.pad))
     return out
 
@@ -114,8 +117,9 @@ def conv2d_dgrad(grad_out, weight, x_shape, scale=None, add=None, relu_mask=None
     return gx
 
 
-def conv2d_wgrad(x, grad_out, w_shape, stride=1, pad=0):
-    """grad_weight (fp32, logical [Cout, Cin, kh, kw], channels_last memory == KRSC) on the tcgen05 engine."""
+def conv2d_wgrad(x, grad_out, w_shape, stride=1, pad=0, scale=None):
+    """grad_weight (fp32, logical [Cout, Cin, kh, kw], channels_last memory == KRSC) on the tcgen05 engine,
+    optionally multiplied by a per-Cout `scale` (the frozen-BN scale of the forward epilogue)."""
     x = _nhwc(x, "conv2d_wgrad(x)")
     grad_out = _nhwc(grad_out, "conv2d_wgrad(grad_out)")
     if x.dtype != torch.bfloat16 or grad_out.dtype != torch.bfloat16:
@@ -125,10 +129,24 @@ def conv2d_wgrad(x, grad_out, w_shape, stride=1, pad=0):
         raise RuntimeError("conv2d_wgrad: grad_out shape mismatch")
     gw = torch.empty(tuple(w_shape), dtype=torch.float32, device=x.device).contiguous(memory_format=torch.channels_last)
     with torch.cuda.device(x.device):
-        _c.check(lib.mrb_conv2d_wgrad(ctypes.byref(p), _c._ptr(x), _c._ptr(grad_out), _c._ptr(gw), _c._stream()),
-                 "mrb_conv2d_wgrad")
+        _c.check(lib.mrb_conv2d_wgrad(ctypes.byref(p), _c._ptr(x), _c._ptr(grad_out), _c._ptr(scale), _c._ptr(gw),
+                                      _c._stream()), "mrb_conv2d_wgrad")
     _count(1, ("wgrad", p.batch, p.cin, p.height, p.width, p.cout, p.kh, p.stride, p.pad))
     return gw
+
+
+def bias_grad(grad_out):
+    """sum over N, H, W of an NHWC bf16 gradient -> fp32 [C]."""
+    grad_out = _nhwc(grad_out, "bias_grad(grad_out)")
+    if grad_out.dtype != torch.bfloat16:
+        raise RuntimeError("bias_grad: bf16 gradient required")
+    n, c, h, w = grad_out.shape
+    out = torch.empty(c, dtype=torch.float32, device=grad_out.device)
+    with torch.cuda.device(grad_out.device):
+        _c.check(lib.mrb_bias_grad(_c._ptr(grad_out), _c._ptr(out), ctypes.c_longlong(n * h * w), c, _c._stream()),
+                 "mrb_bias_grad")
+    _count(1)
+    return out
 
 
 # ------------------------------------------------------------------------- fused FPN ROIAlign

@@ -146,6 +146,33 @@ def test_conv_dgrad_stride2_accumulate_and_mask(ops):
     _assert_close(gx, want, tol=1e-2)
 
 
+def test_conv_fwd_residual_upsampled(ops):
+    """FPN inner block: conv1x1(C_i) + bias + nearest_upsample_2x(P_{i+1}) with the upsample folded into the epilogue."""
+    n, c, h, w, co = 2, 512, 50, 84, 256
+    x, wt = _mk(n, c, h, w, co, 1, 21)
+    g = torch.Generator().manual_seed(22)
+    top = torch.randn(n, co, h // 2, w // 2, generator=g).to(torch.bfloat16)
+    bias = torch.randn(co, generator=g)
+    want = F.conv2d(x.float(), wt.float()) + bias[None, :, None, None] + F.interpolate(top.float(), scale_factor=2, mode="nearest")
+    got = ops.conv2d_fwd(x.to(DEV), wt.to(DEV), None, bias.to(DEV), top.to(DEV), 1, 0, False, torch.float32, residual_up2=True)
+    _assert_close(got, want)
+
+
+def test_wgrad_scale_and_bias_grad(ops):
+    n, c, h, w, co, k = 2, 128, 25, 42, 256, 3
+    x, wt = _mk(n, c, h, w, co, k, 23)
+    g = torch.Generator().manual_seed(24)
+    go = torch.randn(n, co, h, w, generator=g).to(torch.bfloat16)
+    scale = torch.rand(co, generator=g) + 0.5
+    wf = wt.float().requires_grad_(True)
+    F.conv2d(x.float(), wf, padding=1).backward(go.float())
+    got = ops.conv2d_wgrad(x.to(DEV), go.to(DEV), wt.shape, 1, 1, scale.to(DEV))
+    _assert_close(got, wf.grad * scale[:, None, None, None], tol=2e-4)
+    _assert_close(ops.bias_grad(go.to(DEV)), go.float().sum((0, 2, 3)), tol=1e-4)
+    odd = torch.randn(3, 16, 7, 5, generator=g).to(torch.bfloat16)
+    _assert_close(ops.bias_grad(odd.to(DEV)), odd.float().sum((0, 2, 3)), tol=1e-4)
+
+
 def test_conv_rejects_unsupported(ops):
     x, wt = _mk(1, 64, 16, 16, 64, 3, 8)
     with pytest.raises(RuntimeError, match="unsupported"):
