@@ -200,8 +200,8 @@ def run_reference(args, rank, world):
 
 
 def workload_config(n_gpus):
-    return {"workload": "e2e_mask_rcnn_R_50_FPN_1x train step (fwd + bwd + SGD), synthetic 800x1333 images zero-padded to "
-                        "800x1344 NCHW, 8 GT boxes/image, random-init weights",
+    return {"workload": "e2e_mask_rcnn_R_50_FPN_1x train step (fwd + bwd + SGD momentum/wd update), synthetic 800x1333 images "
+                        "zero-padded to 800x1344 NCHW, 8 GT boxes/image, random-init weights",
             "global_batch": IMGS_PER_GPU * n_gpus, "images_per_gpu": IMGS_PER_GPU, "parallelism": "dp%d" % n_gpus,
             "l2": "per-step working set (activations + gradients, several GB) exceeds the 126 MB L2; no explicit flush"}
 
@@ -216,6 +216,8 @@ def main():
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--dump-shapes", default=None, help="write the per-shape conv table (JSON) here")
     ap.add_argument("--wgrad", default="tc", choices=["tc", "cudnn"], help="weight-gradient kernel (A/B switch)")
+    ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
+                    help="capture the whole train step (fwd+bwd+SGD) in one CUDA graph (auto: single-GPU runs)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -235,32 +237,73 @@ def main():
     from mrb_b200.model import build_model
 
     torch.manual_seed(0)
+    from mrb_b200.model import RCNNConfig
     from mrb_b200.model.backend import B200Backend
-    model = build_model(backend=B200Backend(wgrad=args.wgrad), device=device).train()
+    from mrb_b200.optim import FlatSGD
+    use_graph = args.graph == "on" or (args.graph == "auto" and world == 1)
+    # graph capture needs a step without host synchronisation: fixed-shape mask head (see RCNNConfig)
+    cfg = RCNNConfig(mask_rois_per_image=128 if use_graph else 0)
+    model = build_model(cfg, backend=B200Backend(wgrad=args.wgrad), device=device).train()
     step_model = model
     if world > 1:
         step_model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], broadcast_buffers=False)
     params = [p for p in model.parameters() if p.requires_grad]
-    opt = torch.optim.SGD(params, lr=1e-4, momentum=0.9, weight_decay=1e-4)
+    # SOLVER defaults of the reference (config/defaults.py:383-401): momentum 0.9, wd 1e-4, bias lr x2, bias wd 0
+    opt = FlatSGD(model.named_parameters(), lr=1e-4, momentum=0.9, weight_decay=1e-4)
     sizes = [(IMG_H, IMG_W)] * IMGS_PER_GPU
     # distinct synthetic batches, pinned on the host (e2e) and resident in HBM (value)
     n_batches = 4
     host = [synth_batch(IMGS_PER_GPU, 100 * rank + i, pin=True) for i in range(n_batches)]
     dev = [tuple(t.to(device) for t in b) for b in host]
 
-    def step(batch):
+    def eager_step(batch):
         images, boxes, labels = batch
         losses = step_model(images, sizes, targets_of(boxes, labels))
         loss = sum(losses.values())
-        opt.zero_grad(set_to_none=True)
+        opt.zero_grad()
         loss.backward()
         opt.step()
         model.be.refresh_weights(params)   # bf16 operand copies of the updated weights: one multi-tensor cast
         return loss
 
+    graph_info = {"enabled": False}
+    step = eager_step
+    if use_graph:
+        static = tuple(torch.empty_like(t) for t in dev[0])
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for i in range(3):
+                    for a, b in zip(static, dev[i % n_batches]):
+                        a.copy_(b)
+                    eager_step(static)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            opt.zero_grad()
+            ops.STATS["launches"] = 0
+            ops.STATS["conv_calls"] = []
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                static_loss = eager_step(static)
+            graph_info = {"enabled": True, "launches_per_step": ops.STATS["launches"], "conv_calls": list(ops.STATS["conv_calls"])}
+            ops.STATS["conv_calls"] = None
+
+            def step(batch):  # noqa: F811
+                for a, b in zip(static, batch):
+                    a.copy_(b, non_blocking=True)
+                graph.replay()
+                return static_loss
+        except Exception as e:  # fall back to eager, and say so in the JSON line
+            graph_info = {"enabled": False, "error": repr(e)[:300]}
+            torch.cuda.synchronize()
+            step = eager_step
+
     def step_e2e(hbatch):
-        batch = tuple(t.to(device, non_blocking=True) for t in hbatch)
-        loss = step(batch)
+        if graph_info["enabled"]:
+            loss = step(hbatch)             # pinned host -> static device buffers (H2D), then the captured step
+        else:
+            loss = step(tuple(t.to(device, non_blocking=True) for t in hbatch))
         return loss.detach().float().cpu()  # D2H of the step's result
 
     def barrier():
@@ -284,8 +327,12 @@ def main():
     e1.record()
     barrier()
     t_dev = e0.elapsed_time(e1) * 1e-3
-    launches = ops.STATS["launches"]
-    conv_calls = list(ops.STATS["conv_calls"])
+    if graph_info["enabled"]:
+        launches = graph_info["launches_per_step"] * args.steps
+        conv_calls = graph_info.pop("conv_calls") * args.steps
+    else:
+        launches = ops.STATS["launches"]
+        conv_calls = list(ops.STATS["conv_calls"])
     ops.STATS["conv_calls"] = None
     # ---- timed: end to end from pinned host memory
     step_e2e(host[0])
@@ -313,10 +360,10 @@ def main():
            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
            "config": workload_config(world), "clocks": clocks,
            "e2e": {"value": round(imgs / t_e2e, 3), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
-           "gpu_launches": launches,
+           "gpu_launches": launches, "cuda_graph": graph_info,
            "library_ops": {"wgrad": model.be.wgrad_impl, "note": "conv forward, data-gradient and weight-gradient run on the "
-                           "in-house tcgen05 kernels; max-pool, nearest-upsample, ReLU-mask, topk/sort, losses and the "
-                           "optimizer are PyTorch"}}
+                           "in-house tcgen05 kernels; max-pool, top-k/sort, box arithmetic, losses and the multi-tensor "
+                           "SGD update are PyTorch"}}
     if not args.no_roofline and conv_calls:
         per_step = conv_calls[:len(conv_calls) // args.steps]
         rf, rows = conv_roofline(per_step, peaks, device)

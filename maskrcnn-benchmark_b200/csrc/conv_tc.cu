@@ -236,6 +236,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int et = threadIdx.x - 64;           // 0..127 among the epilogue threads
     const int hh = row / a.tw, ww = row - hh * a.tw;
     float* s_aff = reinterpret_cast<float*>(smem_raw + (tmem_slot - smem_u32(smem_raw)) + 16);  // [2 acc][2][256]
+    uint4* stg4 = reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(s_aff) + 4096 + (warp - 2) * 4096);  // [32 rows][8 x 16 B]
     const bool has_scale = a.scale != nullptr, has_bias = a.bias != nullptr;
     const bool cout8 = (a.cout & 7) == 0;
     int acc = 0; uint32_t acc_phase = 0;
@@ -259,14 +260,105 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * a.bn);
-      for (int col = 0; col < a.bn; col += 32) {
+      const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+      int col = 0;
+      while (col < a.bn) {
         const int c0 = n_tile * a.bn + col;
         if (c0 >= a.cout) break;  // warp-uniform
+        if (!a.out_f32 && cout8 && c0 + 64 <= a.cout && col + 64 <= a.bn) {
+          // ---- 64 channels (128 B per pixel) at a time, global traffic staged through a per-warp 4 KB smem
+          // block so that every warp-level load/store covers whole 128-byte lines (8 lanes per pixel row)
+          // instead of 32 separate 16-byte pieces.
+          uint4 rr[8], mm[8];
+          if (a.residual) {
+            const long long my = rpix + c0;
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int r = it * 4 + (lane >> 3), sg = lane & 7;
+              const long long off = __shfl_sync(0xffffffffu, my, r);
+              if ((vmask >> r) & 1u) stg4[r * 8 + (sg ^ (r & 7))] = __ldg(reinterpret_cast<const uint4*>(a.residual + off + sg * 8));
+            }
+            __syncwarp();
+#pragma unroll
+            for (int sg = 0; sg < 8; ++sg) rr[sg] = stg4[lane * 8 + (sg ^ (lane & 7))];
+            __syncwarp();
+          }
+          if (a.relu_mask) {
+            const long long my = pix + c0;
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int r = it * 4 + (lane >> 3), sg = lane & 7;
+              const long long off = __shfl_sync(0xffffffffu, my, r);
+              if ((vmask >> r) & 1u) stg4[r * 8 + (sg ^ (r & 7))] = __ldg(reinterpret_cast<const uint4*>(a.relu_mask + off + sg * 8));
+            }
+            __syncwarp();
+#pragma unroll
+            for (int sg = 0; sg < 8; ++sg) mm[sg] = stg4[lane * 8 + (sg ^ (lane & 7))];
+            __syncwarp();
+          }
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            uint32_t v[32];
+            tmem_ld32(t_row + (uint32_t)(col + 32 * half), v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              float f[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[q * 8 + j]);
+              if (has_scale || has_bias) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], sc[col + half * 32 + q * 8 + j], bi[col + half * 32 + q * 8 + j]);
+              }
+              if (a.residual) {
+                const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rr[half * 4 + q]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float2 t = __bfloat1622float2(r2[j]);
+                  f[2 * j] += t.x; f[2 * j + 1] += t.y;
+                }
+              }
+              if (a.relu) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+              }
+              if (a.relu_mask) {
+                const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&mm[half * 4 + q]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float2 t = __bfloat1622float2(r2[j]);
+                  if (!(t.x > 0.f)) f[2 * j] = 0.f;
+                  if (!(t.y > 0.f)) f[2 * j + 1] = 0.f;
+                }
+              }
+              uint4 pk;
+              __nv_bfloat162* p2 = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) p2[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+              stg4[lane * 8 + ((half * 4 + q) ^ (lane & 7))] = pk;
+            }
+          }
+          __syncwarp();
+          {
+            const long long my = pix + c0;
+            __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(a.out);
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int r = it * 4 + (lane >> 3), sg = lane & 7;
+              const long long off = __shfl_sync(0xffffffffu, my, r);
+              if ((vmask >> r) & 1u) *reinterpret_cast<uint4*>(outp + off + sg * 8) = stg4[r * 8 + (sg ^ (r & 7))];
+            }
+          }
+          __syncwarp();
+          col += 64;
+          continue;
+        }
+        // ---- fallback: 32 channels per step, per-thread 16-byte accesses (fp32 output, ragged Cout tails)
         uint32_t v[32];
         __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge lanes that skipped the stores of the last chunk
         tmem_ld32(t_row + (uint32_t)col, v);
         tmem_ld_wait();
-        if (!valid) continue;
+        if (!valid) { col += 32; continue; }
         const long long o = pix + c0;
         const long long ro = rpix + c0;
         const bool full = (c0 + 32 <= a.cout) && cout8;
@@ -330,6 +422,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
           }
         }
+              col += 32;
       }
       tc_fence_before();
       mbar_arrive(tempty_bar(acc));
@@ -600,10 +693,10 @@ static int conv_launch(const ConvPlan& pl, const void* x, const void* w, int cin
   a.res_up2 = res_up2;
   a.res_w = cout; a.res_h = (long long)res_ww * cout; a.res_n = (long long)res_hh * res_ww * cout;
   const uint32_t stage_bytes = kABytes + bn * 128;
-  int stages = (int)((196 * 1024) / stage_bytes);
+  int stages = (int)((200 * 1024) / stage_bytes);
   if (stages > 8) stages = 8;
   a.stages = stages;
-  const size_t smem = (size_t)stages * stage_bytes + 8 * (2 * stages + 4) + 16 + 4096 + 1024;  // + scale/bias staging
+  const size_t smem = (size_t)stages * stage_bytes + 8 * (2 * stages + 4) + 16 + 4096 + 16384 + 1024;  // + scale/bias + epilogue staging
 
   CUtensorMap map_a, map_b;
   {

@@ -256,10 +256,10 @@ MRB_API int mrb_roi_align_fpn_fwd(const void* const* feats_host, const int* heig
   if (smem > 200 * 1024) return MRB_ERR_UNSUPPORTED;
   dim3 grid(num_rois, ceil_div(channels, kFpnSlab));
   if (dtype == MRB_BF16) {
-    MRB_CUDA_TRY(cudaFuncSetAttribute(roi_align_fpn_fwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 48 * 1024) MRB_CUDA_TRY(cudaFuncSetAttribute(roi_align_fpn_fwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     roi_align_fpn_fwd_kernel<__nv_bfloat16><<<grid, kFpnThreads, smem, (cudaStream_t)stream>>>(a, rois, (__nv_bfloat16*)output);
   } else if (dtype == MRB_F32) {
-    MRB_CUDA_TRY(cudaFuncSetAttribute(roi_align_fpn_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 48 * 1024) MRB_CUDA_TRY(cudaFuncSetAttribute(roi_align_fpn_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     roi_align_fpn_fwd_kernel<float><<<grid, kFpnThreads, smem, (cudaStream_t)stream>>>(a, rois, (float*)output);
   } else {
     return MRB_ERR_BAD_ARG;
@@ -283,10 +283,10 @@ MRB_API int mrb_roi_align_fpn_bwd(const void* grad_output, float* const* grad_fe
   if (smem > 200 * 1024) return MRB_ERR_UNSUPPORTED;
   dim3 grid(num_rois, ceil_div(channels, kFpnSlab));
   if (dtype == MRB_BF16) {
-    MRB_CUDA_TRY(cudaFuncSetAttribute(roi_align_fpn_bwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 48 * 1024) MRB_CUDA_TRY(cudaFuncSetAttribute(roi_align_fpn_bwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     roi_align_fpn_bwd_kernel<__nv_bfloat16><<<grid, kFpnThreads, smem, (cudaStream_t)stream>>>(a, rois, (const __nv_bfloat16*)grad_output);
   } else if (dtype == MRB_F32) {
-    MRB_CUDA_TRY(cudaFuncSetAttribute(roi_align_fpn_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 48 * 1024) MRB_CUDA_TRY(cudaFuncSetAttribute(roi_align_fpn_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     roi_align_fpn_bwd_kernel<float><<<grid, kFpnThreads, smem, (cudaStream_t)stream>>>(a, rois, (const float*)grad_output);
   } else {
     return MRB_ERR_BAD_ARG;

@@ -51,5 +51,11 @@ class RCNNConfig:
     mask_sampling_ratio: int = 2
     mask_conv_layers: Tuple[int, ...] = (256, 256, 256, 256)
     mask_resolution: int = 28
+    # 0: the mask head runs on the gathered positive ROIs (one `nonzero` host sync per step, as the reference's
+    # keep_only_positive_boxes).  > 0: fixed-shape variant -- the first `mask_rois_per_image` sampled ROIs of each
+    # image in positives-first order, non-positives weighted 0 in the loss (identical loss value; the sampler never
+    # yields more than int(roi_batch_size * roi_positive_fraction) = 128 positives per image) -- which makes the
+    # whole train step free of host synchronisation and therefore CUDA-graph capturable.
+    mask_rois_per_image: int = 0
     size_divisibility: int = 32               # DATALOADER.SIZE_DIVISIBILITY (yaml:35-36)
     pixel_mean: Tuple[float, ...] = field(default=(102.9801, 115.9465, 122.7717))

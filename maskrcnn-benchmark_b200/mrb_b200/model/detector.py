@@ -54,14 +54,30 @@ class GeneralizedRCNN(nn.Module):
             losses.update({"loss_classifier": lc, "loss_box_reg": lb})
             if self.cfg.mask_on:
                 mask = self.roi_heads.mask
-                lab = labels.reshape(-1)
-                pos = (lab > 0).nonzero().squeeze(1)                 # keep_only_positive_boxes (mask_head.py:11-32)
-                rois_pos = rois[pos]
-                logits = mask.run(be, feats, rois_pos)
                 n, s = labels.shape
-                gt_all = torch.stack([t["boxes"][gidx[i]] for i, t in enumerate(targets)]).reshape(n * s, 4)
-                tgt = mask.mask_targets(gt_all[pos], rois_pos[:, 1:], self.cfg.mask_resolution)
-                losses["loss_mask"] = mask.loss(logits, lab[pos], tgt)
+                res = self.cfg.mask_resolution
+                gt_all = torch.stack([t["boxes"][gidx[i]] for i, t in enumerate(targets)])          # [n, s, 4]
+                m = self.cfg.mask_rois_per_image
+                if m > 0:
+                    posm = labels > 0
+                    order = torch.sort((~posm).to(torch.int8), dim=1, stable=True)[1][:, :m]        # positives first
+                    wsel = torch.gather(posm, 1, order).reshape(-1).float()
+                    rois_sel = torch.gather(rois.view(n, s, 5), 1, order[..., None].expand(-1, -1, 5)).reshape(-1, 5)
+                    lab_sel = torch.gather(labels, 1, order).reshape(-1).clamp(min=0)
+                    gt_sel = torch.gather(gt_all, 1, order[..., None].expand(-1, -1, 4)).reshape(-1, 4)
+                    logits = mask.run(be, feats, rois_sel)
+                    tgt = mask.mask_targets(gt_sel, rois_sel[:, 1:], res)
+                    idx = torch.arange(logits.shape[0], device=logits.device)
+                    bce = torch.nn.functional.binary_cross_entropy_with_logits(logits[idx, lab_sel].float(), tgt,
+                                                                               reduction="none").mean((1, 2))
+                    losses["loss_mask"] = (bce * wsel).sum() / wsel.sum().clamp(min=1)
+                else:
+                    lab = labels.reshape(-1)
+                    pos = (lab > 0).nonzero().squeeze(1)             # keep_only_positive_boxes (mask_head.py:11-32)
+                    rois_pos = rois[pos]
+                    logits = mask.run(be, feats, rois_pos)
+                    tgt = mask.mask_targets(gt_all.reshape(n * s, 4)[pos], rois_pos[:, 1:], res)
+                    losses["loss_mask"] = mask.loss(logits, lab[pos], tgt)
             return losses
         boxes, _, valid = proposals
         rois = _to_rois(boxes)

@@ -93,6 +93,7 @@ class RPN(nn.Module):
         self.head = RPNHead(in_channels, self.anchor_generator.num_anchors_per_location()[0])
         self.box_coder = box_ops.BoxCoder((1.0, 1.0, 1.0, 1.0))
         self.matcher = box_ops.Matcher(cfg.rpn_fg_iou, cfg.rpn_bg_iou, allow_low_quality_matches=True)
+        self._size_cache = {}
 
     # ------------------------------------------------------------------ proposals (no_grad)
     @torch.no_grad()
@@ -105,8 +106,11 @@ class RPN(nn.Module):
         pre_n = cfg.pre_nms_top_n_train if training else cfg.pre_nms_top_n_test
         post_n = cfg.post_nms_top_n_train if training else cfg.post_nms_top_n_test
         fpn_post_n = cfg.fpn_post_nms_top_n_train if training else cfg.fpn_post_nms_top_n_test
-        widths = torch.tensor([s[1] for s in image_sizes], device=dev, dtype=torch.float32)
-        heights = torch.tensor([s[0] for s in image_sizes], device=dev, dtype=torch.float32)
+        key = (tuple(tuple(s) for s in image_sizes), str(dev))
+        if key not in self._size_cache:     # host -> device copies must not sit inside a captured step
+            self._size_cache[key] = (torch.tensor([s[1] for s in image_sizes], device=dev, dtype=torch.float32),
+                                     torch.tensor([s[0] for s in image_sizes], device=dev, dtype=torch.float32))
+        widths, heights = self._size_cache[key]
         all_boxes, all_scores, ks = [], [], []
         for anc, lg, dl in zip(anchors, logits, deltas):
             k = min(pre_n, lg.shape[1])
