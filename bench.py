@@ -217,7 +217,8 @@ def main():
     ap.add_argument("--dump-shapes", default=None, help="write the per-shape conv table (JSON) here")
     ap.add_argument("--wgrad", default="tc", choices=["tc", "cudnn"], help="weight-gradient kernel (A/B switch)")
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
-                    help="capture the whole train step (fwd+bwd+SGD) in one CUDA graph (auto: single-GPU runs)")
+                    help="capture the whole train step (fwd+bwd+all-reduce+SGD) in one CUDA graph; falls back to eager "
+                         "(and says so) if capture fails")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -240,14 +241,18 @@ def main():
     from mrb_b200.model import RCNNConfig
     from mrb_b200.model.backend import B200Backend
     from mrb_b200.optim import FlatSGD
-    use_graph = args.graph == "on" or (args.graph == "auto" and world == 1)
+    use_graph = args.graph in ("on", "auto")
     # graph capture needs a step without host synchronisation: fixed-shape mask head (see RCNNConfig)
     cfg = RCNNConfig(mask_rois_per_image=128 if use_graph else 0)
     model = build_model(cfg, backend=B200Backend(wgrad=args.wgrad), device=device).train()
-    step_model = model
-    if world > 1:
-        step_model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], broadcast_buffers=False)
     params = [p for p in model.parameters() if p.requires_grad]
+    grad_sync = None
+    if world > 1:
+        # same initial weights everywhere (DDP's constructor broadcast), then one flat gradient all-reduce per step
+        for t in list(model.parameters()) + list(model.buffers()):
+            dist.broadcast(t.data, 0)
+        from mrb_b200.parallel import FlatGradSync
+        grad_sync = FlatGradSync(params, world)
     # SOLVER defaults of the reference (config/defaults.py:383-401): momentum 0.9, wd 1e-4, bias lr x2, bias wd 0
     opt = FlatSGD(model.named_parameters(), lr=1e-4, momentum=0.9, weight_decay=1e-4)
     sizes = [(IMG_H, IMG_W)] * IMGS_PER_GPU
@@ -258,10 +263,12 @@ def main():
 
     def eager_step(batch):
         images, boxes, labels = batch
-        losses = step_model(images, sizes, targets_of(boxes, labels))
+        losses = model(images, sizes, targets_of(boxes, labels))
         loss = sum(losses.values())
         opt.zero_grad()
         loss.backward()
+        if grad_sync is not None:
+            grad_sync.sync()               # NCCL all-reduce of one flat fp32 gradient buffer (mean over ranks)
         opt.step()
         model.be.refresh_weights(params)   # bf16 operand copies of the updated weights: one multi-tensor cast
         return loss
@@ -295,6 +302,8 @@ def main():
                 graph.replay()
                 return static_loss
         except Exception as e:  # fall back to eager, and say so in the JSON line
+            import traceback
+            sys.stderr.write("CUDA graph capture failed, running eagerly:\n" + traceback.format_exc() + "\n")
             graph_info = {"enabled": False, "error": repr(e)[:300]}
             torch.cuda.synchronize()
             step = eager_step

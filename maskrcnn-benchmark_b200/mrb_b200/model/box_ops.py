@@ -95,19 +95,26 @@ class Matcher:
 
 def sample_pos_neg(labels, batch_size, positive_fraction, generator=None):
     """modeling/balanced_positive_negative_sampler.py:19-68 for one image.
-    labels: -1 ignore, 0 negative, >0 positive.  Returns boolean masks (pos, neg).  Sync-free: a random
-    key per element, top-k by key among the candidates == a uniform random subset."""
+    labels: -1 ignore, 0 negative, >0 positive.  Returns boolean masks (pos, neg).  Sync-free and sort-free:
+    every element draws a random key; the `cap` smallest keys among the candidates (two top-k calls over the
+    label vector -- 268k anchors for the RPN) are a uniform random subset, exactly what randperm()[:num] is."""
     n = labels.numel()
-    num_pos_cap = int(batch_size * positive_fraction)
+    num_pos_cap = min(int(batch_size * positive_fraction), n)
     pos, neg = labels >= 1, labels == 0
     key = torch.rand(n, device=labels.device, generator=generator)
-    # rank of each positive among positives by random key
-    pos_rank = torch.argsort(torch.argsort(torch.where(pos, key, key.new_full((), 2.0))))
-    num_pos = torch.clamp(pos.sum(), max=num_pos_cap)
-    pos_sel = pos & (pos_rank < num_pos)
-    neg_rank = torch.argsort(torch.argsort(torch.where(neg, key, key.new_full((), 2.0))))
-    num_neg = torch.minimum(neg.sum(), batch_size - num_pos)
-    neg_sel = neg & (neg_rank < num_neg)
+    big = key.new_full((), 2.0)
+    # positives: the (up to) num_pos_cap smallest keys
+    pk, pi = torch.topk(torch.where(pos, key, big), num_pos_cap, largest=False, sorted=True)
+    p_ok = pk < 1.5
+    pos_sel = torch.zeros(n, dtype=torch.bool, device=labels.device)
+    pos_sel[pi] = p_ok
+    num_pos = p_ok.sum()
+    # negatives: the num_neg = min(#neg, batch - num_pos) smallest keys
+    kneg = min(batch_size, n)
+    nk, ni = torch.topk(torch.where(neg, key, big), kneg, largest=False, sorted=True)
+    n_ok = (nk < 1.5) & (torch.arange(kneg, device=labels.device) < (batch_size - num_pos))
+    neg_sel = torch.zeros(n, dtype=torch.bool, device=labels.device)
+    neg_sel[ni] = n_ok
     return pos_sel, neg_sel
 
 

@@ -43,6 +43,14 @@ ddp = torch.nn.parallel.DistributedDataParallel(model, broadcast_buffers=False)
 got = grads(ddp, 10 + rank)
 for a, b in zip(got, want):
     torch.testing.assert_close(a, b, rtol=1e-4, atol=1e-6)
+# the explicit single-bucket form used by bench.py (graph-capturable): same result as DDP
+from mrb_b200.parallel import FlatGradSync
+sync = FlatGradSync(model.parameters(), world)
+mine = grads(model, 10 + rank)
+sync.sync()
+for p, a, b in zip([q for q in model.parameters() if q.requires_grad], got, want):
+    torch.testing.assert_close(p.grad, b, rtol=1e-4, atol=1e-6)
+    assert p.grad.stride() == p.stride()
 flat = torch.cat([g.reshape(-1) for g in got])
 gathered = [torch.zeros_like(flat) for _ in range(world)]
 dist.all_gather(gathered, flat)
