@@ -149,6 +149,77 @@ __device__ __forceinline__ void tile_coords(const ConvArgs& a, int tile, int& n_
   w0 = wt * a.tw;
 }
 
+// Slow-path epilogue for one 32-column chunk: fp32 outputs and ragged Cout tails (see conv_tc_kernel).
+__device__ __noinline__ void epilogue_chunk32_slow(const ConvArgs& a, uint32_t taddr, int c0, bool valid, long long pix,
+                                                   long long rpix, const float* sc, const float* bi, bool affine) {
+  uint32_t v[32];
+  tmem_ld32(taddr, v);
+  tmem_ld_wait();
+  if (!valid) return;
+  const long long o = pix + c0;
+  const long long ro = rpix + c0;
+  const bool full = (c0 + 32 <= a.cout) && ((a.cout & 7) == 0);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {          // 8 channels per step, all indices static
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[q * 8 + j]);
+    if (affine) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], sc[q * 8 + j], bi[q * 8 + j]);
+    }
+    if (full) {
+      if (a.residual) {
+        const uint4 rr = __ldg(reinterpret_cast<const uint4*>(a.residual + ro + q * 8));
+        const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rr);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 t = __bfloat1622float2(r2[j]);
+          f[2 * j] += t.x; f[2 * j + 1] += t.y;
+        }
+      }
+      if (a.relu) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+      }
+      if (a.relu_mask) {
+        const uint4 rr = __ldg(reinterpret_cast<const uint4*>(a.relu_mask + o + q * 8));
+        const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rr);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 t = __bfloat1622float2(r2[j]);
+          if (!(t.x > 0.f)) f[2 * j] = 0.f;
+          if (!(t.y > 0.f)) f[2 * j + 1] = 0.f;
+        }
+      }
+      if (a.out_f32) {
+        float* dst = reinterpret_cast<float*>(a.out) + o + q * 8;
+        *reinterpret_cast<float4*>(dst) = make_float4(f[0], f[1], f[2], f[3]);
+        *reinterpret_cast<float4*>(dst + 4) = make_float4(f[4], f[5], f[6], f[7]);
+      } else {
+        uint4 pk;
+        __nv_bfloat162* p2 = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) p2[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+        *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.out) + o + q * 8) = pk;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = c0 + q * 8 + j;
+        if (c < a.cout) {
+          float x = f[j];
+          if (a.residual) x += __bfloat162float(a.residual[ro + q * 8 + j]);
+          if (a.relu) x = fmaxf(x, 0.f);
+          if (a.relu_mask && !(__bfloat162float(a.relu_mask[o + q * 8 + j]) > 0.f)) x = 0.f;
+          if (a.out_f32) reinterpret_cast<float*>(a.out)[o + q * 8 + j] = x;
+          else reinterpret_cast<__nv_bfloat16*>(a.out)[o + q * 8 + j] = __float2bfloat16_rn(x);
+        }
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const ConvArgs a) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -269,7 +340,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           // ---- 64 channels (128 B per pixel) at a time, global traffic staged through a per-warp 4 KB smem
           // block so that every warp-level load/store covers whole 128-byte lines (8 lanes per pixel row)
           // instead of 32 separate 16-byte pieces.
-          uint4 rr[8], mm[8];
           if (a.residual) {
             const long long my = rpix + c0;
 #pragma unroll
@@ -279,24 +349,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               if ((vmask >> r) & 1u) stg4[r * 8 + (sg ^ (r & 7))] = __ldg(reinterpret_cast<const uint4*>(a.residual + off + sg * 8));
             }
             __syncwarp();
-#pragma unroll
-            for (int sg = 0; sg < 8; ++sg) rr[sg] = stg4[lane * 8 + (sg ^ (lane & 7))];
-            __syncwarp();
           }
-          if (a.relu_mask) {
-            const long long my = pix + c0;
-#pragma unroll
-            for (int it = 0; it < 8; ++it) {
-              const int r = it * 4 + (lane >> 3), sg = lane & 7;
-              const long long off = __shfl_sync(0xffffffffu, my, r);
-              if ((vmask >> r) & 1u) stg4[r * 8 + (sg ^ (r & 7))] = __ldg(reinterpret_cast<const uint4*>(a.relu_mask + off + sg * 8));
-            }
-            __syncwarp();
-#pragma unroll
-            for (int sg = 0; sg < 8; ++sg) mm[sg] = stg4[lane * 8 + (sg ^ (lane & 7))];
-            __syncwarp();
-          }
-#pragma unroll
+#pragma unroll 1
           for (int half = 0; half < 2; ++half) {
             uint32_t v[32];
             tmem_ld32(t_row + (uint32_t)(col + 32 * half), v);
@@ -307,11 +361,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
               for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[q * 8 + j]);
               if (has_scale || has_bias) {
+                const float* scq = sc + col + half * 32 + q * 8;
+                const float* biq = bi + col + half * 32 + q * 8;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], sc[col + half * 32 + q * 8 + j], bi[col + half * 32 + q * 8 + j]);
+                for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], scq[j], biq[j]);
               }
+              uint4* slot = stg4 + lane * 8 + ((half * 4 + q) ^ (lane & 7));   // this thread's private 16 B
               if (a.residual) {
-                const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rr[half * 4 + q]);
+                const uint4 rr = *slot;
+                const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rr);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                   const float2 t = __bfloat1622float2(r2[j]);
@@ -322,107 +380,51 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
                 for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
               }
-              if (a.relu_mask) {
-                const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&mm[half * 4 + q]);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const float2 t = __bfloat1622float2(r2[j]);
-                  if (!(t.x > 0.f)) f[2 * j] = 0.f;
-                  if (!(t.y > 0.f)) f[2 * j + 1] = 0.f;
-                }
-              }
               uint4 pk;
               __nv_bfloat162* p2 = reinterpret_cast<__nv_bfloat162*>(&pk);
 #pragma unroll
               for (int j = 0; j < 4; ++j) p2[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
-              stg4[lane * 8 + ((half * 4 + q) ^ (lane & 7))] = pk;
+              *slot = pk;
             }
           }
           __syncwarp();
           {
+            // coalesced write-out: 8 lanes per pixel row; the ReLU-backward mask (dgrad) is applied here, on the
+            // same (row, segment) the lane stores, straight from its coalesced global read
             const long long my = pix + c0;
             __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(a.out);
-#pragma unroll
+#pragma unroll 2
             for (int it = 0; it < 8; ++it) {
               const int r = it * 4 + (lane >> 3), sg = lane & 7;
               const long long off = __shfl_sync(0xffffffffu, my, r);
-              if ((vmask >> r) & 1u) *reinterpret_cast<uint4*>(outp + off + sg * 8) = stg4[r * 8 + (sg ^ (r & 7))];
+              if ((vmask >> r) & 1u) {
+                uint4 val = stg4[r * 8 + (sg ^ (r & 7))];
+                if (a.relu_mask) {
+                  const uint4 mk = __ldg(reinterpret_cast<const uint4*>(a.relu_mask + off + sg * 8));
+                  const __nv_bfloat162* m2 = reinterpret_cast<const __nv_bfloat162*>(&mk);
+                  __nv_bfloat162* v2 = reinterpret_cast<__nv_bfloat162*>(&val);
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const float2 t = __bfloat1622float2(m2[j]);
+                    float2 x = __bfloat1622float2(v2[j]);
+                    if (!(t.x > 0.f)) x.x = 0.f;
+                    if (!(t.y > 0.f)) x.y = 0.f;
+                    v2[j] = __floats2bfloat162_rn(x.x, x.y);
+                  }
+                }
+                *reinterpret_cast<uint4*>(outp + off + sg * 8) = val;
+              }
             }
           }
           __syncwarp();
           col += 64;
           continue;
         }
-        // ---- fallback: 32 channels per step, per-thread 16-byte accesses (fp32 output, ragged Cout tails)
-        uint32_t v[32];
-        __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge lanes that skipped the stores of the last chunk
-        tmem_ld32(t_row + (uint32_t)col, v);
-        tmem_ld_wait();
-        if (!valid) { col += 32; continue; }
-        const long long o = pix + c0;
-        const long long ro = rpix + c0;
-        const bool full = (c0 + 32 <= a.cout) && cout8;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {          // 8 channels per step, all indices static
-          float f[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[q * 8 + j]);
-          if (has_scale || has_bias) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], sc[col + q * 8 + j], bi[col + q * 8 + j]);
-          }
-          if (full) {
-            if (a.residual) {
-              const uint4 rr = __ldg(reinterpret_cast<const uint4*>(a.residual + ro + q * 8));
-              const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rr);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float2 t = __bfloat1622float2(r2[j]);
-                f[2 * j] += t.x; f[2 * j + 1] += t.y;
-              }
-            }
-            if (a.relu) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
-            }
-            if (a.relu_mask) {
-              const uint4 rr = __ldg(reinterpret_cast<const uint4*>(a.relu_mask + o + q * 8));
-              const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rr);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float2 t = __bfloat1622float2(r2[j]);
-                if (!(t.x > 0.f)) f[2 * j] = 0.f;
-                if (!(t.y > 0.f)) f[2 * j + 1] = 0.f;
-              }
-            }
-            if (a.out_f32) {
-              float* dst = reinterpret_cast<float*>(a.out) + o + q * 8;
-              *reinterpret_cast<float4*>(dst) = make_float4(f[0], f[1], f[2], f[3]);
-              *reinterpret_cast<float4*>(dst + 4) = make_float4(f[4], f[5], f[6], f[7]);
-            } else {
-              uint4 pk;
-              __nv_bfloat162* p2 = reinterpret_cast<__nv_bfloat162*>(&pk);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) p2[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
-              *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.out) + o + q * 8) = pk;
-            }
-          } else {
-            // ragged tail (Cout not a multiple of 8 / of the chunk): predicated scalar path, static indices
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const int c = c0 + q * 8 + j;
-              if (c < a.cout) {
-                float x = f[j];
-                if (a.residual) x += __bfloat162float(a.residual[ro + q * 8 + j]);
-                if (a.relu) x = fmaxf(x, 0.f);
-                if (a.relu_mask && !(__bfloat162float(a.relu_mask[o + q * 8 + j]) > 0.f)) x = 0.f;
-                if (a.out_f32) reinterpret_cast<float*>(a.out)[o + q * 8 + j] = x;
-                else reinterpret_cast<__nv_bfloat16*>(a.out)[o + q * 8 + j] = __float2bfloat16_rn(x);
-              }
-            }
-          }
-        }
-              col += 32;
+        // ---- fallback: 32 channels per step, per-thread 16-byte accesses (fp32 output, ragged Cout tails).
+        // Kept out of line: it is rare and would otherwise double the instruction footprint of this loop.
+        __syncwarp();
+        epilogue_chunk32_slow(a, t_row + (uint32_t)col, c0, valid, pix, rpix, sc + col, bi + col, has_scale || has_bias);
+        col += 32;
       }
       tc_fence_before();
       mbar_arrive(tempty_bar(acc));

@@ -153,7 +153,7 @@ class RPN(nn.Module):
             topn = min(fpn_post_n, flat.numel())
             _, sel = flat.topk(topn, sorted=True)
             m = torch.zeros_like(flat, dtype=torch.bool)
-            m[sel] = True
+            m.index_fill_(0, sel, True)      # (m[sel] = True would stage a CPU scalar: not graph-capturable)
             v = v & m.view_as(v)
             # compact every image to a fixed width of `topn` columns, valid rows first (stable)
             order = torch.sort((~v).to(torch.int8), dim=1, stable=True)[1][:, :topn]
