@@ -119,7 +119,10 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
 }
 
 // ------------------------------------------------------------------------------- kernel
-constexpr int kConvThreads = 192;
+constexpr int kEpiWarps = 8;                  // epilogue warps: 2 per TMEM lane quadrant (latency hiding: each SMSP
+                                              // gets 2 epilogue warps; a lone warp per scheduler stalls on every LDTM/LDS/SHFL)
+constexpr int kConvThreads = 64 + 32 * kEpiWarps;
+constexpr int kWgradThreads = 192;
 constexpr int kTileM = 128;
 constexpr int kBlockK = 64;                 // channels per k-block (128 B of bf16)
 constexpr int kABytes = kTileM * kBlockK * 2;  // 16 KB
@@ -239,7 +242,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < a.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 128); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 32 * kEpiWarps); }
     fence_barrier_init();
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
@@ -302,12 +305,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // Everything below indexes registers with compile-time constants only: the 32-column chunk must never
     // spill to local memory (with ~200 KB of shared memory carved out, L1 is tiny and local traffic runs at
     // L2 latency).  Per-channel scale/bias of the tile are staged in shared memory once per tile.
-    const int quad = warp & 3;                 // TMEM lane quadrant this warp may read
+    const int quad = warp & 3;                 // TMEM lane quadrant this warp may read (hardware: warp id % 4)
+    const int grp = (warp - 2) >> 2;           // which of the kEpiWarps/4 warps of this quadrant: takes every
+    constexpr int kGroups = kEpiWarps / 4;     // kGroups-th 32-column chunk
     const int row = quad * 32 + lane;          // accumulator row == pixel within the tile
-    const int et = threadIdx.x - 64;           // 0..127 among the epilogue threads
+    const int et = threadIdx.x - 64;           // 0..32*kEpiWarps-1 among the epilogue threads
     const int hh = row / a.tw, ww = row - hh * a.tw;
     float* s_aff = reinterpret_cast<float*>(smem_raw + (tmem_slot - smem_u32(smem_raw)) + 16);  // [2 acc][2][256]
-    uint4* stg4 = reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(s_aff) + 4096 + (warp - 2) * 4096);  // [32 rows][8 x 16 B]
+    uint4* stg4 = reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(s_aff) + 4096 + (warp - 2) * 2048);  // [32 rows][4 x 16 B]
     const bool has_scale = a.scale != nullptr, has_bias = a.bias != nullptr;
     const bool cout8 = (a.cout & 7) == 0;
     int acc = 0; uint32_t acc_phase = 0;
@@ -321,39 +326,39 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       float* sc = s_aff + acc * 512;
       float* bi = sc + 256;
       if (has_scale || has_bias) {
-        for (int c = et; c < a.bn; c += 128) {
+        for (int c = et; c < a.bn; c += 32 * kEpiWarps) {
           const int cg = n_tile * a.bn + c;
           sc[c] = (has_scale && cg < a.cout) ? __ldg(a.scale + cg) : 1.f;
           bi[c] = (has_bias && cg < a.cout) ? __ldg(a.bias + cg) : 0.f;
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
       }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * a.bn);
       const unsigned vmask = __ballot_sync(0xffffffffu, valid);
-      int col = 0;
-      while (col < a.bn) {
+      const bool fast = !a.out_f32 && cout8;
+      for (int col = grp * 32; col < a.bn; col += 32 * kGroups) {
         const int c0 = n_tile * a.bn + col;
         if (c0 >= a.cout) break;  // warp-uniform
-        if (!a.out_f32 && cout8 && c0 + 64 <= a.cout && col + 64 <= a.bn) {
-          // ---- 64 channels (128 B per pixel) at a time, global traffic staged through a per-warp 4 KB smem
-          // block so that every warp-level load/store covers whole 128-byte lines (8 lanes per pixel row)
-          // instead of 32 separate 16-byte pieces.
+        if (fast && c0 + 32 <= a.cout) {
+          // ---- 32 channels (64 B per pixel) per step.  Global traffic is staged through a per-warp 2 KB smem block
+          // so that every warp-level load/store moves whole 32-byte sectors of 8 pixel rows (4 lanes x 16 B per row)
+          // instead of 32 scattered 16-byte pieces; slot (row, seg) lives at seg ^ ((row >> 1) & 3): conflict-free
+          // both for the thread-private accesses (row == lane) and for the coalesced ones.
           if (a.residual) {
             const long long my = rpix + c0;
 #pragma unroll
-            for (int it = 0; it < 8; ++it) {
-              const int r = it * 4 + (lane >> 3), sg = lane & 7;
+            for (int it = 0; it < 4; ++it) {
+              const int r = it * 8 + (lane >> 2), sg = lane & 3;
               const long long off = __shfl_sync(0xffffffffu, my, r);
-              if ((vmask >> r) & 1u) stg4[r * 8 + (sg ^ (r & 7))] = __ldg(reinterpret_cast<const uint4*>(a.residual + off + sg * 8));
+              if ((vmask >> r) & 1u) stg4[r * 4 + (sg ^ ((r >> 1) & 3))] = __ldg(reinterpret_cast<const uint4*>(a.residual + off + sg * 8));
             }
             __syncwarp();
           }
-#pragma unroll 1
-          for (int half = 0; half < 2; ++half) {
+          {
             uint32_t v[32];
-            tmem_ld32(t_row + (uint32_t)(col + 32 * half), v);
+            tmem_ld32(t_row + (uint32_t)col, v);
             tmem_ld_wait();
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -361,12 +366,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
               for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[q * 8 + j]);
               if (has_scale || has_bias) {
-                const float* scq = sc + col + half * 32 + q * 8;
-                const float* biq = bi + col + half * 32 + q * 8;
+                const float* scq = sc + col + q * 8;
+                const float* biq = bi + col + q * 8;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], scq[j], biq[j]);
               }
-              uint4* slot = stg4 + lane * 8 + ((half * 4 + q) ^ (lane & 7));   // this thread's private 16 B
+              uint4* slot = stg4 + lane * 4 + (q ^ ((lane >> 1) & 3));   // this thread's private 16 B
               if (a.residual) {
                 const uint4 rr = *slot;
                 const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rr);
@@ -389,16 +394,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           }
           __syncwarp();
           {
-            // coalesced write-out: 8 lanes per pixel row; the ReLU-backward mask (dgrad) is applied here, on the
-            // same (row, segment) the lane stores, straight from its coalesced global read
+            // coalesced write-out; the ReLU-backward mask (dgrad) is applied here, on the same (row, segment) the lane
+            // stores, straight from its coalesced global read
             const long long my = pix + c0;
             __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(a.out);
-#pragma unroll 2
-            for (int it = 0; it < 8; ++it) {
-              const int r = it * 4 + (lane >> 3), sg = lane & 7;
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+              const int r = it * 8 + (lane >> 2), sg = lane & 3;
               const long long off = __shfl_sync(0xffffffffu, my, r);
               if ((vmask >> r) & 1u) {
-                uint4 val = stg4[r * 8 + (sg ^ (r & 7))];
+                uint4 val = stg4[r * 4 + (sg ^ ((r >> 1) & 3))];
                 if (a.relu_mask) {
                   const uint4 mk = __ldg(reinterpret_cast<const uint4*>(a.relu_mask + off + sg * 8));
                   const __nv_bfloat162* m2 = reinterpret_cast<const __nv_bfloat162*>(&mk);
@@ -417,14 +422,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
           }
           __syncwarp();
-          col += 64;
           continue;
         }
-        // ---- fallback: 32 channels per step, per-thread 16-byte accesses (fp32 output, ragged Cout tails).
+        // ---- fallback: per-thread 16-byte accesses (fp32 output, ragged Cout tails).
         // Kept out of line: it is rare and would otherwise double the instruction footprint of this loop.
         __syncwarp();
         epilogue_chunk32_slow(a, t_row + (uint32_t)col, c0, valid, pix, rpix, sc + col, bi + col, has_scale || has_bias);
-        col += 32;
       }
       tc_fence_before();
       mbar_arrive(tempty_bar(acc));
@@ -473,7 +476,7 @@ __device__ __forceinline__ void wg_item(const WgradArgs& a, int item, int& co_t,
   co_t = item / a.taps;
 }
 
-__global__ void __launch_bounds__(kConvThreads, 1)
+__global__ void __launch_bounds__(kWgradThreads, 1)
 conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant__ CUtensorMap map_x, const WgradArgs a) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -698,7 +701,7 @@ static int conv_launch(const ConvPlan& pl, const void* x, const void* w, int cin
   int stages = (int)((200 * 1024) / stage_bytes);
   if (stages > 8) stages = 8;
   a.stages = stages;
-  const size_t smem = (size_t)stages * stage_bytes + 8 * (2 * stages + 4) + 16 + 4096 + 16384 + 1024;  // + scale/bias + epilogue staging
+  const size_t smem = (size_t)stages * stage_bytes + 8 * (2 * stages + 4) + 16 + 4096 + 2048 * kEpiWarps + 1024;  // + scale/bias + epilogue staging
 
   CUtensorMap map_a, map_b;
   {
@@ -923,7 +926,7 @@ MRB_API int mrb_conv2d_wgrad(const mrb_conv_params* p, const void* input, const 
   });
   if (attr_err != cudaSuccess) return (int)attr_err;
   const int grid = a.items_total < kNumSMs ? a.items_total : kNumSMs;
-  conv_wgrad_tc_kernel<<<grid, kConvThreads, smem, stream>>>(map_g, map_x, a);
+  conv_wgrad_tc_kernel<<<grid, kWgradThreads, smem, stream>>>(map_g, map_x, a);
   MRB_LAUNCH_CHECK();
   return MRB_OK;
 }
