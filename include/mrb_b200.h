@@ -213,6 +213,15 @@ int mrb_conv2d_dgrad(const mrb_conv_params* p, const void* grad_output_bf16, con
                      const float* scale, const void* add, const void* relu_mask, void* grad_input,
                      void* workspace, size_t workspace_bytes, mrb_stream_t stream);
 
+/* The flipped/transposed (and BN-scaled) weights of many layers in ONE launch, for use with
+ * mrb_conv2d_dgrad_prepared: prepared[l] must hold Cout*taps*Cin bf16 ([Cin][taps][Cout] layout).  All arrays are
+ * HOST arrays of num_layers entries (scales_host may be NULL, or hold NULL entries). */
+int mrb_conv2d_prepare_dgrad_weights(int num_layers, const void* const* weights_host, const float* const* scales_host,
+                                     void* const* prepared_host, const int* couts_host, const int* taps_host,
+                                     const int* cins_host, mrb_stream_t stream);
+int mrb_conv2d_dgrad_prepared(const mrb_conv_params* p, const void* grad_output_bf16, const void* prepared_weight,
+                              const void* add, const void* relu_mask, void* grad_input, mrb_stream_t stream);
+
 /* wgrad: grad_weight[Cout][kh][kw][Cin] (fp32, KRSC == torch channels_last of [Cout,Cin,kh,kw]) =
  * sum over N,Ho,Wo of grad_output (x) input, on tcgen05 with MN-major operands; the pixel axis is split
  * across CTAs and reduced with red.global.add.f32 into the buffer, which is zeroed inside.  input and

@@ -626,6 +626,32 @@ __global__ void conv_prepare_dgrad_weights_kernel(const __nv_bfloat16* __restric
   }
 }
 
+// one launch for many layers (descriptors travel as kernel parameters: no device-side table, no H2D copy)
+constexpr int kPrepBatch = 40;
+struct PrepBatch {
+  const __nv_bfloat16* w[kPrepBatch];
+  const float* scale[kPrepBatch];
+  __nv_bfloat16* wd[kPrepBatch];
+  int cout[kPrepBatch], taps[kPrepBatch], cin[kPrepBatch];
+};
+__global__ void __launch_bounds__(256)
+conv_prepare_dgrad_weights_batched_kernel(PrepBatch b) {
+  const int l = blockIdx.y;
+  const int cout = b.cout[l], taps = b.taps[l], cin = b.cin[l];
+  const int total = cout * taps * cin;
+  const __nv_bfloat16* __restrict__ w = b.w[l];
+  const float* __restrict__ scale = b.scale[l];
+  __nv_bfloat16* __restrict__ wd = b.wd[l];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int co = i % cout;
+    const int tp = (i / cout) % taps;
+    const int ci = i / cout / taps;
+    float v = __bfloat162float(w[((size_t)co * taps + (taps - 1 - tp)) * cin + ci]);
+    if (scale) v *= scale[co];
+    wd[i] = __float2bfloat16_rn(v);
+  }
+}
+
 // ------------------------------------------------------------------------------- host side
 typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                         const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -793,6 +819,45 @@ MRB_API size_t mrb_conv2d_dgrad_workspace_bytes(const mrb_conv_params* p) {
   return ((size_t)p->cout * p->kh * p->kw * p->cin * 2 + 255) & ~(size_t)255;
 }
 
+MRB_API int mrb_conv2d_prepare_dgrad_weights(int num_layers, const void* const* weights_host, const float* const* scales_host,
+                                             void* const* prepared_host, const int* couts_host, const int* taps_host,
+                                             const int* cins_host, mrb_stream_t stream_) {
+  if (num_layers < 0 || (num_layers && (!weights_host || !prepared_host || !couts_host || !taps_host || !cins_host)))
+    return MRB_ERR_BAD_ARG;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  for (int l0 = 0; l0 < num_layers; l0 += kPrepBatch) {
+    PrepBatch b;
+    const int n = min(kPrepBatch, num_layers - l0);
+    int max_total = 0;
+    for (int i = 0; i < kPrepBatch; ++i) {
+      const int l = l0 + (i < n ? i : 0);
+      if (!weights_host[l] || !prepared_host[l] || couts_host[l] <= 0 || taps_host[l] <= 0 || cins_host[l] <= 0) return MRB_ERR_BAD_ARG;
+      b.w[i] = (const __nv_bfloat16*)weights_host[l];
+      b.scale[i] = scales_host ? scales_host[l] : nullptr;
+      b.wd[i] = (__nv_bfloat16*)prepared_host[l];
+      b.cout[i] = couts_host[l]; b.taps[i] = taps_host[l]; b.cin[i] = cins_host[l];
+      max_total = max(max_total, couts_host[l] * taps_host[l] * cins_host[l]);
+    }
+    dim3 grid(min(ceil_div(max_total, 256 * 4), 64), n);
+    conv_prepare_dgrad_weights_batched_kernel<<<grid, 256, 0, stream>>>(b);
+    MRB_LAUNCH_CHECK();
+  }
+  return MRB_OK;
+}
+
+static int conv2d_dgrad_impl(const mrb_conv_params* p, const void* grad_output, const __nv_bfloat16* wd, const void* add,
+                             const void* relu_mask, void* grad_input, cudaStream_t stream);
+
+MRB_API int mrb_conv2d_dgrad_prepared(const mrb_conv_params* p, const void* grad_output, const void* prepared_weight,
+                                      const void* add, const void* relu_mask, void* grad_input, mrb_stream_t stream) {
+  int rc = conv_check(p);
+  if (rc) return rc;
+  if (p->batch == 0) return MRB_OK;
+  if (!grad_output || !prepared_weight || !grad_input) return MRB_ERR_BAD_ARG;
+  if (p->out_h || p->out_w) return MRB_ERR_UNSUPPORTED;
+  return conv2d_dgrad_impl(p, grad_output, (const __nv_bfloat16*)prepared_weight, add, relu_mask, grad_input, (cudaStream_t)stream);
+}
+
 MRB_API int mrb_conv2d_dgrad(const mrb_conv_params* p, const void* grad_output, const void* weight, const float* scale,
                              const void* add, const void* relu_mask, void* grad_input, void* workspace,
                              size_t workspace_bytes, mrb_stream_t stream_) {
@@ -803,7 +868,6 @@ MRB_API int mrb_conv2d_dgrad(const mrb_conv_params* p, const void* grad_output, 
   if (p->out_h || p->out_w) return MRB_ERR_UNSUPPORTED;
   if (workspace_bytes < mrb_conv2d_dgrad_workspace_bytes(p)) return MRB_ERR_WORKSPACE;
   cudaStream_t stream = (cudaStream_t)stream_;
-  const int Ho = (p->height + 2 * p->pad - p->kh) / p->stride + 1, Wo = (p->width + 2 * p->pad - p->kw) / p->stride + 1;
   const int taps = p->kh * p->kw;
   __nv_bfloat16* wd = (__nv_bfloat16*)workspace;
   {
@@ -812,6 +876,12 @@ MRB_API int mrb_conv2d_dgrad(const mrb_conv_params* p, const void* grad_output, 
                                                                                      p->cout, taps, p->cin);
     MRB_LAUNCH_CHECK();
   }
+  return conv2d_dgrad_impl(p, grad_output, wd, add, relu_mask, grad_input, stream);
+}
+
+static int conv2d_dgrad_impl(const mrb_conv_params* p, const void* grad_output, const __nv_bfloat16* wd, const void* add,
+                             const void* relu_mask, void* grad_input, cudaStream_t stream) {
+  const int Ho = (p->height + 2 * p->pad - p->kh) / p->stride + 1, Wo = (p->width + 2 * p->pad - p->kw) / p->stride + 1;
   // dgrad == forward conv of grad_output [N,Ho,Wo,Cout] with Wd [Cin][taps][Cout], pad' = k - 1 - pad
   ConvPlan pl;
   const long long Ci = p->cin, Co = p->cout;
@@ -890,8 +960,9 @@ MRB_API int mrb_conv2d_wgrad(const mrb_conv_params* p, const void* input, const 
   if (a.bn > 256) a.bn = 256;
   a.co_tiles = ceil_div(p->cout, 128); a.ci_tiles = ceil_div(p->cin, a.bn);
   const int out_tiles = a.co_tiles * a.ci_tiles * taps;
-  int splits = ceil_div(2 * kNumSMs, out_tiles);          // ~2 work items per SM
-  const int max_splits = ceil_div(a.kblocks_total, 8);     // at least 8 k-blocks per item
+  // one wave of equally sized work items (items <= #SMs): every extra split costs a 128 x BN fp32 red.add flush
+  int splits = kNumSMs / out_tiles;
+  const int max_splits = ceil_div(a.kblocks_total, 8);     // at least 8 k-blocks (512 pixels) per item
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
   a.kblocks_per_split = ceil_div(a.kblocks_total, splits);

@@ -39,7 +39,7 @@ class _ConvFn(Function):
 
     @staticmethod
     def forward(ctx, x, weight, bias, residual, w16, scale, shift, stride, pad, relu, out_fp32, wgrad_fn,
-                premask_x=False, gy_premasked=False, residual_up2=False):
+                premask_x=False, gy_premasked=False, residual_up2=False, be=None):
         from mrb_b200 import ops
         add = shift if shift is not None else (bias.detach().float() if bias is not None else None)
         y = ops.conv2d_fwd(x, w16, scale, add, residual, stride, pad, relu,
@@ -47,6 +47,8 @@ class _ConvFn(Function):
         ctx.residual_up2 = residual_up2
         ctx.cfg = (stride, pad, relu and not gy_premasked, tuple(x.shape), wgrad_fn)
         ctx.premask_x = premask_x
+        ctx.wparam = weight if isinstance(weight, torch.nn.Parameter) else None
+        ctx.be = be
         ctx.has_bias = bias is not None
         ctx.has_res = residual is not None
         ctx.save_for_backward(x, w16, scale, y if relu else None)
@@ -66,7 +68,8 @@ class _ConvFn(Function):
         gx = gw = gb = gres = None
         if ctx.needs_input_grad[0]:
             # premask_x: x is the ReLU output of its producer, whose backward then skips its own mask pass
-            gx = ops.conv2d_dgrad(g, w16, x_shape, scale, None, x if ctx.premask_x else None, stride, pad)
+            prep = ctx.be.dgrad_weights(ctx.wparam, w16, scale) if ctx.be is not None else None
+            gx = ops.conv2d_dgrad(g, w16, x_shape, scale, None, x if ctx.premask_x else None, stride, pad, prepared=prep)
         if ctx.needs_input_grad[1]:
             gw = wgrad_fn(x, g, w16, stride, pad, scale)
         if ctx.has_bias and ctx.needs_input_grad[2]:
@@ -74,7 +77,7 @@ class _ConvFn(Function):
         if ctx.has_res and ctx.needs_input_grad[3]:
             # nearest-2x upsample backward == sum over each 2x2 block
             gres = F.avg_pool2d(g, 2).mul_(4) if ctx.residual_up2 else g
-        return gx, gw, gb, gres, None, None, None, None, None, None, None, None, None, None, None
+        return gx, gw, gb, gres, None, None, None, None, None, None, None, None, None, None, None, None
 
 
 class _BottleneckFn(Function):
@@ -104,6 +107,7 @@ class _BottleneckFn(Function):
         out = ops.conv2d_fwd(y2, w16[2], a3, b3, idn, 1, 0, True)
         ctx.be, ctx.strides, ctx.g_premasked = be, (s1, s3, sd), g_premasked
         ctx.has_d = wd is not None
+        ctx.wparams = (w1, w2, w3, wd)
         ctx.save_for_backward(x, y1, y2, out, w16[0], w16[1], w16[2], wd16, a1, a2, a3, ad)
         return out
 
@@ -120,23 +124,26 @@ class _BottleneckFn(Function):
         gw1 = gw2 = gw3 = gwd = gx = None
         if need[3]:
             gw3 = wg(y2, g, w3, 1, 0, a3)
-        g2 = ops.conv2d_dgrad(g, w3, y2.shape, a3, None, y2, 1, 0)
+        be = ctx.be
+        p1, p2, p3, pd = ctx.wparams
+        g2 = ops.conv2d_dgrad(g, w3, y2.shape, a3, None, y2, 1, 0, prepared=be.dgrad_weights(p3, w3, a3))
         if need[2]:
             gw2 = wg(y1, g2, w2, s3, 1, a2)
-        g1 = ops.conv2d_dgrad(g2, w2, y1.shape, a2, None, y1, s3, 1)
+        g1 = ops.conv2d_dgrad(g2, w2, y1.shape, a2, None, y1, s3, 1, prepared=be.dgrad_weights(p2, w2, a2))
         if need[1]:
             gw1 = wg(x, g1, w1, s1, 0, a1)
         if ctx.has_d and need[4]:
             gwd = wg(x, g, wd, sd, 0, ad)
         if need[0]:
+            pw1 = be.dgrad_weights(p1, w1, a1)
             if not ctx.has_d:
-                gx = ops.conv2d_dgrad(g1, w1, x.shape, a1, g, x, s1, 0)
+                gx = ops.conv2d_dgrad(g1, w1, x.shape, a1, g, x, s1, 0, prepared=pw1)
             elif sd == 1:
-                gi = ops.conv2d_dgrad(g, wd, x.shape, ad, None, None, 1, 0)
-                gx = ops.conv2d_dgrad(g1, w1, x.shape, a1, gi, x, s1, 0)
+                gi = ops.conv2d_dgrad(g, wd, x.shape, ad, None, None, 1, 0, prepared=be.dgrad_weights(pd, wd, ad))
+                gx = ops.conv2d_dgrad(g1, w1, x.shape, a1, gi, x, s1, 0, prepared=pw1)
             else:
-                gx = ops.conv2d_dgrad(g, wd, x.shape, ad, None, None, sd, 0)
-                gx = ops.conv2d_dgrad(g1, w1, x.shape, a1, None, x, s1, 0, accumulate_into=gx)
+                gx = ops.conv2d_dgrad(g, wd, x.shape, ad, None, None, sd, 0, prepared=be.dgrad_weights(pd, wd, ad))
+                gx = ops.conv2d_dgrad(g1, w1, x.shape, a1, None, x, s1, 0, accumulate_into=gx, prepared=pw1)
         return gx, gw1, gw2, gw3, gwd, None, None, None
 
 
@@ -160,6 +167,7 @@ class B200Backend(Backend):
 
     def __init__(self, wgrad="tc"):
         self._w16 = {}
+        self._wd = {}     # (id(param), id(scale)) -> [param, scale, version, w16, prepared dgrad weights]
         if wgrad == "tc":
             self.wgrad_fn, self.wgrad_impl = _wgrad_tc, "mrb_conv2d_wgrad (tcgen05, in-house)"
         else:
@@ -209,7 +217,7 @@ class B200Backend(Backend):
         if w16 is None:
             w16 = self._weight16(weight)
         y = _ConvFn.apply(x, weight, bias, residual, w16, scale, shift, stride, pad, relu, out_fp32, self.wgrad_fn,
-                          premask_x, gy_premasked, residual_up2)
+                          premask_x, gy_premasked, residual_up2, self)
         return y[:, :co] if co % 8 else y
 
     def bottleneck(self, blk, x, g_premasked):
@@ -250,6 +258,24 @@ class B200Backend(Backend):
         # the 2x nearest upsample is folded into the epilogue's residual read: no upsampled map in HBM
         return self.conv(feat, weight, bias=bias, residual=top, premask_x=True, residual_up2=top is not None)
 
+    def dgrad_weights(self, wparam, w16, scale):
+        """Flipped/transposed/BN-scaled bf16 weights for the data gradient of a parameter-backed conv, cached per
+        parameter version.  refresh_weights() rebuilds all of them in one launch right after the optimizer step, so
+        inside a step this is a pure lookup; the first use (or a stale entry) costs one small launch."""
+        if wparam is None:
+            return None
+        from mrb_b200 import ops
+        key = (id(wparam), id(scale) if scale is not None else 0)
+        ent = self._wd.get(key)
+        if ent is None or ent[0] is not wparam or ent[4].device != w16.device:
+            ent = [wparam, scale, -1, w16, torch.empty(w16.numel(), dtype=torch.bfloat16, device=w16.device)]
+            self._wd[key] = ent
+        if ent[2] != wparam._version:
+            ent[3] = w16
+            ops.prepare_dgrad_weights([w16], [scale], [ent[4]])
+            ent[2] = wparam._version
+        return ent[4]
+
     def refresh_weights(self, params):
         """Re-derive the bf16 operand copies of all (changed) parameters with one multi-tensor copy instead of
         one cast kernel per layer; call once per step after the optimizer update."""
@@ -266,6 +292,15 @@ class B200Backend(Backend):
                 self._w16[id(w)] = (w, w._version, ent[2])
         if src:
             torch._foreach_copy_(dst, src)
+        # ... and the data-gradient copies (flipped / transposed / BN-scaled) of every conv seen so far, in one launch
+        stale = [e for e in self._wd.values() if e[2] != e[0]._version]
+        if stale:
+            from mrb_b200 import ops
+            for e in stale:
+                e[3] = self._weight16(e[0])
+            ops.prepare_dgrad_weights([e[3] for e in stale], [e[1] for e in stale], [e[4] for e in stale])
+            for e in stale:
+                e[2] = e[0]._version
 
     def linear(self, x, weight, bias, relu=False, out_fp32=False, premask_x=False, gy_premasked=False):
         """Fully connected layer on the conv engine: [R, K] x [Cout, K]^T as a 1x1 conv over R "pixels"."""

@@ -79,8 +79,30 @@ def conv2d_fwd(x, weight, scale=None, bias=None, residual=None, stride=1, pad=0,
     return out
 
 
+def prepare_dgrad_weights(weights, scales, out=None):
+    """Flipped/transposed (+ per-Cout scaled) bf16 copies of many conv weights in one launch.
+    weights: list of bf16 channels_last [Cout,Cin,kh,kw]; scales: list of fp32 [Cout] or None.  Returns the list of
+    prepared tensors (flat bf16, Cout*kh*kw*Cin elements), reusing `out` when given."""
+    n = len(weights)
+    if out is None:
+        out = [torch.empty(w.numel(), dtype=torch.bfloat16, device=w.device) for w in weights]
+    if n == 0:
+        return out
+    ws = [_nhwc(w, "prepare_dgrad_weights") for w in weights]
+    wp = (ctypes.c_void_p * n)(*[w.data_ptr() for w in ws])
+    sp = (ctypes.c_void_p * n)(*[(s.data_ptr() if s is not None else None) for s in scales])
+    op = (ctypes.c_void_p * n)(*[o.data_ptr() for o in out])
+    co = (ctypes.c_int * n)(*[w.shape[0] for w in ws])
+    tp = (ctypes.c_int * n)(*[w.shape[2] * w.shape[3] for w in ws])
+    ci = (ctypes.c_int * n)(*[w.shape[1] for w in ws])
+    with torch.cuda.device(ws[0].device):
+        _c.check(lib.mrb_conv2d_prepare_dgrad_weights(n, wp, sp, op, co, tp, ci, _c._stream()), "mrb_conv2d_prepare_dgrad_weights")
+    _count((n + 39) // 40)
+    return out
+
+
 def conv2d_dgrad(grad_out, weight, x_shape, scale=None, add=None, relu_mask=None, stride=1, pad=0,
-                 out_dtype=torch.bfloat16, accumulate_into=None):
+                 out_dtype=torch.bfloat16, accumulate_into=None, prepared=None):
     """grad_x = conv_transpose(grad_out, weight * scale[cout]) (+ add) masked by (relu_mask > 0).
     `accumulate_into` (bf16, shaped like x) makes the call in-place: result = accumulate_into + dgrad,
     written back into it (the only form of `add` the stride-2 path supports)."""
@@ -108,6 +130,12 @@ def conv2d_dgrad(grad_out, weight, x_shape, scale=None, add=None, relu_mask=None
         add = _nhwc(add, "add")
     relu_mask = _nhwc(relu_mask, "relu_mask") if relu_mask is not None else None
     with torch.cuda.device(grad_out.device):
+        if prepared is not None:
+            # `prepared` already holds the flipped/transposed/scaled weights (prepare_dgrad_weights)
+            _c.check(lib.mrb_conv2d_dgrad_prepared(ctypes.byref(p), _c._ptr(grad_out), _c._ptr(prepared), _c._ptr(add),
+                                                   _c._ptr(relu_mask), _c._ptr(gx), _c._stream()), "mrb_conv2d_dgrad_prepared")
+            _count(1, ("dgrad", p.batch, p.cin, p.height, p.width, p.cout, p.kh, p.stride, p.pad))
+            return gx
         nbytes = lib.mrb_conv2d_dgrad_workspace_bytes(ctypes.byref(p))
         ws = torch.empty(nbytes, dtype=torch.uint8, device=grad_out.device)
         _c.check(lib.mrb_conv2d_dgrad(ctypes.byref(p), _c._ptr(grad_out), _c._ptr(weight), _c._ptr(scale), _c._ptr(add),

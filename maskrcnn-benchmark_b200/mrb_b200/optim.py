@@ -23,8 +23,10 @@ class FlatSGD:
             (b if "bias" in name else w).append(p)
         for ps, glr, gwd in ((w, lr, weight_decay), (b, lr * bias_lr_factor, weight_decay_bias)):
             if ps:
-                self.groups.append({"params": ps, "lr": glr, "wd": gwd, "flat": [_flat(p.data) for p in ps],
-                                    "buf": [torch.zeros_like(_flat(p.data)) for p in ps]})
+                # views of p.detach() (NOT p.data): they share the parameter's version counter, so the in-place update
+                # is visible to everything that caches derived copies keyed on p._version (bf16 operand copies)
+                self.groups.append({"params": ps, "lr": glr, "wd": gwd, "flat": [_flat(p.detach()) for p in ps],
+                                    "buf": [torch.zeros_like(_flat(p.detach())) for p in ps]})
         self.momentum = momentum
 
     def zero_grad(self):

@@ -172,3 +172,28 @@ print("OK", n, len(keys))
     r = subprocess.run([os.sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.strip().startswith("OK")
+
+
+def test_flat_sgd_matches_torch_sgd_and_bumps_versions():
+    """mrb_b200.optim.FlatSGD == torch.optim.SGD (momentum, weight decay) on channels_last conv weights, and the
+    update is visible through p._version (the bf16 operand caches of the backend key on it)."""
+    import copy
+    from mrb_b200.optim import FlatSGD
+    torch.manual_seed(0)
+    m = torch.nn.Sequential(torch.nn.Conv2d(4, 8, 3), torch.nn.Conv2d(8, 8, 1))
+    for p in m.parameters():
+        if p.dim() == 4:
+            p.data = p.data.contiguous(memory_format=torch.channels_last)
+    m2 = copy.deepcopy(m)
+    o1 = FlatSGD(m.named_parameters(), lr=0.1, momentum=0.9, weight_decay=0.01, bias_lr_factor=1.0, weight_decay_bias=0.01)
+    o2 = torch.optim.SGD(m2.parameters(), lr=0.1, momentum=0.9, weight_decay=0.01)
+    versions = [p._version for p in m.parameters()]
+    for it in range(3):
+        x = torch.randn(2, 4, 8, 8)
+        for mm, oo in ((m, o1), (m2, o2)):
+            oo.zero_grad()
+            mm(x).square().mean().backward()
+            oo.step()
+    for a, b in zip(m.parameters(), m2.parameters()):
+        torch.testing.assert_close(a, b, rtol=1e-6, atol=1e-7)
+    assert all(p._version > v for p, v in zip(m.parameters(), versions))

@@ -133,6 +133,22 @@ def main():
     alg = 4 * 201600 * 80 * 3 + 4 * 201600
     out["ops"].append({"op": "sigmoid_focalloss_backward", "A": 201600, "us": round(t * 1e6, 1), "achieved_gbs": round(alg / t / 1e9, 1),
                        "frac": round(alg / t / 1e9 / hbm, 4)})
+    # ---------------- deformable conv v2 on the three R-50 DCN layer shapes (configs/dcn/*_R_50_FPN_1x.yaml)
+    from maskrcnn_benchmark import layers
+    for (c, h, w) in ((128, 100, 168), (256, 50, 84), (512, 25, 42)):
+        g = torch.Generator().manual_seed(c)
+        x = torch.randn(2, c, h, w, generator=g).to(DEV).requires_grad_(True)
+        wt = (torch.randn(c, c, 3, 3, generator=g) / (3 * c ** 0.5)).to(DEV).requires_grad_(True)
+        off = (torch.randn(2, 18, h, w, generator=g) * 2).to(DEV).requires_grad_(True)
+        msk = torch.rand(2, 9, h, w, generator=g).to(DEV).requires_grad_(True)
+        flops = 2.0 * 2 * h * w * c * c * 9
+        tf = timed(lambda: layers.modulated_deform_conv(x, off, msk, wt, None, 1, 1, 1, 1, 1), flush, reps=3)
+        y = layers.modulated_deform_conv(x, off, msk, wt, None, 1, 1, 1, 1, 1)
+        go = torch.randn_like(y)
+        tb = timed(lambda: torch.autograd.grad(y, (x, off, msk, wt), go, retain_graph=True), flush, reps=3)
+        out["ops"].append({"op": "modulated_deform_conv 3x3 (fp32, SIMT GEMM)", "shape": [2, c, h, w], "fwd_us": round(tf * 1e6, 1),
+                           "fwd_tflops": round(flops / tf / 1e12, 2), "bwd_us": round(tb * 1e6, 1),
+                           "bwd_tflops": round(2 * flops / tb / 1e12, 2)})
     print(json.dumps(out, indent=1))
 
 
