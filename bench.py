@@ -206,6 +206,17 @@ def workload_config(n_gpus):
             "l2": "per-step working set (activations + gradients, several GB) exceeds the 126 MB L2; no explicit flush"}
 
 
+def _finish(world):
+    """Leave a multi-rank run without tearing NCCL down: the communicator is referenced by the captured CUDA graph,
+    and destroy_process_group() with ranks arriving minutes apart (rank 0 still measures the roofline and the CPU
+    baseline) has been seen to block until the launcher's timeout.  All results are already printed."""
+    sys.stdout.flush()
+    sys.stderr.flush()
+    if world > 1:
+        torch.cuda.synchronize()
+        os._exit(0)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -216,6 +227,8 @@ def main():
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--dump-shapes", default=None, help="write the per-shape conv table (JSON) here")
     ap.add_argument("--wgrad", default="tc", choices=["tc", "cudnn"], help="weight-gradient kernel (A/B switch)")
+    ap.add_argument("--optim", default="arena", choices=["arena", "flat"],
+                    help="arena: flat parameter/gradient buffers + fused update kernel; flat: foreach SGD (A/B switch)")
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
                     help="capture the whole train step (fwd+bwd+all-reduce+SGD) in one CUDA graph; falls back to eager "
                          "(and says so) if capture fails")
@@ -240,7 +253,7 @@ def main():
     torch.manual_seed(0)
     from mrb_b200.model import RCNNConfig
     from mrb_b200.model.backend import B200Backend
-    from mrb_b200.optim import FlatSGD
+    from mrb_b200.optim import FlatSGD, ParamArena
     use_graph = args.graph in ("on", "auto")
     # graph capture needs a step without host synchronisation: fixed-shape mask head (see RCNNConfig)
     cfg = RCNNConfig(mask_rois_per_image=128 if use_graph else 0)
@@ -251,10 +264,17 @@ def main():
         # same initial weights everywhere (DDP's constructor broadcast), then one flat gradient all-reduce per step
         for t in list(model.parameters()) + list(model.buffers()):
             dist.broadcast(t.data, 0)
-        from mrb_b200.parallel import FlatGradSync
-        grad_sync = FlatGradSync(params, world)
     # SOLVER defaults of the reference (config/defaults.py:383-401): momentum 0.9, wd 1e-4, bias lr x2, bias wd 0
-    opt = FlatSGD(model.named_parameters(), lr=1e-4, momentum=0.9, weight_decay=1e-4)
+    if args.optim == "arena":
+        # parameters / gradient accumulators / momentum / bf16 operand copies in four flat buffers: kernels red.add
+        # gradients in place, one NCCL all-reduce over the gradient buffer, one fused update launch per group
+        opt = grad_sync = ParamArena(model.named_parameters(), model.be, lr=1e-4, momentum=0.9, weight_decay=1e-4,
+                                     world_size=world)
+    else:
+        if world > 1:
+            from mrb_b200.parallel import FlatGradSync
+            grad_sync = FlatGradSync(params, world)
+        opt = FlatSGD(model.named_parameters(), lr=1e-4, momentum=0.9, weight_decay=1e-4)
     sizes = [(IMG_H, IMG_W)] * IMGS_PER_GPU
     # distinct synthetic batches, pinned on the host (e2e) and resident in HBM (value)
     n_batches = 4
@@ -270,7 +290,8 @@ def main():
         if grad_sync is not None:
             grad_sync.sync()               # NCCL all-reduce of one flat fp32 gradient buffer (mean over ranks)
         opt.step()
-        model.be.refresh_weights(params)   # bf16 operand copies of the updated weights: one multi-tensor cast
+        if args.optim != "arena":
+            model.be.refresh_weights(params)   # bf16 operand copies of the updated weights: one multi-tensor cast
         return loss
 
     graph_info = {"enabled": False}
@@ -306,6 +327,8 @@ def main():
             sys.stderr.write("CUDA graph capture failed, running eagerly:\n" + traceback.format_exc() + "\n")
             graph_info = {"enabled": False, "error": repr(e)[:300]}
             torch.cuda.synchronize()
+            if args.optim == "arena":
+                opt.grad.zero_()            # drop the partial accumulation of the aborted capture
             step = eager_step
 
     def step_e2e(hbatch):
@@ -347,8 +370,9 @@ def main():
     step_e2e(host[0])
     barrier()
     e0.record()
+    last_loss = None
     for i in range(args.steps):
-        step_e2e(host[i % n_batches])
+        last_loss = step_e2e(host[i % n_batches])
     e1.record()
     barrier()
     t_e2e = e0.elapsed_time(e1) * 1e-3
@@ -358,8 +382,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t_dev, t_e2e = float(t[0]), float(t[1])
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        _finish(world)
         return
     imgs = IMGS_PER_GPU * world * args.steps
     h2d = sum(t.numel() * t.element_size() for t in host[0])
@@ -369,7 +392,7 @@ def main():
            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
            "config": workload_config(world), "clocks": clocks,
            "e2e": {"value": round(imgs / t_e2e, 3), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
-           "gpu_launches": launches, "cuda_graph": graph_info,
+           "gpu_launches": launches, "cuda_graph": graph_info, "loss_last_step": round(float(last_loss), 4),
            "library_ops": {"wgrad": model.be.wgrad_impl, "note": "conv forward, data-gradient and weight-gradient run on the "
                            "in-house tcgen05 kernels; max-pool, top-k/sort, box arithmetic, losses and the multi-tensor "
                            "SGD update are PyTorch"}}
@@ -394,8 +417,7 @@ def main():
         except Exception as e:  # the baseline must never break the bench line
             out["cpu_baseline"] = {"value": None, "error": repr(e)[:200]}
     print(json.dumps(out))
-    if world > 1:
-        dist.destroy_process_group()
+    _finish(world)
 
 
 if __name__ == "__main__":

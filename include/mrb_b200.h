@@ -237,6 +237,23 @@ int mrb_conv2d_fwd_up2(const mrb_conv_params* p, const void* input_bf16, const v
 /* grad_bias[c] = sum over pixels of an NHWC bf16 gradient [pixels, channels] (fp32, zeroed inside). */
 int mrb_bias_grad(const void* grad_bf16_nhwc, float* grad_bias, long long pixels, int channels,
                   mrb_stream_t stream);
+/* The same two reductions WITHOUT the zero-fill: the result is red.add-ed into the caller's fp32 gradient
+ * accumulator (what autograd's AccumulateGrad node does to `param.grad`, torch/csrc/autograd/functions/
+ * accumulate_grad.h, minus the temporary, its fill and the add pass). */
+int mrb_conv2d_wgrad_accumulate(const mrb_conv_params* p, const void* input_bf16, const void* grad_output_bf16,
+                                const float* scale /* optional [Cout] */, float* grad_weight, mrb_stream_t stream);
+int mrb_bias_grad_accumulate(const void* grad_bf16_nhwc, float* grad_bias, long long pixels, int channels,
+                             mrb_stream_t stream);
+
+/* ---- parameter update of the train step (reference solver/build.py:7-20 -> torch.optim.SGD) ----------------
+ * One streaming pass over n contiguous fp32 parameters:
+ *     d = grad * grad_scale + weight_decay * param;  m = momentum * m + d;  param -= lr * m
+ * and, in the same pass, param_bf16 (optional) <- bf16(param)  -- the operand copy the conv engine reads --
+ * and grad <- 0 when zero_grad != 0 (the accumulate entry points above add into it next step).
+ * param/grad/momentum_buf 16-byte aligned, param_bf16 8-byte aligned.  26 B of HBM traffic per parameter. */
+int mrb_sgd_momentum_step(float* param, float* grad, float* momentum_buf, void* param_bf16 /* optional */, long long n,
+                          float lr, float momentum, float weight_decay, float grad_scale, int zero_grad,
+                          mrb_stream_t stream);
 
 #ifdef __cplusplus
 }

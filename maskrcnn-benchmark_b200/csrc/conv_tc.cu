@@ -917,15 +917,15 @@ static int conv2d_dgrad_impl(const mrb_conv_params* p, const void* grad_output, 
                      grad_input, 0, p->out_dtype == MRB_F32, stream);
 }
 
-MRB_API int mrb_conv2d_wgrad(const mrb_conv_params* p, const void* input, const void* grad_output, const float* scale,
-                             float* grad_weight, mrb_stream_t stream_) {
+static int conv_wgrad_impl(const mrb_conv_params* p, const void* input, const void* grad_output, const float* scale,
+                           float* grad_weight, bool accumulate, mrb_stream_t stream_) {
   int rc = conv_check(p);
   if (rc) return rc;
   if (p->out_h || p->out_w) return MRB_ERR_UNSUPPORTED;
   if (!grad_weight) return MRB_ERR_BAD_ARG;
   cudaStream_t stream = (cudaStream_t)stream_;
   const int taps = p->kh * p->kw;
-  MRB_CUDA_TRY(cudaMemsetAsync(grad_weight, 0, (size_t)p->cout * taps * p->cin * sizeof(float), stream));
+  if (!accumulate) MRB_CUDA_TRY(cudaMemsetAsync(grad_weight, 0, (size_t)p->cout * taps * p->cin * sizeof(float), stream));
   if (p->batch == 0) return MRB_OK;
   if (!input || !grad_output) return MRB_ERR_BAD_ARG;
   if (p->cin % 8 || p->cout % 8 || ((uintptr_t)input & 15) || ((uintptr_t)grad_output & 15) || ((uintptr_t)grad_weight & 15))
@@ -1002,6 +1002,15 @@ MRB_API int mrb_conv2d_wgrad(const mrb_conv_params* p, const void* input, const 
   return MRB_OK;
 }
 
+MRB_API int mrb_conv2d_wgrad(const mrb_conv_params* p, const void* input, const void* grad_output, const float* scale,
+                             float* grad_weight, mrb_stream_t stream) {
+  return conv_wgrad_impl(p, input, grad_output, scale, grad_weight, false, stream);
+}
+MRB_API int mrb_conv2d_wgrad_accumulate(const mrb_conv_params* p, const void* input, const void* grad_output,
+                                        const float* scale, float* grad_weight, mrb_stream_t stream) {
+  return conv_wgrad_impl(p, input, grad_output, scale, grad_weight, true, stream);
+}
+
 // ------------------------------------------------------------------------------- bias gradient
 // db[c] = sum over pixels of g[pixel, c] for an NHWC bf16 gradient: each thread owns 2 adjacent channels
 // (one bf16x2 word), a CTA walks a slab of pixels with fully coalesced rows, one red.add per channel pair.
@@ -1023,11 +1032,12 @@ bias_grad_kernel(const __nv_bfloat16* __restrict__ g, float* __restrict__ db, lo
   }
 }
 
-MRB_API int mrb_bias_grad(const void* grad_bf16_nhwc, float* grad_bias, long long pixels, int channels, mrb_stream_t stream_) {
+static int bias_grad_impl(const void* grad_bf16_nhwc, float* grad_bias, long long pixels, int channels, bool accumulate,
+                          mrb_stream_t stream_) {
   if (pixels < 0 || channels <= 0 || (channels & 1)) return MRB_ERR_BAD_ARG;
   if (!grad_bias) return MRB_ERR_BAD_ARG;
   cudaStream_t stream = (cudaStream_t)stream_;
-  MRB_CUDA_TRY(cudaMemsetAsync(grad_bias, 0, sizeof(float) * channels, stream));
+  if (!accumulate) MRB_CUDA_TRY(cudaMemsetAsync(grad_bias, 0, sizeof(float) * channels, stream));
   if (pixels == 0) return MRB_OK;
   if (!grad_bf16_nhwc || ((uintptr_t)grad_bf16_nhwc & 3)) return MRB_ERR_BAD_ARG;
   long long ctas = (pixels + 63) / 64;
@@ -1038,4 +1048,12 @@ MRB_API int mrb_bias_grad(const void* grad_bf16_nhwc, float* grad_bias, long lon
   bias_grad_kernel<<<(unsigned)ctas, 256, 0, stream>>>((const __nv_bfloat16*)grad_bf16_nhwc, grad_bias, pixels, channels, rows);
   MRB_LAUNCH_CHECK();
   return MRB_OK;
+}
+
+MRB_API int mrb_bias_grad(const void* grad_bf16_nhwc, float* grad_bias, long long pixels, int channels, mrb_stream_t stream) {
+  return bias_grad_impl(grad_bf16_nhwc, grad_bias, pixels, channels, false, stream);
+}
+MRB_API int mrb_bias_grad_accumulate(const void* grad_bf16_nhwc, float* grad_bias, long long pixels, int channels,
+                                     mrb_stream_t stream) {
+  return bias_grad_impl(grad_bf16_nhwc, grad_bias, pixels, channels, true, stream);
 }

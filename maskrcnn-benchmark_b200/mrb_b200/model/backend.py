@@ -39,7 +39,7 @@ class _ConvFn(Function):
 
     @staticmethod
     def forward(ctx, x, weight, bias, residual, w16, scale, shift, stride, pad, relu, out_fp32, wgrad_fn,
-                premask_x=False, gy_premasked=False, residual_up2=False, be=None):
+                premask_x=False, gy_premasked=False, residual_up2=False, be=None, wsink=None, bsink=None):
         from mrb_b200 import ops
         add = shift if shift is not None else (bias.detach().float() if bias is not None else None)
         y = ops.conv2d_fwd(x, w16, scale, add, residual, stride, pad, relu,
@@ -49,6 +49,7 @@ class _ConvFn(Function):
         ctx.premask_x = premask_x
         ctx.wparam = weight if isinstance(weight, torch.nn.Parameter) else None
         ctx.be = be
+        ctx.wsink, ctx.bsink = wsink, bsink      # persistent fp32 accumulators of weight / bias (ParamArena) or None
         ctx.has_bias = bias is not None
         ctx.has_res = residual is not None
         ctx.save_for_backward(x, w16, scale, y if relu else None)
@@ -71,13 +72,19 @@ class _ConvFn(Function):
             prep = ctx.be.dgrad_weights(ctx.wparam, w16, scale) if ctx.be is not None else None
             gx = ops.conv2d_dgrad(g, w16, x_shape, scale, None, x if ctx.premask_x else None, stride, pad, prepared=prep)
         if ctx.needs_input_grad[1]:
-            gw = wgrad_fn(x, g, w16, stride, pad, scale)
+            if ctx.wsink is not None:
+                ops.conv2d_wgrad(x, g, w16.shape, stride, pad, scale, accumulate_into=ctx.wsink.view(w16.shape))
+            else:
+                gw = wgrad_fn(x, g, w16, stride, pad, scale)
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            gb = ops.bias_grad(g)
+            if ctx.bsink is not None:
+                ops.bias_grad(g, accumulate_into=ctx.bsink)
+            else:
+                gb = ops.bias_grad(g)
         if ctx.has_res and ctx.needs_input_grad[3]:
             # nearest-2x upsample backward == sum over each 2x2 block
             gres = F.avg_pool2d(g, 2).mul_(4) if ctx.residual_up2 else g
-        return gx, gw, gb, gres, None, None, None, None, None, None, None, None, None, None, None, None
+        return (gx, gw, gb, gres) + (None,) * 14
 
 
 class _BottleneckFn(Function):
@@ -116,24 +123,30 @@ class _BottleneckFn(Function):
         from mrb_b200 import ops
         x, y1, y2, out, w1, w2, w3, wd, a1, a2, a3, ad = ctx.saved_tensors
         s1, s3, sd = ctx.strides
-        wg = ctx.be.wgrad_fn
+        be = ctx.be
+        p1, p2, p3, pd = ctx.wparams
+
+        def wg(xin, gout, w16, stride, pad, scale, param):
+            sink = be.grad_sink(param)
+            if sink is None:
+                return be.wgrad_fn(xin, gout, w16, stride, pad, scale)
+            ops.conv2d_wgrad(xin, gout, w16.shape, stride, pad, scale, accumulate_into=sink)
+            return None
         if not ctx.g_premasked:
             g = torch.where(out > 0, g, torch.zeros((), dtype=g.dtype, device=g.device))
         g = g.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
         need = ctx.needs_input_grad
         gw1 = gw2 = gw3 = gwd = gx = None
         if need[3]:
-            gw3 = wg(y2, g, w3, 1, 0, a3)
-        be = ctx.be
-        p1, p2, p3, pd = ctx.wparams
+            gw3 = wg(y2, g, w3, 1, 0, a3, p3)
         g2 = ops.conv2d_dgrad(g, w3, y2.shape, a3, None, y2, 1, 0, prepared=be.dgrad_weights(p3, w3, a3))
         if need[2]:
-            gw2 = wg(y1, g2, w2, s3, 1, a2)
+            gw2 = wg(y1, g2, w2, s3, 1, a2, p2)
         g1 = ops.conv2d_dgrad(g2, w2, y1.shape, a2, None, y1, s3, 1, prepared=be.dgrad_weights(p2, w2, a2))
         if need[1]:
-            gw1 = wg(x, g1, w1, s1, 0, a1)
+            gw1 = wg(x, g1, w1, s1, 0, a1, p1)
         if ctx.has_d and need[4]:
-            gwd = wg(x, g, wd, sd, 0, ad)
+            gwd = wg(x, g, wd, sd, 0, ad, pd)
         if need[0]:
             pw1 = be.dgrad_weights(p1, w1, a1)
             if not ctx.has_d:
@@ -168,10 +181,32 @@ class B200Backend(Backend):
     def __init__(self, wgrad="tc"):
         self._w16 = {}
         self._wd = {}     # (id(param), id(scale)) -> [param, scale, version, w16, prepared dgrad weights]
+        self.arena = None
         if wgrad == "tc":
             self.wgrad_fn, self.wgrad_impl = _wgrad_tc, "mrb_conv2d_wgrad (tcgen05, in-house)"
         else:
             self.wgrad_fn, self.wgrad_impl = _wgrad_cudnn, "aten.convolution_backward (cuDNN)"
+
+    def attach_arena(self, arena):
+        """Parameters now live in a ParamArena: their bf16 operand copies are the arena's (kept current by its fused
+        update kernel) and their gradients accumulate into the arena's persistent fp32 views."""
+        self.arena = arena
+        self._w16 = {k: v for k, v in self._w16.items() if not isinstance(k, int)}
+        self._wd.clear()
+        for p in arena.params:
+            if p.dim() in (2, 4):
+                self._w16[id(p)] = (p, p._version, arena.views16[id(p)])
+
+    def arena_updated(self):
+        """The arena's update kernel rewrote parameters and bf16 copies behind autograd's back (no version bump):
+        re-derive the flipped/scaled data-gradient weights of every conv seen so far, one batched launch."""
+        stale = [e for e in self._wd.values() if self.arena.grad_sink(e[0]) is not None]
+        if stale:
+            from mrb_b200 import ops
+            ops.prepare_dgrad_weights([e[3] for e in stale], [e[1] for e in stale], [e[4] for e in stale])
+
+    def grad_sink(self, p):
+        return self.arena.grad_sink(p) if (self.arena is not None and p is not None) else None
 
     def _weight16(self, w):
         """bf16 KRSC copy of a weight.  Cached per nn.Parameter (refreshed when the optimizer bumps its
@@ -184,6 +219,15 @@ class B200Backend(Backend):
             return conv(w)
         key = id(w)
         ent = self._w16.get(key)
+        if self.arena is not None and self.arena.grad_sink(w) is not None:
+            # arena-resident copy: kept current by the fused update; re-cast in place if someone else wrote the parameter
+            if ent[1] != w._version:
+                ent[2].copy_(w.detach())
+                self._w16[key] = (w, w._version, ent[2])
+                for e in self._wd.values():
+                    if e[0] is w:
+                        e[2] = -1
+            return ent[2]
         if ent is None or ent[0] is not w or ent[1] != w._version or ent[2].device != w.device:
             self._w16[key] = (w, w._version, conv(w))   # holding `w` keeps its id from being recycled
         return self._w16[key][2]
@@ -192,7 +236,10 @@ class B200Backend(Backend):
         return images.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
 
     def conv(self, x, weight, scale=None, shift=None, bias=None, residual=None, stride=1, pad=0, relu=False,
-             out_fp32=False, w16=None, premask_x=False, gy_premasked=False, residual_up2=False):
+             out_fp32=False, w16=None, premask_x=False, gy_premasked=False, residual_up2=False, wparam=None):
+        """`wparam`: the nn.Parameter `weight` is a plain view of (linear's [Cout, K] -> [Cout, K, 1, 1]), if any."""
+        wsink = self.grad_sink(weight if isinstance(weight, torch.nn.Parameter) else wparam)
+        bsink = self.grad_sink(bias) if isinstance(bias, torch.nn.Parameter) else None
         if x.numel() == 0:
             n, _, h, w = x.shape
             kh, kw = weight.shape[2:]
@@ -213,11 +260,11 @@ class B200Backend(Backend):
                 shift = torch.cat([shift, shift.new_zeros(padn)])
             if scale is not None:
                 scale = torch.cat([scale, scale.new_ones(padn)])
-            w16 = None
+            w16 = wsink = bsink = None
         if w16 is None:
             w16 = self._weight16(weight)
         y = _ConvFn.apply(x, weight, bias, residual, w16, scale, shift, stride, pad, relu, out_fp32, self.wgrad_fn,
-                          premask_x, gy_premasked, residual_up2, self)
+                          premask_x, gy_premasked, residual_up2, self, wsink, bsink)
         return y[:, :co] if co % 8 else y
 
     def bottleneck(self, blk, x, g_premasked):
@@ -308,7 +355,8 @@ class B200Backend(Backend):
         co = weight.shape[0]
         w16 = self._weight16(weight).view(co, k, 1, 1)
         y = self.conv(x.to(torch.bfloat16).reshape(r, k, 1, 1), weight.view(co, k, 1, 1), bias=bias, relu=relu,
-                      out_fp32=out_fp32, w16=w16, premask_x=premask_x, gy_premasked=gy_premasked)
+                      out_fp32=out_fp32, w16=w16, premask_x=premask_x, gy_premasked=gy_premasked,
+                      wparam=weight if isinstance(weight, torch.nn.Parameter) else None)
         return y.reshape(r, co)
 
     def deconv2x2(self, x, weight, bias, relu=False, premask_x=False, gy_premasked=False):

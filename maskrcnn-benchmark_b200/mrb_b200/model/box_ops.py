@@ -7,7 +7,8 @@ import torch
 
 def box_area(b):
     """structures/bounding_box.py:214-226 (xyxy, TO_REMOVE = 1)"""
-    return (b[:, 2] - b[:, 0] + 1) * (b[:, 3] - b[:, 1] + 1)
+    wh = b[:, 2:] - b[:, :2] + 1
+    return wh[:, 0] * wh[:, 1]
 
 
 def box_iou(a, b):
@@ -28,16 +29,17 @@ class BoxCoder:
         self.clip = bbox_xform_clip
 
     def encode(self, reference_boxes, proposals):
-        ew = proposals[:, 2] - proposals[:, 0] + 1
-        eh = proposals[:, 3] - proposals[:, 1] + 1
-        ex = proposals[:, 0] + 0.5 * ew
-        ey = proposals[:, 1] + 0.5 * eh
-        gw = reference_boxes[:, 2] - reference_boxes[:, 0] + 1
-        gh = reference_boxes[:, 3] - reference_boxes[:, 1] + 1
-        gx = reference_boxes[:, 0] + 0.5 * gw
-        gy = reference_boxes[:, 1] + 0.5 * gh
+        # same arithmetic as modeling/box_coder.py:22-50, on (x, y) pairs at once (half the launches)
+        e_wh = proposals[:, 2:] - proposals[:, :2] + 1
+        e_ctr = proposals[:, :2] + 0.5 * e_wh
+        g_wh = reference_boxes[:, 2:] - reference_boxes[:, :2] + 1
+        g_ctr = reference_boxes[:, :2] + 0.5 * g_wh
         wx, wy, ww, wh = self.weights
-        return torch.stack((wx * (gx - ex) / ew, wy * (gy - ey) / eh, ww * torch.log(gw / ew), wh * torch.log(gh / eh)), 1)
+        d_ctr = (g_ctr - e_ctr) / e_wh
+        d_wh = torch.log(g_wh / e_wh)
+        if wx == wy and ww == wh:          # every reference config: (1,1,1,1) for the RPN, (10,10,5,5) for the box head
+            return torch.cat((wx * d_ctr, ww * d_wh), 1)
+        return torch.stack((wx * d_ctr[:, 0], wy * d_ctr[:, 1], ww * d_wh[:, 0], wh * d_wh[:, 1]), 1)
 
     def decode(self, rel_codes, boxes):
         boxes = boxes.to(rel_codes.dtype)
@@ -93,28 +95,41 @@ class Matcher:
         return matches
 
 
+def _pick_random(mask, key, cap, limit):
+    """Boolean mask of min(#mask, limit) uniformly random elements of `mask` (limit <= cap; limit may be a device
+    scalar).  Every element carries an iid uniform key; the answer is the `limit` smallest keys among the masked
+    ones.  Sync-free and sort-free on the long vector: for large inputs (268k RPN anchors) the candidates are first
+    thinned by a key threshold that keeps ~4*cap of them in expectation (all of them if there are fewer), compacted
+    with nonzero_static into a fixed 16*cap buffer, and only that short buffer goes through top-k."""
+    n = mask.numel()
+    dev = mask.device
+    if n <= 16384:
+        k, idx = torch.where(mask, key, key.new_full((), 2.0)), None
+        kk, sel = torch.topk(k, min(cap, n), largest=False, sorted=True)
+    else:
+        cnt = mask.sum().clamp(min=1).to(key.dtype)
+        cand = mask & (key < (4.0 * cap) / cnt)
+        c = min(n, 16 * cap)
+        idx = torch.nonzero_static(cand, size=c, fill_value=n).squeeze(1)          # padded with n
+        k = torch.where(idx < n, key[idx.clamp(max=n - 1)], key.new_full((), 2.0))
+        kk, order = torch.topk(k, min(cap, c), largest=False, sorted=True)
+        sel = idx[order]
+    ok = (kk < 1.5) & (torch.arange(kk.numel(), device=dev) < limit)
+    out = torch.zeros(n + 1, dtype=torch.bool, device=dev)                           # slot n swallows the padding
+    out[sel.clamp(max=n)] = ok
+    return out[:n], ok.sum()
+
+
 def sample_pos_neg(labels, batch_size, positive_fraction, generator=None):
     """modeling/balanced_positive_negative_sampler.py:19-68 for one image.
-    labels: -1 ignore, 0 negative, >0 positive.  Returns boolean masks (pos, neg).  Sync-free and sort-free:
-    every element draws a random key; the `cap` smallest keys among the candidates (two top-k calls over the
-    label vector -- 268k anchors for the RPN) are a uniform random subset, exactly what randperm()[:num] is."""
+    labels: -1 ignore, 0 negative, >0 positive.  Returns boolean masks (pos, neg): up to
+    int(batch_size * positive_fraction) random positives, the rest (up to batch_size) random negatives --
+    the distribution of randperm(...)[:num], without host synchronisation."""
     n = labels.numel()
     num_pos_cap = min(int(batch_size * positive_fraction), n)
-    pos, neg = labels >= 1, labels == 0
     key = torch.rand(n, device=labels.device, generator=generator)
-    big = key.new_full((), 2.0)
-    # positives: the (up to) num_pos_cap smallest keys
-    pk, pi = torch.topk(torch.where(pos, key, big), num_pos_cap, largest=False, sorted=True)
-    p_ok = pk < 1.5
-    pos_sel = torch.zeros(n, dtype=torch.bool, device=labels.device)
-    pos_sel[pi] = p_ok
-    num_pos = p_ok.sum()
-    # negatives: the num_neg = min(#neg, batch - num_pos) smallest keys
-    kneg = min(batch_size, n)
-    nk, ni = torch.topk(torch.where(neg, key, big), kneg, largest=False, sorted=True)
-    n_ok = (nk < 1.5) & (torch.arange(kneg, device=labels.device) < (batch_size - num_pos))
-    neg_sel = torch.zeros(n, dtype=torch.bool, device=labels.device)
-    neg_sel[ni] = n_ok
+    pos_sel, num_pos = _pick_random(labels >= 1, key, num_pos_cap, num_pos_cap)
+    neg_sel, _ = _pick_random(labels == 0, key, min(batch_size, n), batch_size - num_pos)
     return pos_sel, neg_sel
 
 

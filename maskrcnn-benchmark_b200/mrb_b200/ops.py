@@ -145,9 +145,11 @@ def conv2d_dgrad(grad_out, weight, x_shape, scale=None, add=None, relu_mask=None
     return gx
 
 
-def conv2d_wgrad(x, grad_out, w_shape, stride=1, pad=0, scale=None):
+def conv2d_wgrad(x, grad_out, w_shape, stride=1, pad=0, scale=None, accumulate_into=None):
     """grad_weight (fp32, logical [Cout, Cin, kh, kw], channels_last memory == KRSC) on the tcgen05 engine,
-    optionally multiplied by a per-Cout `scale` (the frozen-BN scale of the forward epilogue)."""
+    optionally multiplied by a per-Cout `scale` (the frozen-BN scale of the forward epilogue).
+    `accumulate_into` (fp32, that shape and memory order): the result is ADDED into it (red.add) instead of being
+    returned in a fresh zero-filled tensor."""
     x = _nhwc(x, "conv2d_wgrad(x)")
     grad_out = _nhwc(grad_out, "conv2d_wgrad(grad_out)")
     if x.dtype != torch.bfloat16 or grad_out.dtype != torch.bfloat16:
@@ -155,26 +157,55 @@ def conv2d_wgrad(x, grad_out, w_shape, stride=1, pad=0, scale=None):
     p, ho, wo = _params(x.shape, tuple(w_shape), stride, pad, False, torch.float32)
     if tuple(grad_out.shape) != (p.batch, p.cout, ho, wo):
         raise RuntimeError("conv2d_wgrad: grad_out shape mismatch")
-    gw = torch.empty(tuple(w_shape), dtype=torch.float32, device=x.device).contiguous(memory_format=torch.channels_last)
+    if accumulate_into is not None:
+        gw = accumulate_into
+        if gw.dtype != torch.float32 or tuple(gw.shape) != tuple(w_shape) or \
+                not gw.is_contiguous(memory_format=torch.channels_last):
+            raise RuntimeError("conv2d_wgrad: accumulate_into must be fp32 channels_last shaped like the weight")
+        fn = lib.mrb_conv2d_wgrad_accumulate
+    else:
+        gw = torch.empty(tuple(w_shape), dtype=torch.float32, device=x.device).contiguous(memory_format=torch.channels_last)
+        fn = lib.mrb_conv2d_wgrad
     with torch.cuda.device(x.device):
-        _c.check(lib.mrb_conv2d_wgrad(ctypes.byref(p), _c._ptr(x), _c._ptr(grad_out), _c._ptr(scale), _c._ptr(gw),
-                                      _c._stream()), "mrb_conv2d_wgrad")
+        _c.check(fn(ctypes.byref(p), _c._ptr(x), _c._ptr(grad_out), _c._ptr(scale), _c._ptr(gw), _c._stream()),
+                 "mrb_conv2d_wgrad")
     _count(1, ("wgrad", p.batch, p.cin, p.height, p.width, p.cout, p.kh, p.stride, p.pad))
     return gw
 
 
-def bias_grad(grad_out):
-    """sum over N, H, W of an NHWC bf16 gradient -> fp32 [C]."""
+def bias_grad(grad_out, accumulate_into=None):
+    """sum over N, H, W of an NHWC bf16 gradient -> fp32 [C] (added into `accumulate_into` when given)."""
     grad_out = _nhwc(grad_out, "bias_grad(grad_out)")
     if grad_out.dtype != torch.bfloat16:
         raise RuntimeError("bias_grad: bf16 gradient required")
     n, c, h, w = grad_out.shape
-    out = torch.empty(c, dtype=torch.float32, device=grad_out.device)
+    if accumulate_into is not None:
+        out, fn = accumulate_into, lib.mrb_bias_grad_accumulate
+        if out.dtype != torch.float32 or out.numel() != c or not out.is_contiguous():
+            raise RuntimeError("bias_grad: accumulate_into must be contiguous fp32 [C]")
+    else:
+        out, fn = torch.empty(c, dtype=torch.float32, device=grad_out.device), lib.mrb_bias_grad
     with torch.cuda.device(grad_out.device):
-        _c.check(lib.mrb_bias_grad(_c._ptr(grad_out), _c._ptr(out), ctypes.c_longlong(n * h * w), c, _c._stream()),
-                 "mrb_bias_grad")
+        _c.check(fn(_c._ptr(grad_out), _c._ptr(out), ctypes.c_longlong(n * h * w), c, _c._stream()), "mrb_bias_grad")
     _count(1)
     return out
+
+
+def sgd_momentum_step(param, grad, momentum_buf, param_bf16, lr, momentum, weight_decay, grad_scale=1.0, zero_grad=True):
+    """In-place fused SGD update of flat fp32 tensors (see mrb_sgd_momentum_step): also refreshes the bf16 operand
+    copy `param_bf16` (may be None) and zeroes `grad`."""
+    n = param.numel()
+    for t in (param, grad, momentum_buf):
+        if t.dtype != torch.float32 or t.numel() != n or not t.is_contiguous() or not t.is_cuda:
+            raise RuntimeError("sgd_momentum_step: param/grad/momentum_buf must be contiguous fp32 CUDA tensors of one size")
+    if param_bf16 is not None and (param_bf16.dtype != torch.bfloat16 or param_bf16.numel() != n or not param_bf16.is_contiguous()):
+        raise RuntimeError("sgd_momentum_step: param_bf16 must be a contiguous bf16 tensor of the same size")
+    with torch.cuda.device(param.device):
+        _c.check(lib.mrb_sgd_momentum_step(_c._ptr(param), _c._ptr(grad), _c._ptr(momentum_buf), _c._ptr(param_bf16),
+                                           ctypes.c_longlong(n), ctypes.c_float(lr), ctypes.c_float(momentum),
+                                           ctypes.c_float(weight_decay), ctypes.c_float(grad_scale), int(bool(zero_grad)),
+                                           _c._stream()), "mrb_sgd_momentum_step")
+    _count(1)
 
 
 # ------------------------------------------------------------------------- fused FPN ROIAlign

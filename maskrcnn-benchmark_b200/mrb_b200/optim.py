@@ -50,3 +50,87 @@ class FlatSGD:
             torch._foreach_mul_(g["buf"], self.momentum)
             torch._foreach_add_(g["buf"], grads)
             torch._foreach_add_(g["flat"], g["buf"], alpha=-g["lr"])
+
+
+class ParamArena:
+    """All trainable parameters of a model packed into four flat device buffers -- fp32 parameters, fp32 gradient
+    accumulators, fp32 momentum, bf16 operand copies -- so that the per-step bookkeeping around the kernels is
+    three launches instead of several hundred:
+
+      * every `p` becomes a view of the parameter buffer and `p.grad` a PERSISTENT view of the gradient buffer with
+        the parameter's own memory order (KRSC for conv weights).  The weight/bias-gradient kernels red.add straight
+        into these views (B200Backend looks them up through `grad_sink`), so there is no per-layer zero-fill, no
+        temporary and no AccumulateGrad add; gradients that still arrive through autograd (padded / concatenated
+        heads) are accumulated in place by autograd itself;
+      * data-parallel averaging is ONE all-reduce of the gradient buffer (no packing copy), its 1/world folded into
+        the update;
+      * `step()` is mrb_sgd_momentum_step once per group (weights; biases with lr x BIAS_LR_FACTOR and
+        WEIGHT_DECAY_BIAS, reference solver/build.py:12-18): update, bf16 operand refresh and gradient zeroing in a
+        single pass.  The whole step stays CUDA-graph capturable.
+
+    zero_grad() is a no-op by construction (the update leaves the accumulators at zero)."""
+
+    ALIGN = 64      # elements: every parameter starts 256 B (fp32) / 128 B (bf16) aligned -> TMA / vector friendly
+
+    def __init__(self, named_params, backend, lr=0.02, momentum=0.9, weight_decay=1e-4, bias_lr_factor=2.0,
+                 weight_decay_bias=0.0, world_size=1, group=None):
+        named = [(n, p) for n, p in named_params if p.requires_grad]
+        for n, p in named:
+            if not (p.is_contiguous() or p.is_contiguous(memory_format=torch.channels_last)):
+                raise ValueError("ParamArena: parameter %s is not dense" % n)
+        w = [(n, p) for n, p in named if "bias" not in n]
+        b = [(n, p) for n, p in named if "bias" in n]
+        self.params = [p for _, p in w + b]
+        dev = self.params[0].device
+
+        def up(x):
+            return (x + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        n_w = sum(up(p.numel()) for _, p in w)
+        n_b = sum(up(p.numel()) for _, p in b)
+        total = n_w + n_b
+        self.param = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.mom = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.param16 = torch.zeros(total, dtype=torch.bfloat16, device=dev)
+        self.groups = [g for g in ((0, n_w, lr, weight_decay), (n_w, total, lr * bias_lr_factor, weight_decay_bias))
+                       if g[1] > g[0]]
+        self.momentum, self.world, self.group, self.backend = momentum, world_size, group, backend
+        self.sinks, self.views16 = {}, {}
+        off = 0
+        with torch.no_grad():
+            for _, p in w + b:
+                n = p.numel()
+                view = torch.as_strided(self.param, p.shape, p.stride(), off)
+                view.copy_(p)
+                p.data = view                    # before any optimizer / graph / cache has seen the old storage
+                gview = torch.as_strided(self.grad, p.shape, p.stride(), off)
+                p.grad = gview
+                self.sinks[id(p)] = (p, gview)
+                self.views16[id(p)] = torch.as_strided(self.param16, p.shape, p.stride(), off)
+                off += up(n)
+            self.param16.copy_(self.param)
+        if backend is not None:
+            backend.attach_arena(self)
+
+    def grad_sink(self, p):
+        ent = self.sinks.get(id(p))
+        return ent[1] if ent is not None and ent[0] is p else None
+
+    def zero_grad(self):
+        pass
+
+    @torch.no_grad()
+    def sync(self):
+        """Sum the gradient accumulators over the data-parallel ranks (the mean's 1/world is applied by step())."""
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=self.group)
+
+    @torch.no_grad()
+    def step(self):
+        from mrb_b200 import ops
+        for lo, hi, lr, wd in self.groups:
+            ops.sgd_momentum_step(self.param[lo:hi], self.grad[lo:hi], self.mom[lo:hi], self.param16[lo:hi], lr,
+                                  self.momentum, wd, 1.0 / self.world, True)
+        if self.backend is not None:
+            self.backend.arena_updated()

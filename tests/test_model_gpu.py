@@ -127,3 +127,89 @@ def test_conv_autograd_matches_torch(built_lib):
     assert _rel(xd.grad, xr.grad) < 2e-2
     assert _rel(wd.grad, wr.grad) < 2e-2
     assert _rel(rd.grad, rr.grad) < 1e-2
+
+
+def test_sgd_momentum_step_matches_torch_sgd(built_lib):
+    """mrb_sgd_momentum_step == torch.optim.SGD(momentum, weight_decay) over several steps (reference
+    solver/build.py:7-20), with the bf16 copy refreshed and the gradient buffer zeroed in the same pass."""
+    from mrb_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    n = 4 * 5000 + 3                                      # ragged tail on purpose
+    p0 = torch.randn(n, generator=g)
+    pr = p0.clone().requires_grad_(True)
+    opt = torch.optim.SGD([pr], lr=0.05, momentum=0.9, weight_decay=1e-2)
+    p, m, p16 = p0.to(DEV), torch.zeros(n, device=DEV), torch.zeros(n, dtype=torch.bfloat16, device=DEV)
+    for it in range(4):
+        gr = torch.randn(n, generator=g)
+        pr.grad = gr.clone()
+        opt.step()
+        gd = (gr * 2.0).to(DEV)                           # grad_scale 0.5 undoes the doubling (the 1/world fold)
+        ops.sgd_momentum_step(p, gd, m, p16, 0.05, 0.9, 1e-2, 0.5, True)
+        assert torch.count_nonzero(gd) == 0
+        assert torch.allclose(p.cpu(), pr.detach(), rtol=1e-5, atol=1e-6), it
+        assert torch.equal(p16, p.to(torch.bfloat16))
+
+
+def test_wgrad_and_bias_grad_accumulate(built_lib):
+    from mrb_b200 import ops
+    g = torch.Generator().manual_seed(12)
+    x = torch.randn(2, 64, 20, 28, generator=g).to(DEV).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    go = torch.randn(2, 128, 20, 28, generator=g).to(DEV).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    fresh = ops.conv2d_wgrad(x, go, (128, 64, 3, 3), 1, 1)
+    acc = torch.full((128, 64, 3, 3), 1.5, device=DEV).contiguous(memory_format=torch.channels_last)
+    ops.conv2d_wgrad(x, go, (128, 64, 3, 3), 1, 1, accumulate_into=acc)
+    assert _rel(acc - 1.5, fresh) < 1e-5
+    bf = ops.bias_grad(go)
+    ba = torch.full((128,), -2.0, device=DEV)
+    ops.bias_grad(go, accumulate_into=ba)
+    assert _rel(ba + 2.0, bf) < 1e-5
+
+
+def test_param_arena_step_equals_flat_sgd(built_lib):
+    """One full train step with gradients red.add-ed into the ParamArena and the fused update kernel must leave
+    the same parameters as autograd gradients + FlatSGD (same seed => same sampling), and must leave the bf16
+    operand copies and the (zeroed) accumulators consistent."""
+    from mrb_b200.model import GeneralizedRCNN
+    from mrb_b200.model.backend import B200Backend
+    from mrb_b200.optim import FlatSGD, ParamArena
+    cfg = _tiny_cfg()
+    g = torch.Generator().manual_seed(2)
+    imgs = (torch.randn(2, 3, 256, 320, generator=g) * 50).to(DEV)
+    sizes = [(256, 300), (240, 320)]
+    tg = [{"boxes": torch.tensor([[10., 10, 120, 150], [90, 60, 280, 220]], device=DEV), "labels": torch.tensor([3, 7], device=DEV)},
+          {"boxes": torch.tensor([[30., 40, 200, 200]], device=DEV), "labels": torch.tensor([5], device=DEV)}]
+    results = []
+    for kind in ("flat", "arena"):
+        torch.manual_seed(0)
+        model = GeneralizedRCNN(cfg, B200Backend()).to(DEV).train()
+        for p in model.parameters():
+            if p.dim() == 4:
+                p.data = p.data.contiguous(memory_format=torch.channels_last)
+        if kind == "flat":
+            opt = FlatSGD(model.named_parameters(), lr=1e-3, momentum=0.9, weight_decay=1e-4)
+        else:
+            opt = ParamArena(model.named_parameters(), model.be, lr=1e-3, momentum=0.9, weight_decay=1e-4)
+        before = {n: p.detach().float().clone() for n, p in model.named_parameters() if p.requires_grad}
+        for it in range(2):
+            torch.manual_seed(100 + it)
+            loss = sum(model(imgs, sizes, tg).values())
+            assert torch.isfinite(loss), (kind, it)
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+            if kind == "flat":
+                model.be.refresh_weights([p for p in model.parameters() if p.requires_grad])
+            if it == 0:   # the first update is a deterministic function of the seed (same sampling on both paths)
+                results.append({n: p.detach().float() - before[n] for n, p in model.named_parameters() if p.requires_grad})
+        if kind == "arena":
+            assert torch.count_nonzero(opt.grad) == 0
+            assert torch.equal(opt.param16, opt.param.to(torch.bfloat16))
+            for n, p in model.named_parameters():
+                if p.requires_grad and p.dim() in (2, 4):
+                    assert model.be._weight16(p).data_ptr() == opt.views16[id(p)].data_ptr(), n
+    flat, arena = results
+    for n in flat:
+        # identical math up to the fp32 summation order of the split-K red.adds / atomics
+        d = (flat[n] - arena[n]).abs().max().item()
+        ref = flat[n].abs().max().item()
+        assert d <= 5e-2 * ref + 1e-8, (n, d, ref)
