@@ -112,8 +112,10 @@ def conv_roofline(calls, peaks, device):
     for key, count in sorted(shapes.items()):
         kind, n, cin, h, w, cout, k, stride, pad = key
         x = torch.randn(n, cin, h, w, device=device).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
-        wt = torch.randn(cout, cin, k, k, device=device).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
-        ho, wo = (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
+        kh, kw = (k, k) if isinstance(k, int) else k
+        ph, pw = (pad, pad) if isinstance(pad, int) else pad
+        wt = torch.randn(cout, cin, kh, kw, device=device).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        ho, wo = (h + 2 * ph - kh) // stride + 1, (w + 2 * pw - kw) // stride + 1
         if kind in ("dgrad", "wgrad"):
             go = torch.randn(n, cout, ho, wo, device=device).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
             if kind == "dgrad":
@@ -133,10 +135,10 @@ def conv_roofline(calls, peaks, device):
             e1.synchronize()
             ts.append(e0.elapsed_time(e1) * 1e-3)
         t = sorted(ts)[1]
-        flops = 2.0 * n * ho * wo * cout * cin * k * k
+        flops = 2.0 * n * ho * wo * cout * cin * kh * kw
         tot_flops += flops * count
         tot_time += t * count
-        rows.append({"kind": kind, "n": n, "cin": cin, "h": h, "w": w, "cout": cout, "k": k, "stride": stride, "count": count,
+        rows.append({"kind": kind, "n": n, "cin": cin, "h": h, "w": w, "cout": cout, "k": k if isinstance(k, int) else list(k), "stride": stride, "count": count,
                      "us": round(t * 1e6, 1), "tflops": round(flops / t / 1e12, 1)})
     peak = peaks.get("bf16_tflops", 1590.0)
     ach = tot_flops / max(tot_time, 1e-12) / 1e12

@@ -186,15 +186,26 @@ int mrb_deform_psroi_bwd(const float* out_grad, const float* data, const float* 
  *     y = act( acc * scale[c] + bias[c] + residual )        (scale/bias/residual optional)
  * TMA feeds shared memory directly from the NHWC tensor (im2col is folded into the TMA
  * box coordinates; no column matrix exists anywhere). */
+#define MRB_CONV_PAD_W 1              /* mrb_conv_params.flags: `pad_w` holds the width padding (else pad_w == pad) */
 typedef struct mrb_conv_params {
   int batch, height, width, cin;   /* input  NHWC */
-  int cout, kh, kw;                /* filter KRSC */
-  int stride, pad;                 /* symmetric; dilation 1; groups 1; stride 2 only for 1x1 */
+  int cout, kh, kw;                /* filter KRSC (rectangular kernels allowed) */
+  int stride, pad;                 /* pad: height (and, by default, width) padding; dilation 1; groups 1; stride 2 only
+                                      for 1x1 */
   int relu;                        /* fused ReLU in the epilogue */
   int out_dtype;                   /* MRB_BF16 or MRB_F32 */
   int out_h, out_w;                /* 0 = (in + 2*pad - k)/stride + 1; a smaller explicit size computes only the
                                       top-left out_h x out_w outputs (used by the space-to-depth stem, whose 4x4
                                       kernel needs padding 2 on the left/top but 1 on the right/bottom) */
+  int pad_w, flags;                /* see MRB_CONV_PAD_W */
+  /* Optional element strides {image, row, pixel} (channel stride is always 1) of the input-side tensor (`input` of
+   * fwd/wgrad, `grad_input`/`add`/`relu_mask` of dgrad) and of the output-side tensor (`output`/`residual` of fwd,
+   * `grad_output` of dgrad/wgrad).  All zero = dense NHWC.  Multiples of 8 elements (TMA: 16 B); stride 1 only.
+   * This is how a convolution reads or writes a strided window of a larger tensor in place: the 2x2/stride-2
+   * transposed convolution of the mask head writes its sub-pixel planes straight into the [N,2H,2W,C] result, and
+   * the 7x7/2 stem reads overlapping 4-pixel windows of its space-to-depth input as 64-channel pixels. */
+  long long x_pitch[3];
+  long long y_pitch[3];
 } mrb_conv_params;
 int mrb_conv2d_fwd(const mrb_conv_params* p, const void* input_bf16, const void* weight_bf16,
                    const float* scale, const float* bias, const void* residual, void* output,

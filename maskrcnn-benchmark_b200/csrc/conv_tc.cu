@@ -130,7 +130,7 @@ constexpr int kABytes = kTileM * kBlockK * 2;  // 16 KB
 struct ConvArgs {
   int tiles_total, tiles_n, tiles_w, tiles_h;  // tiles_total = batch * tiles_h * tiles_w * tiles_n
   int th, tw, Ho, Wo;
-  int cin_blocks, kh, kw, pad;
+  int cin_blocks, kh, kw, pad_h, pad_w;
   int cout, bn, stages, relu, out_f32;
   long long out_n, out_h, out_w;  // output strides in elements (channel stride 1)
   const float* scale;
@@ -267,7 +267,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           mbar_wait(empty_bar(s), phase ^ 1u);
           mbar_expect_tx(full_bar(s), stage_bytes);
           const uint32_t sa = smem_base + (uint32_t)s * stage_bytes;
-          tma_load_4d(sa, &map_a, full_bar(s), cb * kBlockK, w0 + q - a.pad, h0 + r - a.pad, img);
+          tma_load_4d(sa, &map_a, full_bar(s), cb * kBlockK, w0 + q - a.pad_w, h0 + r - a.pad_h, img);
           tma_load_3d(sa + kABytes, &map_b, full_bar(s), cb * kBlockK, tap, n_tile * a.bn);
           if (++s == a.stages) { s = 0; phase ^= 1u; }
         }
@@ -456,7 +456,7 @@ constexpr int kWgGroupBytes = kWgBlockK * 128;      // one 64-channel group of o
 
 struct WgradArgs {
   int items_total, co_tiles, ci_tiles, taps, splits;
-  int kh, kw, pad;
+  int kh, kw, pad_h, pad_w;
   int th, tw, tiles_w, tiles_h, batch;   // pixel tiling of the OUTPUT (G) plane
   int kblocks_total, kblocks_per_split;
   int cin, cout, bn, stages;
@@ -528,7 +528,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_con
           tma_load_4d(sa + kWgGroupBytes, &map_g, full_bar(s), co_t * 128 + 64, w0, h0, img);
           for (int gi = 0; gi < b_groups; ++gi)
             tma_load_4d(sa + a_bytes + (uint32_t)gi * kWgGroupBytes, &map_x, full_bar(s), ci_t * a.bn + gi * 64,
-                        w0 + q - a.pad, h0 + r - a.pad, img);
+                        w0 + q - a.pad_w, h0 + r - a.pad_h, img);
           if (++s == a.stages) { s = 0; phase ^= 1u; }
         }
       }
@@ -691,7 +691,7 @@ struct ConvPlan {
 
 // Launch one implicit-GEMM convolution.  `x` is the TMA-visible input [batch][Hin][Win][cin] with the
 // given element strides; `w` is [cout][taps][cin].
-static int conv_launch(const ConvPlan& pl, const void* x, const void* w, int cin, int cout, int kh, int kw, int pad,
+static int conv_launch(const ConvPlan& pl, const void* x, const void* w, int cin, int cout, int kh, int kw, int pad_h, int pad_w,
                        const float* scale, const float* bias, const void* residual, const void* relu_mask, void* out,
                        int relu, int out_f32, cudaStream_t stream, int res_up2 = 0, int res_hh = 0, int res_ww = 0) {
   if (cin % 8 || ((uintptr_t)x & 15) || ((uintptr_t)w & 15) || ((uintptr_t)out & 15)) return MRB_ERR_UNSUPPORTED;
@@ -708,15 +708,30 @@ static int conv_launch(const ConvPlan& pl, const void* x, const void* w, int cin
     if (best < 0 || cost < best) { best = cost; best_th = th; best_tw = tw; }
   }
   const int th = best_th, tw = best_tw;
+  // N tile: 256 columns amortise the A tile best, but a small image plane gives few M tiles -- then narrower N
+  // tiles are what fills the 148 SMs (e.g. res4 3x3 at 50x84: 66 M tiles; res5 at 25x42: 17).  Cost model: waves of
+  // the persistent grid x relative tile time, with a mild penalty per halving for the lost A reuse.
   int bn = (cout + 15) / 16 * 16;
   if (bn > 256) bn = 256;
+  if (bn == 256 || bn == 128) {
+    const long long m_tiles = (long long)pl.batch * ceil_div(pl.Ho, th) * ceil_div(pl.Wo, tw);
+    double best_cost = 0;
+    int best_bn = bn;
+    for (int cand = bn, halvings = 0; cand >= 64; cand >>= 1, ++halvings) {
+      const long long t = m_tiles * ceil_div(cout, cand);
+      const double waves = (double)ceil_div(t, kNumSMs);
+      const double cost = waves * ((cand < 96 ? 96 : cand) / 256.0) * (1.0 + 0.15 * halvings);
+      if (halvings == 0 || cost < best_cost * 0.98) { best_cost = cost; best_bn = cand; }
+    }
+    bn = best_bn;
+  }
   ConvArgs a;
   a.th = th; a.tw = tw; a.Ho = pl.Ho; a.Wo = pl.Wo;
   a.tiles_h = ceil_div(pl.Ho, th); a.tiles_w = ceil_div(pl.Wo, tw); a.tiles_n = ceil_div(cout, bn);
   const long long tiles = (long long)pl.batch * a.tiles_h * a.tiles_w * a.tiles_n;
   if (tiles <= 0 || tiles >= (1ll << 31)) return tiles == 0 ? MRB_OK : MRB_ERR_UNSUPPORTED;
   a.tiles_total = (int)tiles;
-  a.cin_blocks = ceil_div(cin, kBlockK); a.kh = kh; a.kw = kw; a.pad = pad;
+  a.cin_blocks = ceil_div(cin, kBlockK); a.kh = kh; a.kw = kw; a.pad_h = pad_h; a.pad_w = pad_w;
   a.cout = cout; a.bn = bn; a.relu = relu; a.out_f32 = out_f32;
   a.out_n = pl.out_n; a.out_h = pl.out_h; a.out_w = pl.out_w;
   a.scale = scale; a.bias = bias; a.residual = (const __nv_bfloat16*)residual; a.relu_mask = (const __nv_bfloat16*)relu_mask;
@@ -757,13 +772,19 @@ static int conv_launch(const ConvPlan& pl, const void* x, const void* w, int cin
   return MRB_OK;
 }
 
+static inline int pad_w_of(const mrb_conv_params* p) { return (p->flags & MRB_CONV_PAD_W) ? p->pad_w : p->pad; }
+static inline bool has_pitch(const long long* v) { return v[0] || v[1] || v[2]; }
+
 static int conv_check(const mrb_conv_params* p) {
   if (!p) return MRB_ERR_BAD_ARG;
   if (p->batch < 0 || p->height <= 0 || p->width <= 0 || p->cin <= 0 || p->cout <= 0 || p->kh <= 0 || p->kw <= 0 ||
       p->stride <= 0 || p->pad < 0)
     return MRB_ERR_BAD_ARG;
-  if (p->kh != p->kw) return MRB_ERR_UNSUPPORTED;
-  if (p->stride != 1 && !(p->stride == 2 && p->kh == 1 && p->pad == 0)) return MRB_ERR_UNSUPPORTED;
+  if (p->stride != 1 && !(p->stride == 2 && p->kh == 1 && p->kw == 1 && p->pad == 0 && pad_w_of(p) == 0)) return MRB_ERR_UNSUPPORTED;
+  if ((p->flags & MRB_CONV_PAD_W) && p->pad_w < 0) return MRB_ERR_BAD_ARG;
+  for (int i = 0; i < 3; ++i)
+    if (p->x_pitch[i] < 0 || p->y_pitch[i] < 0) return MRB_ERR_BAD_ARG;
+  if ((has_pitch(p->x_pitch) || has_pitch(p->y_pitch)) && p->stride != 1) return MRB_ERR_UNSUPPORTED;
   return MRB_OK;
 }
 
@@ -789,7 +810,8 @@ static int conv2d_fwd_impl(const mrb_conv_params* p, const void* input, const vo
   if (rc) return rc;
   if (p->batch == 0) return MRB_OK;
   if (!input || !weight || !output) return MRB_ERR_BAD_ARG;
-  int Ho = (p->height + 2 * p->pad - p->kh) / p->stride + 1, Wo = (p->width + 2 * p->pad - p->kw) / p->stride + 1;
+  const int pad_w = pad_w_of(p);
+  int Ho = (p->height + 2 * p->pad - p->kh) / p->stride + 1, Wo = (p->width + 2 * pad_w - p->kw) / p->stride + 1;
   if (Ho <= 0 || Wo <= 0) return MRB_ERR_BAD_ARG;
   if (p->out_h > 0 || p->out_w > 0) {
     if (p->out_h <= 0 || p->out_w <= 0 || p->out_h > Ho || p->out_w > Wo || p->stride != 1) return MRB_ERR_BAD_ARG;
@@ -798,7 +820,9 @@ static int conv2d_fwd_impl(const mrb_conv_params* p, const void* input, const vo
   ConvPlan pl;
   const long long C = p->cin, Co = p->cout;
   if (residual_up2 && (!residual || p->stride != 1)) return MRB_ERR_BAD_ARG;
-  if (p->kh == 1 && p->stride == 1 && p->pad == 0 && p->out_h == 0 && !residual_up2) {
+  const bool pitched = has_pitch(p->x_pitch) || has_pitch(p->y_pitch);
+  if (pitched && residual_up2) return MRB_ERR_UNSUPPORTED;
+  if (p->kh == 1 && p->kw == 1 && p->stride == 1 && p->pad == 0 && pad_w == 0 && p->out_h == 0 && !residual_up2 && !pitched) {
     // pure GEMM: all pixels of the batch on one axis, zero tile waste
     pl.batch = 1; pl.Hin = 1; pl.Win = p->batch * p->height * p->width;
     pl.in_w = C; pl.in_h = (long long)pl.Win * C; pl.in_n = pl.in_h;
@@ -809,8 +833,10 @@ static int conv2d_fwd_impl(const mrb_conv_params* p, const void* input, const vo
     pl.in_w = C * p->stride; pl.in_h = (long long)p->width * C * p->stride; pl.in_n = (long long)p->height * p->width * C;
     pl.Ho = Ho; pl.Wo = Wo;
     pl.out_w = Co; pl.out_h = (long long)Wo * Co; pl.out_n = (long long)Ho * Wo * Co;
+    if (has_pitch(p->x_pitch)) { pl.in_n = p->x_pitch[0]; pl.in_h = p->x_pitch[1]; pl.in_w = p->x_pitch[2]; }
+    if (has_pitch(p->y_pitch)) { pl.out_n = p->y_pitch[0]; pl.out_h = p->y_pitch[1]; pl.out_w = p->y_pitch[2]; }
   }
-  return conv_launch(pl, input, weight, p->cin, p->cout, p->kh, p->kw, p->pad, scale, bias, residual, nullptr, output,
+  return conv_launch(pl, input, weight, p->cin, p->cout, p->kh, p->kw, p->pad, pad_w, scale, bias, residual, nullptr, output,
                      p->relu, p->out_dtype == MRB_F32, (cudaStream_t)stream, residual_up2, (Ho + 1) / 2, (Wo + 1) / 2);
 }
 
@@ -881,7 +907,9 @@ MRB_API int mrb_conv2d_dgrad(const mrb_conv_params* p, const void* grad_output, 
 
 static int conv2d_dgrad_impl(const mrb_conv_params* p, const void* grad_output, const __nv_bfloat16* wd, const void* add,
                              const void* relu_mask, void* grad_input, cudaStream_t stream) {
-  const int Ho = (p->height + 2 * p->pad - p->kh) / p->stride + 1, Wo = (p->width + 2 * p->pad - p->kw) / p->stride + 1;
+  const int pad_w = pad_w_of(p);
+  const int Ho = (p->height + 2 * p->pad - p->kh) / p->stride + 1, Wo = (p->width + 2 * pad_w - p->kw) / p->stride + 1;
+  const bool pitched = has_pitch(p->x_pitch) || has_pitch(p->y_pitch);
   // dgrad == forward conv of grad_output [N,Ho,Wo,Cout] with Wd [Cin][taps][Cout], pad' = k - 1 - pad
   ConvPlan pl;
   const long long Ci = p->cin, Co = p->cout;
@@ -899,10 +927,10 @@ static int conv2d_dgrad_impl(const mrb_conv_params* p, const void* grad_output, 
     pl.in_w = Co; pl.in_h = (long long)Wo * Co; pl.in_n = (long long)Ho * Wo * Co;
     pl.Ho = Ho; pl.Wo = Wo;
     pl.out_w = 2 * Ci; pl.out_h = 2ll * p->width * Ci; pl.out_n = (long long)p->height * p->width * Ci;
-    return conv_launch(pl, grad_output, wd, p->cout, p->cin, 1, 1, 0, nullptr, nullptr, add, relu_mask, grad_input, 0,
+    return conv_launch(pl, grad_output, wd, p->cout, p->cin, 1, 1, 0, 0, nullptr, nullptr, add, relu_mask, grad_input, 0,
                        p->out_dtype == MRB_F32, stream);
   }
-  if (p->kh == 1 && p->pad == 0) {
+  if (p->kh == 1 && p->kw == 1 && p->pad == 0 && pad_w == 0 && !pitched) {
     pl.batch = 1; pl.Hin = 1; pl.Win = p->batch * Ho * Wo;
     pl.in_w = Co; pl.in_h = (long long)pl.Win * Co; pl.in_n = pl.in_h;
     pl.Ho = 1; pl.Wo = pl.Win;
@@ -912,8 +940,10 @@ static int conv2d_dgrad_impl(const mrb_conv_params* p, const void* grad_output, 
     pl.in_w = Co; pl.in_h = (long long)Wo * Co; pl.in_n = (long long)Ho * Wo * Co;
     pl.Ho = p->height; pl.Wo = p->width;
     pl.out_w = Ci; pl.out_h = (long long)p->width * Ci; pl.out_n = (long long)p->height * p->width * Ci;
+    if (has_pitch(p->y_pitch)) { pl.in_n = p->y_pitch[0]; pl.in_h = p->y_pitch[1]; pl.in_w = p->y_pitch[2]; }
+    if (has_pitch(p->x_pitch)) { pl.out_n = p->x_pitch[0]; pl.out_h = p->x_pitch[1]; pl.out_w = p->x_pitch[2]; }
   }
-  return conv_launch(pl, grad_output, wd, p->cout, p->cin, p->kh, p->kw, p->kh - 1 - p->pad, nullptr, nullptr, add, relu_mask,
+  return conv_launch(pl, grad_output, wd, p->cout, p->cin, p->kh, p->kw, p->kh - 1 - p->pad, p->kw - 1 - pad_w, nullptr, nullptr, add, relu_mask,
                      grad_input, 0, p->out_dtype == MRB_F32, stream);
 }
 
@@ -930,17 +960,22 @@ static int conv_wgrad_impl(const mrb_conv_params* p, const void* input, const vo
   if (!input || !grad_output) return MRB_ERR_BAD_ARG;
   if (p->cin % 8 || p->cout % 8 || ((uintptr_t)input & 15) || ((uintptr_t)grad_output & 15) || ((uintptr_t)grad_weight & 15))
     return MRB_ERR_UNSUPPORTED;
-  const int Ho = (p->height + 2 * p->pad - p->kh) / p->stride + 1, Wo = (p->width + 2 * p->pad - p->kw) / p->stride + 1;
+  const int pad_w = pad_w_of(p);
+  const bool pitched = has_pitch(p->x_pitch) || has_pitch(p->y_pitch);
+  const int Ho = (p->height + 2 * p->pad - p->kh) / p->stride + 1, Wo = (p->width + 2 * pad_w - p->kw) / p->stride + 1;
   if (Ho <= 0 || Wo <= 0) return MRB_ERR_BAD_ARG;
   // geometry of the pixel (reduction) axis; 1x1 stride-1 layers flatten the batch onto one axis
   int batch = p->batch, gh = Ho, gw = Wo, xh = p->stride == 2 ? Ho : p->height, xw = p->stride == 2 ? Wo : p->width;
   long long g_w = p->cout, g_h = (long long)Wo * p->cout, g_n = (long long)Ho * Wo * p->cout;
   long long x_w = (long long)p->cin * p->stride, x_h = (long long)p->width * p->cin * p->stride,
             x_n = (long long)p->height * p->width * p->cin;
-  if (p->kh == 1 && p->stride == 1 && p->pad == 0) {
+  if (p->kh == 1 && p->kw == 1 && p->stride == 1 && p->pad == 0 && pad_w == 0 && !pitched) {
     gw = xw = p->batch * Ho * Wo; gh = xh = 1; batch = 1;
     g_h = g_n = (long long)gw * p->cout; x_h = x_n = (long long)xw * p->cin;
   }
+  if (has_pitch(p->x_pitch)) { x_n = p->x_pitch[0]; x_h = p->x_pitch[1]; x_w = p->x_pitch[2]; }
+  if (has_pitch(p->y_pitch)) { g_n = p->y_pitch[0]; g_h = p->y_pitch[1]; g_w = p->y_pitch[2]; }
+  if ((x_w | x_h | x_n | g_w | g_h | g_n) & 7) return MRB_ERR_UNSUPPORTED;   // TMA strides: multiples of 16 B
   WgradArgs a;
   int best_th = 1, best_tw = 64;
   long long best = -1;
@@ -954,7 +989,7 @@ static int conv_wgrad_impl(const mrb_conv_params* p, const void* input, const vo
   const long long kblocks = (long long)batch * a.tiles_h * a.tiles_w;
   if (kblocks >= (1ll << 31)) return MRB_ERR_UNSUPPORTED;
   a.kblocks_total = (int)kblocks;
-  a.kh = p->kh; a.kw = p->kw; a.pad = p->pad; a.taps = taps;
+  a.kh = p->kh; a.kw = p->kw; a.pad_h = p->pad; a.pad_w = pad_w; a.taps = taps;
   a.cin = p->cin; a.cout = p->cout;
   a.bn = ceil_div(p->cin, 64) * 64;
   if (a.bn > 256) a.bn = 256;

@@ -34,7 +34,8 @@ class DcnParams(ctypes.Structure):
 class ConvParams(ctypes.Structure):
     """struct mrb_conv_params (include/mrb_b200.h)"""
     _fields_ = [(n, _c_int) for n in (
-        "batch", "height", "width", "cin", "cout", "kh", "kw", "stride", "pad", "relu", "out_dtype", "out_h", "out_w")]
+        "batch", "height", "width", "cin", "cout", "kh", "kw", "stride", "pad", "relu", "out_dtype", "out_h", "out_w",
+        "pad_w", "flags")] + [("x_pitch", ctypes.c_longlong * 3), ("y_pitch", ctypes.c_longlong * 3)]
 
 
 def _load():

@@ -87,6 +87,58 @@ class _ConvFn(Function):
         return (gx, gw, gb, gres) + (None,) * 14
 
 
+class _Deconv2x2Fn(Function):
+    """ConvTranspose2d(k=2, s=2) (+bias, +ReLU) of the mask head (reference roi_heads/mask_head/
+    roi_mask_predictors.py:17-35) on the conv engine with NO pixel shuffle: out[r, 2h+i, 2w+j, :] = W[:, :, i, j]^T x[r, h, w, :]
+    is, for a fixed row parity i, a 1x1 convolution with 2*Cout outputs (j, co) whose result rows are the odd/even rows
+    of the NHWC output -- a strided window (row pitch 4*W*Cout, pixel pitch 2*Cout) that the epilogue writes in place.
+    Backward reads the same windows of grad_out through TMA: dgrad_0 + dgrad_1 (accumulated in the epilogue, ReLU mask
+    of the producer on the second launch), two weight gradients, one bias reduction."""
+
+    @staticmethod
+    def _windows(t, r, c, h, w):
+        base = t.storage_offset()
+        return [torch.as_strided(t, (1, 2 * c, r * h, w), (r * h * w * 4 * c, 1, 4 * w * c, 2 * c), base + i * 2 * w * c)
+                for i in (0, 1)]
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, relu, premask_x, gy_premasked):
+        from mrb_b200 import ops
+        r, cin, h, w = x.shape
+        cout = weight.shape[1]
+        x = x.contiguous(memory_format=torch.channels_last)
+        xv = torch.as_strided(x, (1, cin, r * h, w), (r * h * w * cin, 1, w * cin, cin), x.storage_offset())
+        w2 = weight.detach().permute(2, 3, 1, 0).reshape(2, 2 * cout, cin, 1, 1).to(torch.bfloat16)   # [i][(j, co)][ci]
+        b2 = bias.detach().float().repeat(2) if bias is not None else None
+        out = torch.empty((r, cout, 2 * h, 2 * w), dtype=torch.bfloat16, device=x.device, memory_format=torch.channels_last)
+        for i, ov in enumerate(_Deconv2x2Fn._windows(out, r, cout, h, w)):
+            ops.conv2d_fwd(xv, w2[i], None, b2, None, 1, 0, relu, out=ov)
+        ctx.cfg = (relu and not gy_premasked, premask_x, bias is not None, (r, cin, h, w), cout)
+        ctx.save_for_backward(xv, w2, out if relu else None)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        from mrb_b200 import ops
+        xv, w2, y = ctx.saved_tensors
+        relu, premask_x, has_bias, (r, cin, h, w), cout = ctx.cfg
+        if relu:
+            g = torch.where(y > 0, g, torch.zeros((), dtype=g.dtype, device=g.device))
+        g = g.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        gv = _Deconv2x2Fn._windows(g, r, cout, h, w)
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = ops.conv2d_dgrad(gv[0], w2[0], xv.shape, None, None, None, 1, 0)
+            gx = ops.conv2d_dgrad(gv[1], w2[1], xv.shape, None, None, xv if premask_x else None, 1, 0, accumulate_into=gx)
+            gx = torch.as_strided(gx, (r, cin, h, w), (h * w * cin, 1, w * cin, cin), gx.storage_offset())
+        if ctx.needs_input_grad[1]:
+            gw2 = torch.stack([ops.conv2d_wgrad(xv, gv[i], (2 * cout, cin, 1, 1), 1, 0) for i in (0, 1)])
+            gw = gw2.view(2, 2, cout, cin).permute(3, 2, 0, 1)           # [i, j, co, ci] -> [ci, co, i, j]
+        if has_bias and ctx.needs_input_grad[2]:
+            gb = ops.bias_grad(g)
+        return gx, gw, gb, None, None, None
+
+
 class _BottleneckFn(Function):
     """One ResNet bottleneck (reference modeling/backbone/resnet.py:324-344) as a single autograd node:
     4 fused forward convs and a hand-scheduled backward in which every ReLU mask, the frozen-BN scale and
@@ -281,8 +333,15 @@ class B200Backend(Backend):
         n, c, h, w = images.shape
         if (h | w) & 1:
             images = F.pad(images, (0, w & 1, 0, h & 1))
-        x = F.pixel_unshuffle(images, 2)
-        x = F.pad(x, (0, 0, 0, 0, 0, 16 - x.shape[1])).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        x = F.pixel_unshuffle(images, 2)                                                # [n, 4c, hs, ws]
+        hs, ws = x.shape[2:]
+        # 12 -> 16 channels; 2 zero columns on the left, 1 on the right: the 4 horizontal taps of output column o are
+        # then the memory columns o..o+3 = 64 CONTIGUOUS bf16 of the NHWC row, i.e. one 64-channel "pixel" of an
+        # overlapping-window view (pixel pitch 16).  The conv becomes 4x1 over 64 channels: K = 4 full k-blocks
+        # instead of 16 quarter-full ones.
+        x = F.pad(x, (2, 1, 0, 0, 0, 16 - x.shape[1])).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        wp = ws + 3
+        xv = torch.as_strided(x, (n, 64, hs, ws), (hs * wp * 16, 1, wp * 16, 16))
         key = ("stem", id(weight))
         ent = self._w16.get(key)
         if ent is None or ent[0] is not weight or ent[1] != weight._version or ent[2].device != weight.device:
@@ -290,10 +349,11 @@ class B200Backend(Backend):
             w8 = F.pad(weight.detach(), (1, 0, 1, 0))                                   # [co, 3, 8, 8]
             w4 = w8.view(co, c, 4, 2, 4, 2).permute(0, 1, 3, 5, 2, 4).reshape(co, c * 4, 4, 4)
             w4 = F.pad(w4, (0, 0, 0, 0, 0, 16 - c * 4)).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+            w4 = torch.as_strided(w4, (co, 64, 4, 1), (256, 1, 64, 64))                 # memory [co][kh][kw*16 + ch]
             self._w16[key] = (weight, weight._version, w4)
         else:
             w4 = ent[2]
-        return ops.conv2d_fwd(x, w4, scale, shift, None, 1, 2, True, out_hw=((h + 1) // 2, (w + 1) // 2))
+        return ops.conv2d_fwd(xv, w4, scale, shift, None, 1, (2, 0), True, out_hw=(hs, ws))
 
     def max_pool(self, x, k, s, p):
         return F.max_pool2d(x, k, s, p)
@@ -360,15 +420,10 @@ class B200Backend(Backend):
         return y.reshape(r, co)
 
     def deconv2x2(self, x, weight, bias, relu=False, premask_x=False, gy_premasked=False):
-        """ConvTranspose2d(k=2, s=2): four independent 1x1 convs (one per output sub-pixel) run as ONE
-        1x1 conv with 4*Cout outputs on the conv engine, then a pixel shuffle.  weight [Cin, Cout, 2, 2]."""
-        cin, cout = weight.shape[:2]
-        w4 = weight.permute(2, 3, 1, 0).reshape(4 * cout, cin, 1, 1)       # ((i, j, co), ci)
-        b4 = bias.repeat(4) if bias is not None else None
-        y = self.conv(x, w4, bias=b4, relu=relu, premask_x=premask_x, gy_premasked=gy_premasked)  # [N, 4*Cout, H, W]
-        n, _, h, w = y.shape
-        y = y.view(n, 2, 2, cout, h, w).permute(0, 3, 4, 1, 5, 2).reshape(n, cout, 2 * h, 2 * w)
-        return y.contiguous(memory_format=torch.channels_last)
+        """ConvTranspose2d(k=2, s=2), weight [Cin, Cout, 2, 2]: see _Deconv2x2Fn (two strided 1x1 convs, no shuffle)."""
+        if weight.shape[1] % 8 or x.shape[1] % 8:
+            raise RuntimeError("deconv2x2: channel counts must be multiples of 8")
+        return _Deconv2x2Fn.apply(x.to(torch.bfloat16), weight, bias, relu, premask_x, gy_premasked)
 
     def roi_align_fpn(self, feats, rois, scales, pooled, sampling_ratio, nhwc):
         from mrb_b200 import ops

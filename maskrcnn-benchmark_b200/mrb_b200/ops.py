@@ -26,6 +26,14 @@ def _count(n, conv_key=None):
         STATS["conv_calls"].append(conv_key)
 
 
+def _kk(p):
+    return p.kh if p.kh == p.kw else (p.kh, p.kw)
+
+
+def _pp(p):
+    return p.pad if not p.flags else (p.pad, p.pad_w)
+
+
 def _nhwc(t, name):
     if not t.is_cuda:
         raise RuntimeError("%s: expected a CUDA tensor (no CPU path)" % name)
@@ -36,33 +44,70 @@ def _nhwc(t, name):
     return t
 
 
-def _params(x_shape, w_shape, stride, pad, relu, out_dtype, out_hw=None):
+def _view(t, name):
+    """NHWC operand: returns (tensor, pitch).  Dense channels_last tensors have pitch None; a strided window of a
+    larger NHWC tensor (channel stride 1, other strides multiples of 8 elements) is passed in place with its
+    {image, row, pixel} element strides; anything else is copied to dense channels_last."""
+    if not t.is_cuda:
+        raise RuntimeError("%s: expected a CUDA tensor (no CPU path)" % name)
+    if t.dim() != 4:
+        raise RuntimeError("%s: expected a 4-D tensor" % name)
+    if t.is_contiguous(memory_format=torch.channels_last):
+        return t, None
+    n, _, h, _ = t.shape
+    sn, sc, sh, sw = t.stride()
+    if sc == 1 and sh % 8 == 0 and sw % 8 == 0 and sh > 0 and sw > 0 and (n == 1 or (sn % 8 == 0 and sn > 0)) \
+            and t.data_ptr() % 16 == 0:
+        return t, (sn if n > 1 else sh * h, sh, sw)
+    return t.contiguous(memory_format=torch.channels_last), None
+
+
+def _params(x_shape, w_shape, stride, pad, relu, out_dtype, out_hw=None, x_pitch=None, y_pitch=None):
     n, c, h, w = x_shape
     co, ci, kh, kw = w_shape
     if ci != c:
         raise RuntimeError("conv2d: weight expects %d input channels, got %d" % (ci, c))
+    ph, pw = (pad, pad) if isinstance(pad, int) else pad
     p = _c.ConvParams()
     p.batch, p.height, p.width, p.cin = n, h, w, c
     p.cout, p.kh, p.kw = co, kh, kw
-    p.stride, p.pad, p.relu, p.out_dtype = stride, pad, int(bool(relu)), _DT[out_dtype]
-    ho = (h + 2 * pad - kh) // stride + 1
-    wo = (w + 2 * pad - kw) // stride + 1
+    p.stride, p.pad, p.relu, p.out_dtype = stride, ph, int(bool(relu)), _DT[out_dtype]
+    if pw != ph:
+        p.pad_w, p.flags = pw, 1          # MRB_CONV_PAD_W
+    ho = (h + 2 * ph - kh) // stride + 1
+    wo = (w + 2 * pw - kw) // stride + 1
     if out_hw is not None:
         p.out_h, p.out_w = ho, wo = int(out_hw[0]), int(out_hw[1])
+    if x_pitch is not None:
+        p.x_pitch[0], p.x_pitch[1], p.x_pitch[2] = x_pitch
+    if y_pitch is not None:
+        p.y_pitch[0], p.y_pitch[1], p.y_pitch[2] = y_pitch
     return p, ho, wo
 
 
 def conv2d_fwd(x, weight, scale=None, bias=None, residual=None, stride=1, pad=0, relu=False,
-               out_dtype=torch.bfloat16, out_hw=None, residual_up2=False):
+               out_dtype=torch.bfloat16, out_hw=None, residual_up2=False, out=None):
     """y = act(conv(x, weight) * scale[c] + bias[c] + residual).  x, weight bf16 channels_last.
-    residual_up2: `residual` has half the output resolution and is read through a nearest 2x upsample."""
-    x = _nhwc(x, "conv2d_fwd(x)")
+    residual_up2: `residual` has half the output resolution and is read through a nearest 2x upsample.
+    pad: int or (pad_h, pad_w).  x may be a strided NHWC window (see _view); `out` (optional) is a preallocated
+    result, possibly a strided window of a larger tensor, written in place."""
+    x, x_pitch = _view(x, "conv2d_fwd(x)")
     weight = _nhwc(weight, "conv2d_fwd(weight)")
     if x.dtype != torch.bfloat16 or weight.dtype != torch.bfloat16:
         raise RuntimeError("conv2d_fwd: bf16 operands required")
-    p, ho, wo = _params(x.shape, weight.shape, stride, pad, relu, out_dtype, out_hw)
-    out = torch.empty((p.batch, p.cout, ho, wo), dtype=out_dtype, device=x.device,
-                      memory_format=torch.channels_last)
+    y_pitch = None
+    if out is not None:
+        out_v, y_pitch = _view(out, "conv2d_fwd(out)")
+        if out_v is not out:
+            raise RuntimeError("conv2d_fwd: `out` must be NHWC (channel stride 1, other strides multiples of 8)")
+        out_dtype = out.dtype
+        if residual is not None and y_pitch is not None:
+            raise RuntimeError("conv2d_fwd: residual with a strided `out` is not supported")
+    p, ho, wo = _params(x.shape, weight.shape, stride, pad, relu, out_dtype, out_hw, x_pitch, y_pitch)
+    if out is None:
+        out = torch.empty((p.batch, p.cout, ho, wo), dtype=out_dtype, device=x.device, memory_format=torch.channels_last)
+    elif tuple(out.shape) != (p.batch, p.cout, ho, wo):
+        raise RuntimeError("conv2d_fwd: out shaped %s, expected %s" % (tuple(out.shape), (p.batch, p.cout, ho, wo)))
     if residual is not None:
         residual = _nhwc(residual, "conv2d_fwd(residual)")
         want = (p.batch, p.cout, (ho + 1) // 2, (wo + 1) // 2) if residual_up2 else tuple(out.shape)
@@ -75,7 +120,7 @@ def conv2d_fwd(x, weight, scale=None, bias=None, residual=None, stride=1, pad=0,
         fn = lib.mrb_conv2d_fwd_up2 if residual_up2 else lib.mrb_conv2d_fwd
         _c.check(fn(ctypes.byref(p), _c._ptr(x), _c._ptr(weight), _c._ptr(scale), _c._ptr(bias),
                     _c._ptr(residual), _c._ptr(out), _c._stream()), "mrb_conv2d_fwd")
-    _count(1, ("fwd", p.batch, p.cin, p.height, p.width, p.cout, p.kh, p.stride, p.pad))
+    _count(1, ("fwd", p.batch, p.cin, p.height, p.width, p.cout, _kk(p), p.stride, _pp(p)))
     return out
 
 
@@ -106,11 +151,11 @@ def conv2d_dgrad(grad_out, weight, x_shape, scale=None, add=None, relu_mask=None
     """grad_x = conv_transpose(grad_out, weight * scale[cout]) (+ add) masked by (relu_mask > 0).
     `accumulate_into` (bf16, shaped like x) makes the call in-place: result = accumulate_into + dgrad,
     written back into it (the only form of `add` the stride-2 path supports)."""
-    grad_out = _nhwc(grad_out, "conv2d_dgrad(grad_out)")
+    grad_out, y_pitch = _view(grad_out, "conv2d_dgrad(grad_out)")
     weight = _nhwc(weight, "conv2d_dgrad(weight)")
     if grad_out.dtype != torch.bfloat16 or weight.dtype != torch.bfloat16:
         raise RuntimeError("conv2d_dgrad: bf16 operands required")
-    p, ho, wo = _params(tuple(x_shape), weight.shape, stride, pad, False, out_dtype)
+    p, ho, wo = _params(tuple(x_shape), weight.shape, stride, pad, False, out_dtype, None, None, y_pitch)
     if tuple(grad_out.shape) != (p.batch, p.cout, ho, wo):
         raise RuntimeError("conv2d_dgrad: grad_out shape %s != %s" % (tuple(grad_out.shape), (p.batch, p.cout, ho, wo)))
     if accumulate_into is not None:
@@ -134,14 +179,14 @@ def conv2d_dgrad(grad_out, weight, x_shape, scale=None, add=None, relu_mask=None
             # `prepared` already holds the flipped/transposed/scaled weights (prepare_dgrad_weights)
             _c.check(lib.mrb_conv2d_dgrad_prepared(ctypes.byref(p), _c._ptr(grad_out), _c._ptr(prepared), _c._ptr(add),
                                                    _c._ptr(relu_mask), _c._ptr(gx), _c._stream()), "mrb_conv2d_dgrad_prepared")
-            _count(1, ("dgrad", p.batch, p.cin, p.height, p.width, p.cout, p.kh, p.stride, p.pad))
+            _count(1, ("dgrad", p.batch, p.cin, p.height, p.width, p.cout, _kk(p), p.stride, _pp(p)))
             return gx
         nbytes = lib.mrb_conv2d_dgrad_workspace_bytes(ctypes.byref(p))
         ws = torch.empty(nbytes, dtype=torch.uint8, device=grad_out.device)
         _c.check(lib.mrb_conv2d_dgrad(ctypes.byref(p), _c._ptr(grad_out), _c._ptr(weight), _c._ptr(scale), _c._ptr(add),
                                       _c._ptr(relu_mask), _c._ptr(gx), _c._ptr(ws), ctypes.c_size_t(nbytes),
                                       _c._stream()), "mrb_conv2d_dgrad")
-    _count(2, ("dgrad", p.batch, p.cin, p.height, p.width, p.cout, p.kh, p.stride, p.pad))
+    _count(2, ("dgrad", p.batch, p.cin, p.height, p.width, p.cout, _kk(p), p.stride, _pp(p)))
     return gx
 
 
@@ -150,11 +195,11 @@ def conv2d_wgrad(x, grad_out, w_shape, stride=1, pad=0, scale=None, accumulate_i
     optionally multiplied by a per-Cout `scale` (the frozen-BN scale of the forward epilogue).
     `accumulate_into` (fp32, that shape and memory order): the result is ADDED into it (red.add) instead of being
     returned in a fresh zero-filled tensor."""
-    x = _nhwc(x, "conv2d_wgrad(x)")
-    grad_out = _nhwc(grad_out, "conv2d_wgrad(grad_out)")
+    x, x_pitch = _view(x, "conv2d_wgrad(x)")
+    grad_out, y_pitch = _view(grad_out, "conv2d_wgrad(grad_out)")
     if x.dtype != torch.bfloat16 or grad_out.dtype != torch.bfloat16:
         raise RuntimeError("conv2d_wgrad: bf16 operands required")
-    p, ho, wo = _params(x.shape, tuple(w_shape), stride, pad, False, torch.float32)
+    p, ho, wo = _params(x.shape, tuple(w_shape), stride, pad, False, torch.float32, None, x_pitch, y_pitch)
     if tuple(grad_out.shape) != (p.batch, p.cout, ho, wo):
         raise RuntimeError("conv2d_wgrad: grad_out shape mismatch")
     if accumulate_into is not None:
@@ -169,7 +214,7 @@ def conv2d_wgrad(x, grad_out, w_shape, stride=1, pad=0, scale=None, accumulate_i
     with torch.cuda.device(x.device):
         _c.check(fn(ctypes.byref(p), _c._ptr(x), _c._ptr(grad_out), _c._ptr(scale), _c._ptr(gw), _c._stream()),
                  "mrb_conv2d_wgrad")
-    _count(1, ("wgrad", p.batch, p.cin, p.height, p.width, p.cout, p.kh, p.stride, p.pad))
+    _count(1, ("wgrad", p.batch, p.cin, p.height, p.width, p.cout, _kk(p), p.stride, _pp(p)))
     return gw
 
 

@@ -179,3 +179,49 @@ def test_conv_rejects_unsupported(ops):
         ops.conv2d_fwd(x.to(DEV), wt.to(DEV), stride=2, pad=1)  # 3x3 stride 2: not in the R-50 hot path
     with pytest.raises(RuntimeError):
         ops.conv2d_fwd(x.float().to(DEV), wt.to(DEV))
+
+
+def test_conv_rectangular_kernel_and_padding(ops):
+    """kh != kw with separate paddings (forward, data gradient, weight gradient)."""
+    g = torch.Generator().manual_seed(21)
+    x = torch.randn(2, 64, 19, 27, generator=g).to(torch.bfloat16)
+    wt = (torch.randn(128, 64, 3, 1, generator=g) / 14).to(torch.bfloat16)
+    go = torch.randn(2, 128, 19, 27, generator=g).to(torch.bfloat16)
+    xf, wf = x.float().requires_grad_(True), wt.float().requires_grad_(True)
+    y = F.conv2d(xf, wf, padding=(1, 0))
+    y.backward(go.float())
+    xd, wd, gd = x.to(DEV), wt.to(DEV), go.to(DEV)
+    _assert_close(ops.conv2d_fwd(xd, wd, pad=(1, 0), out_dtype=torch.float32), y.detach())
+    _assert_close(ops.conv2d_dgrad(gd, wd, x.shape, pad=(1, 0), out_dtype=torch.float32), xf.grad, tol=2e-4)
+    _assert_close(ops.conv2d_wgrad(xd, gd, wt.shape, 1, (1, 0)), wf.grad, tol=2e-4)
+
+
+def test_conv_strided_windows(ops):
+    """Operands / results that are strided NHWC windows of larger tensors are used in place (TMA strides for reads,
+    epilogue pitches for writes): output rows interleaved into a taller tensor; overlapping 4-pixel input windows."""
+    g = torch.Generator().manual_seed(22)
+    # (a) write every other row of a [1, 2H, W, 2C]-like buffer, read it back as grad_out for dgrad / wgrad
+    n, c, h, w, co = 1, 64, 24, 14, 128
+    x = torch.randn(n, c, h, w, generator=g).to(torch.bfloat16)
+    wt = (torch.randn(co, c, 1, 1, generator=g) / 8).to(torch.bfloat16)
+    want = F.conv2d(x.float(), wt.float())
+    big = torch.full((n, co, 2 * h, w), 7.0, dtype=torch.bfloat16, device=DEV).contiguous(memory_format=torch.channels_last)
+    win = torch.as_strided(big, (n, co, h, w), (2 * h * w * co, 1, 2 * w * co, co), w * co)     # the odd rows
+    ops.conv2d_fwd(x.to(DEV), wt.to(DEV), out=win)
+    _assert_close(big[:, :, 1::2].float(), want.to(torch.bfloat16).float(), tol=1e-2)
+    assert bool((big[:, :, 0::2] == 7.0).all())                                                  # untouched rows
+    go = torch.randn(n, co, 2 * h, w, generator=g).to(torch.bfloat16)
+    god = go.to(DEV).contiguous(memory_format=torch.channels_last)
+    gwin = torch.as_strided(god, (n, co, h, w), (2 * h * w * co, 1, 2 * w * co, co), w * co)
+    xf, wf = x.float().requires_grad_(True), wt.float().requires_grad_(True)
+    F.conv2d(xf, wf).backward(go[:, :, 1::2].float())
+    _assert_close(ops.conv2d_dgrad(gwin, wt.to(DEV), x.shape, out_dtype=torch.float32), xf.grad, tol=2e-4)
+    _assert_close(ops.conv2d_wgrad(x.to(DEV), gwin, wt.shape), wf.grad, tol=2e-4)
+    # (b) overlapping windows: a 1x4 conv over 16 channels == a 1x1 conv over the 64-element window view
+    x16 = torch.randn(2, 16, 10, 35, generator=g).to(torch.bfloat16)
+    w16 = (torch.randn(32, 16, 1, 4, generator=g) / 8).to(torch.bfloat16)
+    want = F.conv2d(x16.float(), w16.float())                                                    # [2, 32, 10, 32]
+    xd = x16.to(DEV).contiguous(memory_format=torch.channels_last)
+    xv = torch.as_strided(xd, (2, 64, 10, 32), (10 * 35 * 16, 1, 35 * 16, 16))
+    wv = w16.to(DEV).permute(0, 2, 3, 1).reshape(32, 64, 1, 1).contiguous(memory_format=torch.channels_last)
+    _assert_close(ops.conv2d_fwd(xv, wv, out_dtype=torch.float32), want)

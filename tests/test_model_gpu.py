@@ -213,3 +213,28 @@ def test_param_arena_step_equals_flat_sgd(built_lib):
         d = (flat[n] - arena[n]).abs().max().item()
         ref = flat[n].abs().max().item()
         assert d <= 5e-2 * ref + 1e-8, (n, d, ref)
+
+
+def test_deconv2x2_matches_conv_transpose(built_lib):
+    """Mask-head ConvTranspose2d(2, 2) + ReLU on the conv engine (strided in-place sub-pixel planes) vs autograd."""
+    import torch.nn.functional as F
+    from mrb_b200.model.backend import B200Backend
+    be = B200Backend()
+    g = torch.Generator().manual_seed(31)
+    x = torch.randn(5, 64, 14, 14, generator=g).relu()
+    wt = torch.randn(64, 32, 2, 2, generator=g) / 8
+    b = torch.randn(32, generator=g) * 0.1
+    go = torch.randn(5, 32, 28, 28, generator=g)
+    x16, w16 = x.to(torch.bfloat16).float(), wt.to(torch.bfloat16).float()
+    xr, wr, br = x16.clone().requires_grad_(True), w16.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    y = F.relu(F.conv_transpose2d(xr, wr, br, stride=2))
+    y.backward(go.to(torch.bfloat16).float())
+    xd = x.to(DEV).to(torch.bfloat16).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    wd, bd = w16.to(DEV).requires_grad_(True), b.to(DEV).requires_grad_(True)
+    yd = be.deconv2x2(xd, wd, bd, relu=True, premask_x=True)
+    assert yd.shape == y.shape and yd.is_contiguous(memory_format=torch.channels_last)
+    assert _rel(yd.detach(), y.detach()) < 1e-2
+    yd.backward(go.to(DEV).to(torch.bfloat16))
+    assert _rel(xd.grad, xr.grad * (x16 > 0)) < 2e-2          # premask_x: the producer's ReLU mask rides along
+    assert _rel(wd.grad, wr.grad) < 2e-2
+    assert _rel(bd.grad, br.grad) < 2e-2

@@ -1,0 +1,112 @@
+"""Kernel timeline of ONE eager train step (the bench.py workload) from the CUPTI activity trace (torch.profiler):
+per-kernel device time in normal back-to-back execution (warm caches, not serialised), aggregated by kernel, plus
+the idle time between kernels.  Cheaper than an ncu launch list (seconds instead of minutes); the committed ncu list
+stays the reference evidence.  Usage: python tools/step_timeline.py [--top 45] [--json out.json]"""
+import argparse
+import collections
+import json
+import os
+import re
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "maskrcnn-benchmark_b200")]
+import torch  # noqa: E402
+import bench  # noqa: E402
+
+
+def short(name):
+    name = re.sub(r"^void ", "", name)
+    m = re.search(r"(mrb::\w+)", name)
+    if m:
+        return m.group(1)
+    m = re.search(r"(\w+Functor\w*|\w+_kernel_cuda\w*|\w+_kernel_impl\w*|launch_clamp_scalar|compare_scalar_kernel|"
+                  r"multi_tensor_apply_kernel|\w+topk::\w+|radixSort\w+|DeviceRadixSort\w+|DeviceScan\w+|DeviceSelect\w+|"
+                  r"DeviceReduce\w+|reduce_kernel|index_elementwise_kernel|_scatter_gather_elementwise_kernel|"
+                  r"vectorized_gather_kernel|nccl\w+|max_pool\w+|upsample\w+|cat\w*Kernel\w*|CatArrayBatchedCopy\w*|"
+                  r"distribution_elementwise\w+|arange\w+|nll_loss\w+|smooth_l1\w+|softmax\w+|Memset|Memcpy \w+)", name)
+    base = name.split("<")[0].split("(")[0][-40:]
+    return (base + "|" + m.group(1)) if m else name[:70]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--top", type=int, default=45)
+    ap.add_argument("--json", default=None)
+    ap.add_argument("--by-op", action="store_true", help="also attribute device time to the launching aten op, its "
+                    "input shapes and the innermost mrb_b200/ source line (PyTorch glue only)")
+    args = ap.parse_args()
+    from mrb_b200.model import RCNNConfig, build_model
+    from mrb_b200.model.backend import B200Backend
+    from mrb_b200.optim import ParamArena
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(0)
+    model = build_model(RCNNConfig(mask_rois_per_image=128), backend=B200Backend(), device=dev).train()
+    opt = ParamArena(model.named_parameters(), model.be, lr=1e-4)
+    sizes = [(bench.IMG_H, bench.IMG_W)] * bench.IMGS_PER_GPU
+    batches = [tuple(t.to(dev) for t in bench.synth_batch(bench.IMGS_PER_GPU, i)) for i in range(2)]
+
+    def step(b):
+        images, boxes, labels = b
+        loss = sum(model(images, sizes, bench.targets_of(boxes, labels)).values())
+        loss.backward()
+        opt.sync()
+        opt.step()
+        return loss
+
+    for i in range(3):
+        step(batches[i % 2])
+    torch.cuda.synchronize()
+    from torch.profiler import profile, ProfilerActivity
+    with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU], record_shapes=args.by_op,
+                 with_stack=args.by_op) as prof:
+        step(batches[1])
+        torch.cuda.synchronize()
+    evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+    ks = sorted(((e.time_range.start, e.time_range.end, e.name) for e in evs), key=lambda t: t[0])
+    agg = collections.defaultdict(lambda: [0, 0.0])
+    busy, last_end = 0.0, None
+    for s, e, n in ks:
+        k = short(n)
+        agg[k][0] += 1
+        agg[k][1] += e - s
+        busy += e - s
+    span = ks[-1][1] - ks[0][0]
+    rows = sorted(agg.items(), key=lambda kv: -kv[1][1])
+    mine = sum(v[1] for k, v in rows if k.startswith("mrb::"))
+    print("device activities: %d   span %.2f ms   sum of durations %.2f ms   libmrb share of busy time %.1f%%"
+          % (len(ks), span / 1e3, busy / 1e3, 100 * mine / busy))
+    print("| kernel | launches | total us | share of busy |")
+    print("|---|---|---|---|")
+    for k, (n, t) in rows[:args.top]:
+        print("| %s | %d | %.1f | %.1f%% |" % (k, n, t, 100 * t / busy))
+    rest = rows[args.top:]
+    if rest:
+        print("| (%d more) | %d | %.1f | %.1f%% |" % (len(rest), sum(v[0] for _, v in rest), sum(v[1] for _, v in rest),
+                                                     100 * sum(v[1] for _, v in rest) / busy))
+    if args.by_op:
+        ops_ = collections.defaultdict(lambda: [0, 0.0])
+        for e in prof.events():
+            if e.device_type != torch.autograd.DeviceType.CPU or not e.kernels:
+                continue
+            if any(c.kernels for c in (e.cpu_children or [])):
+                continue                                   # attribute to the innermost op that owns the launch
+            t = sum(k.duration for k in e.kernels)
+            if any("mrb::" in k.name for k in e.kernels):
+                continue
+            where = next((f for f in (e.stack or []) if "mrb_b200/" in f or "bench.py" in f or "step_timeline" in f), "?")
+            where = where.split("mrb_b200/")[-1][:60]
+            shp = str([list(x) for x in (e.input_shapes or []) if x])[:70]
+            ops_[(e.name, shp, where)][0] += len(e.kernels)
+            ops_[(e.name, shp, where)][1] += t
+        print("\n| aten op | input shapes | source | kernels | total us |")
+        print("|---|---|---|---|---|")
+        for (n, shp, where), (c, t) in sorted(ops_.items(), key=lambda kv: -kv[1][1])[:args.top]:
+            print("| %s | %s | %s | %d | %.1f |" % (n, shp, where, c, t))
+    if args.json:
+        json.dump({"span_us": span, "busy_us": busy, "kernels": [{"name": k, "launches": n, "us": t} for k, (n, t) in rows]},
+                  open(args.json, "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
