@@ -256,6 +256,17 @@ int mrb_conv2d_wgrad_accumulate(const mrb_conv_params* p, const void* input_bf16
 int mrb_bias_grad_accumulate(const void* grad_bf16_nhwc, float* grad_bias, long long pixels, int channels,
                              mrb_stream_t stream);
 
+/* ---- pooling passes of the ResNet+FPN path (NHWC bf16, channels % 8 == 0) ---------------------------------------
+ * mrb_max_pool_nhwc: F.max_pool2d(kernel, stride, pad) forward without an index tensor -- the stem pool of
+ * modeling/backbone/resnet.py:307 (3, 2, 1; frozen, never differentiated) and FPN's P6 subsample (1, 2, 0;
+ * modeling/backbone/fpn.py:77-79).  output is [N, (H+2p-k)/s+1, (W+2p-k)/s+1, C].
+ * mrb_sum_pool2x2_nhwc: out[n, i, j, :] = sum of the (up to) 2x2 block of grad at (2i.., 2j..): the backward of the
+ * nearest-2x upsample in FPN's top-down path (fpn.py:59-64).  out is [N, ceil(H/2), ceil(W/2), C]. */
+int mrb_max_pool_nhwc(const void* input_bf16, void* output_bf16, int batch, int height, int width, int channels,
+                      int kernel, int stride, int pad, mrb_stream_t stream);
+int mrb_sum_pool2x2_nhwc(const void* grad_bf16, void* out_bf16, int batch, int height, int width, int channels,
+                         mrb_stream_t stream);
+
 /* ---- parameter update of the train step (reference solver/build.py:7-20 -> torch.optim.SGD) ----------------
  * One streaming pass over n contiguous fp32 parameters:
  *     d = grad * grad_scale + weight_decay * param;  m = momentum * m + d;  param -= lr * m

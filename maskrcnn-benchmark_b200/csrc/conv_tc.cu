@@ -634,6 +634,52 @@ struct PrepBatch {
   __nv_bfloat16* wd[kPrepBatch];
   int cout[kPrepBatch], taps[kPrepBatch], cin[kPrepBatch];
 };
+// Tiled version for the common case (Cin % 8 == 0 and Cout % 8 == 0): per tap a [Cout x Cin] -> [Cin x Cout]
+// transpose through a 64 x 64 shared-memory tile, 16-byte global accesses on both sides.
+struct PrepTiles {
+  PrepBatch b;
+  int tile_start[kPrepBatch + 1];   // exclusive prefix sum of taps * ceil(cout/64) * ceil(cin/64) per layer
+};
+__global__ void __launch_bounds__(256)
+conv_prepare_dgrad_weights_tiled_kernel(PrepTiles t) {
+  __shared__ __nv_bfloat16 tile[64][64 + 8];
+  int l = 0;
+  const int tidx = blockIdx.x;
+  while (tidx >= t.tile_start[l + 1]) ++l;
+  const int cout = t.b.cout[l], taps = t.b.taps[l], cin = t.b.cin[l];
+  int rem = tidx - t.tile_start[l];
+  const int ci_tiles = (cin + 63) >> 6, co_tiles = (cout + 63) >> 6;
+  const int ci_t = rem % ci_tiles; rem /= ci_tiles;
+  const int co_t = rem % co_tiles;
+  const int tap = rem / co_tiles;
+  const __nv_bfloat16* __restrict__ w = t.b.w[l];
+  const float* __restrict__ scale = t.b.scale[l];
+  __nv_bfloat16* __restrict__ wd = t.b.wd[l];
+  const int chunk = threadIdx.x & 7, row = threadIdx.x >> 3;      // 8 x 16-byte chunks per 64-element row, 32 rows per pass
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+    const int co = co_t * 64 + pass * 32 + row, ci = ci_t * 64 + chunk * 8;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (co < cout && ci < cin) v = __ldg(reinterpret_cast<const uint4*>(w + ((size_t)co * taps + (taps - 1 - tap)) * cin + ci));
+    *reinterpret_cast<uint4*>(&tile[pass * 32 + row][chunk * 8]) = v;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+    const int ci_l = pass * 32 + row, ci = ci_t * 64 + ci_l, co = co_t * 64 + chunk * 8;
+    if (ci < cin && co < cout) {
+      __align__(16) __nv_bfloat16 o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float f = __bfloat162float(tile[chunk * 8 + j][ci_l]);
+        if (scale) f *= __ldg(scale + co + j);
+        o[j] = __float2bfloat16_rn(f);
+      }
+      *reinterpret_cast<uint4*>(wd + ((size_t)ci * taps + tap) * cout + co) = *reinterpret_cast<const uint4*>(o);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256)
 conv_prepare_dgrad_weights_batched_kernel(PrepBatch b) {
   const int l = blockIdx.y;
@@ -852,9 +898,12 @@ MRB_API int mrb_conv2d_prepare_dgrad_weights(int num_layers, const void* const* 
     return MRB_ERR_BAD_ARG;
   cudaStream_t stream = (cudaStream_t)stream_;
   for (int l0 = 0; l0 < num_layers; l0 += kPrepBatch) {
-    PrepBatch b;
+    PrepTiles pt;
+    PrepBatch& b = pt.b;
     const int n = min(kPrepBatch, num_layers - l0);
     int max_total = 0;
+    bool tiled = true;
+    long long tiles = 0;
     for (int i = 0; i < kPrepBatch; ++i) {
       const int l = l0 + (i < n ? i : 0);
       if (!weights_host[l] || !prepared_host[l] || couts_host[l] <= 0 || taps_host[l] <= 0 || cins_host[l] <= 0) return MRB_ERR_BAD_ARG;
@@ -863,6 +912,17 @@ MRB_API int mrb_conv2d_prepare_dgrad_weights(int num_layers, const void* const* 
       b.wd[i] = (__nv_bfloat16*)prepared_host[l];
       b.cout[i] = couts_host[l]; b.taps[i] = taps_host[l]; b.cin[i] = cins_host[l];
       max_total = max(max_total, couts_host[l] * taps_host[l] * cins_host[l]);
+      if ((couts_host[l] | cins_host[l]) & 7 || ((uintptr_t)weights_host[l] | (uintptr_t)prepared_host[l]) & 15) tiled = false;
+      if (i < n) {
+        pt.tile_start[i] = (int)tiles;
+        tiles += (long long)taps_host[l] * ceil_div(couts_host[l], 64) * ceil_div(cins_host[l], 64);
+      }
+    }
+    for (int i = n; i <= kPrepBatch; ++i) pt.tile_start[i] = (int)tiles;
+    if (tiled && tiles > 0 && tiles < (1ll << 30)) {
+      conv_prepare_dgrad_weights_tiled_kernel<<<(unsigned)tiles, 256, 0, stream>>>(pt);
+      MRB_LAUNCH_CHECK();
+      continue;
     }
     dim3 grid(min(ceil_div(max_total, 256 * 4), 64), n);
     conv_prepare_dgrad_weights_batched_kernel<<<grid, 256, 0, stream>>>(b);
@@ -1067,6 +1127,39 @@ bias_grad_kernel(const __nv_bfloat16* __restrict__ g, float* __restrict__ db, lo
   }
 }
 
+// Vector version (C % 8 == 0, C <= 2048): a thread owns 8 adjacent channels (one 16-byte word) of every rpi-th pixel of
+// the CTA's slab, C/8 threads cover a pixel row, so the whole block streams full lines; partial sums meet in shared
+// memory and leave as one red.add per channel per CTA.
+__global__ void __launch_bounds__(256)
+bias_grad_vec_kernel(const uint4* __restrict__ g, float* __restrict__ db, long long pixels, int C8, int rows_per_cta) {
+  __shared__ float part[256 * 8];
+  const int rpi = 256 / C8;                              // pixel rows per block iteration
+  const int c8 = threadIdx.x % C8, r = threadIdx.x / C8;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const long long p0 = (long long)blockIdx.x * rows_per_cta;
+  const long long p1 = p0 + rows_per_cta < pixels ? p0 + rows_per_cta : pixels;
+  if (r < rpi) {
+#pragma unroll 4
+    for (long long p = p0 + r; p < p1; p += rpi) {
+      const uint4 v = __ldcs(g + p * C8 + c8);
+      const __nv_bfloat162* v2 = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __bfloat1622float2(v2[j]);
+        acc[2 * j] += f.x; acc[2 * j + 1] += f.y;
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) part[threadIdx.x * 8 + j] = acc[j];
+  __syncthreads();
+  for (int c = threadIdx.x; c < C8 * 8; c += 256) {
+    float s = 0.f;
+    for (int rr = 0; rr < rpi; ++rr) s += part[(rr * C8 + (c >> 3)) * 8 + (c & 7)];
+    atomicAdd(db + c, s);
+  }
+}
+
 static int bias_grad_impl(const void* grad_bf16_nhwc, float* grad_bias, long long pixels, int channels, bool accumulate,
                           mrb_stream_t stream_) {
   if (pixels < 0 || channels <= 0 || (channels & 1)) return MRB_ERR_BAD_ARG;
@@ -1075,6 +1168,17 @@ static int bias_grad_impl(const void* grad_bf16_nhwc, float* grad_bias, long lon
   if (!accumulate) MRB_CUDA_TRY(cudaMemsetAsync(grad_bias, 0, sizeof(float) * channels, stream));
   if (pixels == 0) return MRB_OK;
   if (!grad_bf16_nhwc || ((uintptr_t)grad_bf16_nhwc & 3)) return MRB_ERR_BAD_ARG;
+  if ((channels & 7) == 0 && channels <= 2048 && ((uintptr_t)grad_bf16_nhwc & 15) == 0) {
+    const int C8 = channels >> 3, rpi = 256 / C8;
+    long long ctas = (pixels + (long long)rpi * 8 - 1) / ((long long)rpi * 8);
+    const long long cap = (long long)kNumSMs * 4;
+    if (ctas > cap) ctas = cap;
+    const int rows = (int)((pixels + ctas - 1) / ctas);
+    ctas = (pixels + rows - 1) / rows;
+    bias_grad_vec_kernel<<<(unsigned)ctas, 256, 0, stream>>>((const uint4*)grad_bf16_nhwc, grad_bias, pixels, C8, rows);
+    MRB_LAUNCH_CHECK();
+    return MRB_OK;
+  }
   long long ctas = (pixels + 63) / 64;
   const long long cap = (long long)kNumSMs * 8;
   if (ctas > cap) ctas = cap;

@@ -83,7 +83,7 @@ class _ConvFn(Function):
                 gb = ops.bias_grad(g)
         if ctx.has_res and ctx.needs_input_grad[3]:
             # nearest-2x upsample backward == sum over each 2x2 block
-            gres = F.avg_pool2d(g, 2).mul_(4) if ctx.residual_up2 else g
+            gres = ops.sum_pool2x2_nhwc(g) if ctx.residual_up2 else g
         return (gx, gw, gb, gres) + (None,) * 14
 
 
@@ -356,7 +356,10 @@ class B200Backend(Backend):
         return ops.conv2d_fwd(xv, w4, scale, shift, None, 1, (2, 0), True, out_hw=(hs, ws))
 
     def max_pool(self, x, k, s, p):
-        return F.max_pool2d(x, k, s, p)
+        if x.requires_grad and torch.is_grad_enabled():
+            return F.max_pool2d(x, k, s, p)          # differentiated pools keep ATen's kernel (argmax + backward)
+        from mrb_b200 import ops
+        return ops.max_pool_nhwc(x, k, s, p)
 
     def upsample2x(self, x):
         return F.interpolate(x, scale_factor=2, mode="nearest")

@@ -95,16 +95,17 @@ class Matcher:
         return matches
 
 
-def _pick_random(mask, key, cap, limit):
-    """Boolean mask of min(#mask, limit) uniformly random elements of `mask` (limit <= cap; limit may be a device
-    scalar).  Every element carries an iid uniform key; the answer is the `limit` smallest keys among the masked
-    ones.  Sync-free and sort-free on the long vector: for large inputs (268k RPN anchors) the candidates are first
-    thinned by a key threshold that keeps ~4*cap of them in expectation (all of them if there are fewer), compacted
-    with nonzero_static into a fixed 16*cap buffer, and only that short buffer goes through top-k."""
+def _pick_random_idx(mask, key, cap, limit):
+    """min(#mask, limit) uniformly random elements of `mask` (limit <= cap; limit may be a device scalar) as a
+    FIXED-SIZE index list: returns (idx [min(cap, n)], ok) -- idx is clamped into range, ok flags the real picks.
+    Every element carries an iid uniform key; the answer is the `limit` smallest keys among the masked ones.
+    Sync-free and sort-free on the long vector: for large inputs (268k RPN anchors) the candidates are first thinned
+    by a key threshold that keeps ~4*cap of them in expectation (all of them if there are fewer), compacted with
+    nonzero_static into a fixed 16*cap buffer, and only that short buffer goes through top-k."""
     n = mask.numel()
     dev = mask.device
     if n <= 16384:
-        k, idx = torch.where(mask, key, key.new_full((), 2.0)), None
+        k = torch.where(mask, key, key.new_full((), 2.0))
         kk, sel = torch.topk(k, min(cap, n), largest=False, sorted=True)
     else:
         cnt = mask.sum().clamp(min=1).to(key.dtype)
@@ -115,22 +116,33 @@ def _pick_random(mask, key, cap, limit):
         kk, order = torch.topk(k, min(cap, c), largest=False, sorted=True)
         sel = idx[order]
     ok = (kk < 1.5) & (torch.arange(kk.numel(), device=dev) < limit)
-    out = torch.zeros(n + 1, dtype=torch.bool, device=dev)                           # slot n swallows the padding
-    out[sel.clamp(max=n)] = ok
-    return out[:n], ok.sum()
+    return sel.clamp(max=n - 1), ok
 
 
-def sample_pos_neg(labels, batch_size, positive_fraction, generator=None):
-    """modeling/balanced_positive_negative_sampler.py:19-68 for one image.
-    labels: -1 ignore, 0 negative, >0 positive.  Returns boolean masks (pos, neg): up to
-    int(batch_size * positive_fraction) random positives, the rest (up to batch_size) random negatives --
-    the distribution of randperm(...)[:num], without host synchronisation."""
+def _mask_of(idx, ok, n):
+    out = torch.zeros(n + 1, dtype=torch.bool, device=idx.device)                    # slot n swallows the padding
+    out[torch.where(ok, idx, torch.full_like(idx, n))] = ok
+    return out[:n]
+
+
+def sample_pos_neg_idx(labels, batch_size, positive_fraction, generator=None):
+    """modeling/balanced_positive_negative_sampler.py:19-68 for one image, as fixed-size index lists:
+    (pos_idx [P], pos_ok [P], neg_idx [B], neg_ok [B]) with P = int(batch_size * positive_fraction), B = batch_size:
+    up to P random positives, the rest (up to batch_size in total) random negatives -- the distribution of
+    randperm(...)[:num], without host synchronisation.  labels: -1 ignore, 0 negative, >0 positive."""
     n = labels.numel()
     num_pos_cap = min(int(batch_size * positive_fraction), n)
     key = torch.rand(n, device=labels.device, generator=generator)
-    pos_sel, num_pos = _pick_random(labels >= 1, key, num_pos_cap, num_pos_cap)
-    neg_sel, _ = _pick_random(labels == 0, key, min(batch_size, n), batch_size - num_pos)
-    return pos_sel, neg_sel
+    pos_idx, pos_ok = _pick_random_idx(labels >= 1, key, num_pos_cap, num_pos_cap)
+    neg_idx, neg_ok = _pick_random_idx(labels == 0, key, min(batch_size, n), batch_size - pos_ok.sum())
+    return pos_idx, pos_ok, neg_idx, neg_ok
+
+
+def sample_pos_neg(labels, batch_size, positive_fraction, generator=None):
+    """The same sample as boolean masks (pos, neg) over the elements of `labels`."""
+    n = labels.numel()
+    pos_idx, pos_ok, neg_idx, neg_ok = sample_pos_neg_idx(labels, batch_size, positive_fraction, generator)
+    return _mask_of(pos_idx, pos_ok, n), _mask_of(neg_idx, neg_ok, n)
 
 
 # ---------------------------------------------------------------------------------- anchors

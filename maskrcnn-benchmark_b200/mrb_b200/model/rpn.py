@@ -183,32 +183,34 @@ class RPN(nn.Module):
         cfg = self.cfg
         obj = torch.cat(logits, 1)            # [N, A_total]
         reg = torch.cat(deltas, 1)            # [N, A_total, 4]
-        labels, reg_targets, pos_m, neg_m = [], [], [], []
-        with torch.no_grad():
-            for i, t in enumerate(targets):
+        # loss.py:40-131 evaluated on the SAMPLED anchors only: matching and labelling run over all ~268k anchors, but
+        # box-regression targets, smooth-L1 and BCE touch just the <= 256 fixed-size sampled rows per image (the
+        # reference computes them densely and then indexes with the sampled positions: same values).
+        box_sum = obj_sum = num_sampled = 0
+        beta = 1.0 / 9
+        for i, t in enumerate(targets):
+            with torch.no_grad():
                 q = box_ops.box_iou(t["boxes"], anchors_all)                           # loss.py:40-52
                 midx = self.matcher(q)
                 lab = (midx >= 0).float()
                 lab = torch.where(midx == box_ops.Matcher.BELOW_LOW, torch.zeros_like(lab), lab)
                 lab = torch.where(~visibility[i], -torch.ones_like(lab), lab)          # not_visibility
                 lab = torch.where(midx == box_ops.Matcher.BETWEEN, -torch.ones_like(lab), lab)
-                reg_targets.append(self.box_coder.encode(t["boxes"][midx.clamp(min=0)], anchors_all))
-                labels.append(lab)
-                p, ng = box_ops.sample_pos_neg(lab, cfg.rpn_batch_size, cfg.rpn_positive_fraction, generator)
-                pos_m.append(p)
-                neg_m.append(ng)
-            labels, reg_targets = torch.stack(labels), torch.stack(reg_targets)
-            pos_m, neg_m = torch.stack(pos_m), torch.stack(neg_m)
-            sampled = pos_m | neg_m
-            num_sampled = sampled.sum().clamp(min=1).float()
-        # loss.py:117-131, written with masks instead of index gathers (no nonzero sync)
-        diff = torch.abs(reg.float() - reg_targets)
-        beta = 1.0 / 9
-        l1 = torch.where(diff < beta, 0.5 * diff * diff / beta, diff - 0.5 * beta)
-        box_loss = (l1 * pos_m[..., None]).sum() / num_sampled
-        bce = F.binary_cross_entropy_with_logits(obj.float(), labels.clamp(min=0), reduction="none")
-        objectness_loss = (bce * sampled).sum() / num_sampled
-        return objectness_loss, box_loss
+                pos_idx, pos_ok, neg_idx, neg_ok = box_ops.sample_pos_neg_idx(lab, cfg.rpn_batch_size,
+                                                                                cfg.rpn_positive_fraction, generator)
+                gt = t["boxes"][midx[pos_idx].clamp(min=0)]
+                reg_t = self.box_coder.encode(gt, anchors_all[pos_idx])
+                num_sampled = num_sampled + pos_ok.sum() + neg_ok.sum()
+                sel = torch.cat([pos_idx, neg_idx])
+                sel_lab = torch.cat([torch.ones_like(pos_ok, dtype=torch.float32), torch.zeros_like(neg_ok, dtype=torch.float32)])
+                sel_w = torch.cat([pos_ok, neg_ok]).float()
+            diff = torch.abs(reg[i][pos_idx].float() - reg_t)
+            l1 = torch.where(diff < beta, 0.5 * diff * diff / beta, diff - 0.5 * beta)
+            box_sum = box_sum + (l1 * pos_ok[:, None]).sum()
+            bce = F.binary_cross_entropy_with_logits(obj[i][sel].float(), sel_lab, reduction="none")
+            obj_sum = obj_sum + (bce * sel_w).sum()
+        num_sampled = num_sampled.clamp(min=1).float()
+        return obj_sum / num_sampled, box_sum / num_sampled
 
     def run(self, be, feats, image_sizes, targets, training, generator=None):
         logits, deltas = self.head.run(be, feats)

@@ -236,6 +236,33 @@ def bias_grad(grad_out, accumulate_into=None):
     return out
 
 
+def max_pool_nhwc(x, kernel, stride, pad):
+    """F.max_pool2d forward on an NHWC bf16 tensor (no indices: for inputs that are not differentiated)."""
+    x = _nhwc(x, "max_pool_nhwc")
+    if x.dtype != torch.bfloat16:
+        raise RuntimeError("max_pool_nhwc: bf16 input required")
+    n, c, h, w = x.shape
+    ho, wo = (h + 2 * pad - kernel) // stride + 1, (w + 2 * pad - kernel) // stride + 1
+    out = torch.empty((n, c, ho, wo), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
+    with torch.cuda.device(x.device):
+        _c.check(lib.mrb_max_pool_nhwc(_c._ptr(x), _c._ptr(out), n, h, w, c, kernel, stride, pad, _c._stream()), "mrb_max_pool_nhwc")
+    _count(1)
+    return out
+
+
+def sum_pool2x2_nhwc(g):
+    """Sum over 2x2 blocks (ceil-sized output) of an NHWC bf16 tensor: backward of the nearest-2x upsample."""
+    g = _nhwc(g, "sum_pool2x2_nhwc")
+    if g.dtype != torch.bfloat16:
+        raise RuntimeError("sum_pool2x2_nhwc: bf16 input required")
+    n, c, h, w = g.shape
+    out = torch.empty((n, c, (h + 1) // 2, (w + 1) // 2), dtype=g.dtype, device=g.device, memory_format=torch.channels_last)
+    with torch.cuda.device(g.device):
+        _c.check(lib.mrb_sum_pool2x2_nhwc(_c._ptr(g), _c._ptr(out), n, h, w, c, _c._stream()), "mrb_sum_pool2x2_nhwc")
+    _count(1)
+    return out
+
+
 def sgd_momentum_step(param, grad, momentum_buf, param_bf16, lr, momentum, weight_decay, grad_scale=1.0, zero_grad=True):
     """In-place fused SGD update of flat fp32 tensors (see mrb_sgd_momentum_step): also refreshes the bf16 operand
     copy `param_bf16` (may be None) and zeroes `grad`."""

@@ -225,3 +225,42 @@ def test_conv_strided_windows(ops):
     xv = torch.as_strided(xd, (2, 64, 10, 32), (10 * 35 * 16, 1, 35 * 16, 16))
     wv = w16.to(DEV).permute(0, 2, 3, 1).reshape(32, 64, 1, 1).contiguous(memory_format=torch.channels_last)
     _assert_close(ops.conv2d_fwd(xv, wv, out_dtype=torch.float32), want)
+
+
+def test_prepare_dgrad_weights_batched(ops):
+    """[Cout][taps][Cin] -> [Cin][flipped taps][Cout] (* scale[Cout]) for many layers in one launch: tiled path
+    (channels % 8 == 0) and the generic fallback (odd channel counts), > 40 layers to cross a batch boundary."""
+    g = torch.Generator().manual_seed(41)
+    shapes = [(64, 64, 1), (256, 64, 3), (72, 200, 3), (128, 24, 1), (2048, 512, 1)] + [(64, 32, 3)] * 40 + [(20, 12, 3)]
+    ws, scs = [], []
+    for i, (co, ci, k) in enumerate(shapes):
+        ws.append(torch.randn(co, ci, k, k, generator=g).to(torch.bfloat16).to(DEV).contiguous(memory_format=torch.channels_last))
+        scs.append((torch.rand(co, generator=g) + 0.5).to(DEV) if i % 2 == 0 else None)
+    outs = ops.prepare_dgrad_weights(ws, scs)
+    for w, sc, o in zip(ws, scs, outs):
+        co, ci, k, _ = w.shape
+        wf = w.float() * (sc[:, None, None, None] if sc is not None else 1.0)
+        want = wf.flip(2, 3).permute(1, 2, 3, 0).reshape(-1).to(torch.bfloat16)    # [ci][kh'][kw'][co]
+        assert torch.equal(o, want), (co, ci, k)
+
+
+def test_pool_kernels(ops):
+    g = torch.Generator().manual_seed(42)
+    for (n, c, h, w, k, s, p) in [(2, 64, 37, 50, 3, 2, 1), (1, 256, 25, 42, 1, 2, 0), (1, 8, 9, 9, 2, 2, 0)]:
+        x = torch.randn(n, c, h, w, generator=g).to(torch.bfloat16)
+        got = ops.max_pool_nhwc(x.to(DEV), k, s, p)
+        want = F.max_pool2d(x.float(), k, s, p).to(torch.bfloat16)
+        assert got.shape == want.shape and torch.equal(got.cpu(), want)
+    for (n, c, h, w) in [(2, 64, 20, 28), (1, 16, 25, 13)]:
+        x = torch.randn(n, c, h, w, generator=g).to(torch.bfloat16)
+        got = ops.sum_pool2x2_nhwc(x.to(DEV))
+        want = F.avg_pool2d(x.float(), 2, ceil_mode=True, count_include_pad=True, divisor_override=1)
+        assert got.shape == want.shape
+        _assert_close(got, want, tol=1e-2)
+
+
+def test_bias_grad_shapes(ops):
+    g = torch.Generator().manual_seed(43)
+    for (n, c, h, w) in [(2, 256, 50, 84), (1024, 1024, 1, 1), (3, 408, 7, 5), (2, 8, 33, 17), (1, 6, 9, 4)]:
+        go = torch.randn(n, c, h, w, generator=g).to(torch.bfloat16)
+        _assert_close(ops.bias_grad(go.to(DEV)), go.float().sum((0, 2, 3)), tol=2e-4)
