@@ -231,6 +231,8 @@ def main():
     ap.add_argument("--wgrad", default="tc", choices=["tc", "cudnn"], help="weight-gradient kernel (A/B switch)")
     ap.add_argument("--optim", default="arena", choices=["arena", "flat"],
                     help="arena: flat parameter/gradient buffers + fused update kernel; flat: foreach SGD (A/B switch)")
+    ap.add_argument("--overlap", default="on", choices=["on", "off"],
+                    help="weight-/bias-gradient kernels on a second stream (needs --optim arena)")
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
                     help="capture the whole train step (fwd+bwd+all-reduce+SGD) in one CUDA graph; falls back to eager "
                          "(and says so) if capture fails")
@@ -272,6 +274,7 @@ def main():
         # gradients in place, one NCCL all-reduce over the gradient buffer, one fused update launch per group
         opt = grad_sync = ParamArena(model.named_parameters(), model.be, lr=1e-4, momentum=0.9, weight_decay=1e-4,
                                      world_size=world)
+        model.be.enable_overlap(args.overlap == "on")
     else:
         if world > 1:
             from mrb_b200.parallel import FlatGradSync

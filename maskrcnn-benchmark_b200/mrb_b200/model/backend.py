@@ -73,12 +73,14 @@ class _ConvFn(Function):
             gx = ops.conv2d_dgrad(g, w16, x_shape, scale, None, x if ctx.premask_x else None, stride, pad, prepared=prep)
         if ctx.needs_input_grad[1]:
             if ctx.wsink is not None:
-                ops.conv2d_wgrad(x, g, w16.shape, stride, pad, scale, accumulate_into=ctx.wsink.view(w16.shape))
+                sink = ctx.wsink.view(w16.shape)
+                ctx.be.side_launch((x, g), lambda: ops.conv2d_wgrad(x, g, w16.shape, stride, pad, scale, accumulate_into=sink))
             else:
                 gw = wgrad_fn(x, g, w16, stride, pad, scale)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             if ctx.bsink is not None:
-                ops.bias_grad(g, accumulate_into=ctx.bsink)
+                bsink = ctx.bsink
+                ctx.be.side_launch((g,), lambda: ops.bias_grad(g, accumulate_into=bsink))
             else:
                 gb = ops.bias_grad(g)
         if ctx.has_res and ctx.needs_input_grad[3]:
@@ -182,7 +184,7 @@ class _BottleneckFn(Function):
             sink = be.grad_sink(param)
             if sink is None:
                 return be.wgrad_fn(xin, gout, w16, stride, pad, scale)
-            ops.conv2d_wgrad(xin, gout, w16.shape, stride, pad, scale, accumulate_into=sink)
+            be.side_launch((xin, gout), lambda: ops.conv2d_wgrad(xin, gout, w16.shape, stride, pad, scale, accumulate_into=sink))
             return None
         if not ctx.g_premasked:
             g = torch.where(out > 0, g, torch.zeros((), dtype=g.dtype, device=g.device))
@@ -234,6 +236,8 @@ class B200Backend(Backend):
         self._w16 = {}
         self._wd = {}     # (id(param), id(scale)) -> [param, scale, version, w16, prepared dgrad weights]
         self.arena = None
+        self.side = None          # second stream for gradient-sink kernels (see side_launch)
+        self._side_busy = False
         if wgrad == "tc":
             self.wgrad_fn, self.wgrad_impl = _wgrad_tc, "mrb_conv2d_wgrad (tcgen05, in-house)"
         else:
@@ -256,6 +260,28 @@ class B200Backend(Backend):
         if stale:
             from mrb_b200 import ops
             ops.prepare_dgrad_weights([e[3] for e in stale], [e[1] for e in stale], [e[4] for e in stale])
+
+    def enable_overlap(self, on=True):
+        """Run the weight-/bias-gradient kernels that accumulate into arena sinks on a second stream: nothing in the
+        backward pass reads their result, so they overlap the data-gradient chain (most layers of res4/res5 and the
+        heads fill well under 148 SMs).  Captured into the CUDA graph as parallel branches; join_side() is the join."""
+        self.side = torch.cuda.Stream() if on else None
+
+    def side_launch(self, tensors, fn):
+        if self.side is None:
+            fn()
+            return
+        self.side.wait_stream(torch.cuda.current_stream())        # inputs were produced on the current stream
+        with torch.cuda.stream(self.side):
+            fn()
+        for t in tensors:
+            t.record_stream(self.side)                             # keep the allocator from recycling them early
+        self._side_busy = True
+
+    def join_side(self):
+        if self.side is not None and self._side_busy:
+            torch.cuda.current_stream().wait_stream(self.side)
+            self._side_busy = False
 
     def grad_sink(self, p):
         return self.arena.grad_sink(p) if (self.arena is not None and p is not None) else None

@@ -122,6 +122,8 @@ class ParamArena:
     @torch.no_grad()
     def sync(self):
         """Sum the gradient accumulators over the data-parallel ranks (the mean's 1/world is applied by step())."""
+        if self.backend is not None:
+            self.backend.join_side()           # gradient kernels running on the backend's second stream
         if self.world > 1:
             import torch.distributed as dist
             dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=self.group)
@@ -129,6 +131,8 @@ class ParamArena:
     @torch.no_grad()
     def step(self):
         from mrb_b200 import ops
+        if self.backend is not None:
+            self.backend.join_side()
         for lo, hi, lr, wd in self.groups:
             ops.sgd_momentum_step(self.param[lo:hi], self.grad[lo:hi], self.mom[lo:hi], self.param16[lo:hi], lr,
                                   self.momentum, wd, 1.0 / self.world, True)

@@ -33,6 +33,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--top", type=int, default=45)
     ap.add_argument("--json", default=None)
+    ap.add_argument("--convs", default=None, help="write the in-situ duration of every tcgen05 conv launch of the step, "
+                    "joined with its geometry (launch order == call order), aggregated per shape, to this JSON")
     ap.add_argument("--by-op", action="store_true", help="also attribute device time to the launching aten op, its "
                     "input shapes and the innermost mrb_b200/ source line (PyTorch glue only)")
     args = ap.parse_args()
@@ -58,10 +60,13 @@ def main():
         step(batches[i % 2])
     torch.cuda.synchronize()
     from torch.profiler import profile, ProfilerActivity
+    from mrb_b200 import ops
+    ops.STATS["conv_calls"] = []
     with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU], record_shapes=args.by_op,
                  with_stack=args.by_op) as prof:
         step(batches[1])
         torch.cuda.synchronize()
+    conv_calls, ops.STATS["conv_calls"] = ops.STATS["conv_calls"], None
     evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
     ks = sorted(((e.time_range.start, e.time_range.end, e.name) for e in evs), key=lambda t: t[0])
     agg = collections.defaultdict(lambda: [0, 0.0])
@@ -84,6 +89,28 @@ def main():
     if rest:
         print("| (%d more) | %d | %.1f | %.1f%% |" % (len(rest), sum(v[0] for _, v in rest), sum(v[1] for _, v in rest),
                                                      100 * sum(v[1] for _, v in rest) / busy))
+    if args.convs:
+        tc = [(s_, e - s_) for s_, e, n in ks if "conv_tc_kernel" in n]
+        wg = [(s_, e - s_) for s_, e, n in ks if "conv_wgrad_tc_kernel" in n]
+        c_tc = [c for c in conv_calls if c[0] != "wgrad"]
+        c_wg = [c for c in conv_calls if c[0] == "wgrad"]
+        assert len(tc) == len(c_tc) and len(wg) == len(c_wg), (len(tc), len(c_tc), len(wg), len(c_wg))
+        per = collections.defaultdict(list)
+        for (st, d), c in list(zip(tc, c_tc)) + list(zip(wg, c_wg)):
+            per[c].append(d)
+        rows_c = []
+        for c, ds in per.items():
+            kind, n, cin, h, w, cout, k, stride, pad = c
+            kh, kw = (k, k) if isinstance(k, int) else k
+            ph, pw = (pad, pad) if isinstance(pad, int) else pad
+            ho, wo = (h + 2 * ph - kh) // stride + 1, (w + 2 * pw - kw) // stride + 1
+            fl = 2.0 * n * ho * wo * cout * cin * kh * kw
+            rows_c.append({"kind": kind, "n": n, "cin": cin, "h": h, "w": w, "cout": cout, "k": k, "stride": stride,
+                           "count": len(ds), "us": round(sum(ds) / len(ds), 1), "us_min": round(min(ds), 1),
+                           "tflops": round(fl / (sum(ds) / len(ds)) / 1e6, 1)})
+        rows_c.sort(key=lambda r: -r["us"] * r["count"])
+        json.dump(rows_c, open(args.convs, "w"), indent=1)
+        print("\nin-situ conv time: fwd+dgrad %.1f us, wgrad %.1f us" % (sum(d for _, d in tc), sum(d for _, d in wg)))
     if args.by_op:
         ops_ = collections.defaultdict(lambda: [0, 0.0])
         for e in prof.events():
