@@ -32,6 +32,7 @@
 #include <mutex>
 
 #include "common.cuh"
+#include <cstdlib>
 
 namespace mrb {
 
@@ -117,6 +118,9 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
   return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
+
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------- kernel
 constexpr int kEpiWarps = 8;                  // epilogue warps: 2 per TMEM lane quadrant (latency hiding: each SMSP
@@ -253,6 +257,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) touched no
+  // global memory and may overlap the tail of the previous kernel in the stream; from here on we need its results
+  // (and it must be done reading any buffer we are about to overwrite).  Our own dependents may start their
+  // prologue right away: they block at the same point until this grid has fully completed.
+  pdl_wait();
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ================================ TMA producer ================================
@@ -506,6 +516,12 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_con
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) touched no
+  // global memory and may overlap the tail of the previous kernel in the stream; from here on we need its results
+  // (and it must be done reading any buffer we are about to overwrite).  Our own dependents may start their
+  // prologue right away: they block at the same point until this grid has fully completed.
+  pdl_wait();
+  pdl_launch_dependents();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -727,6 +743,21 @@ static int encode_bf16(CUtensorMap* m, const void* base, int rank, const cuuint6
   return r == CUDA_SUCCESS ? MRB_OK : MRB_ERR_BAD_ARG;
 }
 
+// Launch with the programmatic-stream-serialization attribute (see pdl_wait in the kernels).  MRB_NO_PDL=1 in the
+// environment falls back to a plain launch (A/B switch for measurements).
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t stream, Args... args) {
+  static const bool no_pdl = [] { const char* e = getenv("MRB_NO_PDL"); return e && e[0] == '1'; }();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block);
+  cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = no_pdl ? 0 : 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 struct ConvPlan {
   // logical GEMM-side geometry after the 1x1 flattening
   int batch, Hin, Win;        // TMA view of the input (already subsampled for stride 2)
@@ -813,8 +844,7 @@ static int conv_launch(const ConvPlan& pl, const void* x, const void* w, int cin
   });
   if (attr_err != cudaSuccess) return (int)attr_err;
   const int grid = a.tiles_total < kNumSMs ? a.tiles_total : kNumSMs;
-  conv_tc_kernel<<<grid, kConvThreads, smem, stream>>>(map_a, map_b, a);
-  MRB_LAUNCH_CHECK();
+  MRB_CUDA_TRY(launch_pdl(conv_tc_kernel, grid, kConvThreads, smem, stream, map_a, map_b, a));
   return MRB_OK;
 }
 
@@ -1092,8 +1122,7 @@ static int conv_wgrad_impl(const mrb_conv_params* p, const void* input, const vo
   });
   if (attr_err != cudaSuccess) return (int)attr_err;
   const int grid = a.items_total < kNumSMs ? a.items_total : kNumSMs;
-  conv_wgrad_tc_kernel<<<grid, kWgradThreads, smem, stream>>>(map_g, map_x, a);
-  MRB_LAUNCH_CHECK();
+  MRB_CUDA_TRY(launch_pdl(conv_wgrad_tc_kernel, grid, kWgradThreads, smem, stream, map_g, map_x, a));
   return MRB_OK;
 }
 

@@ -89,6 +89,29 @@ class _ConvFn(Function):
         return (gx, gw, gb, gres) + (None,) * 14
 
 
+class _SelectChannelFn(Function):
+    """out[r, h, w] = y[r, label[r], h, w] for an NHWC tensor (the class-specific mask logit of each ROI, reference
+    roi_heads/mask_head/loss.py:120-126 `mask_logits[positive_inds, labels_pos]`).  The backward writes the gradient
+    straight into a zeroed bf16 NHWC tensor -- the layout the conv engine's dgrad/wgrad read -- instead of going
+    through index_put + slice-pad + cast + layout copies of the full 81-channel fp32 logits."""
+
+    @staticmethod
+    def forward(ctx, y, labels):
+        r, c, h, w = y.shape
+        idx = labels.view(r, 1, 1, 1).expand(r, h, w, 1)
+        ctx.save_for_backward(idx)
+        ctx.shape = (r, c, h, w)
+        return torch.gather(y.permute(0, 2, 3, 1), 3, idx).squeeze(3)
+
+    @staticmethod
+    def backward(ctx, g):
+        (idx,) = ctx.saved_tensors
+        r, c, h, w = ctx.shape
+        gy = torch.empty((r, c, h, w), dtype=torch.bfloat16, device=g.device, memory_format=torch.channels_last).zero_()
+        gy.permute(0, 2, 3, 1).scatter_(3, idx, g.to(torch.bfloat16).unsqueeze(3))
+        return gy, None
+
+
 class _Deconv2x2Fn(Function):
     """ConvTranspose2d(k=2, s=2) (+bias, +ReLU) of the mask head (reference roi_heads/mask_head/
     roi_mask_predictors.py:17-35) on the conv engine with NO pixel shuffle: out[r, 2h+i, 2w+j, :] = W[:, :, i, j]^T x[r, h, w, :]
@@ -278,6 +301,34 @@ class B200Backend(Backend):
             t.record_stream(self.side)                             # keep the allocator from recycling them early
         self._side_busy = True
 
+    def fork(self, inputs, fn):
+        """Run fn() (no autograd, independent of everything launched since) on the second stream; returns a handle for
+        join().  Without a second stream it just runs inline."""
+        if self.side is None:
+            return ("done", fn())
+        cur = torch.cuda.current_stream()
+        self.side.wait_stream(cur)
+        with torch.cuda.stream(self.side):
+            out = fn()
+        for t in inputs:
+            t.record_stream(self.side)
+        return ("side", out)
+
+    def join(self, handle):
+        kind, out = handle
+        if kind == "side":
+            cur = torch.cuda.current_stream()
+            cur.wait_stream(self.side)
+
+            def mark(o):
+                if isinstance(o, torch.Tensor):
+                    o.record_stream(cur)
+                elif isinstance(o, (list, tuple)):
+                    for x in o:
+                        mark(x)
+            mark(out)
+        return out
+
     def join_side(self):
         if self.side is not None and self._side_busy:
             torch.cuda.current_stream().wait_stream(self.side)
@@ -314,8 +365,10 @@ class B200Backend(Backend):
         return images.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
 
     def conv(self, x, weight, scale=None, shift=None, bias=None, residual=None, stride=1, pad=0, relu=False,
-             out_fp32=False, w16=None, premask_x=False, gy_premasked=False, residual_up2=False, wparam=None):
-        """`wparam`: the nn.Parameter `weight` is a plain view of (linear's [Cout, K] -> [Cout, K, 1, 1]), if any."""
+             out_fp32=False, w16=None, premask_x=False, gy_premasked=False, residual_up2=False, wparam=None,
+             keep_padded=False):
+        """`wparam`: the nn.Parameter `weight` is a plain view of (linear's [Cout, K] -> [Cout, K, 1, 1]), if any.
+        keep_padded: return all round-up-to-8 output channels (the extra ones are exactly zero)."""
         wsink = self.grad_sink(weight if isinstance(weight, torch.nn.Parameter) else wparam)
         bsink = self.grad_sink(bias) if isinstance(bias, torch.nn.Parameter) else None
         if x.numel() == 0:
@@ -343,7 +396,12 @@ class B200Backend(Backend):
             w16 = self._weight16(weight)
         y = _ConvFn.apply(x, weight, bias, residual, w16, scale, shift, stride, pad, relu, out_fp32, self.wgrad_fn,
                           premask_x, gy_premasked, residual_up2, self, wsink, bsink)
-        return y[:, :co] if co % 8 else y
+        return y[:, :co] if (co % 8 and not keep_padded) else y
+
+    def conv_select(self, x, weight, bias, labels, premask_x=False):
+        """1x1 conv with fp32 output followed by the per-sample channel pick y[r, labels[r]] (mask logits + loss.py:120-126)."""
+        y = self.conv(x, weight, bias=bias, out_fp32=True, premask_x=premask_x, keep_padded=True)
+        return _SelectChannelFn.apply(y, labels)
 
     def bottleneck(self, blk, x, g_premasked):
         """Whole bottleneck as one autograd node (see _BottleneckFn).  Requires STRIDE_IN_1X1 geometry."""

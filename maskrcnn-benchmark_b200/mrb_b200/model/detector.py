@@ -65,10 +65,9 @@ class GeneralizedRCNN(nn.Module):
                     rois_sel = torch.gather(rois.view(n, s, 5), 1, order[..., None].expand(-1, -1, 5)).reshape(-1, 5)
                     lab_sel = torch.gather(labels, 1, order).reshape(-1).clamp(min=0)
                     gt_sel = torch.gather(gt_all, 1, order[..., None].expand(-1, -1, 4)).reshape(-1, 4)
-                    logits = mask.run(be, feats, rois_sel)
+                    sel_logits = mask.run(be, feats, rois_sel, select=lab_sel)
                     tgt = mask.mask_targets(gt_sel, rois_sel[:, 1:], res)
-                    idx = torch.arange(logits.shape[0], device=logits.device)
-                    bce = torch.nn.functional.binary_cross_entropy_with_logits(logits[idx, lab_sel].float(), tgt,
+                    bce = torch.nn.functional.binary_cross_entropy_with_logits(sel_logits.float(), tgt,
                                                                                reduction="none").mean((1, 2))
                     losses["loss_mask"] = (bce * wsel).sum() / wsel.sum().clamp(min=1)
                 else:

@@ -166,7 +166,9 @@ class MaskHead(nn.Module):
                 nn.init.kaiming_normal_(p, mode="fan_out", nonlinearity="relu")
         self.predictor = pr
 
-    def run(self, be, feats, rois):
+    def run(self, be, feats, rois, select=None):
+        """Mask logits [R, num_classes, M, M]; with `select` (class index per ROI, training) only the selected class
+        plane of each ROI, [R, M, M] (mask_head/loss.py:120-126)."""
         cfg = self.cfg
         x = be.roi_align_fpn(feats[:4], rois, cfg.pooler_scales, cfg.mask_resolution_pool, cfg.mask_sampling_ratio,
                              nhwc=True)
@@ -175,7 +177,12 @@ class MaskHead(nn.Module):
             c = getattr(fe, name)
             x = be.conv(x, c.weight, bias=c.bias, pad=1, relu=True, premask_x=i > 0, gy_premasked=True)
         x = be.deconv2x2(x, pr.conv5_mask.weight, pr.conv5_mask.bias, relu=True, premask_x=True, gy_premasked=True)
-        return be.conv(x, pr.mask_fcn_logits.weight, bias=pr.mask_fcn_logits.bias, out_fp32=True, premask_x=True)
+        if select is not None and hasattr(be, "conv_select"):
+            return be.conv_select(x, pr.mask_fcn_logits.weight, pr.mask_fcn_logits.bias, select, premask_x=True)
+        logits = be.conv(x, pr.mask_fcn_logits.weight, bias=pr.mask_fcn_logits.bias, out_fp32=True, premask_x=True)
+        if select is not None:
+            logits = logits[torch.arange(logits.shape[0], device=logits.device), select]
+        return logits
 
     @staticmethod
     @torch.no_grad()

@@ -179,49 +179,69 @@ class RPN(nn.Module):
         return b, s, v
 
     # ------------------------------------------------------------------ loss
-    def loss(self, anchors_all, visibility, logits, deltas, targets, generator=None):
+    @torch.no_grad()
+    def loss_targets(self, anchors_all, visibility, targets, generator=None):
+        """Anchor labelling + sampling + regression targets (loss.py:40-131, no gradients, independent of the
+        network outputs): matching and labelling run over all ~268k anchors, everything after the sampling touches
+        just the fixed-size sampled rows (the reference computes targets densely and then indexes with the sampled
+        positions: same values).  Per image: (pos_idx, pos_ok, reg_t, sel, sel_lab, sel_w)."""
         cfg = self.cfg
+        out = []
+        for i, t in enumerate(targets):
+            q = box_ops.box_iou(t["boxes"], anchors_all)                           # loss.py:40-52
+            midx = self.matcher(q)
+            lab = (midx >= 0).float()
+            lab = torch.where(midx == box_ops.Matcher.BELOW_LOW, torch.zeros_like(lab), lab)
+            lab = torch.where(~visibility[i], -torch.ones_like(lab), lab)          # not_visibility
+            lab = torch.where(midx == box_ops.Matcher.BETWEEN, -torch.ones_like(lab), lab)
+            pos_idx, pos_ok, neg_idx, neg_ok = box_ops.sample_pos_neg_idx(lab, cfg.rpn_batch_size,
+                                                                            cfg.rpn_positive_fraction, generator)
+            gt = t["boxes"][midx[pos_idx].clamp(min=0)]
+            reg_t = self.box_coder.encode(gt, anchors_all[pos_idx])
+            sel = torch.cat([pos_idx, neg_idx])
+            sel_lab = torch.cat([torch.ones_like(pos_ok, dtype=torch.float32), torch.zeros_like(neg_ok, dtype=torch.float32)])
+            sel_w = torch.cat([pos_ok, neg_ok]).float()
+            out.append((pos_idx, pos_ok, reg_t, sel, sel_lab, sel_w))
+        return out
+
+    def loss(self, anchors_all, visibility, logits, deltas, targets, generator=None, prepared=None):
         obj = torch.cat(logits, 1)            # [N, A_total]
         reg = torch.cat(deltas, 1)            # [N, A_total, 4]
-        # loss.py:40-131 evaluated on the SAMPLED anchors only: matching and labelling run over all ~268k anchors, but
-        # box-regression targets, smooth-L1 and BCE touch just the <= 256 fixed-size sampled rows per image (the
-        # reference computes them densely and then indexes with the sampled positions: same values).
+        if prepared is None:
+            prepared = self.loss_targets(anchors_all, visibility, targets, generator)
         box_sum = obj_sum = num_sampled = 0
         beta = 1.0 / 9
-        for i, t in enumerate(targets):
-            with torch.no_grad():
-                q = box_ops.box_iou(t["boxes"], anchors_all)                           # loss.py:40-52
-                midx = self.matcher(q)
-                lab = (midx >= 0).float()
-                lab = torch.where(midx == box_ops.Matcher.BELOW_LOW, torch.zeros_like(lab), lab)
-                lab = torch.where(~visibility[i], -torch.ones_like(lab), lab)          # not_visibility
-                lab = torch.where(midx == box_ops.Matcher.BETWEEN, -torch.ones_like(lab), lab)
-                pos_idx, pos_ok, neg_idx, neg_ok = box_ops.sample_pos_neg_idx(lab, cfg.rpn_batch_size,
-                                                                                cfg.rpn_positive_fraction, generator)
-                gt = t["boxes"][midx[pos_idx].clamp(min=0)]
-                reg_t = self.box_coder.encode(gt, anchors_all[pos_idx])
-                num_sampled = num_sampled + pos_ok.sum() + neg_ok.sum()
-                sel = torch.cat([pos_idx, neg_idx])
-                sel_lab = torch.cat([torch.ones_like(pos_ok, dtype=torch.float32), torch.zeros_like(neg_ok, dtype=torch.float32)])
-                sel_w = torch.cat([pos_ok, neg_ok]).float()
+        for i, (pos_idx, pos_ok, reg_t, sel, sel_lab, sel_w) in enumerate(prepared):
+            num_sampled = num_sampled + sel_w.sum()
             diff = torch.abs(reg[i][pos_idx].float() - reg_t)
             l1 = torch.where(diff < beta, 0.5 * diff * diff / beta, diff - 0.5 * beta)
             box_sum = box_sum + (l1 * pos_ok[:, None]).sum()
             bce = F.binary_cross_entropy_with_logits(obj[i][sel].float(), sel_lab, reduction="none")
             obj_sum = obj_sum + (bce * sel_w).sum()
-        num_sampled = num_sampled.clamp(min=1).float()
+        num_sampled = num_sampled.clamp(min=1)
         return obj_sum / num_sampled, box_sum / num_sampled
 
     def run(self, be, feats, image_sizes, targets, training, generator=None):
-        logits, deltas = self.head.run(be, feats)
         grid_sizes = [f.shape[-2:] for f in feats]
         anchors = self.anchor_generator.grid(grid_sizes, feats[0].device)
+        prepared = None
+        if training:
+            anchors_all = torch.cat(anchors, 0)
+            vis = torch.stack([self.anchor_generator.visibility(anchors_all, w, h) for (h, w) in image_sizes])
+            # the target assignment needs nothing from the network: with a backend that offers a second stream it runs
+            # there, concurrently with the RPN head convolutions and the proposal selection (a few hundred tiny kernels
+            # that would otherwise sit on the critical path between two tensor-core phases)
+            fork = getattr(be, "fork", None)
+            if fork is not None:
+                prepared = fork((anchors_all, vis) + tuple(t["boxes"] for t in targets),
+                                lambda: self.loss_targets(anchors_all, vis, targets, generator))
+        logits, deltas = self.head.run(be, feats)
         proposals = self.select_proposals(be, anchors, [l.detach() for l in logits], [d.detach() for d in deltas],
                                           image_sizes, targets, training)
         losses = {}
         if training:
-            anchors_all = torch.cat(anchors, 0)
-            vis = torch.stack([self.anchor_generator.visibility(anchors_all, w, h) for (h, w) in image_sizes])
-            lo, lb = self.loss(anchors_all, vis, logits, deltas, targets, generator)
+            if prepared is not None:
+                prepared = be.join(prepared)
+            lo, lb = self.loss(anchors_all, vis, logits, deltas, targets, generator, prepared)
             losses = {"loss_objectness": lo, "loss_rpn_box_reg": lb}
         return proposals, losses

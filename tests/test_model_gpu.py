@@ -239,3 +239,28 @@ def test_deconv2x2_matches_conv_transpose(built_lib):
     assert _rel(xd.grad, xr.grad * (x16 > 0)) < 2e-2          # premask_x: the producer's ReLU mask rides along
     assert _rel(wd.grad, wr.grad) < 2e-2
     assert _rel(bd.grad, br.grad) < 2e-2
+
+
+def test_conv_select_matches_index_expression(built_lib):
+    """be.conv_select == conv(x)[arange, labels] (mask logits + mask_head/loss.py:120-126), values and gradients."""
+    import torch.nn.functional as F
+    from mrb_b200.model.backend import B200Backend
+    be = B200Backend()
+    g = torch.Generator().manual_seed(33)
+    x = torch.randn(6, 64, 12, 12, generator=g).relu()
+    wt = torch.randn(81, 64, 1, 1, generator=g) / 8
+    b = torch.randn(81, generator=g) * 0.1
+    lab = torch.tensor([3, 80, 0, 17, 17, 42])
+    go = torch.randn(6, 12, 12, generator=g)
+    x16, w16 = x.to(torch.bfloat16).float(), wt.to(torch.bfloat16).float()
+    xr, wr, br = x16.clone().requires_grad_(True), w16.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    y = F.conv2d(xr, wr, br)[torch.arange(6), lab]
+    y.backward(go)
+    xd = x.to(DEV).to(torch.bfloat16).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    wd, bd = w16.to(DEV).requires_grad_(True), b.to(DEV).requires_grad_(True)
+    yd = be.conv_select(xd, wd, bd, lab.to(DEV))
+    assert yd.shape == y.shape and _rel(yd.detach(), y.detach()) < 1e-2
+    yd.backward(go.to(DEV))
+    assert _rel(xd.grad, xr.grad) < 2e-2
+    assert _rel(wd.grad, wr.grad) < 2e-2
+    assert _rel(bd.grad, br.grad) < 2e-2
