@@ -84,6 +84,31 @@ __device__ __forceinline__ Tap fpn_tap(int H, int W, float y, float x) {
   return s;
 }
 
+// One axis of a bin with two samples: (row, weight) pairs of both samples with coinciding rows merged (weight 0 =
+// unused entry).  Same clamping / validity rules as fpn_tap.
+struct Axis2 {
+  int r[4];
+  float w[4];
+};
+__device__ __forceinline__ void axis2(int L, float c0, float c1, Axis2& a) {
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    float c = i ? c1 : c0;
+    const bool valid = !(c < -1.0f || c > (float)L);
+    if (c <= 0) c = 0;
+    int lo = (int)c, hi;
+    if (lo >= L - 1) { hi = lo = L - 1; c = (float)lo; } else { hi = lo + 1; }
+    float l = __fsub_rn(c, (float)lo), h = __fsub_rn(1.f, l);
+    if (!valid) { l = 0.f; h = 0.f; lo = 0; hi = 0; }
+    a.r[2 * i] = lo; a.w[2 * i] = h;
+    a.r[2 * i + 1] = hi; a.w[2 * i + 1] = l;
+  }
+  if (a.r[2] == a.r[0]) { a.w[0] += a.w[2]; a.w[2] = 0.f; }
+  else if (a.r[2] == a.r[1]) { a.w[1] += a.w[2]; a.w[2] = 0.f; }
+  if (a.r[3] == a.r[1]) { a.w[1] += a.w[3]; a.w[3] = 0.f; }
+  else if (a.r[3] == a.r[0]) { a.w[0] += a.w[3]; a.w[3] = 0.f; }
+}
+
 template <typename T> __device__ __forceinline__ void load4(const T* p, float (&v)[4]);
 template <> __device__ __forceinline__ void load4<float>(const float* p, float (&v)[4]) {
   const float4 t = __ldg(reinterpret_cast<const float4*>(p));
@@ -194,6 +219,27 @@ roi_align_fpn_bwd_kernel(FpnArgs a, const float* __restrict__ rois, const T* __r
     } else {
 #pragma unroll
       for (int k = 0; k < 4; ++k) t4[k] = tile[(lane * 4 + k) * PPS + bin];
+    }
+    if (g.gh == 2 && g.gw == 2) {
+      // sampling_ratio 2 (every reference config).  Bilinear weights and the validity test are separable, so the
+      // 2 x 2 samples x 4 corners of a bin collapse to (distinct rows) x (distinct columns) of summed weights:
+      // typically 2-3 x 2-3 red.adds per bin instead of 16 (samples are half a bin apart, bins ~1-2 pixels wide).
+      Axis2 ay, ax;
+      axis2(H, fpn_coord(g.sh, ph, g.bin_h, 0, 2), fpn_coord(g.sh, ph, g.bin_h, 1, 2), ay);
+      axis2(W, fpn_coord(g.sw, pw, g.bin_w, 0, 2), fpn_coord(g.sw, pw, g.bin_w, 1, 2), ax);
+      const float inv = __fdiv_rn(1.f, g.count);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (ay.w[i] == 0.f) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float wgt = ay.w[i] * ax.w[j] * inv;
+          if (wgt == 0.f) continue;
+          atomicAdd(reinterpret_cast<float4*>(dst + ((size_t)ay.r[i] * W + ax.r[j]) * C),
+                    make_float4(t4[0] * wgt, t4[1] * wgt, t4[2] * wgt, t4[3] * wgt));
+        }
+      }
+      continue;
     }
     for (int iy = 0; iy < g.gh; ++iy) {
       const float y = fpn_coord(g.sh, ph, g.bin_h, iy, g.gh);
