@@ -33,6 +33,7 @@
 
 #include "common.cuh"
 #include <cstdlib>
+#include <cstring>
 
 namespace mrb {
 
@@ -75,6 +76,23 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
+}
+// smem -> global tile store (bulk async group) and the fences around it
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
@@ -144,6 +162,8 @@ struct ConvArgs {
   long long res_n, res_h, res_w;   // its strides in elements
   const __nv_bfloat16* relu_mask;  // same indexing as out: result zeroed where mask <= 0
   void* out;
+  int tma_epi;                     // epilogue through TMA tile buffers (see conv_tc_kernel); else per-thread global access
+  int tile_bufs;                   // 1, or 2 when both a residual and a mask tile are staged
 };
 
 __device__ __forceinline__ void tile_coords(const ConvArgs& a, int tile, int& n_tile, int& img, int& h0, int& w0) {
@@ -228,17 +248,23 @@ __device__ __noinline__ void epilogue_chunk32_slow(const ConvArgs& a, uint32_t t
 }
 
 __global__ void __launch_bounds__(kConvThreads, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const ConvArgs a) {
+conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+               const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_res,
+               const __grid_constant__ CUtensorMap map_mask, const ConvArgs a) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t stage_bytes = kABytes + (uint32_t)a.bn * 128u;
-  const uint32_t bar_base = smem_base + (uint32_t)a.stages * stage_bytes;
-  // barriers: full[stages], empty[stages], tmem_full[2], tmem_empty[2]; then the TMEM base slot
+  // [ring: stages x (A 16 KB + B)] [tile buffers: tile_bufs x ceil(BN/64) x 16 KB (TMA epilogue only)] [barriers] ...
+  const uint32_t tile_base = smem_base + (uint32_t)a.stages * stage_bytes;
+  const uint32_t tile_buf_bytes = (uint32_t)((a.bn + 63) >> 6) * kABytes;
+  const uint32_t bar_base = tile_base + (a.tma_epi ? (uint32_t)a.tile_bufs * tile_buf_bytes : 0u);
+  // barriers: full[stages], empty[stages], tmem_full[2], tmem_empty[2], tile; then the TMEM base slot
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (a.stages + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * a.stages + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * a.stages + 2 + s); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * a.stages + 4);
+  const uint32_t tile_bar = bar_base + 8u * (2 * a.stages + 4);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * a.stages + 6);   // keeps what follows 16-byte aligned
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int k_blocks = a.kh * a.kw * a.cin_blocks;
   uint32_t tmem_cols = 32;
@@ -247,9 +273,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (threadIdx.x == 0) {
     for (int s = 0; s < a.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 32 * kEpiWarps); }
+    mbar_init(tile_bar, 1);
     fence_barrier_init();
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
+    if (a.tma_epi) {
+      tma_prefetch_desc(&map_out);
+      if (a.residual) tma_prefetch_desc(&map_res);
+      if (a.relu_mask) tma_prefetch_desc(&map_mask);
+    }
   }
   if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
   tc_fence_before();
@@ -326,7 +358,114 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const bool has_scale = a.scale != nullptr, has_bias = a.bias != nullptr;
     const bool cout8 = (a.cout & 7) == 0;
     int acc = 0; uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < a.tiles_total; tile += gridDim.x) {
+    if (a.tma_epi) {
+      // ---- TMA epilogue.  The output tile lives in a swizzled shared-memory tile buffer T ([BN/64 boxes][128 rows]
+      // [128 B], the layout TMA produces/consumes with SWIZZLE_128B): the residual (or, without one, the ReLU-backward
+      // mask) of the tile is TMA-loaded INTO it ahead of time, every thread updates its own row in place, and one
+      // thread TMA-stores the finished tile.  All global traffic of the epilogue is bulk and asynchronous -- with
+      // per-thread loads a 1x1 layer with a residual ran at ~1.4 TB/s (too few bytes in flight per SM).
+      const bool has_res = a.residual != nullptr, has_mask = a.relu_mask != nullptr;
+      const uint32_t buf_t = tile_base;
+      const uint32_t buf_m = (has_res && has_mask) ? tile_base + tile_buf_bytes : tile_base;   // mask shares T when alone
+      auto arm = [&](int tile) {     // one thread: stage the inputs of `tile` (or just release T) -> completes tile_bar
+        int n_tile, img, h0, w0;
+        tile_coords(a, tile, n_tile, img, h0, w0);
+        const int cols = min(a.bn, a.cout - n_tile * a.bn), nb = (cols + 63) >> 6;
+        if (has_res || has_mask) {
+          mbar_expect_tx(tile_bar, (uint32_t)nb * kABytes * (uint32_t)((has_res ? 1 : 0) + (has_mask ? 1 : 0)));
+          for (int b = 0; b < nb; ++b) {
+            if (has_res) tma_load_4d(buf_t + (uint32_t)b * kABytes, &map_res, tile_bar, n_tile * a.bn + b * 64, w0, h0, img);
+            if (has_mask) tma_load_4d(buf_m + (uint32_t)b * kABytes, &map_mask, tile_bar, n_tile * a.bn + b * 64, w0, h0, img);
+          }
+        } else {
+          mbar_arrive(tile_bar);
+        }
+      };
+      if (et == 0 && (int)blockIdx.x < a.tiles_total) arm(blockIdx.x);
+      uint32_t tile_phase = 0;
+      const uint32_t row_off = (uint32_t)row * 128u, row_sw = (uint32_t)(row & 7);
+      for (int tile = blockIdx.x; tile < a.tiles_total; tile += gridDim.x) {
+        int n_tile, img, h0, w0;
+        tile_coords(a, tile, n_tile, img, h0, w0);
+        float* sc = s_aff + acc * 512;
+        float* bi = sc + 256;
+        if (has_scale || has_bias) {
+          for (int c = et; c < a.bn; c += 32 * kEpiWarps) {
+            const int cg = n_tile * a.bn + c;
+            sc[c] = (has_scale && cg < a.cout) ? __ldg(a.scale + cg) : 1.f;
+            bi[c] = (has_bias && cg < a.cout) ? __ldg(a.bias + cg) : 0.f;
+          }
+          asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+        }
+        mbar_wait(tile_bar, tile_phase);
+        tile_phase ^= 1u;
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tc_fence_after();
+        const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * a.bn);
+        for (int col = grp * 32; col < a.bn; col += 32 * kGroups) {
+          if (n_tile * a.bn + col >= a.cout) break;  // warp-uniform
+          uint32_t v[32];
+          tmem_ld32(t_row + (uint32_t)col, v);
+          tmem_ld_wait();
+          const uint32_t box = (uint32_t)(col >> 6) * kABytes + row_off;
+          const uint32_t u0 = (uint32_t)(col & 63) >> 3;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float f[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[q * 8 + j]);
+            if (has_scale || has_bias) {
+              const float* scq = sc + col + q * 8;
+              const float* biq = bi + col + q * 8;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], scq[j], biq[j]);
+            }
+            const uint32_t slot = box + (((u0 + (uint32_t)q) ^ row_sw) << 4);     // this thread's 16 B of its row
+            if (has_res) {
+              const uint4 rr = lds128(buf_t + slot);
+              const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rr);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 t = __bfloat1622float2(r2[j]);
+                f[2 * j] += t.x; f[2 * j + 1] += t.y;
+              }
+            }
+            if (a.relu) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+            }
+            if (has_mask) {
+              const uint4 mk = lds128(buf_m + slot);
+              const __nv_bfloat162* m2 = reinterpret_cast<const __nv_bfloat162*>(&mk);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 t = __bfloat1622float2(m2[j]);
+                if (!(t.x > 0.f)) f[2 * j] = 0.f;
+                if (!(t.y > 0.f)) f[2 * j + 1] = 0.f;
+              }
+            }
+            uint4 pk;
+            __nv_bfloat162* p2 = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) p2[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+            sts128(buf_t + slot, pk);
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(tempty_bar(acc));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        fence_proxy_async_smem();            // this thread's tile-buffer writes -> visible to the TMA (async proxy)
+        asm volatile("bar.sync 2, %0;" ::"n"(32 * kEpiWarps) : "memory");
+        if (et == 0) {
+          const int cols = min(a.bn, a.cout - n_tile * a.bn), nb = (cols + 63) >> 6;
+          for (int b = 0; b < nb; ++b) tma_store_4d(&map_out, buf_t + (uint32_t)b * kABytes, n_tile * a.bn + b * 64, w0, h0, img);
+          bulk_commit();
+          bulk_wait_read0();                 // T has been read out: it may be refilled
+          if (tile + (int)gridDim.x < a.tiles_total) arm(tile + gridDim.x);
+        }
+      }
+    }
+    for (int tile = blockIdx.x; tile < a.tiles_total && !a.tma_epi; tile += gridDim.x) {
       int n_tile, img, h0, w0;
       tile_coords(a, tile, n_tile, img, h0, w0);
       const int h = h0 + hh, w = w0 + ww;
@@ -802,6 +941,12 @@ static int conv_launch(const ConvPlan& pl, const void* x, const void* w, int cin
     }
     bn = best_bn;
   }
+  // Epilogue through TMA tile buffers (bf16 result, Cout % 8 == 0, same-resolution residual): the tile's residual /
+  // ReLU-backward mask is TMA-loaded into shared memory, updated in place and TMA-stored.  A residual AND a mask need
+  // two buffers, which only fit next to the operand ring with N tiles of <= 128 columns.
+  const bool tma_epi = !out_f32 && (cout % 8) == 0 && !res_up2 && ((pl.out_w | pl.out_h | pl.out_n) % 8) == 0;
+  const int tile_bufs = (tma_epi && residual && relu_mask) ? 2 : 1;
+  if (tile_bufs == 2 && bn > 128) bn = 128;
   ConvArgs a;
   a.th = th; a.tw = tw; a.Ho = pl.Ho; a.Wo = pl.Wo;
   a.tiles_h = ceil_div(pl.Ho, th); a.tiles_w = ceil_div(pl.Wo, tw); a.tiles_n = ceil_div(cout, bn);
@@ -815,13 +960,33 @@ static int conv_launch(const ConvPlan& pl, const void* x, const void* w, int cin
   a.out = out;
   a.res_up2 = res_up2;
   a.res_w = cout; a.res_h = (long long)res_ww * cout; a.res_n = (long long)res_hh * res_ww * cout;
+  a.tma_epi = tma_epi ? 1 : 0;
+  a.tile_bufs = tile_bufs;
   const uint32_t stage_bytes = kABytes + bn * 128;
-  int stages = (int)((200 * 1024) / stage_bytes);
+  // fixed part: barriers + TMEM slot + scale/bias (4 KB) + alignment slack, plus either the tile buffers or the
+  // per-warp staging blocks of the per-thread epilogue
+  const size_t epi_bytes = tma_epi ? (size_t)tile_bufs * ceil_div(bn, 64) * kABytes : (size_t)2048 * kEpiWarps;
+  const size_t fixed = 8 * (2 * 8 + 6) + 16 + 4096 + 1024 + epi_bytes;
+  int stages = (int)((227 * 1024 - fixed) / stage_bytes);
   if (stages > 8) stages = 8;
+  if (stages < 2) return MRB_ERR_UNSUPPORTED;
   a.stages = stages;
-  const size_t smem = (size_t)stages * stage_bytes + 8 * (2 * stages + 4) + 16 + 4096 + 2048 * kEpiWarps + 1024;  // + scale/bias + epilogue staging
+  const size_t smem = (size_t)stages * stage_bytes + fixed;
 
-  CUtensorMap map_a, map_b;
+  CUtensorMap map_a, map_b, map_out, map_res, map_mask;
+  if (tma_epi) {
+    // output-side tensors [batch][Ho][Wo][cout] with the plan's element strides; box = one 64-channel slice of a tile
+    cuuint64_t dims[4] = {(cuuint64_t)cout, (cuuint64_t)pl.Wo, (cuuint64_t)pl.Ho, (cuuint64_t)pl.batch};
+    cuuint64_t strides[3] = {(cuuint64_t)pl.out_w * 2, (cuuint64_t)pl.out_h * 2, (cuuint64_t)pl.out_n * 2};
+    cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)tw, (cuuint32_t)th, 1};
+    int rc = encode_bf16(&map_out, out, 4, dims, strides, box);
+    if (rc) return rc;
+    map_res = map_out; map_mask = map_out;
+    if (residual && (rc = encode_bf16(&map_res, residual, 4, dims, strides, box))) return rc;
+    if (relu_mask && (rc = encode_bf16(&map_mask, relu_mask, 4, dims, strides, box))) return rc;
+  } else {
+    memset(&map_out, 0, sizeof(map_out)); map_res = map_out; map_mask = map_out;
+  }
   {
     cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)pl.Win, (cuuint64_t)pl.Hin, (cuuint64_t)pl.batch};
     cuuint64_t strides[3] = {(cuuint64_t)pl.in_w * 2, (cuuint64_t)pl.in_h * 2, (cuuint64_t)pl.in_n * 2};
@@ -844,7 +1009,7 @@ static int conv_launch(const ConvPlan& pl, const void* x, const void* w, int cin
   });
   if (attr_err != cudaSuccess) return (int)attr_err;
   const int grid = a.tiles_total < kNumSMs ? a.tiles_total : kNumSMs;
-  MRB_CUDA_TRY(launch_pdl(conv_tc_kernel, grid, kConvThreads, smem, stream, map_a, map_b, a));
+  MRB_CUDA_TRY(launch_pdl(conv_tc_kernel, grid, kConvThreads, smem, stream, map_a, map_b, map_out, map_res, map_mask, a));
   return MRB_OK;
 }
 
