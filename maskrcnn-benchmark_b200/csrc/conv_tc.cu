@@ -944,9 +944,18 @@ static int conv_launch(const ConvPlan& pl, const void* x, const void* w, int cin
   // Epilogue through TMA tile buffers (bf16 result, Cout % 8 == 0, same-resolution residual): the tile's residual /
   // ReLU-backward mask is TMA-loaded into shared memory, updated in place and TMA-stored.  A residual AND a mask need
   // two buffers, which only fit next to the operand ring with N tiles of <= 128 columns.
-  const bool tma_epi = !out_f32 && (cout % 8) == 0 && !res_up2 && ((pl.out_w | pl.out_h | pl.out_n) % 8) == 0;
-  const int tile_bufs = (tma_epi && residual && relu_mask) ? 2 : 1;
-  if (tile_bufs == 2 && bn > 128) bn = 128;
+  // Used where the epilogue is what bounds the layer: few k-blocks per tile (1x1 layers: a 128 x 256 tile moves
+  // 64-192 KB through the epilogue per 16-48 KB k-block) or narrow N tiles.  Long-K 256-wide tiles keep the per-thread
+  // epilogue: it hides behind the next tile's main loop, and the 64 KB tile buffer would cost a ring stage (measured
+  // -15% on the 3x3 256->256 layers with 3 instead of 4 stages).
+  const int k_blocks_tile = kh * kw * ceil_div(cin, kBlockK);
+  bool tma_epi = !out_f32 && (cout % 8) == 0 && !res_up2 && ((pl.out_w | pl.out_h | pl.out_n) % 8) == 0;
+  int tile_bufs = (residual && relu_mask) ? 2 : 1;
+  if (tma_epi && bn > 128) {
+    if (k_blocks_tile > 8) tma_epi = false;
+    else if (tile_bufs == 2) bn = 128;
+  }
+  if (!tma_epi) tile_bufs = 1;
   ConvArgs a;
   a.th = th; a.tw = tw; a.Ho = pl.Ho; a.Wo = pl.Wo;
   a.tiles_h = ceil_div(pl.Ho, th); a.tiles_w = ceil_div(pl.Wo, tw); a.tiles_n = ceil_div(cout, bn);
