@@ -108,7 +108,7 @@ class _SelectChannelFn(Function):
         (idx,) = ctx.saved_tensors
         r, c, h, w = ctx.shape
         gy = torch.empty((r, c, h, w), dtype=torch.bfloat16, device=g.device, memory_format=torch.channels_last).zero_()
-        gy.permute(0, 2, 3, 1).scatter_(3, idx, g.to(torch.bfloat16).unsqueeze(3))
+        gy.permute(0, 2, 3, 1).scatter_(3, idx, g.to(torch.bfloat16).unsqueeze(3))   # g arrives in y's dtype
         return gy, None
 
 
@@ -400,8 +400,10 @@ class B200Backend(Backend):
 
     def conv_select(self, x, weight, bias, labels, premask_x=False):
         """1x1 conv with fp32 output followed by the per-sample channel pick y[r, labels[r]] (mask logits + loss.py:120-126)."""
-        y = self.conv(x, weight, bias=bias, out_fp32=True, premask_x=premask_x, keep_padded=True)
-        return _SelectChannelFn.apply(y, labels)
+        # bf16 logits: the loss only reads one plane per ROI (converted to fp32 after the pick); an fp32 [R, 88, M, M]
+        # tensor would be the largest write of the mask head and its gradient would travel fp32 -> bf16 again
+        y = self.conv(x, weight, bias=bias, out_fp32=False, premask_x=premask_x, keep_padded=True)
+        return _SelectChannelFn.apply(y, labels).float()
 
     def bottleneck(self, blk, x, g_premasked):
         """Whole bottleneck as one autograd node (see _BottleneckFn).  Requires STRIDE_IN_1X1 geometry."""

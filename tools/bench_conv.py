@@ -29,7 +29,8 @@ for kind, n, cin, h, w, cout, k, stride, pad in SHAPES:
     ho, wo = (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
     go = torch.randn(n, cout, ho, wo, device=DEV).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
     if kind == "fwd":
-        fn = lambda: ops.conv2d_fwd(x, wt, None, None, None, stride, pad, True)  # noqa: E731
+        odt = torch.float32 if os.environ.get("MRB_BENCH_FP32") == "1" else torch.bfloat16
+        fn = lambda: ops.conv2d_fwd(x, wt, None, None, None, stride, pad, True, out_dtype=odt)  # noqa: E731
     elif kind == "dgrad":
         prep = ops.prepare_dgrad_weights([wt], [None])[0]
         fn = lambda: ops.conv2d_dgrad(go, wt, x.shape, None, None, None, stride, pad, prepared=prep)  # noqa: E731
