@@ -398,14 +398,24 @@ def main():
            "config": workload_config(world), "clocks": clocks,
            "e2e": {"value": round(imgs / t_e2e, 3), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
            "gpu_launches": launches, "cuda_graph": graph_info, "loss_last_step": round(float(last_loss), 4),
-           "library_ops": {"wgrad": model.be.wgrad_impl, "note": "conv forward, data-gradient and weight-gradient run on the "
-                           "in-house tcgen05 kernels; max-pool, top-k/sort, box arithmetic, losses and the multi-tensor "
-                           "SGD update are PyTorch"}}
+           "library_ops": {"wgrad": model.be.wgrad_impl, "note": "in-house sm_100a kernels (libmrb_b200.so): conv forward / "
+                           "data gradient / weight gradient / bias gradient (tcgen05 + TMA), fused multi-level ROIAlign fwd+bwd, "
+                           "batched NMS, max/sum pooling, fused SGD update; PyTorch: top-k/sort, box arithmetic, anchor "
+                           "matching, losses, gradient accumulation glue"}}
     if not args.no_roofline and conv_calls:
         per_step = conv_calls[:len(conv_calls) // args.steps]
         rf, rows = conv_roofline(per_step, peaks, device)
         # conv-FLOP roofline of the whole step (~1631 GFLOP/image fwd+bwd upper bound)
         rf["step_conv_flop_roofline_frac"] = round((imgs / t_dev) / (peaks.get("bf16_tflops", 1590.0) * 1e3 / 1631.0) / world, 4)
+        # DRAM traffic of the dominant launch shape from the committed `ncu --set full` capture (per launch, like `achieved`)
+        try:
+            cap = json.load(open(os.path.join(ROOT, "profiles", "ncu_conv_r1_summary.json")))[0]
+            m = cap["metrics"]
+            rf["traffic"] = round((float(m["dram__bytes_read.sum"]["value"]) + float(m["dram__bytes_write.sum"]["value"])) * 1e6)
+            rf["traffic_note"] = ("bytes of ONE launch of the top shape (%s): algorithmic 70.0e6 (x + y + w), tensor pipe "
+                                  "%.1f%% active" % (cap["what"].split(" (")[0], float(m["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"]["value"])))
+        except Exception:
+            pass
         out["roofline"] = rf
         if args.dump_shapes:
             json.dump(rows, open(args.dump_shapes, "w"), indent=1)

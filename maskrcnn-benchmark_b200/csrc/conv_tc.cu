@@ -164,6 +164,7 @@ struct ConvArgs {
   void* out;
   int tma_epi;                     // epilogue through TMA tile buffers (see conv_tc_kernel); else per-thread global access
   int tile_bufs;                   // 1, or 2 when both a residual and a mask tile are staged
+  int tile_dbl;                    // 2: the tile buffers are double-buffered across tiles (store / prefetch overlap)
 };
 
 __device__ __forceinline__ void tile_coords(const ConvArgs& a, int tile, int& n_tile, int& img, int& h0, int& w0) {
@@ -257,13 +258,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   // [ring: stages x (A 16 KB + B)] [tile buffers: tile_bufs x ceil(BN/64) x 16 KB (TMA epilogue only)] [barriers] ...
   const uint32_t tile_base = smem_base + (uint32_t)a.stages * stage_bytes;
   const uint32_t tile_buf_bytes = (uint32_t)((a.bn + 63) >> 6) * kABytes;
-  const uint32_t bar_base = tile_base + (a.tma_epi ? (uint32_t)a.tile_bufs * tile_buf_bytes : 0u);
-  // barriers: full[stages], empty[stages], tmem_full[2], tmem_empty[2], tile; then the TMEM base slot
+  const uint32_t bar_base = tile_base + (a.tma_epi ? (uint32_t)(a.tile_bufs * a.tile_dbl) * tile_buf_bytes : 0u);
+  // barriers: full[stages], empty[stages], tmem_full[2], tmem_empty[2], tile[2]; then the TMEM base slot
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (a.stages + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * a.stages + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * a.stages + 2 + s); };
-  const uint32_t tile_bar = bar_base + 8u * (2 * a.stages + 4);
+  auto tile_bar = [&](int b) { return bar_base + 8u * (2 * a.stages + 4 + b); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * a.stages + 6);   // keeps what follows 16-byte aligned
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int k_blocks = a.kh * a.kw * a.cin_blocks;
@@ -273,7 +274,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (threadIdx.x == 0) {
     for (int s = 0; s < a.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 32 * kEpiWarps); }
-    mbar_init(tile_bar, 1);
+    mbar_init(tile_bar(0), 1);
+    mbar_init(tile_bar(1), 1);
     fence_barrier_init();
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
@@ -365,28 +367,39 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       // thread TMA-stores the finished tile.  All global traffic of the epilogue is bulk and asynchronous -- with
       // per-thread loads a 1x1 layer with a residual ran at ~1.4 TB/s (too few bytes in flight per SM).
       const bool has_res = a.residual != nullptr, has_mask = a.relu_mask != nullptr;
-      const uint32_t buf_t = tile_base;
-      const uint32_t buf_m = (has_res && has_mask) ? tile_base + tile_buf_bytes : tile_base;   // mask shares T when alone
-      auto arm = [&](int tile) {     // one thread: stage the inputs of `tile` (or just release T) -> completes tile_bar
+      const uint32_t set_bytes = (uint32_t)a.tile_bufs * tile_buf_bytes;          // one buffer set (T [+ M])
+      const uint32_t m_off = (has_res && has_mask) ? tile_buf_bytes : 0u;         // the mask shares T when it is alone
+      // With two buffer sets (tile_dbl == 2) the store of tile i and the input prefetch of tile i+1 overlap the
+      // epilogue arithmetic of the neighbouring tiles; with one set they serialise (the wait for the store to drain
+      // was 28% of all warp stalls on an epilogue-bound 1x1 layer).
+      auto arm = [&](int tile, int b) {  // one thread: stage the inputs of `tile` into set b (or just release it)
         int n_tile, img, h0, w0;
         tile_coords(a, tile, n_tile, img, h0, w0);
         const int cols = min(a.bn, a.cout - n_tile * a.bn), nb = (cols + 63) >> 6;
+        const uint32_t bt = tile_base + (uint32_t)b * set_bytes;
         if (has_res || has_mask) {
-          mbar_expect_tx(tile_bar, (uint32_t)nb * kABytes * (uint32_t)((has_res ? 1 : 0) + (has_mask ? 1 : 0)));
-          for (int b = 0; b < nb; ++b) {
-            if (has_res) tma_load_4d(buf_t + (uint32_t)b * kABytes, &map_res, tile_bar, n_tile * a.bn + b * 64, w0, h0, img);
-            if (has_mask) tma_load_4d(buf_m + (uint32_t)b * kABytes, &map_mask, tile_bar, n_tile * a.bn + b * 64, w0, h0, img);
+          mbar_expect_tx(tile_bar(b), (uint32_t)nb * kABytes * (uint32_t)((has_res ? 1 : 0) + (has_mask ? 1 : 0)));
+          for (int x = 0; x < nb; ++x) {
+            if (has_res) tma_load_4d(bt + (uint32_t)x * kABytes, &map_res, tile_bar(b), n_tile * a.bn + x * 64, w0, h0, img);
+            if (has_mask) tma_load_4d(bt + m_off + (uint32_t)x * kABytes, &map_mask, tile_bar(b), n_tile * a.bn + x * 64, w0, h0, img);
           }
         } else {
-          mbar_arrive(tile_bar);
+          mbar_arrive(tile_bar(b));
         }
       };
-      if (et == 0 && (int)blockIdx.x < a.tiles_total) arm(blockIdx.x);
-      uint32_t tile_phase = 0;
+      if (et == 0 && (int)blockIdx.x < a.tiles_total) arm(blockIdx.x, 0);
       const uint32_t row_off = (uint32_t)row * 128u, row_sw = (uint32_t)(row & 7);
-      for (int tile = blockIdx.x; tile < a.tiles_total; tile += gridDim.x) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < a.tiles_total; tile += gridDim.x, ++it) {
         int n_tile, img, h0, w0;
         tile_coords(a, tile, n_tile, img, h0, w0);
+        const int b = (a.tile_dbl == 2) ? (it & 1) : 0;
+        const uint32_t tile_phase = (a.tile_dbl == 2) ? (uint32_t)((it >> 1) & 1) : (uint32_t)(it & 1);
+        const uint32_t buf_t = tile_base + (uint32_t)b * set_bytes, buf_m = buf_t + m_off;
+        if (a.tile_dbl == 2 && et == 0) {
+          bulk_wait_read0();               // the previous tile's store has left the other set: refill it now
+          if (tile + (int)gridDim.x < a.tiles_total) arm(tile + gridDim.x, b ^ 1);
+        }
         float* sc = s_aff + acc * 512;
         float* bi = sc + 256;
         if (has_scale || has_bias) {
@@ -397,8 +410,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           }
           asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
         }
-        mbar_wait(tile_bar, tile_phase);
-        tile_phase ^= 1u;
+        mbar_wait(tile_bar(b), tile_phase);
         mbar_wait(tfull_bar(acc), acc_phase);
         tc_fence_after();
         const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * a.bn);
@@ -458,12 +470,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         asm volatile("bar.sync 2, %0;" ::"n"(32 * kEpiWarps) : "memory");
         if (et == 0) {
           const int cols = min(a.bn, a.cout - n_tile * a.bn), nb = (cols + 63) >> 6;
-          for (int b = 0; b < nb; ++b) tma_store_4d(&map_out, buf_t + (uint32_t)b * kABytes, n_tile * a.bn + b * 64, w0, h0, img);
+          for (int x = 0; x < nb; ++x) tma_store_4d(&map_out, buf_t + (uint32_t)x * kABytes, n_tile * a.bn + x * 64, w0, h0, img);
           bulk_commit();
-          bulk_wait_read0();                 // T has been read out: it may be refilled
-          if (tile + (int)gridDim.x < a.tiles_total) arm(tile + gridDim.x);
+          if (a.tile_dbl != 2) {
+            bulk_wait_read0();               // T has been read out: it may be refilled
+            if (tile + (int)gridDim.x < a.tiles_total) arm(tile + gridDim.x, 0);
+          }
         }
       }
+      if (et == 0) bulk_wait_read0();        // shared memory must outlive the last store's read
     }
     for (int tile = blockIdx.x; tile < a.tiles_total && !a.tma_epi; tile += gridDim.x) {
       int n_tile, img, h0, w0;
@@ -951,11 +966,17 @@ static int conv_launch(const ConvPlan& pl, const void* x, const void* w, int cin
   const int k_blocks_tile = kh * kw * ceil_div(cin, kBlockK);
   bool tma_epi = !out_f32 && (cout % 8) == 0 && !res_up2 && ((pl.out_w | pl.out_h | pl.out_n) % 8) == 0;
   int tile_bufs = (residual && relu_mask) ? 2 : 1;
+  int tile_dbl = 1;
   if (tma_epi && bn > 128) {
     if (k_blocks_tile > 8) tma_epi = false;
-    else if (tile_bufs == 2) bn = 128;
+    else bn = 128;      // short K: epilogue bound -> 128-wide tiles leave room for two buffer sets
   }
   if (!tma_epi) tile_bufs = 1;
+  if (tma_epi) {
+    const size_t need2 = (size_t)2 * tile_bufs * ceil_div(bn, 64) * kABytes;
+    const size_t left = 227 * 1024 - (8 * (2 * 8 + 6) + 16 + 4096 + 1024) - need2;
+    if (need2 < 200 * 1024 && (int)(left / (kABytes + bn * 128)) >= 2) tile_dbl = 2;
+  }
   ConvArgs a;
   a.th = th; a.tw = tw; a.Ho = pl.Ho; a.Wo = pl.Wo;
   a.tiles_h = ceil_div(pl.Ho, th); a.tiles_w = ceil_div(pl.Wo, tw); a.tiles_n = ceil_div(cout, bn);
@@ -971,10 +992,11 @@ static int conv_launch(const ConvPlan& pl, const void* x, const void* w, int cin
   a.res_w = cout; a.res_h = (long long)res_ww * cout; a.res_n = (long long)res_hh * res_ww * cout;
   a.tma_epi = tma_epi ? 1 : 0;
   a.tile_bufs = tile_bufs;
+  a.tile_dbl = tile_dbl;
   const uint32_t stage_bytes = kABytes + bn * 128;
   // fixed part: barriers + TMEM slot + scale/bias (4 KB) + alignment slack, plus either the tile buffers or the
   // per-warp staging blocks of the per-thread epilogue
-  const size_t epi_bytes = tma_epi ? (size_t)tile_bufs * ceil_div(bn, 64) * kABytes : (size_t)2048 * kEpiWarps;
+  const size_t epi_bytes = tma_epi ? (size_t)tile_dbl * tile_bufs * ceil_div(bn, 64) * kABytes : (size_t)2048 * kEpiWarps;
   const size_t fixed = 8 * (2 * 8 + 6) + 16 + 4096 + 1024 + epi_bytes;
   int stages = (int)((227 * 1024 - fixed) / stage_bytes);
   if (stages > 8) stages = 8;
