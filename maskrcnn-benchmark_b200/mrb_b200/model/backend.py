@@ -260,6 +260,7 @@ class B200Backend(Backend):
         self._wd = {}     # (id(param), id(scale)) -> [param, scale, version, w16, prepared dgrad weights]
         self.arena = None
         self.side = None          # second stream for gradient-sink kernels (see side_launch)
+        self.lanes = []
         self._side_busy = False
         if wgrad == "tc":
             self.wgrad_fn, self.wgrad_impl = _wgrad_tc, "mrb_conv2d_wgrad (tcgen05, in-house)"
@@ -289,6 +290,7 @@ class B200Backend(Backend):
         backward pass reads their result, so they overlap the data-gradient chain (most layers of res4/res5 and the
         heads fill well under 148 SMs).  Captured into the CUDA graph as parallel branches; join_side() is the join."""
         self.side = torch.cuda.Stream() if on else None
+        self.lanes = [torch.cuda.Stream() for _ in range(6)] if on else []      # independent glue chains (fork(lane=i))
 
     def side_launch(self, tensors, fn):
         if self.side is None:
@@ -301,24 +303,26 @@ class B200Backend(Backend):
             t.record_stream(self.side)                             # keep the allocator from recycling them early
         self._side_busy = True
 
-    def fork(self, inputs, fn):
-        """Run fn() (no autograd, independent of everything launched since) on the second stream; returns a handle for
-        join().  Without a second stream it just runs inline."""
-        if self.side is None:
-            return ("done", fn())
+    def fork(self, inputs, fn, lane=None):
+        """Run fn() (no autograd, independent of everything launched since) on another stream -- the gradient stream, or
+        one of the `lanes` for mutually independent chains (e.g. the per-level proposal pipelines); returns a handle
+        for join().  Without extra streams it just runs inline."""
+        st = self.side if lane is None else (self.lanes[lane % len(self.lanes)] if self.lanes else None)
+        if st is None:
+            return (None, fn())
         cur = torch.cuda.current_stream()
-        self.side.wait_stream(cur)
-        with torch.cuda.stream(self.side):
+        st.wait_stream(cur)
+        with torch.cuda.stream(st):
             out = fn()
         for t in inputs:
-            t.record_stream(self.side)
-        return ("side", out)
+            t.record_stream(st)
+        return (st, out)
 
     def join(self, handle):
-        kind, out = handle
-        if kind == "side":
+        st, out = handle
+        if st is not None:
             cur = torch.cuda.current_stream()
-            cur.wait_stream(self.side)
+            cur.wait_stream(st)
 
             def mark(o):
                 if isinstance(o, torch.Tensor):

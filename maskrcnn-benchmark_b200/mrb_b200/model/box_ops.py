@@ -141,6 +141,16 @@ def sample_pos_neg_idx(labels, batch_size, positive_fraction, generator=None):
 def sample_pos_neg(labels, batch_size, positive_fraction, generator=None):
     """The same sample as boolean masks (pos, neg) over the elements of `labels`."""
     n = labels.numel()
+    if n <= 4096:
+        # few candidates (the <= ~2000 proposals of an image): rank every element among the masked ones by pairwise
+        # key comparison -- two n x n passes instead of two single-block top-k launches
+        cap = min(int(batch_size * positive_fraction), n)
+        key = torch.rand(n, device=labels.device, generator=generator)
+        pos, neg = labels >= 1, labels == 0
+        lt = key[None, :] < key[:, None]                       # lt[i, j]: element j precedes element i
+        pos_sel = pos & ((lt & pos[None, :]).sum(1) < cap)
+        neg_sel = neg & ((lt & neg[None, :]).sum(1) < (batch_size - pos_sel.sum()))
+        return pos_sel, neg_sel
     pos_idx, pos_ok, neg_idx, neg_ok = sample_pos_neg_idx(labels, batch_size, positive_fraction, generator)
     return _mask_of(pos_idx, pos_ok, n), _mask_of(neg_idx, neg_ok, n)
 

@@ -46,7 +46,7 @@ class GeneralizedRCNN(nn.Module):
         proposals, losses = self.rpn.run(be, feats, image_sizes, targets, self.training, generator)
         box = self.roi_heads.box
         if self.training:
-            boxes, labels, reg_t, gidx = box.subsample(proposals, targets, generator)
+            boxes, labels, reg_t, gidx = box.subsample(proposals, targets, generator, be)
             rois = _to_rois(boxes)
             x = box.features(be, feats, rois)
             cls, reg = box.predict(be, x)

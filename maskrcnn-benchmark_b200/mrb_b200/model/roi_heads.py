@@ -43,15 +43,14 @@ class BoxHead(nn.Module):
         self.matcher = box_ops.Matcher(cfg.roi_fg_iou, cfg.roi_bg_iou, allow_low_quality_matches=False)
 
     @torch.no_grad()
-    def subsample(self, proposals, targets, generator=None):
+    def subsample(self, proposals, targets, generator=None, be=None):
         """box_head/loss.py:41-118: match, label, sample 512 per image (25 % positive).
         -> boxes [N, S, 4], labels [N, S] (-1 = padding), reg targets [N, S, 4], matched gt [N, S]"""
         cfg = self.cfg
         boxes, _, valid = proposals
         n = boxes.shape[0]
         S = cfg.roi_batch_size
-        ob, ol, ot, og = [], [], [], []
-        for i in range(n):
+        def image(i):
             t = targets[i]
             q = box_ops.box_iou(t["boxes"], boxes[i])
             midx = self.matcher(q)
@@ -66,10 +65,17 @@ class BoxHead(nn.Module):
             ok = sel[order]
             b = boxes[i][order]
             g = midx.clamp(min=0)[order]
-            ob.append(b)
-            ol.append(torch.where(ok, lab[order], -torch.ones_like(lab[order])))
-            ot.append(self.box_coder.encode(t["boxes"][g], b))
-            og.append(g)
+            return b, torch.where(ok, lab[order], -torch.ones_like(lab[order])), self.box_coder.encode(t["boxes"][g], b), g
+
+        # images are independent: one stream lane each when the backend offers them
+        fork = getattr(be, "fork", None) if be is not None else None
+        with torch.no_grad():
+            if fork is not None:
+                hs = [fork((boxes, valid, targets[i]["boxes"], targets[i]["labels"]), lambda i=i: image(i), lane=i) for i in range(n)]
+                outs = [be.join(h) for h in hs]
+            else:
+                outs = [image(i) for i in range(n)]
+        ob, ol, ot, og = zip(*outs)
         return torch.stack(ob), torch.stack(ol), torch.stack(ot), torch.stack(og)
 
     def features(self, be, feats, rois):

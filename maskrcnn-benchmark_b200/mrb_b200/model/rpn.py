@@ -111,20 +111,30 @@ class RPN(nn.Module):
             self._size_cache[key] = (torch.tensor([s[1] for s in image_sizes], device=dev, dtype=torch.float32),
                                      torch.tensor([s[0] for s in image_sizes], device=dev, dtype=torch.float32))
         widths, heights = self._size_cache[key]
-        all_boxes, all_scores, ks = [], [], []
-        for anc, lg, dl in zip(anchors, logits, deltas):
+        def level(anc, lg, dl):
             k = min(pre_n, lg.shape[1])
             sc, idx = lg.sigmoid().topk(k, dim=1, sorted=True)                       # inference.py:91-95
             d = torch.gather(dl, 1, idx[..., None].expand(-1, -1, 4))
             bx = self.box_coder.decode(d.reshape(-1, 4).float(), anc[idx.reshape(-1)]).view(n, k, 4)
             # clip_to_image(remove_empty=False); remove_small_boxes(min_size=0) keeps everything
-            bx = torch.stack([bx[..., 0].clamp(min=0).minimum(widths[:, None] - 1),
-                              bx[..., 1].clamp(min=0).minimum(heights[:, None] - 1),
-                              bx[..., 2].clamp(min=0).minimum(widths[:, None] - 1),
-                              bx[..., 3].clamp(min=0).minimum(heights[:, None] - 1)], -1)
+            lim = torch.stack([widths, heights, widths, heights], 1)[:, None, :] - 1      # [N, 1, 4]
+            return torch.minimum(bx.clamp(min=0), lim), sc
+
+        # the per-level pipelines are independent of each other: with a backend that offers extra streams they run
+        # side by side (their top-k kernels are single- or few-block launches that leave the chip empty)
+        fork = getattr(be, "fork", None)
+        handles = []
+        for li, (anc, lg, dl) in enumerate(zip(anchors, logits, deltas)):
+            if fork is not None:
+                handles.append(fork((anc, lg, dl, widths, heights), lambda anc=anc, lg=lg, dl=dl: level(anc, lg, dl), lane=li))
+            else:
+                handles.append(level(anc, lg, dl))
+        all_boxes, all_scores, ks = [], [], []
+        for h in handles:
+            bx, sc = be.join(h) if fork is not None else h
             all_boxes.append(bx)
             all_scores.append(sc)
-            ks.append(k)
+            ks.append(bx.shape[1])
         # one batched NMS over the N x L problems, problem order = (level, image)
         boxes = torch.cat([b.reshape(-1, 4) for b in all_boxes]).contiguous()
         scores = torch.cat([s.reshape(-1) for s in all_scores]).contiguous()

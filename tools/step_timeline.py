@@ -81,6 +81,38 @@ def main():
     mine = sum(v[1] for k, v in rows if k.startswith("mrb::"))
     print("device activities: %d   span %.2f ms   sum of durations %.2f ms   libmrb share of busy time %.1f%%"
           % (len(ks), span / 1e3, busy / 1e3, 100 * mine / busy))
+    # exposure: wall time of the step during which NO libmrb kernel is running on any stream (pure glue), and during
+    # which nothing at all is running (launch gaps; large in this eager trace, absent under the CUDA graph)
+    def union(iv):
+        iv = sorted(iv)
+        out, cs, ce = 0.0, None, None
+        for a, b in iv:
+            if cs is None:
+                cs, ce = a, b
+            elif a <= ce:
+                ce = max(ce, b)
+            else:
+                out += ce - cs
+                cs, ce = a, b
+        return out + (ce - cs if cs is not None else 0.0)
+    u_all = union([(a, b) for a, b, n in ks])
+    u_mrb = union([(a, b) for a, b, n in ks if "mrb::" in n or "bias_grad" in n])
+    print("wall time with any kernel running %.2f ms; with a libmrb kernel running %.2f ms; glue-only %.2f ms; idle %.2f ms"
+          % (u_all / 1e3, u_mrb / 1e3, (u_all - u_mrb) / 1e3, (span - u_all) / 1e3))
+    glue = collections.defaultdict(float)
+    mrb_iv = sorted((a, b) for a, b, n in ks if "mrb::" in n or "bias_grad" in n)
+    import bisect
+    starts = [a for a, _ in mrb_iv]
+    for a, b, n in ks:
+        if "mrb::" in n or "bias_grad" in n:
+            continue
+        i = bisect.bisect_right(starts, a) - 1
+        covered = i >= 0 and mrb_iv[i][1] >= b       # fully under one libmrb kernel (approximation)
+        if not covered:
+            glue[short(n)] += b - a
+    print("exposed glue kernels (not running under a libmrb kernel), top 15 by time:")
+    for k, t in sorted(glue.items(), key=lambda kv: -kv[1])[:15]:
+        print("  %8.1f us  %s" % (t, k))
     print("| kernel | launches | total us | share of busy |")
     print("|---|---|---|---|")
     for k, (n, t) in rows[:args.top]:
