@@ -233,6 +233,8 @@ def main():
                     help="arena: flat parameter/gradient buffers + fused update kernel; flat: foreach SGD (A/B switch)")
     ap.add_argument("--overlap", default="on", choices=["on", "off"],
                     help="weight-/bias-gradient kernels on a second stream (needs --optim arena)")
+    ap.add_argument("--parallel-heads", default="on", choices=["on", "off"],
+                    help="mask branch on its own stream, overlapping the box branch (needs --overlap on)")
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
                     help="capture the whole train step (fwd+bwd+all-reduce+SGD) in one CUDA graph; falls back to eager "
                          "(and says so) if capture fails")
@@ -260,7 +262,8 @@ def main():
     from mrb_b200.optim import FlatSGD, ParamArena
     use_graph = args.graph in ("on", "auto")
     # graph capture needs a step without host synchronisation: fixed-shape mask head (see RCNNConfig)
-    cfg = RCNNConfig(mask_rois_per_image=128 if use_graph else 0)
+    cfg = RCNNConfig(mask_rois_per_image=128 if use_graph else 0,
+                     parallel_heads=(args.parallel_heads == "on" and args.overlap == "on" and args.optim == "arena"))
     model = build_model(cfg, backend=B200Backend(wgrad=args.wgrad), device=device).train()
     params = [p for p in model.parameters() if p.requires_grad]
     grad_sync = None

@@ -57,5 +57,6 @@ class RCNNConfig:
     # yields more than int(roi_batch_size * roi_positive_fraction) = 128 positives per image) -- which makes the
     # whole train step free of host synchronisation and therefore CUDA-graph capturable.
     mask_rois_per_image: int = 0
+    parallel_heads: bool = False   # issue the mask branch on its own CUDA stream (overlaps the box branch, fwd and bwd)
     size_divisibility: int = 32               # DATALOADER.SIZE_DIVISIBILITY (yaml:35-36)
     pixel_mean: Tuple[float, ...] = field(default=(102.9801, 115.9465, 122.7717))

@@ -36,6 +36,31 @@ class GeneralizedRCNN(nn.Module):
             batch[i, :, :im.shape[1], :im.shape[2]] = im
         return batch, sizes
 
+    def _mask_loss(self, be, feats, rois, labels, gidx, targets):
+        mask = self.roi_heads.mask
+        n, s = labels.shape
+        res = self.cfg.mask_resolution
+        gt_all = torch.stack([t["boxes"][gidx[i]] for i, t in enumerate(targets)])          # [n, s, 4]
+        m = self.cfg.mask_rois_per_image
+        if m > 0:
+            posm = labels > 0
+            order = torch.sort((~posm).to(torch.int8), dim=1, stable=True)[1][:, :m]        # positives first
+            wsel = torch.gather(posm, 1, order).reshape(-1).float()
+            rois_sel = torch.gather(rois.view(n, s, 5), 1, order[..., None].expand(-1, -1, 5)).reshape(-1, 5)
+            lab_sel = torch.gather(labels, 1, order).reshape(-1).clamp(min=0)
+            gt_sel = torch.gather(gt_all, 1, order[..., None].expand(-1, -1, 4)).reshape(-1, 4)
+            sel_logits = mask.run(be, feats, rois_sel, select=lab_sel)
+            tgt = mask.mask_targets(gt_sel, rois_sel[:, 1:], res)
+            bce = torch.nn.functional.binary_cross_entropy_with_logits(sel_logits.float(), tgt,
+                                                                       reduction="none").mean((1, 2))
+            return (bce * wsel).sum() / wsel.sum().clamp(min=1)
+        lab = labels.reshape(-1)
+        pos = (lab > 0).nonzero().squeeze(1)             # keep_only_positive_boxes (mask_head.py:11-32)
+        rois_pos = rois[pos]
+        logits = mask.run(be, feats, rois_pos)
+        tgt = mask.mask_targets(gt_all.reshape(n * s, 4)[pos], rois_pos[:, 1:], res)
+        return mask.loss(logits, lab[pos], tgt)
+
     def forward(self, images, image_sizes, targets=None, generator=None):
         """images: [N,3,H,W] fp32 already padded; image_sizes: [(h, w)]; targets: list of dicts with
         'boxes' [G,4] xyxy fp32 and 'labels' [G] int64 (masks == box rectangles)."""
@@ -48,35 +73,33 @@ class GeneralizedRCNN(nn.Module):
         if self.training:
             boxes, labels, reg_t, gidx = box.subsample(proposals, targets, generator, be)
             rois = _to_rois(boxes)
+            if self.cfg.mask_on:
+                # The mask branch needs only the sampled boxes/labels and the FPN features.  With a backend that offers
+                # stream lanes it is issued on its own stream, BEFORE the box branch: autograd replays every node on the
+                # stream of its forward, so forward and backward of the two heads overlap (the box head's FC layers
+                # and losses leave most of the 148 SMs idle).
+                lane = getattr(be, "lanes", None)
+                st = lane[-1] if (lane and getattr(self.cfg, "parallel_heads", False)) else None
+                if st is not None:
+                    cur = torch.cuda.current_stream()
+                    st.wait_stream(cur)
+                    for t in list(feats) + [rois, labels, gidx]:
+                        t.record_stream(st)
+                    with torch.cuda.stream(st):
+                        loss_mask = self._mask_loss(be, feats, rois, labels, gidx, targets)
+                    loss_mask.record_stream(cur)
+                else:
+                    loss_mask = None
             x = box.features(be, feats, rois)
             cls, reg = box.predict(be, x)
             lc, lb = box.loss(cls, reg, labels, reg_t)
             losses.update({"loss_classifier": lc, "loss_box_reg": lb})
             if self.cfg.mask_on:
-                mask = self.roi_heads.mask
-                n, s = labels.shape
-                res = self.cfg.mask_resolution
-                gt_all = torch.stack([t["boxes"][gidx[i]] for i, t in enumerate(targets)])          # [n, s, 4]
-                m = self.cfg.mask_rois_per_image
-                if m > 0:
-                    posm = labels > 0
-                    order = torch.sort((~posm).to(torch.int8), dim=1, stable=True)[1][:, :m]        # positives first
-                    wsel = torch.gather(posm, 1, order).reshape(-1).float()
-                    rois_sel = torch.gather(rois.view(n, s, 5), 1, order[..., None].expand(-1, -1, 5)).reshape(-1, 5)
-                    lab_sel = torch.gather(labels, 1, order).reshape(-1).clamp(min=0)
-                    gt_sel = torch.gather(gt_all, 1, order[..., None].expand(-1, -1, 4)).reshape(-1, 4)
-                    sel_logits = mask.run(be, feats, rois_sel, select=lab_sel)
-                    tgt = mask.mask_targets(gt_sel, rois_sel[:, 1:], res)
-                    bce = torch.nn.functional.binary_cross_entropy_with_logits(sel_logits.float(), tgt,
-                                                                               reduction="none").mean((1, 2))
-                    losses["loss_mask"] = (bce * wsel).sum() / wsel.sum().clamp(min=1)
+                if st is not None:
+                    torch.cuda.current_stream().wait_stream(st)
                 else:
-                    lab = labels.reshape(-1)
-                    pos = (lab > 0).nonzero().squeeze(1)             # keep_only_positive_boxes (mask_head.py:11-32)
-                    rois_pos = rois[pos]
-                    logits = mask.run(be, feats, rois_pos)
-                    tgt = mask.mask_targets(gt_all.reshape(n * s, 4)[pos], rois_pos[:, 1:], res)
-                    losses["loss_mask"] = mask.loss(logits, lab[pos], tgt)
+                    loss_mask = self._mask_loss(be, feats, rois, labels, gidx, targets)
+                losses["loss_mask"] = loss_mask
             return losses
         boxes, _, valid = proposals
         rois = _to_rois(boxes)

@@ -190,6 +190,7 @@ def test_param_arena_step_equals_flat_sgd(built_lib):
         else:
             opt = ParamArena(model.named_parameters(), model.be, lr=1e-3, momentum=0.9, weight_decay=1e-4)
             model.be.enable_overlap(True)          # gradient-sink kernels on the second stream
+            model.cfg.parallel_heads = True        # mask branch on its own stream
         before = {n: p.detach().float().clone() for n, p in model.named_parameters() if p.requires_grad}
         for it in range(2):
             torch.manual_seed(100 + it)
