@@ -374,13 +374,49 @@ def main():
         launches = ops.STATS["launches"]
         conv_calls = list(ops.STATS["conv_calls"])
     ops.STATS["conv_calls"] = None
-    # ---- timed: end to end from pinned host memory
+    # ---- timed: end to end from pinned host memory.  Every step's batch is copied host -> device and every step's
+    # loss is read back (a blocking .cpu()) inside the timed region.  With the captured step the H2D copy of batch i+1
+    # is issued on a copy stream into a staging buffer while step i computes (what a prefetching data loader with pinned
+    # memory does; the reference's loader hands pinned batches to `images.to(device)`, engine/trainer.py:64-68), and a
+    # device-to-device copy moves it into the graph's static input at the start of step i+1.
     step_e2e(host[0])
     barrier()
+    e2e_mode = "h2d serialised with the step"
+    if graph_info["enabled"]:
+        e2e_mode = "h2d of batch i+1 prefetched on a copy stream during step i"
+        copy_stream = torch.cuda.Stream()
+        staging = tuple(torch.empty_like(t) for t in static)
+        ev_staged, ev_consumed = torch.cuda.Event(), torch.cuda.Event()
+
+        def prefetch(hbatch):
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(ev_consumed)            # the previous staging content has been consumed
+                for a, b in zip(staging, hbatch):
+                    a.copy_(b, non_blocking=True)
+                ev_staged.record(copy_stream)
+
+        def step_e2e_prefetched(next_hbatch):
+            cur = torch.cuda.current_stream()
+            cur.wait_event(ev_staged)
+            for a, b in zip(static, staging):
+                a.copy_(b, non_blocking=True)
+            ev_consumed.record(cur)
+            graph.replay()
+            if next_hbatch is not None:
+                prefetch(next_hbatch)
+            return static_loss.detach().float().cpu()
+
+        ev_consumed.record(torch.cuda.current_stream())
+        barrier()
     e0.record()
     last_loss = None
-    for i in range(args.steps):
-        last_loss = step_e2e(host[i % n_batches])
+    if graph_info["enabled"]:
+        prefetch(host[0])
+        for i in range(args.steps):
+            last_loss = step_e2e_prefetched(host[(i + 1) % n_batches] if i + 1 < args.steps else None)
+    else:
+        for i in range(args.steps):
+            last_loss = step_e2e(host[i % n_batches])
     e1.record()
     barrier()
     t_e2e = e0.elapsed_time(e1) * 1e-3
@@ -399,7 +435,8 @@ def main():
            "warmup": args.warmup, "ms_per_step": round(t_dev / args.steps * 1e3, 2), "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
            "config": workload_config(world), "clocks": clocks,
-           "e2e": {"value": round(imgs / t_e2e, 3), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+           "e2e": {"value": round(imgs / t_e2e, 3), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                   "mode": e2e_mode},
            "gpu_launches": launches, "cuda_graph": graph_info, "loss_last_step": round(float(last_loss), 4),
            "library_ops": {"wgrad": model.be.wgrad_impl, "note": "in-house sm_100a kernels (libmrb_b200.so): conv forward / "
                            "data gradient / weight gradient / bias gradient (tcgen05 + TMA), fused multi-level ROIAlign fwd+bwd, "

@@ -89,6 +89,22 @@ class _ConvFn(Function):
         return (gx, gw, gb, gres) + (None,) * 14
 
 
+class _HeadsBoundaryFn(Function):
+    """Identity on the FPN outputs whose backward runs exactly when every consumer downstream (RPN head, both ROI
+    heads) has issued its backward -- the moment the gradients of all their parameters are complete.  The backend uses
+    it to start the data-parallel all-reduce of that bucket while the backbone's backward is still to come."""
+
+    @staticmethod
+    def forward(ctx, be, *feats):
+        ctx.be = be
+        return tuple(f.view_as(f) for f in feats)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        ctx.be.heads_grads_ready()
+        return (None,) + grads
+
+
 class _SelectChannelFn(Function):
     """out[r, h, w] = y[r, label[r], h, w] for an NHWC tensor (the class-specific mask logit of each ROI, reference
     roi_heads/mask_head/loss.py:120-126 `mask_logits[positive_inds, labels_pos]`).  The backward writes the gradient
@@ -337,6 +353,15 @@ class B200Backend(Backend):
         if self.side is not None and self._side_busy:
             torch.cuda.current_stream().wait_stream(self.side)
             self._side_busy = False
+
+    def heads_boundary(self, feats):
+        if self.arena is None or self.arena.world <= 1:
+            return feats
+        return list(_HeadsBoundaryFn.apply(self, *feats))
+
+    def heads_grads_ready(self):
+        if self.arena is not None:
+            self.arena.early_reduce()
 
     def grad_sink(self, p):
         return self.arena.grad_sink(p) if (self.arena is not None and p is not None) else None

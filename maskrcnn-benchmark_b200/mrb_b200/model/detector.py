@@ -68,6 +68,8 @@ class GeneralizedRCNN(nn.Module):
         if self.training and targets is None:
             raise ValueError("In training mode, targets should be passed")
         feats = self.backbone.run(be, images)
+        if self.training and hasattr(be, "heads_boundary"):
+            feats = be.heads_boundary(feats)        # data-parallel runs: marks where the heads' gradients are complete
         proposals, losses = self.rpn.run(be, feats, image_sizes, targets, self.training, generator)
         box = self.roi_heads.box
         if self.training:

@@ -73,7 +73,7 @@ class ParamArena:
     ALIGN = 64      # elements: every parameter starts 256 B (fp32) / 128 B (bf16) aligned -> TMA / vector friendly
 
     def __init__(self, named_params, backend, lr=0.02, momentum=0.9, weight_decay=1e-4, bias_lr_factor=2.0,
-                 weight_decay_bias=0.0, world_size=1, group=None):
+                 weight_decay_bias=0.0, world_size=1, group=None, late_prefix="backbone."):
         named = [(n, p) for n, p in named_params if p.requires_grad]
         for n, p in named:
             if not (p.is_contiguous() or p.is_contiguous(memory_format=torch.channels_last)):
@@ -95,6 +95,17 @@ class ParamArena:
         self.groups = [g for g in ((0, n_w, lr, weight_decay), (n_w, total, lr * bias_lr_factor, weight_decay_bias))
                        if g[1] > g[0]]
         self.momentum, self.world, self.group, self.backend = momentum, world_size, group, backend
+        # data-parallel buckets: [0, split) = the leading parameters whose gradients complete LAST in backward (the
+        # backbone: names starting with `late_prefix`), [split, n_w) = everything downstream of it (RPN + ROI heads),
+        # whose all-reduce can start as soon as the heads' backward has been issued (early_reduce), [n_w, total) = biases
+        self.split = 0
+        for n, p in w:
+            if not n.startswith(late_prefix):
+                break
+            self.split += up(p.numel())
+        self.n_w = n_w
+        self._early = None
+        self._comm = None
         self.sinks, self.views16 = {}, {}
         off = 0
         with torch.no_grad():
@@ -120,13 +131,43 @@ class ParamArena:
         pass
 
     @torch.no_grad()
+    def early_reduce(self):
+        """Called from backward once every gradient of the [split, n_w) bucket has been issued (B200Backend's
+        heads-boundary node): start its all-reduce on a communication stream so that it overlaps the backbone's
+        backward.  No-op for a single rank."""
+        if self.world <= 1 or self._early is not None or self.split in (0, self.n_w):
+            return
+        import torch.distributed as dist
+        bucket = self.grad[self.split:self.n_w]
+        if not self.grad.is_cuda:            # host tensors (gloo, tests): no streams involved
+            self._early = dist.all_reduce(bucket, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            return
+        if self._comm is None:
+            self._comm = torch.cuda.Stream()
+        cur = torch.cuda.current_stream()
+        self._comm.wait_stream(cur)
+        if self.backend is not None and self.backend.side is not None:
+            self._comm.wait_stream(self.backend.side)          # the heads' weight-gradient kernels run there
+        with torch.cuda.stream(self._comm):
+            self._early = dist.all_reduce(bucket, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+
+    @torch.no_grad()
     def sync(self):
         """Sum the gradient accumulators over the data-parallel ranks (the mean's 1/world is applied by step())."""
         if self.backend is not None:
             self.backend.join_side()           # gradient kernels running on the backend's second stream
         if self.world > 1:
             import torch.distributed as dist
-            dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=self.group)
+            if self._early is not None:
+                dist.all_reduce(self.grad[:self.split], op=dist.ReduceOp.SUM, group=self.group)
+                if self.n_w < self.grad.numel():
+                    dist.all_reduce(self.grad[self.n_w:], op=dist.ReduceOp.SUM, group=self.group)
+                self._early.wait()
+                if self._comm is not None:
+                    torch.cuda.current_stream().wait_stream(self._comm)
+                self._early = None
+            else:
+                dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=self.group)
 
     @torch.no_grad()
     def step(self):

@@ -51,6 +51,21 @@ sync.sync()
 for p, a, b in zip([q for q in model.parameters() if q.requires_grad], got, want):
     torch.testing.assert_close(p.grad, b, rtol=1e-4, atol=1e-6)
     assert p.grad.stride() == p.stride()
+# ParamArena (the form bench.py uses): gradients live in one flat buffer; the downstream bucket (RPN + ROI heads) is
+# reduced early, the backbone bucket and the biases at sync(); together they must equal the plain sum over ranks
+from mrb_b200.optim import ParamArena
+arena = ParamArena(model.named_parameters(), None, world_size=world)
+assert 0 < arena.split < arena.n_w < arena.grad.numel()
+torch.manual_seed(1234)                   # (no zero_grad(): p.grad are the arena's persistent, already-zero views)
+imgs, sizes, tg = batch(10 + rank)
+sum(model(imgs, sizes, tg).values()).backward()    # autograd accumulates into the views
+for p, g_local in zip([q for q in model.parameters() if q.requires_grad], local[rank]):
+    torch.testing.assert_close(p.grad, g_local, rtol=1e-5, atol=1e-7)
+    assert p.grad.data_ptr() >= arena.grad.data_ptr()
+arena.early_reduce()
+arena.sync()
+for p, b in zip([q for q in model.parameters() if q.requires_grad], want):
+    torch.testing.assert_close(p.grad, b * world, rtol=1e-4, atol=1e-6)      # sum; step() folds in the 1/world
 flat = torch.cat([g.reshape(-1) for g in got])
 gathered = [torch.zeros_like(flat) for _ in range(world)]
 dist.all_gather(gathered, flat)
