@@ -106,6 +106,8 @@ class ParamArena:
         self.n_w = n_w
         self._early = None
         self._comm = None
+        import os
+        self.early = os.environ.get("MRB_EARLY_REDUCE", "1") != "0"     # A/B switch
         self.sinks, self.views16 = {}, {}
         off = 0
         with torch.no_grad():
@@ -135,7 +137,7 @@ class ParamArena:
         """Called from backward once every gradient of the [split, n_w) bucket has been issued (B200Backend's
         heads-boundary node): start its all-reduce on a communication stream so that it overlaps the backbone's
         backward.  No-op for a single rank."""
-        if self.world <= 1 or self._early is not None or self.split in (0, self.n_w):
+        if self.world <= 1 or self._early is not None or self.split in (0, self.n_w) or not self.early:
             return
         import torch.distributed as dist
         bucket = self.grad[self.split:self.n_w]
