@@ -153,6 +153,29 @@ roi_align_fpn_fwd_kernel(FpnArgs a, const float* __restrict__ rois, T* __restric
   for (int bin = warp; bin < PP; bin += kFpnThreads / 32) {
     const int ph = bin / a.P, pw = bin - ph * a.P;
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    if (sizeof(T) == 2 && g.gh == 2 && g.gw == 2) {
+      // bf16 features, sampling_ratio 2: the separable merged-weight form of the backward kernel -- (distinct rows) x
+      // (distinct columns) loads per bin, typically 4-9 instead of 16.  The fp32 path below keeps the reference's
+      // per-sample summation order (bit-exact); bf16 results are rounded to 8 bits anyway.
+      Axis2 ay, ax;
+      axis2(H, fpn_coord(g.sh, ph, g.bin_h, 0, 2), fpn_coord(g.sh, ph, g.bin_h, 1, 2), ay);
+      axis2(W, fpn_coord(g.sw, pw, g.bin_w, 0, 2), fpn_coord(g.sw, pw, g.bin_w, 1, 2), ax);
+      if (c_ok) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (ay.w[i] == 0.f) continue;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float wgt = ay.w[i] * ax.w[j];
+            if (wgt == 0.f) continue;
+            float v[4];
+            load4<T>(src + ((size_t)ay.r[i] * W + ax.r[j]) * C, v);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc[k] = fmaf(wgt, v[k], acc[k]);
+          }
+        }
+      }
+    } else
     for (int iy = 0; iy < g.gh; ++iy) {
       const float y = fpn_coord(g.sh, ph, g.bin_h, iy, g.gh);
       for (int ix = 0; ix < g.gw; ++ix) {
