@@ -70,7 +70,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", self.index], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -79,15 +79,25 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append([c.strip() for c in line.split(",")] + [time.time()])
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Summary of the samples whose host timestamp lies in [t0, t1] (the timed regions).  The sampler itself is
+        started before the warm-up so that nvidia-smi is already streaming when the (sub-second) timed region begins;
+        if no sample falls inside the window, all samples taken under load since the warm-up are used and
+        `window` says so."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
         self.t.join(timeout=2)
+        window = "timed regions"
+        rows = [r for r in self.rows if t0 is None or t0 <= r[-1] <= t1]
+        if not rows:
+            rows, window = self.rows, "warm-up + timed regions (no sample landed inside the timed window)"
+        self.rows = rows
         sm = sorted(float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit())
         mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        self.window = window
         reasons = set()
         for r in self.rows:
             if len(r) >= 9:
@@ -95,7 +105,7 @@ class ClockSampler:
                     if v.lower().startswith("active"):
                         reasons.add(name)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": self.window}
 
 
 def conv_roofline(calls, peaks, device):
@@ -302,6 +312,9 @@ def main():
             model.be.refresh_weights(params)   # bf16 operand copies of the updated weights: one multi-tensor cast
         return loss
 
+    sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else local_rank)
+    if rank == 0:
+        sampler.start()                 # well before the timed region: nvidia-smi needs a few hundred ms to start streaming
     graph_info = {"enabled": False}
     step = eager_step
     if use_graph:
@@ -357,9 +370,7 @@ def main():
     ops.STATS["launches"] = 0
     ops.STATS["conv_calls"] = []
     barrier()
-    sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else local_rank)
-    if rank == 0:
-        sampler.start()
+    t_clock0 = time.time()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.steps):
@@ -420,7 +431,7 @@ def main():
     e1.record()
     barrier()
     t_e2e = e0.elapsed_time(e1) * 1e-3
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_clock0, time.time()) if rank == 0 else None
     if world > 1:
         t = torch.tensor([t_dev, t_e2e], device=device, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
