@@ -305,7 +305,9 @@ class B200Backend(Backend):
         """Run the weight-/bias-gradient kernels that accumulate into arena sinks on a second stream: nothing in the
         backward pass reads their result, so they overlap the data-gradient chain (most layers of res4/res5 and the
         heads fill well under 148 SMs).  Captured into the CUDA graph as parallel branches; join_side() is the join."""
-        self.side = torch.cuda.Stream() if on else None
+        import os
+        prio = -1 if os.environ.get("MRB_SIDE_PRIORITY", "0") == "1" else 0        # A/B switch; measured 8.44 vs 8.29 ms/step: off
+        self.side = torch.cuda.Stream(priority=prio) if on else None
         self.lanes = [torch.cuda.Stream() for _ in range(6)] if on else []      # independent glue chains (fork(lane=i))
 
     def side_launch(self, tensors, fn):
