@@ -264,3 +264,36 @@ def test_bias_grad_shapes(ops):
     for (n, c, h, w) in [(2, 256, 50, 84), (1024, 1024, 1, 1), (3, 408, 7, 5), (2, 8, 33, 17), (1, 6, 9, 4)]:
         go = torch.randn(n, c, h, w, generator=g).to(torch.bfloat16)
         _assert_close(ops.bias_grad(go.to(DEV)), go.float().sum((0, 2, 3)), tol=2e-4)
+
+
+def test_conv_full_size_properties(ops):
+    """BASELINE-size layers (2 x 256 x 200 x 336, the P2 plane of an 800x1344 batch) through size-independent
+    properties that are EXACT for bf16 operands with fp32 accumulation: identity / delta kernels reproduce or shift the
+    input (forward and data gradient), and the weight gradient satisfies a checksum-of-checksums identity."""
+    g = torch.Generator().manual_seed(51)
+    n, c, h, w = 2, 256, 200, 336
+    x = torch.randn(n, c, h, w, generator=g).to(torch.bfloat16).to(DEV).contiguous(memory_format=torch.channels_last)
+    eye = torch.eye(c)
+    w1 = eye.view(c, c, 1, 1).to(torch.bfloat16).to(DEV).contiguous(memory_format=torch.channels_last)
+    assert torch.equal(ops.conv2d_fwd(x, w1), x)                                   # 1x1 identity (flattened GEMM path)
+    d3 = torch.zeros(c, c, 3, 3)
+    d3[:, :, 1, 1] = eye
+    d3 = d3.to(torch.bfloat16).to(DEV).contiguous(memory_format=torch.channels_last)
+    assert torch.equal(ops.conv2d_fwd(x, d3, pad=1), x)                            # centre tap: identity
+    assert torch.equal(ops.conv2d_dgrad(x, d3, x.shape, pad=1), x)                 # and its data gradient
+    s3 = torch.zeros(c, c, 3, 3)
+    s3[:, :, 0, 0] = eye                                                           # y[h, w] = x[h-1, w-1], zero outside
+    s3 = s3.to(torch.bfloat16).to(DEV).contiguous(memory_format=torch.channels_last)
+    want = F.pad(x, (1, 0, 1, 0))[:, :, :h, :w]
+    assert torch.equal(ops.conv2d_fwd(x, s3, pad=1), want)                         # im2col-in-TMA coordinates + zero fill
+    # weight gradient: sum over (co, ci) of dW[:, :, r, q] == sum over pixels of (sum_co g)(sum_ci x shifted by the tap)
+    go = torch.randn(n, c, h, w, generator=g).to(torch.bfloat16).to(DEV).contiguous(memory_format=torch.channels_last)
+    dw = ops.conv2d_wgrad(x, go, (c, c, 3, 3), 1, 1)
+    gs, xs = go.float().sum(1).double(), x.float().sum(1).double()
+    xs = F.pad(xs, (1, 1, 1, 1))
+    for r in range(3):
+        for q in range(3):
+            want_s = float((gs * xs[:, r:r + h, q:q + w]).sum())
+            got_s = float(dw[:, :, r, q].double().sum())
+            scale = float((gs.abs() * xs[:, r:r + h, q:q + w].abs()).sum())
+            assert abs(got_s - want_s) <= 1e-5 * scale, (r, q, got_s, want_s)
