@@ -1,0 +1,97 @@
+"""Grouped 3x3 convolution (ResNeXt / X-101-32x8d, reference modeling/backbone/resnet.py:283-296 `groups=num_groups`)
+on the dense tcgen05 engine, first (functional, not yet fast) form.
+
+A group of Cg = C / groups <= 64 channels is a diagonal block of a 64 -> 64 "super-group": the layer is C / 64
+independent dense 64 -> 64 convolutions whose weights are block-diagonal (MMA work x 64/Cg, no extra memory traffic:
+the tensor core is not what bounds these layers).  Each super-group is ONE call of the existing kernels on strided
+channel windows of the NHWC tensors (mrb_conv_params.x_pitch / y_pitch), so forward, data gradient and weight
+gradient reuse the validated code paths unchanged.  Status: composed after this round's GPU budget was spent -- the
+weight expansion is pinned on CPU (tests/test_grouped_cpu.py); the GPU test is marked xfail(strict=False) until it
+has run once.  The single-launch form (n_tile doubling as the A-operand channel offset) is DESIGN.md 4b item 4."""
+import torch
+
+SG = 64      # channels of a super-group = one k-block of the engine
+
+
+def check_geometry(cin, cout, groups):
+    if cin != cout or cin % groups or cin % SG or SG % (cin // groups):
+        raise RuntimeError("grouped conv: need Cin == Cout, Cin %% 64 == 0 and (Cin/groups) | 64 (got %d, %d, %d)"
+                           % (cin, cout, groups))
+    return cin // groups, cin // SG
+
+
+def expand_group_weights(w, groups):
+    """[C, C/groups, kh, kw] grouped weights -> [C, 64, kh, kw]: row co holds its group's filter at the position of that
+    group inside co's 64-channel super-group, zeros elsewhere (block-diagonal within each super-group)."""
+    c, cg, kh, kw = w.shape
+    check_geometry(c, c, groups)
+    assert cg == c // groups
+    co = torch.arange(c, device=w.device)
+    local0 = (co // cg) * cg - (co // SG) * SG                   # first local input channel of co's group
+    idx = local0[:, None] + torch.arange(cg, device=w.device)[None, :]        # [C, Cg]
+    out = w.new_zeros((c, SG, kh, kw))
+    out.scatter_(1, idx[:, :, None, None].expand(c, cg, kh, kw), w)
+    return out
+
+
+def collapse_group_grads(gw_exp, groups):
+    """Inverse gather for gradients: [C, 64, kh, kw] (dense super-group gradients) -> [C, C/groups, kh, kw]."""
+    c, _, kh, kw = gw_exp.shape
+    cg = c // groups
+    co = torch.arange(c, device=gw_exp.device)
+    local0 = (co // cg) * cg - (co // SG) * SG
+    idx = local0[:, None] + torch.arange(cg, device=gw_exp.device)[None, :]
+    return torch.gather(gw_exp, 1, idx[:, :, None, None].expand(c, cg, kh, kw))
+
+
+def _window(t, sg):
+    """Channels [64*sg, 64*sg + 64) of an NHWC (channels_last) tensor as a strided view (no copy)."""
+    n, c, h, w = t.shape
+    return torch.as_strided(t, (n, SG, h, w), (h * w * c, 1, w * c, c), t.storage_offset() + sg * SG)
+
+
+class GroupedConvFn(torch.autograd.Function):
+    """y = act(grouped_conv(x, w) * scale + shift), stride 1, on the conv engine (bf16 NHWC)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, scale, shift, groups, pad, relu):
+        from mrb_b200 import ops
+        c = x.shape[1]
+        _, sgs = check_geometry(c, weight.shape[0], groups)
+        x = x.contiguous(memory_format=torch.channels_last)
+        w_exp = expand_group_weights(weight.detach(), groups).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        out = torch.empty_like(x)
+        for sg in range(sgs):
+            sl = slice(sg * SG, (sg + 1) * SG)
+            ops.conv2d_fwd(_window(x, sg), w_exp[sl], None if scale is None else scale[sl].contiguous(),
+                           None if shift is None else shift[sl].contiguous(), None, 1, pad, relu, out=_window(out, sg))
+        ctx.cfg = (groups, pad, relu, sgs)
+        ctx.save_for_backward(x, w_exp, scale, out if relu else None)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        from mrb_b200 import ops
+        x, w_exp, scale, y = ctx.saved_tensors
+        groups, pad, relu, sgs = ctx.cfg
+        if relu:
+            g = torch.where(y > 0, g, torch.zeros((), dtype=g.dtype, device=g.device))
+        g = g.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        n, c, h, w = x.shape
+        gx = gw = None
+        if ctx.needs_input_grad[0]:
+            parts = [ops.conv2d_dgrad(_window(g, sg), w_exp[sg * SG:(sg + 1) * SG], (n, SG, h, w),
+                                      None if scale is None else scale[sg * SG:(sg + 1) * SG].contiguous(), None, None, 1, pad)
+                     for sg in range(sgs)]
+            gx = torch.cat(parts, 1).contiguous(memory_format=torch.channels_last)
+        if ctx.needs_input_grad[1]:
+            k = w_exp.shape[2]
+            parts = [ops.conv2d_wgrad(_window(x, sg), _window(g, sg), (SG, SG, k, k), 1, pad,
+                                      None if scale is None else scale[sg * SG:(sg + 1) * SG].contiguous())
+                     for sg in range(sgs)]
+            gw = collapse_group_grads(torch.cat(parts, 0), groups)
+        return gx, gw, None, None, None, None, None
+
+
+def conv2d_grouped(x, weight, groups, scale=None, shift=None, pad=1, relu=False):
+    return GroupedConvFn.apply(x, weight, scale, shift, groups, pad, relu)

@@ -1,0 +1,33 @@
+"""Grouped 3x3 conv composed from per-super-group calls of the dense engine (mrb_b200/grouped.py).
+Written after round 1's GPU budget was spent: it has not run on a GPU yet, hence xfail(strict=False) -- an XPASS at
+the next round's first run promotes it to a normal parity test."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="unvalidated: composed after the round's GPU budget was spent")]
+DEV = "cuda:0"
+
+
+@pytest.mark.parametrize("c,groups,h,w", [(256, 32, 20, 28), (128, 4, 13, 21)])
+def test_grouped_conv_matches_torch(built_lib, c, groups, h, w):
+    from mrb_b200.grouped import conv2d_grouped
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(2, c, h, w, generator=g).to(torch.bfloat16)
+    wt = (torch.randn(c, c // groups, 3, 3, generator=g) / (9 * c // groups) ** 0.5).to(torch.bfloat16).float()
+    scale, shift = torch.rand(c, generator=g) + 0.5, torch.randn(c, generator=g) * 0.1
+    go = torch.randn(2, c, h, w, generator=g).to(torch.bfloat16)
+    xr, wr = x.float().requires_grad_(True), wt.clone().requires_grad_(True)
+    y = torch.relu(F.conv2d(xr, wr, padding=1, groups=groups) * scale[None, :, None, None] + shift[None, :, None, None])
+    y.backward(go.float())
+    xd = x.to(DEV).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    wd = wt.to(DEV).requires_grad_(True)
+    yd = conv2d_grouped(xd, wd, groups, scale.to(DEV), shift.to(DEV), pad=1, relu=True)
+
+    def rel(a, b):
+        a, b = a.float().cpu(), b.float().cpu()
+        return float((a - b).abs().max() / (b.abs().max() + 1e-12))
+    assert rel(yd.detach(), y.detach()) < 1e-2
+    yd.backward(go.to(DEV))
+    assert rel(xd.grad, xr.grad) < 2e-2
+    assert rel(wd.grad, wr.grad) < 2e-2
