@@ -5,7 +5,7 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="unvalidated: composed after the round's GPU budget was spent")]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(120), pytest.mark.xfail(strict=False, reason="unvalidated: composed after the round's GPU budget was spent")]
 DEV = "cuda:0"
 
 
