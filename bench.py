@@ -2,18 +2,26 @@
 """bench.py -- images/sec of the Mask R-CNN R-50-FPN training step (forward + backward + SGD update) on
 synthetic 800x1333 (padded to 800x1344) batches, 2 images per GPU, through the Blackwell hot path.
 
-  python bench.py --gpus 1 --steps 10 --warmup 3            # this repo's sm_100a path
-  python bench.py --impl reference --gpus 1 --steps 1       # the CPU path timed on the host cores
+  python bench.py --gpus 1 --steps 10 --warmup 3            # this repo's sm_100a path (both arms, see below)
+  python bench.py --impl reference --gpus 1 --steps 1       # the reference's CPU path timed on the host cores
+  python bench.py --impl aten                               # the same reference graph on ATen/cuDNN (GPU A/B arm)
+  python bench.py --config faster_fwd|x101|dcn              # the other BASELINE.json configs (own JSON line each)
   torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...   (one rank per GPU, NCCL)
 
-Prints ONE JSON line (rank 0).  `value` = whole-job images/s with inputs resident in HBM; `e2e` = the
-same step through the public API with pinned-host inputs (H2D of images + targets, D2H of the loss,
-inside the timed region); `roofline` = tcgen05 conv kernel, algorithmic FLOPs / CUDA-event time per
-launch, summed over the launches of one step; `cpu_baseline` = the same train step on the host cores
-(PyTorch CPU convs + the oracle / reference CPU kernels), bounded to one image.
-"""
+Two arms of the product are measured in one run (`--model auto`):
+  * "reference_graph" (headline when the reference mirror baseline/_ref is present): the UNMODIFIED reference
+    `build_detection_model(cfg)` -- its GeneralizedRCNN, RPN, ROI heads, losses, samplers -- running over this
+    repository's `maskrcnn_benchmark.layers` / `_C`, after mrb_b200.fuse.fuse_model(); eager (the reference's host
+    code synchronises), optimizer = mrb_b200.optim.ParamArena (fused SGD, one NCCL all-reduce).
+  * "harness": mrb_b200.model (from-scratch, fixed-shape, sync-free host code), whole step in ONE CUDA graph.
+Prints ONE JSON line (rank 0).  `value` = whole-job images/s of the headline arm with inputs resident in HBM; `e2e`
+= the same with pinned-host inputs (H2D of images + targets, D2H of the loss, inside the timed region); `roofline` =
+the tcgen05 conv kernels, algorithmic FLOPs / CUDA-event time per launch, summed over the launches of one step;
+`ops` = ROIAlign / NMS / focal-loss achieved GB/s measured in this run; `cpu_baseline` = the reference's own
+GeneralizedRCNN train step on the host cores (bounded to one image)."""
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -28,9 +36,22 @@ for p in (ROOT, os.path.join(ROOT, "maskrcnn-benchmark_b200")):
 import torch  # noqa: E402
 
 IMG_H, IMG_W, PAD_W = 800, 1333, 1344
-IMGS_PER_GPU = 2
 GT_PER_IMAGE = 8
-METRIC = "images/sec Mask R-CNN R-50-FPN fwd+bwd @1333x800"
+
+CONFIGS = {
+    # name: (reference yaml, images per GPU, train?, metric, workload text)
+    "mask_r50": ("e2e_mask_rcnn_R_50_FPN_1x.yaml", 2, True, "images/sec Mask R-CNN R-50-FPN fwd+bwd @1333x800",
+                 "e2e_mask_rcnn_R_50_FPN_1x train step (fwd + bwd + SGD momentum/wd update)"),
+    "faster_fwd": ("e2e_faster_rcnn_R_50_FPN_1x.yaml", 2, False, "images/sec Faster R-CNN R-50-FPN forward-only @1333x800",
+                   "e2e_faster_rcnn_R_50_FPN_1x forward-only (eval: proposals + detections)"),
+    "x101": ("e2e_mask_rcnn_X_101_32x8d_FPN_1x.yaml", 1, True, "images/sec Mask R-CNN X-101-32x8d-FPN fwd+bwd @1333x800",
+             "e2e_mask_rcnn_X_101_32x8d_FPN_1x train step (grouped 3x3 convs, stride in the 3x3)"),
+    "dcn": ("dcn/e2e_mask_rcnn_dconv_R_50_FPN_1x.yaml", 2, True, "images/sec Mask R-CNN R-50-FPN-dconv fwd+bwd @1333x800",
+            "configs/dcn/e2e_mask_rcnn_dconv_R_50_FPN_1x train step (deformable 3x3 in res3-res5)"),
+}
+
+
+HARNESS_CONFIGS = ("mask_r50", "faster_fwd")     # configs the from-scratch harness model covers
 
 
 def synth_batch(n, seed, device="cpu", pin=False):
@@ -81,81 +102,31 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")] + [time.time()])
 
-    def stop(self, t0=None, t1=None):
-        """Summary of the samples whose host timestamp lies in [t0, t1] (the timed regions).  The sampler itself is
-        started before the warm-up so that nvidia-smi is already streaming when the (sub-second) timed region begins;
-        if no sample falls inside the window, all samples taken under load since the warm-up are used and
-        `window` says so."""
+    def summary(self, windows):
+        """Samples whose host timestamp lies in one of the [t0, t1] windows (the timed regions); if none landed there,
+        all samples since start (warm-up included) are used and `window` says so."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        self.t.join(timeout=2)
+        rows = [r for r in self.rows if any(t0 <= r[-1] <= t1 for t0, t1 in windows)]
         window = "timed regions"
-        rows = [r for r in self.rows if t0 is None or t0 <= r[-1] <= t1]
         if not rows:
-            rows, window = self.rows, "warm-up + timed regions (no sample landed inside the timed window)"
-        self.rows = rows
-        sm = sorted(float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit())
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
-        self.window = window
+            rows, window = list(self.rows), "warm-up + timed regions (no sample landed inside the timed window)"
+        sm = sorted(float(r[1]) for r in rows if len(r) >= 9 and r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        pw = [float(r[3]) for r in rows if len(r) >= 9 and r[3].replace(".", "").isdigit()]
         reasons = set()
-        for r in self.rows:
+        for r in rows:
             if len(r) >= 9:
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
                     if v.lower().startswith("active"):
                         reasons.add(name)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm), "window": self.window}
+                "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
-
-def conv_roofline(calls, peaks, device):
-    """Time every distinct tcgen05 conv launch of one step in isolation (CUDA events on the launching
-    stream, L2 flushed between launches) and aggregate: achieved = sum(algorithmic FLOPs) / sum(time)."""
-    from mrb_b200 import ops
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)
-    shapes = {}
-    for c in calls:
-        shapes.setdefault(c, 0)
-        shapes[c] += 1
-    tot_flops = tot_time = 0.0
-    rows = []
-    for key, count in sorted(shapes.items()):
-        kind, n, cin, h, w, cout, k, stride, pad = key
-        x = torch.randn(n, cin, h, w, device=device).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
-        kh, kw = (k, k) if isinstance(k, int) else k
-        ph, pw = (pad, pad) if isinstance(pad, int) else pad
-        wt = torch.randn(cout, cin, kh, kw, device=device).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
-        ho, wo = (h + 2 * ph - kh) // stride + 1, (w + 2 * pw - kw) // stride + 1
-        if kind in ("dgrad", "wgrad"):
-            go = torch.randn(n, cout, ho, wo, device=device).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
-            if kind == "dgrad":
-                fn = lambda: ops.conv2d_dgrad(go, wt, (n, cin, h, w), None, None, None, stride, pad)  # noqa: E731
-            else:
-                fn = lambda: ops.conv2d_wgrad(x, go, wt.shape, stride, pad)  # noqa: E731
-        else:
-            fn = lambda: ops.conv2d_fwd(x, wt, None, None, None, stride, pad, True)  # noqa: E731
-        fn()
-        ts = []
-        for _ in range(3):
-            flush.zero_()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            fn()
-            e1.record()
-            e1.synchronize()
-            ts.append(e0.elapsed_time(e1) * 1e-3)
-        t = sorted(ts)[1]
-        flops = 2.0 * n * ho * wo * cout * cin * kh * kw
-        tot_flops += flops * count
-        tot_time += t * count
-        rows.append({"kind": kind, "n": n, "cin": cin, "h": h, "w": w, "cout": cout, "k": k if isinstance(k, int) else list(k), "stride": stride, "count": count,
-                     "us": round(t * 1e6, 1), "tflops": round(flops / t / 1e12, 1)})
-    peak = peaks.get("bf16_tflops", 1590.0)
-    ach = tot_flops / max(tot_time, 1e-12) / 1e12
-    return {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit GEMM, fwd+dgrad launches of one step)",
-            "achieved": round(ach, 1), "peak": peak, "peak_source": peaks.get("_source", "fallback"), "unit": "TFLOP/s",
-            "frac": round(ach / peak, 4), "traffic": None, "launches_per_step": len(calls),
-            "algorithmic_gflop_per_step": round(tot_flops / 1e9, 1), "kernel_ms_per_step": round(tot_time * 1e3, 2)}, rows
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            self.t.join(timeout=2)
 
 
 def load_peaks():
@@ -167,54 +138,268 @@ def load_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "_source": "fallback (B200_PROFILING.md)"}
 
 
-def cpu_train_step(n_images, use_ref, threads=None):
-    """The same train step on the host cores: PyTorch CPU fp32 convs + oracle (or oracle/_ref) kernels."""
-    from oracle.cpu_backend import CpuCheckerBackend
-    from mrb_b200.model import GeneralizedRCNN, RCNNConfig
-    if threads:
-        torch.set_num_threads(threads)
+# =========================================================================================== roofline (conv engine)
+def conv_roofline(calls, peaks, device):
+    """Time every distinct tcgen05 conv launch of one step in isolation (CUDA events on the launching stream, L2
+    flushed between launches, median of 3) and aggregate: achieved = sum(algorithmic FLOPs) / sum(time)."""
+    from mrb_b200 import ops
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)
+    shapes = {}
+    for c in calls:
+        shapes[c] = shapes.get(c, 0) + 1
+    tot_flops = tot_time = 0.0
+    rows = []
+    for key, count in sorted(shapes.items(), key=lambda kv: str(kv[0])):
+        kind, n, cin, h, w, cout, k, stride, pad = key[:9]
+        groups = key[9] if len(key) > 9 else 1
+        x = torch.randn(n, cin, h, w, device=device).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        kh, kw = (k, k) if isinstance(k, int) else k
+        ph, pw = (pad, pad) if isinstance(pad, int) else pad
+        ho, wo = (h + 2 * ph - kh) // stride + 1, (w + 2 * pw - kw) // stride + 1
+        go = torch.randn(n, cout, ho, wo, device=device).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        if groups > 1:
+            wt = torch.randn(cout, 64, kh, kw, device=device).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+            if kind == "dgrad":
+                fn = lambda: ops.conv2d_dgrad_grouped(go, wt.reshape(-1), (n, cin, h, w), stride, pad)  # noqa: E731
+            elif kind == "wgrad":
+                fn = lambda: ops.conv2d_wgrad_grouped(x, go, kh, stride, pad)  # noqa: E731
+            else:
+                fn = lambda: ops.conv2d_fwd(x, wt, None, None, None, stride, pad, True, grouped=True)  # noqa: E731
+        else:
+            wt = torch.randn(cout, cin, kh, kw, device=device).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+            if kind == "dgrad":
+                fn = lambda: ops.conv2d_dgrad(go, wt, (n, cin, h, w), None, None, None, stride, pad)  # noqa: E731
+            elif kind == "wgrad":
+                fn = lambda: ops.conv2d_wgrad(x, go, wt.shape, stride, pad)  # noqa: E731
+            else:
+                fn = lambda: ops.conv2d_fwd(x, wt, None, None, None, stride, pad, True)  # noqa: E731
+        fn()
+        ts = []
+        for _ in range(3):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            e1.synchronize()
+            ts.append(e0.elapsed_time(e1) * 1e-3)
+        t = sorted(ts)[1]
+        flops = 2.0 * n * ho * wo * cout * (cin // groups) * kh * kw
+        tot_flops += flops * count
+        tot_time += t * count
+        rows.append({"kind": kind, "n": n, "cin": cin, "h": h, "w": w, "cout": cout, "k": k if isinstance(k, int) else list(k),
+                     "stride": stride, "groups": groups, "count": count, "us": round(t * 1e6, 1), "tflops": round(flops / t / 1e12, 1)})
+    peak = peaks.get("bf16_tflops", 1590.0)
+    ach = tot_flops / max(tot_time, 1e-12) / 1e12
+    # the dominant shape of the step: its algorithmic HBM bytes (x + y + w of one launch) for the traffic comparison
+    top = max(rows, key=lambda r: r["us"] * r["count"]) if rows else None
+    rf = {"bound": "tensor",
+          "kernel": "conv_tc_kernel + conv_wgrad_tc_kernel (tcgen05 implicit GEMM: the fwd, dgrad AND wgrad launches of one step)",
+          "achieved": round(ach, 1), "peak": peak, "peak_source": peaks.get("_source", "fallback"), "unit": "TFLOP/s",
+          "frac": round(ach / peak, 4), "traffic": None,
+          "traffic_note": "not measured in this run (ncu --set full captures of the top shapes: profiles/ncu_conv_*_summary.json)",
+          "launches_per_step": len(calls), "algorithmic_gflop_per_step": round(tot_flops / 1e9, 1),
+          "kernel_ms_per_step": round(tot_time * 1e3, 2)}
+    if top is not None:
+        kh, kw = (top["k"], top["k"]) if isinstance(top["k"], int) else top["k"]
+        ho, wo = top["h"] // top["stride"], top["w"] // top["stride"]
+        rf["top_shape"] = {k: top[k] for k in ("kind", "n", "cin", "h", "w", "cout", "k", "stride", "count", "us", "tflops")}
+        rf["top_shape"]["algorithmic_MB"] = round(2 * (top["n"] * top["cin"] * top["h"] * top["w"] + top["n"] * top["cout"] * ho * wo
+                                                       + top["cout"] * top["cin"] * kh * kw) / 1e6, 1)
+    return rf, rows
+
+
+# =========================================================================================== op-level metrics
+def ops_metrics(device, peaks):
+    """ROIAlign / NMS / focal-loss numbers of BASELINE.json's metric, measured in this run (CUDA events, L2 flushed,
+    median of 5; algorithmic bytes per SURVEY 8d)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import _inputs
+    from maskrcnn_benchmark import _C
+    from mrb_b200 import ops
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from bench_ops import roi_footprint_elems, timed
+    hbm = peaks.get("hbm_gbs", 6650.0)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+    out = []
+
+    def rec(name, alg, t, **kw):
+        d = {"op": name, "us": round(t * 1e6, 1), "algorithmic_MB": round(alg / 1e6, 2), "achieved_gbs": round(alg / t / 1e9, 1),
+             "frac": round(alg / t / 1e9 / hbm, 4)}
+        d.update(kw)
+        out.append(d)
+
+    # BASELINE config 1: 1x256x200x336 fp32, 100 boxes, 7x7, through the reference-facing `_C` call
+    feat, rois = _inputs.roi_align_config1()
+    n, c, h, w = feat.shape
+    r = rois.shape[0]
+    foot = min(roi_footprint_elems(rois, 0.25, h, w, c), n * c * h * w)
+    rd = rois.to(device)
+    for layout, x in (("NCHW", feat.to(device)), ("NHWC", feat.to(device).contiguous(memory_format=torch.channels_last))):
+        t = timed(lambda: _C.roi_align_forward(x, rd, 0.25, 7, 7, 2), flush, reps=5)
+        rec("roi_align_forward config1 (1x256x200x336 f32, R=100, 7x7)", 4 * (r * c * 49 + foot + 5 * r), t, layout=layout)
+    g = torch.randn(r, c, 7, 7, device=device)
+    t = timed(lambda: _C.roi_align_backward(g, rd, 0.25, 7, 7, n, c, h, w, 2), flush, reps=5)
+    rec("roi_align_backward config1", 4 * (r * c * 49 + 2 * foot + n * c * h * w + 5 * r), t, layout="NCHW")
+    # the shapes the train step runs: fused multi-level ROIAlign on bf16 NHWC P2..P5 of 2 images
+    feats = [f.to(torch.bfloat16).to(device).contiguous(memory_format=torch.channels_last) for f in _inputs.fpn_features(2, 2)]
+    scales = (0.25, 0.125, 0.0625, 0.03125)
+    for r, p, nhwc in ((1024, 7, False), (256, 14, True)):
+        rois = _inputs.rois_for_level(r, 2, 40 + r).to(device)
+        lv = torch.floor(4 + torch.log2(torch.sqrt((rois[:, 3] - rois[:, 1] + 1) * (rois[:, 4] - rois[:, 2] + 1)) / 224 + 1e-6)).clamp(2, 5).long() - 2
+        foot = 0.0
+        for l in range(4):
+            m = lv == l
+            if m.any():
+                hh, ww = feats[l].shape[2:]
+                foot += min(roi_footprint_elems(rois[m].cpu(), scales[l], hh, ww, 256), 2 * 256 * hh * ww)
+        t = timed(lambda: ops.roi_align_fpn(feats, rois, scales, p, 2, out_nhwc=nhwc), flush, reps=5)
+        rec("roi_align_fpn_fwd bf16 (in-step: R=%d, %dx%d)" % (r, p, p), 2 * (r * 256 * p * p + foot) + 20 * r, t)
+        fr = [f.detach().clone().requires_grad_(True) for f in feats]
+        y = ops.roi_align_fpn(fr, rois, scales, p, 2, out_nhwc=nhwc)
+        go = torch.randn_like(y)
+        t = timed(lambda: torch.autograd.grad(y, fr, go, retain_graph=True), flush, reps=5)
+        maps = sum(f.numel() for f in feats)
+        rec("roi_align_fpn_bwd bf16 (in-step: R=%d, %dx%d; incl. zero-fill + cast of the 4 level maps)" % (r, p, p),
+            2 * r * 256 * p * p + 4 * 2 * foot + 4 * maps + 20 * r, t)
+    # NMS: the 10 (image, level) problems of one RPN train step in one launch sequence; one 2000-box call through _C
+    sizes = [2000] * 8 + [819] * 2
+    bs = [_inputs.nms_boxes(s, 500 + i) for i, s in enumerate(sizes)]
+    bd = torch.cat([b for b, _ in bs]).to(device)
+    sd = torch.cat([s for _, s in bs]).to(device)
+    t = timed(lambda: ops.nms_batched(bd, sd, sizes, 0.7), flush, reps=5)
+    alg = sum(20 * s + 16 * s * math.ceil(s / 64) for s in sizes)
+    rec("nms_batched (10 RPN problems, thr 0.7)", alg, t, us_per_problem=round(t * 1e5, 1), note="latency bound: bytes are tiny")
+    b1, s1 = bs[0][0].to(device), bs[0][1].to(device)
+    t = timed(lambda: _C.nms(b1, s1, 0.7), flush, reps=5)
+    rec("nms N=2000 through _C (incl. the 4-byte D2H sizing the result)", 20 * 2000 + 16 * 2000 * 32, t, note="latency bound")
+    # focal loss, RetinaNet 800x1344: 201600 anchors x 80
+    logits, targets = _inputs.focal_inputs(201600, 80, 0)
+    ld, td = logits.to(device), targets.to(device)
+    t = timed(lambda: _C.sigmoid_focalloss_forward(ld, td, 80, 2.0, 0.25), flush, reps=5)
+    rec("sigmoid_focalloss_forward (201600x80)", 4 * 201600 * 80 * 2 + 4 * 201600, t)
+    dl = torch.rand_like(ld)
+    t = timed(lambda: _C.sigmoid_focalloss_backward(ld, td, dl, 80, 2.0, 0.25), flush, reps=5)
+    rec("sigmoid_focalloss_backward (201600x80)", 4 * 201600 * 80 * 3 + 4 * 201600, t)
+    return {"peak_hbm_gbs": hbm, "timing": "CUDA events, L2 flushed between launches, median of 5", "rows": out}
+
+
+# =========================================================================================== CPU reference arm
+def _pure_reference_package():
+    """A `maskrcnn_benchmark` package made ONLY of the reference mirror (its own layers/ included) with `_C` = the
+    reference's csrc/cpu kernels compiled by oracle/build_ref.py (+ the oracle's ROIAlign backward, which the
+    reference does not have on the CPU: csrc/ROIAlign.h:44).  The product package is never imported here."""
+    import types
+    sys.path.insert(0, os.path.join(ROOT, "tests", "_shims"))
+    import mrb_test_compat  # noqa: F401
+    import oracle
+    root = None
+    for cand in (os.environ.get("MRB_REFERENCE_ROOT"), os.path.join(ROOT, "baseline", "_ref"), "/root/reference"):
+        if cand and os.path.isdir(os.path.join(cand, "maskrcnn_benchmark", "modeling")):
+            root = cand
+            break
+    if root is None:
+        return None, None
+    oracle.build()
+    refc = oracle.ref()
+    pkg = types.ModuleType("maskrcnn_benchmark")
+    pkg.__path__ = [os.path.join(root, "maskrcnn_benchmark")]
+    sys.modules["maskrcnn_benchmark"] = pkg
+    c = types.ModuleType("maskrcnn_benchmark._C")
+    if refc is not None:
+        c.nms, c.roi_align_forward = refc.nms, refc.roi_align_forward
+        kind = "reference"
+    else:
+        c.nms = lambda d, s, t: oracle.nms(d.contiguous(), s.contiguous(), t)
+        c.roi_align_forward = lambda x, r, sc, ph, pw, s: oracle.roi_align_forward(x.contiguous(), r.contiguous(), sc, ph, pw, s)
+        kind = "port"
+    c.roi_align_backward = lambda g, r, sc, ph, pw, b, ch, h, w, s: oracle.roi_align_backward(g.contiguous(), r.contiguous(), sc, ph, pw, b, ch, h, w, s)
+    pkg._C = c
+    sys.modules["maskrcnn_benchmark._C"] = c
+    return root, kind
+
+
+def _ref_inputs(n, seed, device, with_masks=True):
+    from maskrcnn_benchmark.structures.bounding_box import BoxList
+    from maskrcnn_benchmark.structures.image_list import ImageList
+    from maskrcnn_benchmark.structures.segmentation_mask import SegmentationMask
+    images, boxes, labels = synth_batch(n, seed)
+    il = ImageList(images.to(device), [(IMG_H, IMG_W)] * n)
+    targets = []
+    for i in range(n):
+        t = BoxList(boxes[i], (IMG_W, IMG_H), mode="xyxy")
+        t.add_field("labels", labels[i])
+        if with_masks:
+            polys = [[[float(b[0]), float(b[1]), float(b[2]), float(b[1]), float(b[2]), float(b[3]), float(b[0]), float(b[3])]]
+                     for b in boxes[i]]
+            t.add_field("masks", SegmentationMask(polys, (IMG_W, IMG_H), mode="poly"))
+        targets.append(t.to(device))
+    return il, targets
+
+
+def cpu_reference_step(cfg_name, n_images, threads):
+    """One step of the reference's own GeneralizedRCNN on the host cores (fp32): -> (images/s, seconds, kind)."""
+    root, kind = _pure_reference_package()
+    if root is None:
+        return None
+    torch.set_num_threads(threads)
+    yaml, _, train, _, _ = CONFIGS[cfg_name]
+    from maskrcnn_benchmark.config import cfg as _cfg
+    from maskrcnn_benchmark.modeling.detector import build_detection_model
+    cfg = _cfg.clone()
+    cfg.merge_from_file(os.path.join(root, "configs", yaml))
+    cfg.merge_from_list(["MODEL.DEVICE", "cpu"])
+    cfg.freeze()
     torch.manual_seed(0)
-    model = GeneralizedRCNN(RCNNConfig(), CpuCheckerBackend(use_ref=use_ref)).train()
-    images, boxes, labels = synth_batch(n_images, 0)
-    sizes = [(IMG_H, IMG_W)] * n_images
+    model = build_detection_model(cfg)
+    model.train(train)
+    il, targets = _ref_inputs(n_images, 0, "cpu", with_masks=cfg.MODEL.MASK_ON)
     t0 = time.perf_counter()
-    losses = model(images, sizes, targets_of(boxes, labels))
-    sum(losses.values()).backward()
+    if train:
+        losses = model(il, targets)
+        sum(losses.values()).backward()
+    else:
+        with torch.no_grad():
+            model(il)
     dt = time.perf_counter() - t0
-    return n_images / dt, dt
+    return n_images / dt, dt, kind
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the CPU implementation of the path on the box's host cores (rank 0 only)."""
+    """--impl reference: the reference's own CPU implementation of the path on the box's host cores (rank 0 only)."""
     if rank != 0:
         return
-    import oracle
-    oracle.build()
-    use_ref = oracle.ref() is not None
-    cores = torch.get_num_threads()
-    vals = []
+    yaml, per_gpu, train, metric, workload = CONFIGS[args.config]
+    cores = os.cpu_count() or 1           # torchrun exports OMP_NUM_THREADS=1: set the thread count explicitly
+    vals, kind = [], "port"
     for i in range(args.warmup + args.steps):
-        v, dt = cpu_train_step(1, use_ref)
+        r = cpu_reference_step(args.config, 1, cores)
+        if r is None:
+            print(json.dumps({"impl": "reference", "unavailable": "no reference mirror (baseline/_ref) on this box"}))
+            return
+        v, dt, kind = r
         if i >= args.warmup:
             vals.append((v, dt))
     v = sum(x for x, _ in vals) / len(vals)
     ms = sum(d for _, d in vals) / len(vals) * 1e3
-    kind = "port"
-    sample = ("1 image (800x1333 padded to 800x1344) per step: full Mask R-CNN R-50-FPN train forward+backward, fp32, "
-              "PyTorch CPU convs + %s ROIAlign/NMS" % ("reference csrc/cpu kernels (oracle/_ref)" if use_ref else "oracle C port"))
-    out = {"impl": "reference", "metric": METRIC, "value": round(v, 4), "unit": "images/s", "n_gpus": args.gpus,
+    sample = ("1 image (800x1333 padded to 800x1344) per step: the reference's own GeneralizedRCNN (%s), fp32 ATen CPU convs, "
+              "%s; ROIAlign backward from the oracle port (the reference has no CPU backward, csrc/ROIAlign.h:44)"
+              % (workload, "reference csrc/cpu ROIAlign/NMS kernels compiled by oracle/build_ref.py" if kind == "reference"
+                 else "oracle C port of the csrc/cpu kernels"))
+    out = {"impl": "reference", "metric": metric, "value": round(v, 4), "unit": "images/s", "n_gpus": args.gpus,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 1), "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": workload_config(args.gpus),
+           "config": workload_config(args.config, args.gpus),
            "cpu_baseline": {"value": round(v, 4), "unit": "images/s", "cores": cores, "kind": kind, "sample": sample},
            "e2e": {"value": round(v, 4), "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out))
 
 
-def workload_config(n_gpus):
-    return {"workload": "e2e_mask_rcnn_R_50_FPN_1x train step (fwd + bwd + SGD momentum/wd update), synthetic 800x1333 images "
-                        "zero-padded to 800x1344 NCHW, 8 GT boxes/image, random-init weights",
-            "global_batch": IMGS_PER_GPU * n_gpus, "images_per_gpu": IMGS_PER_GPU, "parallelism": "dp%d" % n_gpus,
+def workload_config(cfg_name, n_gpus):
+    yaml, per_gpu, train, metric, workload = CONFIGS[cfg_name]
+    return {"workload": workload + ", synthetic 800x1333 images zero-padded to 800x1344 NCHW, 8 GT boxes/image, random-init weights",
+            "reference_config": "configs/" + yaml,
+            "global_batch": per_gpu * n_gpus, "images_per_gpu": per_gpu, "parallelism": "dp%d" % n_gpus,
             "l2": "per-step working set (activations + gradients, several GB) exceeds the 126 MB L2; no explicit flush"}
 
 
@@ -229,78 +414,203 @@ def _finish(world):
         os._exit(0)
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-roofline", action="store_true")
-    ap.add_argument("--dump-shapes", default=None, help="write the per-shape conv table (JSON) here")
-    ap.add_argument("--wgrad", default="tc", choices=["tc", "cudnn"], help="weight-gradient kernel (A/B switch)")
-    ap.add_argument("--optim", default="arena", choices=["arena", "flat"],
-                    help="arena: flat parameter/gradient buffers + fused update kernel; flat: foreach SGD (A/B switch)")
-    ap.add_argument("--overlap", default="on", choices=["on", "off"],
-                    help="weight-/bias-gradient kernels on a second stream (needs --optim arena)")
-    ap.add_argument("--parallel-heads", default="on", choices=["on", "off"],
-                    help="mask branch on its own stream, overlapping the box branch (needs --overlap on)")
-    ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
-                    help="capture the whole train step (fwd+bwd+all-reduce+SGD) in one CUDA graph; falls back to eager "
-                         "(and says so) if capture fails")
-    args = ap.parse_args()
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.impl == "reference":
-        run_reference(args, rank, world)
-        return
-    if args.warmup < 3:
-        args.warmup = 3
-    assert torch.cuda.is_available(), "bench.py --impl b200 needs a CUDA device (no CPU fallback)"
-    torch.cuda.set_device(local_rank)
-    device = torch.device("cuda", local_rank)
-    import torch.distributed as dist
-    if world > 1:
-        dist.init_process_group("nccl", device_id=device)
-    from mrb_b200 import ops
-    from mrb_b200.model import build_model
+class Timer:
+    """K steps bracketed by barrier + synchronize on both sides, CUDA events on the current stream."""
 
+    def __init__(self, world):
+        self.world = world
+        self.windows = []
+
+    def barrier(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def run(self, steps, fn):
+        self.barrier()
+        t0 = time.time()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = None
+        for i in range(steps):
+            out = fn(i)
+        e1.record()
+        self.barrier()
+        self.windows.append((t0, time.time()))
+        t = e0.elapsed_time(e1) * 1e-3
+        if self.world > 1:
+            import torch.distributed as dist
+            tt = torch.tensor([t], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            t = float(tt[0])
+        return t, out
+
+
+# =========================================================================================== arm: reference graph
+def arm_reference_graph(args, cfg_name, device, rank, world, timer, aten=False):
+    """The unmodified reference model over this repo's layers/_C (fused by mrb_b200.fuse), eager."""
+    from mrb_b200 import refenv
+    root = refenv.activate()
+    if root is None:
+        return None
+    yaml, per_gpu, train, metric, workload = CONFIGS[cfg_name]
+    if aten:
+        os.environ["MRB_CONV_ENGINE"] = "0"
+    from maskrcnn_benchmark.config import cfg as _cfg
+    from maskrcnn_benchmark.modeling.detector import build_detection_model
+    from maskrcnn_benchmark.structures.image_list import ImageList
+    from mrb_b200 import engine, ops
+    cfg = _cfg.clone()
+    cfg.merge_from_file(refenv.config_path(yaml))
+    cfg.merge_from_list(["MODEL.DEVICE", "cuda"])
+    cfg.freeze()
     torch.manual_seed(0)
-    from mrb_b200.model import RCNNConfig
-    from mrb_b200.model.backend import B200Backend
-    from mrb_b200.optim import FlatSGD, ParamArena
-    use_graph = args.graph in ("on", "auto")
-    # graph capture needs a step without host synchronisation: fixed-shape mask head (see RCNNConfig)
-    cfg = RCNNConfig(mask_rois_per_image=128 if use_graph else 0,
-                     parallel_heads=(args.parallel_heads == "on" and args.overlap == "on" and args.optim == "arena"))
-    model = build_model(cfg, backend=B200Backend(wgrad=args.wgrad), device=device).train()
-    params = [p for p in model.parameters() if p.requires_grad]
-    grad_sync = None
+    model = build_detection_model(cfg).to(device)
+    model.train(train)
+    report = None
     if world > 1:
-        # same initial weights everywhere (DDP's constructor broadcast), then one flat gradient all-reduce per step
+        import torch.distributed as dist
         for t in list(model.parameters()) + list(model.buffers()):
             dist.broadcast(t.data, 0)
-    # SOLVER defaults of the reference (config/defaults.py:383-401): momentum 0.9, wd 1e-4, bias lr x2, bias wd 0
-    if args.optim == "arena":
-        # parameters / gradient accumulators / momentum / bf16 operand copies in four flat buffers: kernels red.add
-        # gradients in place, one NCCL all-reduce over the gradient buffer, one fused update launch per group
-        opt = grad_sync = ParamArena(model.named_parameters(), model.be, lr=1e-4, momentum=0.9, weight_decay=1e-4,
-                                     world_size=world)
-        model.be.enable_overlap(args.overlap == "on")
+    opt = None
+    if aten:
+        model = model.to(memory_format=torch.channels_last)
+        if train:
+            # reference solver semantics (solver/build.py:7-20): bias lr x2, bias weight decay 0
+            groups = [{"params": [p], "lr": 1e-4 * (2 if "bias" in n else 1), "weight_decay": 0.0 if "bias" in n else 1e-4}
+                      for n, p in model.named_parameters() if p.requires_grad]
+            opt = torch.optim.SGD(groups, lr=1e-4, momentum=0.9)
     else:
-        if world > 1:
-            from mrb_b200.parallel import FlatGradSync
-            grad_sync = FlatGradSync(params, world)
-        opt = FlatSGD(model.named_parameters(), lr=1e-4, momentum=0.9, weight_decay=1e-4)
-    sizes = [(IMG_H, IMG_W)] * IMGS_PER_GPU
-    # distinct synthetic batches, pinned on the host (e2e) and resident in HBM (value)
+        from mrb_b200.fuse import fuse_model
+        from mrb_b200.model.backend import B200Backend
+        be = B200Backend()
+        engine.set_default_backend(be)
+        report = fuse_model(model, be)
+        if train:
+            from mrb_b200.optim import ParamArena
+            opt = ParamArena(model.named_parameters(), be, lr=1e-4, momentum=0.9, weight_decay=1e-4, world_size=world)
+            be.enable_overlap(True)
     n_batches = 4
-    host = [synth_batch(IMGS_PER_GPU, 100 * rank + i, pin=True) for i in range(n_batches)]
+    host = [synth_batch(per_gpu, 100 * rank + i, pin=True) for i in range(n_batches)]
+    mask_on = bool(cfg.MODEL.MASK_ON)
+    dev_batches = [_ref_inputs(per_gpu, 100 * rank + i, device, with_masks=mask_on) for i in range(n_batches)]
+    host_targets = [_ref_inputs(per_gpu, 100 * rank + i, "cpu", with_masks=mask_on)[1] for i in range(n_batches)]
+
+    def fwd_bwd(il, targets):
+        if not train:
+            with torch.no_grad():
+                dets = model(il)
+            return sum(d.bbox.sum() for d in dets)          # a scalar that depends on the detections
+        if aten:
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                losses = model(il, targets)
+            loss = sum(losses.values())
+            opt.zero_grad(set_to_none=True)
+            loss.backward()
+            if world > 1:
+                import torch.distributed as dist
+                for p in model.parameters():
+                    if p.grad is not None:
+                        dist.all_reduce(p.grad)
+                        p.grad /= world
+            opt.step()
+            return loss
+        losses = model(il, targets)
+        loss = sum(losses.values())
+        loss.backward()
+        opt.sync()
+        opt.step()
+        return loss
+
+    def step_dev(i):
+        il, targets = dev_batches[i % n_batches]
+        return fwd_bwd(il, targets)
+
+    def step_e2e(i):
+        images, boxes, labels = host[i % n_batches]
+        il = ImageList(images.to(device, non_blocking=True), [(IMG_H, IMG_W)] * per_gpu)
+        targets = [t.to(device) for t in host_targets[i % n_batches]]            # H2D of the boxes / labels
+        return fwd_bwd(il, targets).detach().float().cpu()                       # D2H of the step's result
+
+    for i in range(args.warmup):
+        step_dev(i)
+    ops.STATS["launches"] = 0
+    ops.STATS["conv_calls"] = []
+    step_dev(0)                                      # one counted step: libmrb launches + conv geometry per step
+    torch.cuda.synchronize()
+    launches_per_step = ops.STATS["launches"]
+    conv_calls = list(ops.STATS["conv_calls"])
+    ops.STATS["conv_calls"] = None
+    t_dev, _ = timer.run(args.steps, step_dev)
+    step_e2e(0)
+    t_e2e, last = timer.run(args.steps, step_e2e)
+    imgs = per_gpu * world * args.steps
+    h2d = sum(t.numel() * t.element_size() for t in host[0])
+    return {"arm": "aten_reference_graph" if aten else "reference_graph",
+            "model_path": ("reference GeneralizedRCNN (baseline/_ref mirror, unmodified) on ATen/cuDNN: bf16 autocast, channels_last, "
+                           "torch.optim.SGD; ROIAlign/NMS from this repo's _C (the reference's CUDA sources need THC)") if aten else
+                          "reference GeneralizedRCNN (baseline/_ref mirror, unmodified) over maskrcnn_benchmark.layers/_C of this "
+                          "repo + mrb_b200.fuse.fuse_model; eager; ParamArena fused SGD",
+            "value": round(imgs / t_dev, 3), "ms_per_step": round(t_dev / args.steps * 1e3, 2),
+            "e2e": {"value": round(imgs / t_e2e, 3), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "mode": "h2d serialised with the step (eager reference training loop, engine/trainer.py:64-75)"},
+            "gpu_launches": launches_per_step * args.steps, "libmrb_launches_per_step": launches_per_step,
+            "conv_calls": conv_calls, "fuse_report": report, "result_last_step": round(float(last), 4),
+            "cuda_graph": {"enabled": False, "why": "the reference's host code synchronises (nonzero, per-image NMS sizing, CPU mask targets)"},
+            "engine_convs": engine.STATS["engine"], "aten_fallbacks": engine.STATS["aten"]}
+
+
+# =========================================================================================== arm: harness
+def arm_harness(args, cfg_name, device, rank, world, timer, sustained_s=0.0):
+    import torch.distributed as dist
+    from mrb_b200 import ops
+    from mrb_b200.model import RCNNConfig, build_model
+    from mrb_b200.model.backend import B200Backend
+    from mrb_b200.optim import FlatSGD, ParamArena
+    yaml, per_gpu, train, metric, workload = CONFIGS[cfg_name]
+    torch.manual_seed(0)
+    use_graph = args.graph in ("on", "auto") and train
+    kw = {}
+    if cfg_name == "faster_fwd":
+        kw = dict(mask_on=False)
+    elif cfg_name == "x101":
+        kw = dict(stage_blocks=(3, 4, 23, 3), num_groups=32, width_per_group=8, stride_in_1x1=False)
+    elif cfg_name == "dcn":
+        kw = dict(stage_with_dcn=(False, True, True, True))
+    # graph capture needs a step without host synchronisation: fixed-shape mask head (see RCNNConfig)
+    cfg = RCNNConfig(mask_rois_per_image=128 if use_graph else 0,
+                     parallel_heads=(args.parallel_heads == "on" and args.overlap == "on" and args.optim == "arena"), **kw)
+    be = B200Backend(wgrad=args.wgrad)
+    model = build_model(cfg, backend=be, device=device)
+    model.train(train)
+    params = [p for p in model.parameters() if p.requires_grad]
+    grad_sync = opt = None
+    if world > 1:
+        for t in list(model.parameters()) + list(model.buffers()):
+            dist.broadcast(t.data, 0)
+    if train:
+        # SOLVER defaults of the reference (config/defaults.py:383-401): momentum 0.9, wd 1e-4, bias lr x2, bias wd 0
+        if args.optim == "arena":
+            opt = grad_sync = ParamArena(model.named_parameters(), model.be, lr=1e-4, momentum=0.9, weight_decay=1e-4,
+                                         world_size=world)
+            model.be.enable_overlap(args.overlap == "on")
+        else:
+            if world > 1:
+                from mrb_b200.parallel import FlatGradSync
+                grad_sync = FlatGradSync(params, world)
+            opt = FlatSGD(model.named_parameters(), lr=1e-4, momentum=0.9, weight_decay=1e-4)
+    sizes = [(IMG_H, IMG_W)] * per_gpu
+    n_batches = 4
+    host = [synth_batch(per_gpu, 100 * rank + i, pin=True) for i in range(n_batches)]
     dev = [tuple(t.to(device) for t in b) for b in host]
 
     def eager_step(batch):
         images, boxes, labels = batch
+        if not train:
+            with torch.no_grad():
+                dets = model(images, sizes)
+            return sum(d["boxes"].sum() for d in dets)
         losses = model(images, sizes, targets_of(boxes, labels))
         loss = sum(losses.values())
         opt.zero_grad()
@@ -309,14 +619,12 @@ def main():
             grad_sync.sync()               # NCCL all-reduce of one flat fp32 gradient buffer (mean over ranks)
         opt.step()
         if args.optim != "arena":
-            model.be.refresh_weights(params)   # bf16 operand copies of the updated weights: one multi-tensor cast
+            model.be.refresh_weights(params)
         return loss
 
-    sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else local_rank)
-    if rank == 0:
-        sampler.start()                 # well before the timed region: nvidia-smi needs a few hundred ms to start streaming
     graph_info = {"enabled": False}
     step = eager_step
+    graph = static = static_loss = None
     if use_graph:
         static = tuple(torch.empty_like(t) for t in dev[0])
         try:
@@ -333,15 +641,10 @@ def main():
             ops.STATS["launches"] = 0
             ops.STATS["conv_calls"] = []
             graph = torch.cuda.CUDAGraph()
-            # A/B switch: capture the main chain from a high-priority stream (MRB_MAIN_PRIORITY=1).  Measured 8.55 vs
-            # 8.36 ms/step -- serving the side streams' gradient kernels late lengthens the tail, so it stays off.
-            prio = -1 if os.environ.get("MRB_MAIN_PRIORITY", "0") == "1" else 0     # measured: -1 is 2% slower
-            cap_stream = torch.cuda.Stream(priority=prio)
+            cap_stream = torch.cuda.Stream()
             with torch.cuda.graph(graph, stream=cap_stream):
                 static_loss = eager_step(static)
-            graph_info_extra = {"main_stream_priority": prio}
             graph_info = {"enabled": True, "launches_per_step": ops.STATS["launches"], "conv_calls": list(ops.STATS["conv_calls"])}
-            graph_info.update(graph_info_extra)
             ops.STATS["conv_calls"] = None
 
             def step(batch):  # noqa: F811
@@ -355,49 +658,33 @@ def main():
             graph_info = {"enabled": False, "error": repr(e)[:300]}
             torch.cuda.synchronize()
             if args.optim == "arena":
-                opt.grad.zero_()            # drop the partial accumulation of the aborted capture
+                opt.grad.zero_()
             step = eager_step
 
     def step_e2e(hbatch):
         if graph_info["enabled"]:
-            loss = step(hbatch)             # pinned host -> static device buffers (H2D), then the captured step
+            loss = step(hbatch)
         else:
             loss = step(tuple(t.to(device, non_blocking=True) for t in hbatch))
-        return loss.detach().float().cpu()  # D2H of the step's result
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+        return loss.detach().float().cpu()
 
     for i in range(args.warmup):
         step(dev[i % n_batches])
-    # ---- timed: device-resident inputs
     ops.STATS["launches"] = 0
     ops.STATS["conv_calls"] = []
-    barrier()
-    t_clock0 = time.time()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(args.steps):
-        step(dev[i % n_batches])
-    e1.record()
-    barrier()
-    t_dev = e0.elapsed_time(e1) * 1e-3
+    t_dev, _ = timer.run(args.steps, lambda i: step(dev[i % n_batches]))
     if graph_info["enabled"]:
         launches = graph_info["launches_per_step"] * args.steps
-        conv_calls = graph_info.pop("conv_calls") * args.steps
+        conv_calls = graph_info.pop("conv_calls")
     else:
         launches = ops.STATS["launches"]
-        conv_calls = list(ops.STATS["conv_calls"])
+        conv_calls = list(ops.STATS["conv_calls"])[:len(ops.STATS["conv_calls"]) // max(args.steps, 1)]
     ops.STATS["conv_calls"] = None
-    # ---- timed: end to end from pinned host memory.  Every step's batch is copied host -> device and every step's
-    # loss is read back (a blocking .cpu()) inside the timed region.  With the captured step the H2D copy of batch i+1
-    # is issued on a copy stream into a staging buffer while step i computes (what a prefetching data loader with pinned
-    # memory does; the reference's loader hands pinned batches to `images.to(device)`, engine/trainer.py:64-68), and a
-    # device-to-device copy moves it into the graph's static input at the start of step i+1.
+    # ---- end to end from pinned host memory: every step's batch is copied host -> device and every step's loss is
+    # read back (blocking) inside the timed region.  With the captured step the H2D copy of batch i+1 is issued on a
+    # copy stream while step i computes (what a prefetching loader with pinned memory does; the reference hands pinned
+    # batches to `images.to(device)`, engine/trainer.py:64-68), a D2D copy moves it into the graph's static input.
     step_e2e(host[0])
-    barrier()
     e2e_mode = "h2d serialised with the step"
     if graph_info["enabled"]:
         e2e_mode = "h2d of batch i+1 prefetched on a copy stream during step i"
@@ -407,85 +694,174 @@ def main():
 
         def prefetch(hbatch):
             with torch.cuda.stream(copy_stream):
-                copy_stream.wait_event(ev_consumed)            # the previous staging content has been consumed
+                copy_stream.wait_event(ev_consumed)
                 for a, b in zip(staging, hbatch):
                     a.copy_(b, non_blocking=True)
                 ev_staged.record(copy_stream)
 
-        def step_e2e_prefetched(next_hbatch):
+        def e2e_fn(i):
+            if i == 0:
+                prefetch(host[0])
             cur = torch.cuda.current_stream()
             cur.wait_event(ev_staged)
             for a, b in zip(static, staging):
                 a.copy_(b, non_blocking=True)
             ev_consumed.record(cur)
             graph.replay()
-            if next_hbatch is not None:
-                prefetch(next_hbatch)
+            if i + 1 < args.steps:
+                prefetch(host[(i + 1) % n_batches])
             return static_loss.detach().float().cpu()
-
         ev_consumed.record(torch.cuda.current_stream())
-        barrier()
-    e0.record()
-    last_loss = None
-    if graph_info["enabled"]:
-        prefetch(host[0])
-        for i in range(args.steps):
-            last_loss = step_e2e_prefetched(host[(i + 1) % n_batches] if i + 1 < args.steps else None)
     else:
-        for i in range(args.steps):
-            last_loss = step_e2e(host[i % n_batches])
-    e1.record()
-    barrier()
-    t_e2e = e0.elapsed_time(e1) * 1e-3
-    clocks = sampler.stop(t_clock0, time.time()) if rank == 0 else None
+        def e2e_fn(i):
+            return step_e2e(host[i % n_batches])
+    t_e2e, last = timer.run(args.steps, e2e_fn)
+    sustained = None
+    if sustained_s > 0 and graph_info["enabled"]:
+        n = max(args.steps, int(sustained_s / (t_dev / args.steps)))
+        t_s, _ = timer.run(n, lambda i: step(dev[i % n_batches]))
+        sustained = {"steps": n, "seconds": round(t_s, 2), "ms_per_step": round(t_s / n * 1e3, 3),
+                     "value": round(per_gpu * world * n / t_s, 2), "window_index": len(timer.windows) - 1}
+    imgs = per_gpu * world * args.steps
+    h2d = sum(t.numel() * t.element_size() for t in host[0])
+    return {"arm": "harness",
+            "model_path": "mrb_b200.model (from-scratch module graph, reference state_dict keys; sync-free fixed-shape host code), "
+                          "whole step in one CUDA graph" if graph_info["enabled"] else "mrb_b200.model, eager",
+            "value": round(imgs / t_dev, 3), "ms_per_step": round(t_dev / args.steps * 1e3, 2),
+            "e2e": {"value": round(imgs / t_e2e, 3), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "mode": e2e_mode},
+            "gpu_launches": launches, "conv_calls": conv_calls, "cuda_graph": graph_info, "result_last_step": round(float(last), 4),
+            "sustained": sustained, "wgrad": model.be.wgrad_impl}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "aten"])
+    ap.add_argument("--config", default="mask_r50", choices=sorted(CONFIGS))
+    ap.add_argument("--model", default="auto", choices=["auto", "reference", "harness"],
+                    help="auto: both arms, the reference graph over layers is the headline when baseline/_ref exists")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--no-ops", action="store_true")
+    ap.add_argument("--sustained", type=float, default=5.0, help="seconds of back-to-back graph replays (harness arm); 0 = off")
+    ap.add_argument("--dump-shapes", default=None, help="write the per-shape conv table (JSON) here")
+    ap.add_argument("--wgrad", default="tc", choices=["tc", "cudnn"], help="weight-gradient kernel (A/B switch)")
+    ap.add_argument("--optim", default="arena", choices=["arena", "flat"])
+    ap.add_argument("--overlap", default="on", choices=["on", "off"])
+    ap.add_argument("--parallel-heads", default="on", choices=["on", "off"])
+    ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"])
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device for --impl b200/aten (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
     if world > 1:
-        t = torch.tensor([t_dev, t_e2e], device=device, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        t_dev, t_e2e = float(t[0]), float(t[1])
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=device)
+    yaml, per_gpu, train, metric, workload = CONFIGS[args.config]
+    sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else local_rank)
+    if rank == 0:
+        sampler.start()                 # well before the timed region: nvidia-smi needs a few hundred ms to start streaming
+    timer = Timer(world)
+    arms = []
+    if args.impl == "aten":
+        a = arm_reference_graph(args, args.config, device, rank, world, timer, aten=True)
+        if a is None:
+            if rank == 0:
+                print(json.dumps({"impl": "aten", "unavailable": "no reference mirror (baseline/_ref) on this box"}))
+            _finish(world)
+            return
+        arms.append(a)
+    else:
+        harness_ok = args.config in HARNESS_CONFIGS
+        if args.model in ("auto", "reference"):
+            try:
+                a = arm_reference_graph(args, args.config, device, rank, world, timer)
+            except Exception:
+                if args.model == "reference":
+                    raise
+                import traceback
+                sys.stderr.write("reference-graph arm failed, continuing with the harness arm:\n" + traceback.format_exc() + "\n")
+                a = None
+            if a is not None:
+                arms.append(a)
+        if args.model in ("auto", "harness") and harness_ok:
+            try:
+                arms.append(arm_harness(args, args.config, device, rank, world, timer,
+                                        sustained_s=args.sustained if (world == 1 and train) else 0.0))
+            except Exception:
+                if not arms:
+                    raise
+                import traceback
+                sys.stderr.write("harness arm failed:\n" + traceback.format_exc() + "\n")
+    sampler.stop()
     if rank != 0:
         _finish(world)
         return
-    imgs = IMGS_PER_GPU * world * args.steps
-    h2d = sum(t.numel() * t.element_size() for t in host[0])
+    head = arms[0]
+    clocks = sampler.summary(timer.windows)
     peaks = load_peaks()
-    out = {"metric": METRIC, "value": round(imgs / t_dev, 3), "unit": "images/s", "n_gpus": world, "steps": args.steps,
-           "warmup": args.warmup, "ms_per_step": round(t_dev / args.steps * 1e3, 2), "higher_is_better": True,
+    out = {"metric": metric, "value": head["value"], "unit": "images/s", "n_gpus": world, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-           "config": workload_config(world), "clocks": clocks,
-           "e2e": {"value": round(imgs / t_e2e, 3), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                   "mode": e2e_mode},
-           "gpu_launches": launches, "cuda_graph": graph_info, "loss_last_step": round(float(last_loss), 4),
-           "library_ops": {"wgrad": model.be.wgrad_impl, "note": "in-house sm_100a kernels (libmrb_b200.so): conv forward / "
-                           "data gradient / weight gradient / bias gradient (tcgen05 + TMA), fused multi-level ROIAlign fwd+bwd, "
-                           "batched NMS, max/sum pooling, fused SGD update; PyTorch: top-k/sort, box arithmetic, anchor "
-                           "matching, losses, gradient accumulation glue"}}
-    if not args.no_roofline and conv_calls:
-        per_step = conv_calls[:len(conv_calls) // args.steps]
-        rf, rows = conv_roofline(per_step, peaks, device)
-        # conv-FLOP roofline of the whole step (~1631 GFLOP/image fwd+bwd upper bound)
-        rf["step_conv_flop_roofline_frac"] = round((imgs / t_dev) / (peaks.get("bf16_tflops", 1590.0) * 1e3 / 1631.0) / world, 4)
-        # DRAM traffic of the dominant launch shape from the committed `ncu --set full` capture (per launch, like `achieved`)
+           "config": dict(workload_config(args.config, world), model_path=head["model_path"], arm=head["arm"]),
+           "clocks": clocks, "e2e": head["e2e"], "gpu_launches": head["gpu_launches"], "cuda_graph": head["cuda_graph"],
+           "result_last_step": head["result_last_step"]}
+    if args.impl == "aten":
+        out["impl"] = "aten"
+    conv_calls = None
+    arms_out = {}
+    for a in arms:
+        cc = a.pop("conv_calls", None)
+        if conv_calls is None and cc:
+            conv_calls = cc
+        arms_out[a["arm"]] = a
+    out["arms"] = arms_out
+    for a in arms:
+        if a.get("sustained"):
+            s = dict(a["sustained"])
+            w = timer.windows[s.pop("window_index")]
+            s["clocks"] = sampler.summary([w])
+            s["note"] = "back-to-back CUDA-graph replays of the harness arm's train step"
+            out["sustained"] = s
+    out["library_ops"] = {"note": "in-house sm_100a kernels (libmrb_b200.so): conv forward / data gradient / weight gradient / bias "
+                          "gradient (tcgen05 + TMA), fused multi-level ROIAlign fwd+bwd, NMS, max/sum pooling, fused SGD update; "
+                          "PyTorch: top-k/sort, box arithmetic, anchor matching, losses, gradient accumulation glue"}
+    if not args.no_roofline and conv_calls and args.impl != "aten":
         try:
-            cap = json.load(open(os.path.join(ROOT, "profiles", "ncu_conv_r1_summary.json")))[0]
-            m = cap["metrics"]
-            rf["traffic"] = round((float(m["dram__bytes_read.sum"]["value"]) + float(m["dram__bytes_write.sum"]["value"])) * 1e6)
-            rf["traffic_note"] = ("bytes of ONE launch of the top shape (%s): algorithmic 70.0e6 (x + y + w), tensor pipe "
-                                  "%.1f%% active" % (cap["what"].split(" (")[0], float(m["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"]["value"])))
-        except Exception:
-            pass
-        out["roofline"] = rf
-        if args.dump_shapes:
-            json.dump(rows, open(args.dump_shapes, "w"), indent=1)
-    if not args.no_cpu_baseline:
+            rf, rows = conv_roofline(conv_calls, peaks, device)
+            flop_img = {"mask_r50": 1631.0}.get(args.config)
+            if flop_img:
+                # conv-FLOP roofline of the whole step (~1631 GFLOP/image fwd+bwd upper bound)
+                rf["step_conv_flop_roofline_frac"] = round(head["value"] / (peaks.get("bf16_tflops", 1590.0) * 1e3 / flop_img) / world, 4)
+            rf["conv_calls_from"] = [a["arm"] for a in arms][0] if arms else None
+            out["roofline"] = rf
+            if args.dump_shapes:
+                json.dump(rows, open(args.dump_shapes, "w"), indent=1)
+        except Exception as e:
+            out["roofline"] = {"error": repr(e)[:300]}
+    if not args.no_ops and world == 1 and args.impl != "aten":
         try:
-            import oracle
-            oracle.lib()
-            use_ref = oracle.ref() is not None
-            v, dt = cpu_train_step(1, use_ref)
-            out["cpu_baseline"] = {"value": round(v, 4), "unit": "images/s", "cores": torch.get_num_threads(),
-                                   "kind": "port", "seconds": round(dt, 1),
-                                   "sample": "1 image, full train fwd+bwd, fp32 PyTorch CPU convs + %s ROIAlign/NMS"
-                                             % ("reference csrc/cpu (oracle/_ref)" if use_ref else "oracle C port")}
+            out["ops"] = ops_metrics(device, peaks)
+        except Exception as e:
+            out["ops"] = {"error": repr(e)[:300]}
+    if not args.no_cpu_baseline and world == 1:
+        # in a subprocess: the reference arm builds a `maskrcnn_benchmark` made only of the reference mirror, which must
+        # not share sys.modules with the product package loaded above
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--config", args.config,
+                                "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=600)
+            line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
+            out["cpu_baseline"] = json.loads(line).get("cpu_baseline", {"value": None, "note": line[:200]})
         except Exception as e:  # the baseline must never break the bench line
             out["cpu_baseline"] = {"value": None, "error": repr(e)[:200]}
     print(json.dumps(out))

@@ -912,6 +912,21 @@ static cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, siz
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize, once per (kernel slot, device ordinal)
+template <typename K>
+static cudaError_t ensure_max_smem(K kernel, int slot) {
+  static std::mutex mu;
+  static bool done[4][64] = {};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lk(mu);
+  if (dev >= 0 && dev < 64 && done[slot][dev]) return cudaSuccess;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e == cudaSuccess && dev >= 0 && dev < 64) done[slot][dev] = true;
+  return e;
+}
+
 struct ConvPlan {
   // logical GEMM-side geometry after the 1x1 flattening
   int batch, Hin, Win;        // TMA view of the input (already subsampled for stride 2)
@@ -1033,12 +1048,8 @@ static int conv_launch(const ConvPlan& pl, const void* x, const void* w, int cin
     int rc = encode_bf16(&map_b, w, 3, dims, strides, box);
     if (rc) return rc;
   }
-  static std::once_flag attr_once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(attr_once, [] {
-    attr_err = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  });
-  if (attr_err != cudaSuccess) return (int)attr_err;
+  // the attribute is per device: one process may drive several GPUs (cuda:0 then cuda:1)
+  MRB_CUDA_TRY(ensure_max_smem(conv_tc_kernel, 0));
   const int grid = a.tiles_total < kNumSMs ? a.tiles_total : kNumSMs;
   MRB_CUDA_TRY(launch_pdl(conv_tc_kernel, grid, kConvThreads, smem, stream, map_a, map_b, map_out, map_res, map_mask, a));
   return MRB_OK;
@@ -1311,12 +1322,7 @@ static int conv_wgrad_impl(const mrb_conv_params* p, const void* input, const vo
     rc = encode_bf16(&map_x, input, 4, dims, strides, box);
     if (rc) return rc;
   }
-  static std::once_flag attr_once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(attr_once, [] {
-    attr_err = cudaFuncSetAttribute(conv_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  });
-  if (attr_err != cudaSuccess) return (int)attr_err;
+  MRB_CUDA_TRY(ensure_max_smem(conv_wgrad_tc_kernel, 1));
   const int grid = a.items_total < kNumSMs ? a.items_total : kNumSMs;
   MRB_CUDA_TRY(launch_pdl(conv_wgrad_tc_kernel, grid, kWgradThreads, smem, stream, map_g, map_x, a));
   return MRB_OK;

@@ -1,4 +1,8 @@
-"""Empty-batch-safe nn wrappers and DFConv2d (reference layers/misc.py:19-203)."""
+"""Empty-batch-safe nn wrappers and DFConv2d (reference layers/misc.py:19-203).
+
+Conv2d / ConvTranspose2d are the drop-in boundary of the dense-conv hot path: for CUDA tensors their forward is
+served by the tcgen05 engine of libmrb_b200.so (mrb_b200.engine), with ATen as the logged fallback for
+geometries the engine does not cover; CPU tensors always take ATen (the reference's CPU path)."""
 import math
 
 import torch
@@ -24,9 +28,18 @@ def _conv_out_hw(hw, padding, dilation, kernel_size, stride):
             for i, p, di, k, d in zip(hw, padding, dilation, kernel_size, stride)]
 
 
+def _engine():
+    from mrb_b200 import engine      # lazy: layers must import without the host-side package being touched on CPU
+    return engine
+
+
 class Conv2d(torch.nn.Conv2d):
     def forward(self, x):
         if x.numel() > 0:
+            if x.is_cuda:
+                y = _engine().conv2d_module(self, x)
+                if y is not None:
+                    return y
             return super().forward(x)
         hw = _conv_out_hw(x.shape[-2:], self.padding, self.dilation, self.kernel_size, self.stride)
         return _NewEmptyTensorOp.apply(x, [x.shape[0], self.weight.shape[0]] + hw)
@@ -35,6 +48,10 @@ class Conv2d(torch.nn.Conv2d):
 class ConvTranspose2d(torch.nn.ConvTranspose2d):
     def forward(self, x):
         if x.numel() > 0:
+            if x.is_cuda:
+                y = _engine().conv_transpose2d_module(self, x)
+                if y is not None:
+                    return y
             return super().forward(x)
         hw = [(i - 1) * d - 2 * p + (di * (k - 1) + 1) + op
               for i, p, di, k, d, op in zip(x.shape[-2:], self.padding, self.dilation, self.kernel_size,

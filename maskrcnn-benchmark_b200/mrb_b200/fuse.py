@@ -1,0 +1,376 @@
+"""Fusion pass over the reference's UNMODIFIED module graph.
+
+`fuse_model(model)` walks an instantiated reference model (maskrcnn_benchmark.modeling.detector.
+build_detection_model(cfg), running on top of this repository's `layers` / `_C`) and rebinds the `forward`
+of the modules whose bodies are chains the conv engine fuses into one launch each:
+
+  reference code (file:line)                                           becomes
+  -------------------------------------------------------------------  ------------------------------------------
+  BaseStem.forward           conv1 -> bn1 -> relu_ -> max_pool2d       stem conv (4x1 over s2d view) + BN + ReLU,
+    (backbone/resnet.py:359-366)                                        NHWC max-pool kernel
+  Bottleneck.forward         (conv -> FrozenBN -> relu_) x2,           4 fused launches forward; hand-scheduled
+    (backbone/resnet.py:324-344)  conv -> FrozenBN, += identity, relu_  backward with ReLU masks / BN scale /
+                                                                        residual join in dgrad epilogues
+  FPN.forward                inner 1x1 + F.interpolate + add, 3x3,     lateral conv with the 2x-upsampled top-down
+    (backbone/fpn.py:43-76)    LastLevelMaxPool                         map read in the epilogue; 3x3; pool
+  RPNHead.forward            relu(conv3x3), cls_logits, bbox_pred      3x3+bias+ReLU; ONE 1x1 with Cout = A + 4A
+    (rpn/rpn.py:98-105)
+  Pooler.forward             LevelMapper + 4 ROIAlign + index_put      one multi-level ROIAlign launch
+    (poolers.py:91-121)
+  FPN2MLPFeatureExtractor    pooler, relu(fc6), relu(fc7)              pool + two GEMMs with bias+ReLU epilogues
+    (box_head/roi_box_feature_extractors.py:74-81)
+  FPNPredictor               cls_score, bbox_pred                      one GEMM, fp32 logits
+    (box_head/roi_box_predictors.py:55-62)
+  MaskRCNNFPNFeatureExtractor  pooler, relu(conv3x3) x4                pool (NHWC) + fused convs
+    (mask_head/roi_mask_feature_extractors.py:59-65)
+  MaskRCNNC4Predictor        relu(conv5_mask), mask_fcn_logits         deconv as two strided 1x1 convs, 1x1 fp32
+    (mask_head/roi_mask_predictors.py:29-32)
+
+Nothing else changes: module classes, parameters, buffers and state_dict keys are the reference's; the anchor
+generator, proposal selection, matcher/sampler, box coder and all losses are the reference's own Python.
+Modules are recognised by structure (attribute names / layer types), not by import, so the pass needs no reference
+checkout; anything that does not match exactly is left alone (it still reaches the engine per conv through
+layers.Conv2d, unfused).  Activations between fused modules travel as bf16 NHWC (`channels_last`); tensors
+handed back to unfused reference code (RPN logits, box/mask logits) are fp32.
+
+Backends: B200Backend (product).  The CPU checker backend of oracle/ implements the same interface, which is how
+tests pin this pass against the unfused reference forward on CPU."""
+import types
+
+import torch
+from torch import nn
+
+from mrb_b200.model.backbone import Bottleneck as _HBottleneck
+from mrb_b200.model.backbone import FrozenAffine
+
+
+# ---------------------------------------------------------------------------------- recognition
+def _is_fbn(m):
+    return type(m).__name__ == "FrozenBatchNorm2d" and hasattr(m, "scale_shift")
+
+
+def _conv_ok(m, k, stride=None, pad=None, bias=None):
+    if not isinstance(m, nn.Conv2d) or isinstance(m, nn.ConvTranspose2d):
+        return False
+    if m.groups != 1 or tuple(m.dilation) != (1, 1) or m.padding_mode != "zeros" or isinstance(m.padding, str):
+        return False
+    if tuple(m.kernel_size) != (k, k) or m.stride[0] != m.stride[1] or m.padding[0] != m.padding[1]:
+        return False
+    if stride is not None and m.stride[0] not in (stride if isinstance(stride, tuple) else (stride,)):
+        return False
+    if pad is not None and m.padding[0] != pad:
+        return False
+    if bias is not None and (m.bias is not None) != bias:
+        return False
+    return m.in_channels % 8 == 0
+
+
+def _act(be, x):
+    """Activation entering a fused module: the backend's dtype / memory format (bf16 NHWC on the B200)."""
+    if x.dtype != be.act_dtype:
+        x = x.to(be.act_dtype)
+    if getattr(be, "channels_last", False) and x.dim() == 4 and not x.is_contiguous(memory_format=torch.channels_last):
+        x = x.contiguous(memory_format=torch.channels_last)
+    return x
+
+
+def _bind(mod, fn):
+    mod.forward = types.MethodType(fn, mod)
+    mod._mrb_fused = True
+
+
+# ---------------------------------------------------------------------------------- backbone
+def _fuse_stem(mod, be, rep):
+    c, b = getattr(mod, "conv1", None), getattr(mod, "bn1", None)
+    if not (isinstance(c, nn.Conv2d) and _is_fbn(b)) or tuple(c.weight.shape[1:]) != (3, 7, 7) or c.bias is not None \
+            or tuple(c.stride) != (2, 2) or tuple(c.padding) != (3, 3) or c.weight.shape[0] % 8:
+        return False
+    if any(p.requires_grad for p in mod.parameters()):
+        rep["skipped"].append("stem is trainable (the fused stem has no backward)")
+        return False
+    aff = FrozenAffine(b)
+
+    def forward(self, x):
+        a, s = aff.get()
+        y = be.stem(x, self.conv1.weight, a, s)
+        return be.max_pool(y, 3, 2, 1)
+    _bind(mod, forward)
+    return True
+
+
+def _bottleneck_kind(mod, be):
+    """'fn' (whole block as one autograd node), 'conv' (per-conv fusion) or None."""
+    need = ("conv1", "bn1", "conv2", "bn2", "conv3", "bn3")
+    if not all(hasattr(mod, n) for n in need) or not hasattr(mod, "downsample"):
+        return None
+    if not all(_is_fbn(getattr(mod, n)) for n in ("bn1", "bn2", "bn3")):
+        return None
+    if not (_conv_ok(mod.conv1, 1, (1, 2), 0, False) and _conv_ok(mod.conv3, 1, 1, 0, False)):
+        return None
+    ds = mod.downsample
+    if ds is not None and not (isinstance(ds, nn.Sequential) and len(ds) == 2 and _conv_ok(ds[0], 1, (1, 2), 0, False)
+                               and _is_fbn(ds[1])):
+        return None
+    c2 = mod.conv2
+    if _conv_ok(c2, 3, 1, 1, False):
+        return "fn" if hasattr(be, "bottleneck") else "conv"
+    if _conv_ok(c2, 3, 2, 1, False) and getattr(be, "stride2_3x3", True):
+        return "conv"
+    if hasattr(be, "bottleneck_general") and be.bottleneck_general_ok(mod):
+        return "general"
+    return None
+
+
+def _fuse_bottleneck(mod, be, kind):
+    mod.strides = (mod.conv1.stride[0], mod.conv2.stride[0], mod.downsample[0].stride[0] if mod.downsample is not None else 1)
+    mod._aff = [FrozenAffine(b) for b in (mod.bn1, mod.bn2, mod.bn3)]
+    mod._aff_d = FrozenAffine(mod.downsample[1]) if mod.downsample is not None else None
+    mod._g_premasked = False                      # decided by _wire_resnet once the consumers are known
+    mod._mrb_premasks_input = kind == "fn"        # _BottleneckFn returns grad_x already multiplied by [x > 0]
+    if kind == "general":
+        def forward(self, x):
+            return be.bottleneck_general(self, _act(be, x))
+    else:
+        def forward(self, x):
+            return _HBottleneck.run(self, be, _act(be, x))
+    _bind(mod, forward)
+
+
+def _fuse_fpn(mod, be, rep):
+    inner, layer = getattr(mod, "inner_blocks", None), getattr(mod, "layer_blocks", None)
+    if not (isinstance(inner, list) and isinstance(layer, list) and inner and len(inner) == len(layer)):
+        return False
+    top = getattr(mod, "top_blocks", None)
+    if top is not None and type(top).__name__ != "LastLevelMaxPool":
+        return False
+    for a, b in zip(inner, layer):
+        if not (_conv_ok(getattr(mod, a, None), 1, 1, 0, True) and _conv_ok(getattr(mod, b, None), 3, 1, 1, True)):
+            return False
+    mod._mrb_premask_inputs = False               # set by _wire_resnet when the producer is a fused ResNet
+
+    def forward(self, x):
+        if len(x) != len(self.inner_blocks):
+            raise RuntimeError("fused FPN: expected %d feature maps, got %d" % (len(self.inner_blocks), len(x)))
+        pm = self._mrb_premask_inputs
+        last, results = None, []
+        for feat, ib, lb in zip(list(x)[::-1], self.inner_blocks[::-1], self.layer_blocks[::-1]):
+            ib, lb = getattr(self, ib), getattr(self, lb)
+            last = be.lateral_topdown(_act(be, feat), ib.weight, ib.bias, last, premask_x=pm)
+            results.insert(0, be.conv(last, lb.weight, bias=lb.bias, pad=1))
+        if self.top_blocks is not None:
+            results.append(be.max_pool(results[-1], 1, 2, 0))          # LastLevelMaxPool (fpn.py:77-79)
+        return tuple(results)
+    _bind(mod, forward)
+    return True
+
+
+def _wire_resnet(model, be):
+    """Decide, per fused bottleneck, whether every consumer of its output hands back a gradient already masked by
+    [out > 0] (then the block skips its own mask pass), and whether a fused FPN may mask the gradients it returns."""
+    for parent in model.modules():
+        body, fpn = getattr(parent, "body", None), getattr(parent, "fpn", None)
+        if body is None or not hasattr(body, "stages") or not hasattr(body, "return_features"):
+            continue
+        stages = [list(getattr(body, s)) for s in body.stages]
+        returned = [bool(body.return_features[s]) for s in body.stages]
+        fpn_fused = fpn is not None and getattr(fpn, "_mrb_fused", False) and hasattr(fpn, "_mrb_premask_inputs") and \
+            sum(returned) == len(fpn.inner_blocks)
+        all_fused = all(getattr(b, "_mrb_fused", False) for st in stages for b in st)
+        if fpn_fused:
+            # every FPN input is the ReLU output of a fused bottleneck: masking grad by [x > 0] is exact
+            fpn._mrb_premask_inputs = all_fused
+        for si, st in enumerate(stages):
+            for bi, blk in enumerate(st):
+                if not getattr(blk, "_mrb_fused", False):
+                    continue
+                if bi + 1 < len(st):
+                    ok = getattr(st[bi + 1], "_mrb_premasks_input", False)
+                else:
+                    ok = True
+                    if si + 1 < len(stages):
+                        ok = ok and getattr(stages[si + 1][0], "_mrb_premasks_input", False)
+                    if returned[si]:
+                        ok = ok and fpn_fused and all_fused
+                    elif si + 1 == len(stages):
+                        ok = False             # last stage output leaves the backbone to an unknown consumer
+                blk._g_premasked = bool(ok)
+
+
+# ---------------------------------------------------------------------------------- RPN head
+def _fuse_rpn_head(mod, be):
+    c, cl, bp = getattr(mod, "conv", None), getattr(mod, "cls_logits", None), getattr(mod, "bbox_pred", None)
+    if not (_conv_ok(c, 3, 1, 1, True) and _conv_ok(cl, 1, 1, 0, True) and _conv_ok(bp, 1, 1, 0, True)):
+        return False
+    if bp.out_channels != 4 * cl.out_channels or len(list(mod.children())) != 3:
+        return False
+
+    def forward(self, x):
+        a = self.cls_logits.out_channels
+        w = torch.cat([self.cls_logits.weight, self.bbox_pred.weight], 0)
+        b = torch.cat([self.cls_logits.bias, self.bbox_pred.bias], 0)
+        logits, bbox_reg = [], []
+        for f in x:
+            t = be.conv(_act(be, f), self.conv.weight, bias=self.conv.bias, pad=1, relu=True, gy_premasked=True)
+            o = be.conv(t, w, bias=b, out_fp32=True, premask_x=True).float()
+            # plain NCHW-contiguous fp32 for the reference's permute_and_flatten / .view chains (rpn/utils.py:11-15)
+            logits.append(o[:, :a].contiguous())
+            bbox_reg.append(o[:, a:].contiguous())
+        return logits, bbox_reg
+    _bind(mod, forward)
+    return True
+
+
+# ---------------------------------------------------------------------------------- ROI heads
+def _pooler_ok(p):
+    if type(p).__name__ != "Pooler" or not hasattr(p, "poolers") or not hasattr(p, "map_levels"):
+        return False
+    ml = p.map_levels
+    scales = [float(r.spatial_scale) for r in p.poolers]
+    if len(scales) != 4 or scales != [0.25, 0.125, 0.0625, 0.03125]:
+        return False
+    if (float(ml.k_min), float(ml.k_max), float(ml.s0), float(ml.lvl0), float(ml.eps)) != (2.0, 5.0, 224.0, 4.0, 1e-6):
+        return False
+    sr = {int(r.sampling_ratio) for r in p.poolers}
+    osz = {tuple(r.output_size) for r in p.poolers}
+    return len(sr) == 1 and len(osz) == 1 and len({o for s in osz for o in s}) == 1
+
+
+def _rois_of(boxes):
+    """convert_to_roi_format (poolers.py:72-89)"""
+    bb = torch.cat([b.bbox for b in boxes], 0).float()
+    ids = torch.cat([torch.full((len(b), 1), float(i), dtype=bb.dtype, device=bb.device) for i, b in enumerate(boxes)], 0)
+    return torch.cat([ids, bb], 1)
+
+
+def _pool(be, pooler, x, boxes, nhwc):
+    n = len(pooler.poolers)
+    feats = [_act(be, f) for f in list(x)[:n]]
+    r0 = pooler.poolers[0]
+    return be.roi_align_fpn(feats, _rois_of(boxes), [float(r.spatial_scale) for r in pooler.poolers],
+                            int(r0.output_size[0]), int(r0.sampling_ratio), nhwc)
+
+
+def _fuse_pooler(mod, be):
+    def forward(self, x, boxes):
+        dt = x[0].dtype
+        return _pool(be, self, x, boxes, False).to(dt)
+    _bind(mod, forward)
+
+
+def _fuse_box_head(fe, pr, be):
+    if not (hasattr(fe, "pooler") and _pooler_ok(fe.pooler) and isinstance(getattr(fe, "fc6", None), nn.Linear)
+            and isinstance(getattr(fe, "fc7", None), nn.Linear) and fe.fc6.bias is not None and fe.fc7.bias is not None):
+        return False
+    if not (isinstance(getattr(pr, "cls_score", None), nn.Linear) and isinstance(getattr(pr, "bbox_pred", None), nn.Linear)
+            and not hasattr(pr, "avgpool") and pr.cls_score.bias is not None and pr.bbox_pred.bias is not None):
+        return False
+    if fe.fc6.in_features % 8 or fe.fc6.out_features % 8 or fe.fc7.out_features % 8:
+        return False
+
+    def fe_forward(self, x, proposals):
+        x = _pool(be, self.pooler, x, proposals, False)
+        x = x.flatten(1)
+        x = be.linear(x, self.fc6.weight, self.fc6.bias, relu=True, gy_premasked=True)
+        return be.linear(x, self.fc7.weight, self.fc7.bias, relu=True, premask_x=True, gy_premasked=True)
+
+    def pr_forward(self, x):
+        if x.dim() == 4:
+            x = x.flatten(1)
+        nc = self.cls_score.out_features
+        w = torch.cat([self.cls_score.weight, self.bbox_pred.weight], 0)
+        b = torch.cat([self.cls_score.bias, self.bbox_pred.bias], 0)
+        o = be.linear(_act(be, x), w, b, relu=False, out_fp32=True, premask_x=True).float()
+        return o[:, :nc], o[:, nc:]
+    _bind(fe, fe_forward)
+    _bind(pr, pr_forward)
+    return True
+
+
+def _fuse_mask_head(fe, pr, be):
+    if not (hasattr(fe, "pooler") and _pooler_ok(fe.pooler) and isinstance(getattr(fe, "blocks", None), list) and fe.blocks):
+        return False
+    if not all(_conv_ok(getattr(fe, n, None), 3, 1, 1, True) for n in fe.blocks):
+        return False
+    dc, lg = getattr(pr, "conv5_mask", None), getattr(pr, "mask_fcn_logits", None)
+    if not (isinstance(dc, nn.ConvTranspose2d) and tuple(dc.kernel_size) == (2, 2) and tuple(dc.stride) == (2, 2)
+            and tuple(dc.padding) == (0, 0) and dc.bias is not None and dc.in_channels % 8 == 0 and dc.out_channels % 8 == 0
+            and _conv_ok(lg, 1, 1, 0, True)):
+        return False
+
+    def fe_forward(self, x, proposals):
+        x = _pool(be, self.pooler, x, proposals, True)
+        for i, name in enumerate(self.blocks):
+            c = getattr(self, name)
+            x = be.conv(x, c.weight, bias=c.bias, pad=1, relu=True, premask_x=i > 0, gy_premasked=True)
+        return x
+
+    def pr_forward(self, x):
+        x = be.deconv2x2(_act(be, x), self.conv5_mask.weight, self.conv5_mask.bias, relu=True, premask_x=True, gy_premasked=True)
+        lgc = self.mask_fcn_logits
+        return be.conv(x, lgc.weight, bias=lgc.bias, out_fp32=True, premask_x=True).float()
+    _bind(fe, fe_forward)
+    _bind(pr, pr_forward)
+    return True
+
+
+# ---------------------------------------------------------------------------------- the pass
+def fuse_model(model, backend=None, channels_last_weights=True):
+    """Rebind the forwards listed in the module docstring, in place.  Returns a report
+    {"fused": {kind: count}, "skipped": [reasons]}.  Idempotent."""
+    if backend is None:
+        from mrb_b200 import engine
+        backend = engine.default_backend()
+    be = backend
+    rep = {"fused": {}, "skipped": []}
+
+    def bump(k):
+        rep["fused"][k] = rep["fused"].get(k, 0) + 1
+
+    if channels_last_weights and getattr(be, "channels_last", False):
+        # conv weights in KRSC memory (torch.channels_last): same logical tensors / state_dict; the tcgen05 weight
+        # gradient, the bf16 operand copies and the optimizer state then share one layout
+        for p in model.parameters():
+            if p.dim() == 4 and not p.is_contiguous(memory_format=torch.channels_last):
+                p.data = p.data.contiguous(memory_format=torch.channels_last)
+    for name, mod in list(model.named_modules()):
+        if getattr(mod, "_mrb_fused", False):
+            continue
+        cls = type(mod).__name__
+        if "Stem" in cls and hasattr(mod, "conv1") and hasattr(mod, "bn1"):
+            if _fuse_stem(mod, be, rep):
+                bump("stem")
+            continue
+        kind = _bottleneck_kind(mod, be)
+        if kind is not None:
+            _fuse_bottleneck(mod, be, kind)
+            bump("bottleneck[%s]" % kind)
+            continue
+        if hasattr(mod, "conv1") and hasattr(mod, "bn3") and hasattr(mod, "downsample"):
+            rep["skipped"].append("%s: bottleneck variant not fused (%s)" % (name, type(mod.conv2).__name__))
+            continue
+        if cls == "FPN":
+            if _fuse_fpn(mod, be, rep):
+                bump("fpn")
+            else:
+                rep["skipped"].append("%s: FPN variant not fused" % name)
+            continue
+        if hasattr(mod, "cls_logits") and hasattr(mod, "bbox_pred") and hasattr(mod, "conv"):
+            if _fuse_rpn_head(mod, be):
+                bump("rpn_head")
+            continue
+        fe, pr = getattr(mod, "feature_extractor", None), getattr(mod, "predictor", None)
+        if fe is not None and pr is not None:
+            if hasattr(pr, "cls_score") and _fuse_box_head(fe, pr, be):
+                bump("box_head")
+            elif hasattr(pr, "mask_fcn_logits") and _fuse_mask_head(fe, pr, be):
+                bump("mask_head")
+            else:
+                rep["skipped"].append("%s: ROI head variant not fused (%s / %s)" % (name, type(fe).__name__, type(pr).__name__))
+            continue
+    for name, mod in model.named_modules():
+        if not getattr(mod, "_mrb_fused", False) and _pooler_ok(mod):
+            _fuse_pooler(mod, be)
+            bump("pooler")
+    _wire_resnet(model, be)
+    model._mrb_backend = be
+    return rep

@@ -56,7 +56,7 @@ class Bottleneck(nn.Module):
     def run(self, be, x):
         if hasattr(be, "bottleneck") and self.strides[1] == 1:
             # every consumer of a bottleneck output (next block, FPN lateral) pre-masks the gradient it returns
-            return be.bottleneck(self, x, g_premasked=True)
+            return be.bottleneck(self, x, g_premasked=getattr(self, "_g_premasked", True))
         s1, s3, sd = self.strides
         (a1, b1), (a2, b2), (a3, b3) = (a.get() for a in self._aff)
         y = be.conv(x, self.conv1.weight, a1, b1, stride=s1, relu=True)

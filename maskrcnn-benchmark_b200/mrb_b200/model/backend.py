@@ -14,10 +14,11 @@ class Backend:
     act_dtype = torch.float32
     channels_last = False
 
-    def lateral_topdown(self, feat, weight, bias, top):
-        """FPN inner block (fpn.py:51-64): conv1x1(feat) + nearest_upsample_2x(top) (top may be None)."""
+    def lateral_topdown(self, feat, weight, bias, top, premask_x=True):
+        """FPN inner block (fpn.py:51-64): conv1x1(feat) + nearest_upsample_2x(top) (top may be None).
+        premask_x: `feat` is a ReLU output whose producer expects its gradient already masked by [feat > 0]."""
         top_down = self.upsample2x(top) if top is not None else None
-        return self.conv(feat, weight, bias=bias, residual=top_down, premask_x=True)
+        return self.conv(feat, weight, bias=bias, residual=top_down, premask_x=premask_x)
 
     def prepare_input(self, images):
         raise NotImplementedError
@@ -270,6 +271,7 @@ class B200Backend(Backend):
     name = "b200"
     act_dtype = torch.bfloat16
     channels_last = True
+    stride2_3x3 = False       # 3x3 stride-2 convs (STRIDE_IN_1X1: False) on the engine
 
     def __init__(self, wgrad="tc"):
         self._w16 = {}
@@ -405,7 +407,8 @@ class B200Backend(Backend):
         if x.numel() == 0:
             n, _, h, w = x.shape
             kh, kw = weight.shape[2:]
-            return x.new_zeros((n, weight.shape[0], (h + 2 * pad - kh) // stride + 1, (w + 2 * pad - kw) // stride + 1),
+            ph, pw = (pad, pad) if isinstance(pad, int) else pad
+            return x.new_zeros((n, weight.shape[0], (h + 2 * ph - kh) // stride + 1, (w + 2 * pw - kw) // stride + 1),
                                dtype=torch.float32 if out_fp32 else torch.bfloat16)
         co = weight.shape[0]
         if co % 8:
@@ -441,7 +444,7 @@ class B200Backend(Backend):
         wd = blk.downsample[0].weight if blk.downsample is not None else None
         return _BottleneckFn.apply(x, blk.conv1.weight, blk.conv2.weight, blk.conv3.weight, wd, self, blk, g_premasked)
 
-    def stem(self, images, weight, scale, shift):
+    def stem(self, images, weight, scale, shift, relu=True, bias=None, out_fp32=False):
         """7x7/2 conv on 3 channels == 4x4/1 conv on the 2x2 space-to-depth image (12 -> 16 channels):
         out(o) = sum_t w[t] in(2o-3+t); with a leading zero tap t' = t+1 the taps pair up as
         in(2(o-2+a)+i), a = 0..3, i = 0..1 -> s2d block o-2+a, phase i: a 4-tap conv with 2 blocks of
@@ -470,7 +473,9 @@ class B200Backend(Backend):
             self._w16[key] = (weight, weight._version, w4)
         else:
             w4 = ent[2]
-        return ops.conv2d_fwd(xv, w4, scale, shift, None, 1, (2, 0), True, out_hw=(hs, ws))
+        add = shift if shift is not None else (bias.detach().float() if bias is not None else None)
+        return ops.conv2d_fwd(xv, w4, scale, add, None, 1, (2, 0), relu, torch.float32 if out_fp32 else torch.bfloat16,
+                              out_hw=(hs, ws))
 
     def max_pool(self, x, k, s, p):
         if x.requires_grad and torch.is_grad_enabled():
@@ -481,9 +486,9 @@ class B200Backend(Backend):
     def upsample2x(self, x):
         return F.interpolate(x, scale_factor=2, mode="nearest")
 
-    def lateral_topdown(self, feat, weight, bias, top):
+    def lateral_topdown(self, feat, weight, bias, top, premask_x=True):
         # the 2x nearest upsample is folded into the epilogue's residual read: no upsampled map in HBM
-        return self.conv(feat, weight, bias=bias, residual=top, premask_x=True, residual_up2=top is not None)
+        return self.conv(feat, weight, bias=bias, residual=top, premask_x=premask_x, residual_up2=top is not None)
 
     def dgrad_weights(self, wparam, w16, scale):
         """Flipped/transposed/BN-scaled bf16 weights for the data gradient of a parameter-backed conv, cached per

@@ -101,7 +101,10 @@ def _pick_random_idx(mask, key, cap, limit):
     Every element carries an iid uniform key; the answer is the `limit` smallest keys among the masked ones.
     Sync-free and sort-free on the long vector: for large inputs (268k RPN anchors) the candidates are first thinned
     by a key threshold that keeps ~4*cap of them in expectation (all of them if there are fewer), compacted with
-    nonzero_static into a fixed 16*cap buffer, and only that short buffer goes through top-k."""
+    nonzero_static into a fixed 16*cap buffer, and only that short buffer goes through top-k.
+    Approximation of randperm[:limit], documented: the thinned set is Binomial(cnt, 4*cap/cnt) ~ Poisson(4*cap); it
+    overflows the 16*cap buffer (tail dropped in index order) or falls short of `limit` <= cap with probability
+    < exp(-cap) (Chernoff; cap >= 128 here => < 1e-55) -- never observed, not detected at run time."""
     n = mask.numel()
     dev = mask.device
     if n <= 16384:
@@ -147,7 +150,10 @@ def sample_pos_neg(labels, batch_size, positive_fraction, generator=None):
         cap = min(int(batch_size * positive_fraction), n)
         key = torch.rand(n, device=labels.device, generator=generator)
         pos, neg = labels >= 1, labels == 0
-        lt = key[None, :] < key[:, None]                       # lt[i, j]: element j precedes element i
+        # lt[i, j]: element j precedes element i.  Ties (float32 rand has 2^24 values: ~10% of 2000-element calls
+        # contain one) are broken by index, so the counts are exact as with the reference's randperm[:num]
+        ar = torch.arange(n, device=labels.device)
+        lt = (key[None, :] < key[:, None]) | ((key[None, :] == key[:, None]) & (ar[None, :] < ar[:, None]))
         pos_sel = pos & ((lt & pos[None, :]).sum(1) < cap)
         neg_sel = neg & ((lt & neg[None, :]).sum(1) < (batch_size - pos_sel.sum()))
         return pos_sel, neg_sel

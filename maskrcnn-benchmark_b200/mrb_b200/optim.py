@@ -73,7 +73,7 @@ class ParamArena:
     ALIGN = 64      # elements: every parameter starts 256 B (fp32) / 128 B (bf16) aligned -> TMA / vector friendly
 
     def __init__(self, named_params, backend, lr=0.02, momentum=0.9, weight_decay=1e-4, bias_lr_factor=2.0,
-                 weight_decay_bias=0.0, world_size=1, group=None, late_prefix="backbone."):
+                 weight_decay_bias=0.0, world_size=1, group=None, late_prefix="backbone.", early_reduce=None):
         named = [(n, p) for n, p in named_params if p.requires_grad]
         for n, p in named:
             if not (p.is_contiguous() or p.is_contiguous(memory_format=torch.channels_last)):
@@ -99,15 +99,23 @@ class ParamArena:
         # backbone: names starting with `late_prefix`), [split, n_w) = everything downstream of it (RPN + ROI heads),
         # whose all-reduce can start as soon as the heads' backward has been issued (early_reduce), [n_w, total) = biases
         self.split = 0
+        seen_other = False
         for n, p in w:
             if not n.startswith(late_prefix):
-                break
+                seen_other = True
+                continue
+            if seen_other:
+                # the early bucket [split, n_w) must hold only parameters downstream of the backbone
+                raise ValueError("ParamArena: backbone weight %s is registered after a non-backbone weight; "
+                                 "the early all-reduce bucket would include it before its gradient is complete" % n)
             self.split += up(p.numel())
         self.n_w = n_w
         self._early = None
         self._comm = None
         import os
-        self.early = os.environ.get("MRB_EARLY_REDUCE", "1") != "0"     # A/B switch
+        # A/B switch.  Must be identical on every rank (collective order): pass `early_reduce` explicitly from rank-0
+        # config in multi-rank programs; the environment variable is only the single-launcher default.
+        self.early = (os.environ.get("MRB_EARLY_REDUCE", "1") != "0") if early_reduce is None else bool(early_reduce)
         self.sinks, self.views16 = {}, {}
         off = 0
         with torch.no_grad():

@@ -1,0 +1,34 @@
+"""mrb_b200.fuse.fuse_model over the UNMODIFIED reference GeneralizedRCNN (its modeling/, structures/, losses,
+samplers; this repository's layers), CPU checker backend: the fused graph reproduces the reference's own train-mode
+forward -- all five losses -- and every parameter gradient of e2e_mask_rcnn_R_50_FPN_1x (width-reduced), with the
+same sampled proposals.  This is the train-step pin of the fusion pass against the reference.  Needs a reference
+checkout (baseline/_ref mirror or /root/reference): skipped elsewhere."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _have_ref():
+    sys.path.insert(0, os.path.join(ROOT, "maskrcnn-benchmark_b200"))
+    from mrb_b200 import refenv
+    return refenv.find_reference_root() is not None
+
+
+@pytest.mark.parametrize("cfgname", ["e2e_mask_rcnn_R_50_FPN_1x.yaml"])
+def test_fused_reference_graph_equals_reference_train_step(built_lib, oracle_mod, cfgname):
+    if not _have_ref():
+        pytest.skip("reference checkout absent")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "refgraph", "run_cpu.py"), cfgname],
+                       capture_output=True, text=True, timeout=900, cwd=os.path.join(ROOT, "tests", "refgraph"))
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    out = json.loads(r.stdout.strip().splitlines()[-1])
+    f = out["report"]["fused"]
+    assert f.get("stem") == 1 and f.get("fpn") == 1 and f.get("rpn_head") == 1 and f.get("box_head") == 1 and f.get("mask_head") == 1
+    assert sum(v for k, v in f.items() if k.startswith("bottleneck")) == 16
+    assert not out["report"]["skipped"]
+    assert out["n_grads"] > 60 and out["worst_rel_grad"] < 1e-3

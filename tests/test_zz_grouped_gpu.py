@@ -1,11 +1,10 @@
 """Grouped 3x3 conv composed from per-super-group calls of the dense engine (mrb_b200/grouped.py).
-Written after round 1's GPU budget was spent: it has not run on a GPU yet, hence xfail(strict=False) -- an XPASS at
-the next round's first run promotes it to a normal parity test."""
+Passed on the driver's B200 at the end of round 1 (XPASS): a normal parity test since round 2."""
 import pytest
 import torch
 import torch.nn.functional as F
 
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(120), pytest.mark.xfail(strict=False, reason="unvalidated: composed after the round's GPU budget was spent")]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(120)]
 DEV = "cuda:0"
 
 
