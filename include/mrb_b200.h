@@ -187,6 +187,14 @@ int mrb_deform_psroi_bwd(const float* out_grad, const float* data, const float* 
  * TMA feeds shared memory directly from the NHWC tensor (im2col is folded into the TMA
  * box coordinates; no column matrix exists anywhere). */
 #define MRB_CONV_PAD_W 1              /* mrb_conv_params.flags: `pad_w` holds the width padding (else pad_w == pad) */
+/* mrb_conv_params.flags: grouped convolution with cin == cout, (cin / groups) dividing 64 (ResNeXt 32x4d/32x8d, reference
+ * modeling/backbone/resnet.py:302-311 `groups=num_groups`), expressed as block-diagonal 64-channel super-groups: output
+ * channels [64b, 64b+64) read input channels [64b, 64b+64) only.  The weight operand is the EXPANDED filter
+ * [Cout][kh][kw][64] (zero outside each group's own channels; mrb_b200/ops.py expand_grouped_weight); dgrad takes the
+ * prepared (flipped, transposed within the block) [Cin][kh][kw][64] through mrb_conv2d_dgrad_prepared; wgrad returns
+ * [Cout][kh][kw][128] -- for every output channel the gradient against the 128 input channels of its Cout tile -- from
+ * which the caller keeps the group's own columns.  Stride 1 only. */
+#define MRB_CONV_GROUPED64 2
 typedef struct mrb_conv_params {
   int batch, height, width, cin;   /* input  NHWC */
   int cout, kh, kw;                /* filter KRSC (rectangular kernels allowed) */

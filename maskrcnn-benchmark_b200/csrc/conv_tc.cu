@@ -32,6 +32,7 @@
 #include <mutex>
 
 #include "common.cuh"
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -143,7 +144,8 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 // ------------------------------------------------------------------------------- kernel
 constexpr int kEpiWarps = 8;                  // epilogue warps: 2 per TMEM lane quadrant (latency hiding: each SMSP
                                               // gets 2 epilogue warps; a lone warp per scheduler stalls on every LDTM/LDS/SHFL)
-constexpr int kConvThreads = 64 + 32 * kEpiWarps;
+constexpr int kCtrlWarps = 3;                 // warp 0: TMA producer, warp 1: MMA issuer, warp 2: epilogue DMA (tile-buffer loads/stores)
+constexpr int kConvThreads = 32 * kCtrlWarps + 32 * kEpiWarps;
 constexpr int kWgradThreads = 192;
 constexpr int kTileM = 128;
 constexpr int kBlockK = 64;                 // channels per k-block (128 B of bf16)
@@ -164,7 +166,9 @@ struct ConvArgs {
   void* out;
   int tma_epi;                     // epilogue through TMA tile buffers (see conv_tc_kernel); else per-thread global access
   int tile_bufs;                   // 1, or 2 when both a residual and a mask tile are staged
-  int tile_dbl;                    // 2: the tile buffers are double-buffered across tiles (store / prefetch overlap)
+  int tile_sets;                   // 2 or 3 buffer sets in a ring across tiles (store drain / input prefetch overlap)
+  int tile_rows;                   // th * tw <= 128 rows of the M = 128 tile carry pixels (the rest is never stored)
+  int grouped;                     // block-diagonal 64-channel super-groups: A channel offset = n_tile * 64, BN = 64
 };
 
 __device__ __forceinline__ void tile_coords(const ConvArgs& a, int tile, int& n_tile, int& img, int& h0, int& w0) {
@@ -258,14 +262,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   // [ring: stages x (A 16 KB + B)] [tile buffers: tile_bufs x ceil(BN/64) x 16 KB (TMA epilogue only)] [barriers] ...
   const uint32_t tile_base = smem_base + (uint32_t)a.stages * stage_bytes;
   const uint32_t tile_buf_bytes = (uint32_t)((a.bn + 63) >> 6) * kABytes;
-  const uint32_t bar_base = tile_base + (a.tma_epi ? (uint32_t)(a.tile_bufs * a.tile_dbl) * tile_buf_bytes : 0u);
-  // barriers: full[stages], empty[stages], tmem_full[2], tmem_empty[2], tile[2]; then the TMEM base slot
+  const uint32_t bar_base = tile_base + (a.tma_epi ? (uint32_t)(a.tile_bufs * a.tile_sets) * tile_buf_bytes : 0u);
+  // barriers: full[stages], empty[stages], tmem_full[2], tmem_empty[2], tile[3] (inputs of a set landed),
+  // done[3] (all epilogue threads finished a set); then the TMEM base slot
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (a.stages + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * a.stages + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * a.stages + 2 + s); };
   auto tile_bar = [&](int b) { return bar_base + 8u * (2 * a.stages + 4 + b); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * a.stages + 6);   // keeps what follows 16-byte aligned
+  auto done_bar = [&](int b) { return bar_base + 8u * (2 * a.stages + 7 + b); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * a.stages + 10);   // keeps what follows 16-byte aligned
+  const uint32_t a_tx = (uint32_t)a.tile_rows * 128u;               // bytes one A / tile-buffer box really transfers
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int k_blocks = a.kh * a.kw * a.cin_blocks;
   uint32_t tmem_cols = 32;
@@ -274,8 +281,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (threadIdx.x == 0) {
     for (int s = 0; s < a.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 32 * kEpiWarps); }
-    mbar_init(tile_bar(0), 1);
-    mbar_init(tile_bar(1), 1);
+    for (int b = 0; b < 3; ++b) { mbar_init(tile_bar(b), 1); mbar_init(done_bar(b), 32 * kEpiWarps); }
     fence_barrier_init();
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
@@ -309,9 +315,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           const int tap = kb / a.cin_blocks, cb = kb - tap * a.cin_blocks;
           const int r = tap / a.kw, q = tap - r * a.kw;
           mbar_wait(empty_bar(s), phase ^ 1u);
-          mbar_expect_tx(full_bar(s), stage_bytes);
+          mbar_expect_tx(full_bar(s), a_tx + (uint32_t)a.bn * 128u);
           const uint32_t sa = smem_base + (uint32_t)s * stage_bytes;
-          tma_load_4d(sa, &map_a, full_bar(s), cb * kBlockK, w0 + q - a.pad_w, h0 + r - a.pad_h, img);
+          tma_load_4d(sa, &map_a, full_bar(s), (a.grouped ? n_tile * 64 : 0) + cb * kBlockK, w0 + q - a.pad_w, h0 + r - a.pad_h, img);
           tma_load_3d(sa + kABytes, &map_b, full_bar(s), cb * kBlockK, tap, n_tile * a.bn);
           if (++s == a.stages) { s = 0; phase ^= 1u; }
         }
@@ -344,41 +350,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
     }
-  } else {
-    // ================================ epilogue ================================
-    // Everything below indexes registers with compile-time constants only: the 32-column chunk must never
-    // spill to local memory (with ~200 KB of shared memory carved out, L1 is tiny and local traffic runs at
-    // L2 latency).  Per-channel scale/bias of the tile are staged in shared memory once per tile.
-    const int quad = warp & 3;                 // TMEM lane quadrant this warp may read (hardware: warp id % 4)
-    const int grp = (warp - 2) >> 2;           // which of the kEpiWarps/4 warps of this quadrant: takes every
-    constexpr int kGroups = kEpiWarps / 4;     // kGroups-th 32-column chunk
-    const int row = quad * 32 + lane;          // accumulator row == pixel within the tile
-    const int et = threadIdx.x - 64;           // 0..32*kEpiWarps-1 among the epilogue threads
-    const int hh = row / a.tw, ww = row - hh * a.tw;
-    float* s_aff = reinterpret_cast<float*>(smem_raw + (tmem_slot - smem_u32(smem_raw)) + 16);  // [2 acc][2][256]
-    uint4* stg4 = reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(s_aff) + 4096 + (warp - 2) * 2048);  // [32 rows][4 x 16 B]
-    const bool has_scale = a.scale != nullptr, has_bias = a.bias != nullptr;
-    const bool cout8 = (a.cout & 7) == 0;
-    int acc = 0; uint32_t acc_phase = 0;
-    if (a.tma_epi) {
-      // ---- TMA epilogue.  The output tile lives in a swizzled shared-memory tile buffer T ([BN/64 boxes][128 rows]
-      // [128 B], the layout TMA produces/consumes with SWIZZLE_128B): the residual (or, without one, the ReLU-backward
-      // mask) of the tile is TMA-loaded INTO it ahead of time, every thread updates its own row in place, and one
-      // thread TMA-stores the finished tile.  All global traffic of the epilogue is bulk and asynchronous -- with
-      // per-thread loads a 1x1 layer with a residual ran at ~1.4 TB/s (too few bytes in flight per SM).
+  } else if (warp == 2) {
+    // ================================ epilogue DMA ================================
+    // One thread owns all bulk traffic of the TMA epilogue: it stages the residual / ReLU-mask tile of upcoming tiles
+    // into the buffer-set ring (or just releases a set), and stores finished tiles.  The epilogue warps never wait for
+    // a store to drain and never meet at a CTA-wide barrier: they hand a finished set over through done_bar.
+    if (lane == 0 && a.tma_epi) {
       const bool has_res = a.residual != nullptr, has_mask = a.relu_mask != nullptr;
       const uint32_t set_bytes = (uint32_t)a.tile_bufs * tile_buf_bytes;          // one buffer set (T [+ M])
       const uint32_t m_off = (has_res && has_mask) ? tile_buf_bytes : 0u;         // the mask shares T when it is alone
-      // With two buffer sets (tile_dbl == 2) the store of tile i and the input prefetch of tile i+1 overlap the
-      // epilogue arithmetic of the neighbouring tiles; with one set they serialise (the wait for the store to drain
-      // was 28% of all warp stalls on an epilogue-bound 1x1 layer).
-      auto arm = [&](int tile, int b) {  // one thread: stage the inputs of `tile` into set b (or just release it)
+      auto arm = [&](int tile, int b) {  // stage the inputs of `tile` into set b (or just release it)
         int n_tile, img, h0, w0;
         tile_coords(a, tile, n_tile, img, h0, w0);
         const int cols = min(a.bn, a.cout - n_tile * a.bn), nb = (cols + 63) >> 6;
         const uint32_t bt = tile_base + (uint32_t)b * set_bytes;
         if (has_res || has_mask) {
-          mbar_expect_tx(tile_bar(b), (uint32_t)nb * kABytes * (uint32_t)((has_res ? 1 : 0) + (has_mask ? 1 : 0)));
+          mbar_expect_tx(tile_bar(b), (uint32_t)nb * a_tx * (uint32_t)((has_res ? 1 : 0) + (has_mask ? 1 : 0)));
           for (int x = 0; x < nb; ++x) {
             if (has_res) tma_load_4d(bt + (uint32_t)x * kABytes, &map_res, tile_bar(b), n_tile * a.bn + x * 64, w0, h0, img);
             if (has_mask) tma_load_4d(bt + m_off + (uint32_t)x * kABytes, &map_mask, tile_bar(b), n_tile * a.bn + x * 64, w0, h0, img);
@@ -387,35 +374,69 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           mbar_arrive(tile_bar(b));
         }
       };
-      if (et == 0 && (int)blockIdx.x < a.tiles_total) arm(blockIdx.x, 0);
-      const uint32_t row_off = (uint32_t)row * 128u, row_sw = (uint32_t)(row & 7);
-      int it = 0;
-      for (int tile = blockIdx.x; tile < a.tiles_total; tile += gridDim.x, ++it) {
+      const int sets = a.tile_sets;
+      {
+        int t = blockIdx.x;
+        for (int j = 0; j < sets && t < a.tiles_total; ++j, t += gridDim.x) arm(t, j);
+      }
+      int sidx = 0; uint32_t dphase = 0;
+      for (int tile = blockIdx.x; tile < a.tiles_total; tile += gridDim.x) {
         int n_tile, img, h0, w0;
         tile_coords(a, tile, n_tile, img, h0, w0);
-        const int b = (a.tile_dbl == 2) ? (it & 1) : 0;
-        const uint32_t tile_phase = (a.tile_dbl == 2) ? (uint32_t)((it >> 1) & 1) : (uint32_t)(it & 1);
-        const uint32_t buf_t = tile_base + (uint32_t)b * set_bytes, buf_m = buf_t + m_off;
-        if (a.tile_dbl == 2 && et == 0) {
-          bulk_wait_read0();               // the previous tile's store has left the other set: refill it now
-          if (tile + (int)gridDim.x < a.tiles_total) arm(tile + gridDim.x, b ^ 1);
+        mbar_wait(done_bar(sidx), dphase);           // every epilogue thread wrote (and proxy-fenced) its row of set sidx
+        const uint32_t buf_t = tile_base + (uint32_t)sidx * set_bytes;
+        const int cols = min(a.bn, a.cout - n_tile * a.bn), nb = (cols + 63) >> 6;
+        for (int x = 0; x < nb; ++x) tma_store_4d(&map_out, buf_t + (uint32_t)x * kABytes, n_tile * a.bn + x * 64, w0, h0, img);
+        bulk_commit();
+        const long long nxt = (long long)tile + (long long)sets * gridDim.x;
+        if (nxt < a.tiles_total) {
+          bulk_wait_read0();                         // the set has been read out: refill / release it
+          arm((int)nxt, sidx);
         }
-        float* sc = s_aff + acc * 512;
-        float* bi = sc + 256;
-        if (has_scale || has_bias) {
-          for (int c = et; c < a.bn; c += 32 * kEpiWarps) {
-            const int cg = n_tile * a.bn + c;
-            sc[c] = (has_scale && cg < a.cout) ? __ldg(a.scale + cg) : 1.f;
-            bi[c] = (has_bias && cg < a.cout) ? __ldg(a.bias + cg) : 0.f;
-          }
-          asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
-        }
-        mbar_wait(tile_bar(b), tile_phase);
+        if (++sidx == sets) { sidx = 0; dphase ^= 1u; }
+      }
+      bulk_wait_read0();                             // shared memory must outlive the last store's read
+    }
+  } else {
+    // ================================ epilogue ================================
+    // Everything below indexes registers with compile-time constants only: the 32-column chunk must never
+    // spill to local memory (with ~200 KB of shared memory carved out, L1 is tiny and local traffic runs at
+    // L2 latency).
+    const int quad = warp & 3;                 // TMEM lane quadrant this warp may read (hardware: warp id % 4)
+    const int grp = (warp - kCtrlWarps) >> 2;  // which of the kEpiWarps/4 warps of this quadrant: takes every
+    constexpr int kGroups = kEpiWarps / 4;     // kGroups-th 32-column chunk
+    const int row = quad * 32 + lane;          // accumulator row == pixel within the tile
+    const int et = threadIdx.x - 32 * kCtrlWarps;   // 0..32*kEpiWarps-1 among the epilogue threads
+    const int hh = row / a.tw, ww = row - hh * a.tw;
+    float* s_aff = reinterpret_cast<float*>(smem_raw + (tmem_slot - smem_u32(smem_raw)) + 16);  // [2 acc][2][256]
+    uint4* stg4 = reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(s_aff) + 4096 + (warp - kCtrlWarps) * 2048);  // [32 rows][4 x 16 B]
+    const bool has_scale = a.scale != nullptr, has_bias = a.bias != nullptr;
+    const bool cout8 = (a.cout & 7) == 0;
+    int acc = 0; uint32_t acc_phase = 0;
+    if (a.tma_epi) {
+      // ---- TMA epilogue.  The output tile lives in a swizzled shared-memory tile buffer T ([BN/64 boxes][128 rows]
+      // [128 B], the layout TMA produces/consumes with SWIZZLE_128B): the residual (or, without one, the ReLU-backward
+      // mask) of the tile is TMA-loaded INTO it ahead of time by the DMA warp, every thread updates its own row in
+      // place and hands the set back (done_bar); the DMA warp TMA-stores it.  All global traffic of the epilogue is bulk
+      // and asynchronous -- with per-thread loads a 1x1 layer with a residual ran at ~1.4 TB/s (too few bytes in flight
+      // per SM) -- and the warps run tile after tile without a CTA-wide barrier (round 1 met at two named barriers per
+      // tile and lane 0 waited for every store to drain: 2.4 us per 128x128 tile on the 1x1 layers).
+      const bool has_res = a.residual != nullptr, has_mask = a.relu_mask != nullptr;
+      const uint32_t set_bytes = (uint32_t)a.tile_bufs * tile_buf_bytes;
+      const uint32_t m_off = (has_res && has_mask) ? tile_buf_bytes : 0u;
+      const uint32_t row_off = (uint32_t)row * 128u, row_sw = (uint32_t)(row & 7);
+      const int sets = a.tile_sets;
+      int sidx = 0; uint32_t sphase = 0;
+      for (int tile = blockIdx.x; tile < a.tiles_total; tile += gridDim.x) {
+        const int n_tile = tile % a.tiles_n;
+        const uint32_t buf_t = tile_base + (uint32_t)sidx * set_bytes, buf_m = buf_t + m_off;
+        mbar_wait(tile_bar(sidx), sphase);
         mbar_wait(tfull_bar(acc), acc_phase);
         tc_fence_after();
         const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * a.bn);
         for (int col = grp * 32; col < a.bn; col += 32 * kGroups) {
-          if (n_tile * a.bn + col >= a.cout) break;  // warp-uniform
+          const int cg0 = n_tile * a.bn + col;
+          if (cg0 >= a.cout) break;  // warp-uniform
           uint32_t v[32];
           tmem_ld32(t_row + (uint32_t)col, v);
           tmem_ld_wait();
@@ -426,11 +447,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             float f[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[q * 8 + j]);
-            if (has_scale || has_bias) {
-              const float* scq = sc + col + q * 8;
-              const float* biq = bi + col + q * 8;
-#pragma unroll
-              for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], scq[j], biq[j]);
+            const int cg = cg0 + q * 8;                      // Cout % 8 == 0: an 8-group is entirely in or out
+            if ((has_scale || has_bias) && cg < a.cout) {
+              // per-channel affine straight from global memory (uniform address: one L1-resident line per warp)
+              float4 s0 = make_float4(1.f, 1.f, 1.f, 1.f), s1 = s0, b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+              if (has_scale) { s0 = __ldg(reinterpret_cast<const float4*>(a.scale + cg)); s1 = __ldg(reinterpret_cast<const float4*>(a.scale + cg + 4)); }
+              if (has_bias) { b0 = __ldg(reinterpret_cast<const float4*>(a.bias + cg)); b1 = __ldg(reinterpret_cast<const float4*>(a.bias + cg + 4)); }
+              f[0] = fmaf(f[0], s0.x, b0.x); f[1] = fmaf(f[1], s0.y, b0.y); f[2] = fmaf(f[2], s0.z, b0.z); f[3] = fmaf(f[3], s0.w, b0.w);
+              f[4] = fmaf(f[4], s1.x, b1.x); f[5] = fmaf(f[5], s1.y, b1.y); f[6] = fmaf(f[6], s1.z, b1.z); f[7] = fmaf(f[7], s1.w, b1.w);
             }
             const uint32_t slot = box + (((u0 + (uint32_t)q) ^ row_sw) << 4);     // this thread's 16 B of its row
             if (has_res) {
@@ -467,24 +491,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         mbar_arrive(tempty_bar(acc));
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         fence_proxy_async_smem();            // this thread's tile-buffer writes -> visible to the TMA (async proxy)
-        asm volatile("bar.sync 2, %0;" ::"n"(32 * kEpiWarps) : "memory");
-        if (et == 0) {
-          const int cols = min(a.bn, a.cout - n_tile * a.bn), nb = (cols + 63) >> 6;
-          for (int x = 0; x < nb; ++x) tma_store_4d(&map_out, buf_t + (uint32_t)x * kABytes, n_tile * a.bn + x * 64, w0, h0, img);
-          bulk_commit();
-          if (a.tile_dbl != 2) {
-            bulk_wait_read0();               // T has been read out: it may be refilled
-            if (tile + (int)gridDim.x < a.tiles_total) arm(tile + gridDim.x, 0);
-          }
-        }
+        mbar_arrive(done_bar(sidx));
+        if (++sidx == sets) { sidx = 0; sphase ^= 1u; }
       }
-      if (et == 0) bulk_wait_read0();        // shared memory must outlive the last store's read
     }
     for (int tile = blockIdx.x; tile < a.tiles_total && !a.tma_epi; tile += gridDim.x) {
       int n_tile, img, h0, w0;
       tile_coords(a, tile, n_tile, img, h0, w0);
       const int h = h0 + hh, w = w0 + ww;
-      const bool valid = (h < a.Ho) && (w < a.Wo);
+      const bool valid = (row < a.tile_rows) && (h < a.Ho) && (w < a.Wo);
       const long long pix = (long long)img * a.out_n + (long long)h * a.out_h + (long long)w * a.out_w;
       const long long rpix = a.res_up2 ? (long long)img * a.res_n + (long long)(h >> 1) * a.res_h + (long long)(w >> 1) * a.res_w : pix;
       float* sc = s_aff + acc * 512;
@@ -624,6 +639,8 @@ struct WgradArgs {
   int th, tw, tiles_w, tiles_h, batch;   // pixel tiling of the OUTPUT (G) plane
   int kblocks_total, kblocks_per_split;
   int cin, cout, bn, stages;
+  int grouped;         // block-diagonal super-groups: the Cin tile of a work item is the Cout tile's own 128 channels,
+                       // dW is [cout][taps][128] (the caller extracts the diagonal blocks)
   float* dw;
   const float* scale;  // optional per-Cout factor (frozen-BN scale of the forward epilogue)
 };
@@ -697,7 +714,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_con
           tma_load_4d(sa, &map_g, full_bar(s), co_t * 128, w0, h0, img);
           tma_load_4d(sa + kWgGroupBytes, &map_g, full_bar(s), co_t * 128 + 64, w0, h0, img);
           for (int gi = 0; gi < b_groups; ++gi)
-            tma_load_4d(sa + a_bytes + (uint32_t)gi * kWgGroupBytes, &map_x, full_bar(s), ci_t * a.bn + gi * 64,
+            tma_load_4d(sa + a_bytes + (uint32_t)gi * kWgGroupBytes, &map_x, full_bar(s), (a.grouped ? co_t * 128 : ci_t * a.bn) + gi * 64,
                         w0 + q - a.pad_w, h0 + r - a.pad_h, img);
           if (++s == a.stages) { s = 0; phase ^= 1u; }
         }
@@ -746,18 +763,19 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_con
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * a.bn);
-      float* __restrict__ dst = a.dw + ((size_t)co * a.taps + tap) * a.cin;
+      const int row_len = a.grouped ? 128 : a.cin;        // elements per (co, tap) row of dW
+      float* __restrict__ dst = a.dw + ((size_t)co * a.taps + tap) * row_len;
       for (int col = 0; col < a.bn; col += 32) {
         const int c0 = ci_t * a.bn + col;
-        if (c0 >= a.cin) break;
+        if (c0 >= row_len) break;
         uint32_t v[32];
         __syncwarp();
         tmem_ld32(t_row + (uint32_t)col, v);
         tmem_ld_wait();
         if (co >= a.cout) continue;
-        const int nvalid = min(32, a.cin - c0);
+        const int nvalid = min(32, row_len - c0);
         const float sco = a.scale ? __ldg(a.scale + co) : 1.f;
-        if (nvalid == 32 && (a.cin & 3) == 0) {
+        if (nvalid == 32 && (row_len & 3) == 0) {
 #pragma unroll
           for (int j = 0; j < 8; ++j)
             atomicAdd(reinterpret_cast<float4*>(dst + c0 + 4 * j),
@@ -939,58 +957,84 @@ struct ConvPlan {
 // given element strides; `w` is [cout][taps][cin].
 static int conv_launch(const ConvPlan& pl, const void* x, const void* w, int cin, int cout, int kh, int kw, int pad_h, int pad_w,
                        const float* scale, const float* bias, const void* residual, const void* relu_mask, void* out,
-                       int relu, int out_f32, cudaStream_t stream, int res_up2 = 0, int res_hh = 0, int res_ww = 0) {
+                       int relu, int out_f32, cudaStream_t stream, int res_up2 = 0, int res_hh = 0, int res_ww = 0, bool grouped = false) {
+  // grouped: block-diagonal 64-channel super-groups (cin == cout, % 64 == 0); `w` is [cout][taps][64]
+  if (grouped && (cin != cout || (cin % 64) != 0)) return MRB_ERR_UNSUPPORTED;
   if (cin % 8 || ((uintptr_t)x & 15) || ((uintptr_t)w & 15) || ((uintptr_t)out & 15)) return MRB_ERR_UNSUPPORTED;
   if ((pl.in_w * 2) % 16 || (pl.in_h * 2) % 16 || (pl.in_n * 2) % 16) return MRB_ERR_UNSUPPORTED;
   if (residual && ((uintptr_t)residual & 15)) return MRB_ERR_UNSUPPORTED;
   if (relu_mask && ((uintptr_t)relu_mask & 15)) return MRB_ERR_UNSUPPORTED;
-  // tile shape: th * tw == 128, minimise padded work
-  int best_th = 1, best_tw = 128;
-  long long best = -1;
-  const int th_order[8] = {8, 4, 16, 2, 32, 1, 64, 128};  // squarer tiles first: better halo reuse in L2
-  for (int i = 0; i < 8; ++i) {
-    const int th = th_order[i], tw = 128 / th;
-    const long long cost = (long long)ceil_div(pl.Ho, th) * th * ceil_div(pl.Wo, tw) * tw;
-    if (best < 0 || cost < best) { best = cost; best_th = th; best_tw = tw; }
-  }
-  const int th = best_th, tw = best_tw;
-  // N tile: 256 columns amortise the A tile best, but a small image plane gives few M tiles -- then narrower N
-  // tiles are what fills the 148 SMs (e.g. res4 3x3 at 50x84: 66 M tiles; res5 at 25x42: 17).  Cost model: waves of
-  // the persistent grid x relative tile time, with a mild penalty per halving for the lost A reuse.
-  int bn = (cout + 15) / 16 * 16;
-  if (bn > 256) bn = 256;
-  if (bn == 256 || bn == 128) {
-    const long long m_tiles = (long long)pl.batch * ceil_div(pl.Ho, th) * ceil_div(pl.Wo, tw);
-    double best_cost = 0;
-    int best_bn = bn;
-    for (int cand = bn, halvings = 0; cand >= 64; cand >>= 1, ++halvings) {
-      const long long t = m_tiles * ceil_div(cout, cand);
-      const double waves = (double)ceil_div(t, kNumSMs);
-      const double cost = waves * ((cand < 96 ? 96 : cand) / 256.0) * (1.0 + 0.15 * halvings);
-      if (halvings == 0 || cost < best_cost * 0.98) { best_cost = cost; best_bn = cand; }
+  // ---- plan: tile rectangle (th x tw <= 128 pixels of one image = the rows of the M = 128 tile that carry data),
+  // N tile, epilogue mode.  The persistent grid runs ceil(tiles / 148) waves, so the plan that wins is usually the
+  // one whose tile count lands just under a multiple of 148 -- a 10 x 12 tile (120 of 128 rows used) gives res4's
+  // 50 x 84 planes 140 tiles = one wave where 4 x 32 gave 156 = two.  Cost = waves x per-tile time, per-tile time =
+  // max(main loop, epilogue) with the main loop bound by the MMA issue rate or by the L2->smem operand stream.
+  const int k_blocks_tile = kh * kw * (grouped ? 1 : ceil_div(cin, kBlockK));
+  const bool tma_ok = !out_f32 && (cout % 8) == 0 && !res_up2 && ((pl.out_w | pl.out_h | pl.out_n) % 8) == 0;
+  int th = 1, tw = 128, bn = 0;
+  bool tma_epi = false;
+  {
+    int bn_max = (cout + 15) / 16 * 16;
+    if (bn_max > 256) bn_max = 256;
+    int cands[3] = {bn_max, 0, 0}, ncand = 1;
+    if (bn_max == 256) { cands[1] = 128; cands[2] = 64; ncand = 3; }
+    else if (bn_max == 128) { cands[1] = 64; ncand = 2; }
+    if (grouped) { cands[0] = 64; ncand = 1; }
+    double best_cost = -1;
+    for (int t_h = 1; t_h <= 128; ++t_h) {
+      if (pl.Ho == 1 && t_h > 1) break;
+      int t_w = 128 / t_h;
+      if (t_w > pl.Wo) t_w = pl.Wo > 0 ? pl.Wo : 1;
+      if (t_h > pl.Ho) break;
+      if (t_w > 256) t_w = 256;
+      const int rows = t_h * t_w;
+      const long long m_tiles = (long long)pl.batch * ceil_div(pl.Ho, t_h) * ceil_div(pl.Wo, t_w);
+      // halo overhead of the A stream (re-fetched rows/columns of neighbouring tiles come from L2)
+      const double halo = (double)(t_h + kh - 1) * (t_w + kw - 1) / (double)rows;
+      for (int ci = 0; ci < ncand; ++ci) {
+        const int cand = cands[ci];
+        for (int mode = 0; mode < 2; ++mode) {        // 0: per-thread epilogue, 1: TMA tile-buffer epilogue
+          if (mode == 1 && (!tma_ok || cand > 128)) continue;
+          if (mode == 0 && tma_ok && cand <= 128 && !grouped) continue;      // narrow tiles: the TMA epilogue always wins
+          const long long tiles = m_tiles * ceil_div(cout, cand);
+          const double waves = (double)ceil_div(tiles, kNumSMs);
+          const double mma = k_blocks_tile * (cand >= 256 ? 520.0 : cand >= 128 ? 270.0 : cand >= 64 ? 200.0 : 160.0);
+          const double load = k_blocks_tile * (rows * 128.0 * (0.5 + 0.5 * halo) + cand * 128.0) / 96.0;
+          const double epi = mode == 1 ? 500.0 + 4.0 * cand + (residual || relu_mask ? 300.0 : 0.0) : 600.0 + 9.0 * cand;
+          double t_tile = mma > load ? mma : load;
+          if (epi > t_tile) t_tile = epi;
+          const double cost = waves * (t_tile + 150.0) * (1.0 + 0.02 * (halo - 1.0));
+          if (best_cost < 0 || cost < best_cost * 0.995) { best_cost = cost; th = t_h; tw = t_w; bn = cand; tma_epi = mode == 1; }
+        }
+      }
     }
-    bn = best_bn;
   }
-  // Epilogue through TMA tile buffers (bf16 result, Cout % 8 == 0, same-resolution residual): the tile's residual /
-  // ReLU-backward mask is TMA-loaded into shared memory, updated in place and TMA-stored.  A residual AND a mask need
-  // two buffers, which only fit next to the operand ring with N tiles of <= 128 columns.
-  // Used where the epilogue is what bounds the layer: few k-blocks per tile (1x1 layers: a 128 x 256 tile moves
-  // 64-192 KB through the epilogue per 16-48 KB k-block) or narrow N tiles.  Long-K 256-wide tiles keep the per-thread
-  // epilogue: it hides behind the next tile's main loop, and the 64 KB tile buffer would cost a ring stage (measured
-  // -15% on the 3x3 256->256 layers with 3 instead of 4 stages).
-  const int k_blocks_tile = kh * kw * ceil_div(cin, kBlockK);
-  bool tma_epi = !out_f32 && (cout % 8) == 0 && !res_up2 && ((pl.out_w | pl.out_h | pl.out_n) % 8) == 0;
-  int tile_bufs = (residual && relu_mask) ? 2 : 1;
-  int tile_dbl = 1;
-  if (tma_epi && bn > 128) {
-    if (k_blocks_tile > 8) tma_epi = false;
-    else bn = 128;      // short K: epilogue bound -> 128-wide tiles leave room for two buffer sets
+  int sets_req = 0;
+  if (const char* e = getenv("MRB_CONV_TILE")) {     // "th,tw,bn,epi[,sets]": measurement override (tools/bench_conv.py sweeps)
+    int v[5] = {0, 0, 0, -1, 0};
+    if (sscanf(e, "%d,%d,%d,%d,%d", &v[0], &v[1], &v[2], &v[3], &v[4]) >= 3 && v[0] > 0 && v[1] > 0 && v[0] * v[1] <= 128 &&
+        v[2] >= 16 && v[2] <= 256 && v[2] % 16 == 0 && !(pl.Ho == 1 && v[0] > 1) && !grouped) {
+      th = v[0]; tw = v[1]; bn = v[2];
+      if (v[3] >= 0) tma_epi = v[3] && tma_ok && bn <= 128;
+      else tma_epi = tma_ok && bn <= 128;
+      sets_req = v[4];
+    }
   }
-  if (!tma_epi) tile_bufs = 1;
+  const int tile_rows = th * tw;
+  int tile_bufs = (tma_epi && residual && relu_mask) ? 2 : 1;
+  // buffer-set ring of the TMA epilogue: 3 sets when the tiles have inputs to prefetch (residual / mask) and the operand
+  // ring keeps >= 3 stages, else 2
+  int tile_sets = 2;
+  const size_t fixed0 = 8 * (2 * 8 + 10) + 16 + 4096 + 1024;
   if (tma_epi) {
-    const size_t need2 = (size_t)2 * tile_bufs * ceil_div(bn, 64) * kABytes;
-    const size_t left = 227 * 1024 - (8 * (2 * 8 + 6) + 16 + 4096 + 1024) - need2;
-    if (need2 < 200 * 1024 && (int)(left / (kABytes + bn * 128)) >= 2) tile_dbl = 2;
+    const size_t set_b = (size_t)tile_bufs * ceil_div(bn, 64) * kABytes;
+    auto stages_with = [&](int sets) { return (int)(((long long)227 * 1024 - (long long)fixed0 - (long long)(sets * set_b)) / (kABytes + bn * 128)); };
+    if ((residual || relu_mask) && stages_with(3) >= 3) tile_sets = 3;
+    if (sets_req == 2 || sets_req == 3) tile_sets = sets_req;
+    if (stages_with(tile_sets) < 2) {
+      if (tile_sets == 3 && stages_with(2) >= 2) tile_sets = 2;
+      else { tma_epi = false; tile_bufs = 1; }
+    }
   }
   ConvArgs a;
   a.th = th; a.tw = tw; a.Ho = pl.Ho; a.Wo = pl.Wo;
@@ -998,7 +1042,7 @@ static int conv_launch(const ConvPlan& pl, const void* x, const void* w, int cin
   const long long tiles = (long long)pl.batch * a.tiles_h * a.tiles_w * a.tiles_n;
   if (tiles <= 0 || tiles >= (1ll << 31)) return tiles == 0 ? MRB_OK : MRB_ERR_UNSUPPORTED;
   a.tiles_total = (int)tiles;
-  a.cin_blocks = ceil_div(cin, kBlockK); a.kh = kh; a.kw = kw; a.pad_h = pad_h; a.pad_w = pad_w;
+  a.cin_blocks = grouped ? 1 : ceil_div(cin, kBlockK); a.kh = kh; a.kw = kw; a.pad_h = pad_h; a.pad_w = pad_w;
   a.cout = cout; a.bn = bn; a.relu = relu; a.out_f32 = out_f32;
   a.out_n = pl.out_n; a.out_h = pl.out_h; a.out_w = pl.out_w;
   a.scale = scale; a.bias = bias; a.residual = (const __nv_bfloat16*)residual; a.relu_mask = (const __nv_bfloat16*)relu_mask;
@@ -1007,12 +1051,14 @@ static int conv_launch(const ConvPlan& pl, const void* x, const void* w, int cin
   a.res_w = cout; a.res_h = (long long)res_ww * cout; a.res_n = (long long)res_hh * res_ww * cout;
   a.tma_epi = tma_epi ? 1 : 0;
   a.tile_bufs = tile_bufs;
-  a.tile_dbl = tile_dbl;
+  a.tile_sets = tile_sets;
+  a.tile_rows = tile_rows;
+  a.grouped = grouped ? 1 : 0;
   const uint32_t stage_bytes = kABytes + bn * 128;
   // fixed part: barriers + TMEM slot + scale/bias (4 KB) + alignment slack, plus either the tile buffers or the
   // per-warp staging blocks of the per-thread epilogue
-  const size_t epi_bytes = tma_epi ? (size_t)tile_dbl * tile_bufs * ceil_div(bn, 64) * kABytes : (size_t)2048 * kEpiWarps;
-  const size_t fixed = 8 * (2 * 8 + 6) + 16 + 4096 + 1024 + epi_bytes;
+  const size_t epi_bytes = tma_epi ? (size_t)tile_sets * tile_bufs * ceil_div(bn, 64) * kABytes : (size_t)2048 * kEpiWarps;
+  const size_t fixed = fixed0 + epi_bytes;
   int stages = (int)((227 * 1024 - fixed) / stage_bytes);
   if (stages > 8) stages = 8;
   if (stages < 2) return MRB_ERR_UNSUPPORTED;
@@ -1042,8 +1088,9 @@ static int conv_launch(const ConvPlan& pl, const void* x, const void* w, int cin
   }
   {
     const int taps = kh * kw;
-    cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)taps, (cuuint64_t)cout};
-    cuuint64_t strides[2] = {(cuuint64_t)cin * 2, (cuuint64_t)taps * cin * 2};
+    const int wk = grouped ? 64 : cin;          // K extent of one weight row
+    cuuint64_t dims[3] = {(cuuint64_t)wk, (cuuint64_t)taps, (cuuint64_t)cout};
+    cuuint64_t strides[2] = {(cuuint64_t)wk * 2, (cuuint64_t)taps * wk * 2};
     cuuint32_t box[3] = {(cuuint32_t)kBlockK, 1, (cuuint32_t)bn};
     int rc = encode_bf16(&map_b, w, 3, dims, strides, box);
     if (rc) return rc;
@@ -1119,8 +1166,10 @@ static int conv2d_fwd_impl(const mrb_conv_params* p, const void* input, const vo
     if (has_pitch(p->x_pitch)) { pl.in_n = p->x_pitch[0]; pl.in_h = p->x_pitch[1]; pl.in_w = p->x_pitch[2]; }
     if (has_pitch(p->y_pitch)) { pl.out_n = p->y_pitch[0]; pl.out_h = p->y_pitch[1]; pl.out_w = p->y_pitch[2]; }
   }
+  const bool grouped = (p->flags & MRB_CONV_GROUPED64) != 0;
+  if (grouped && (p->stride != 1 || residual_up2)) return MRB_ERR_UNSUPPORTED;
   return conv_launch(pl, input, weight, p->cin, p->cout, p->kh, p->kw, p->pad, pad_w, scale, bias, residual, nullptr, output,
-                     p->relu, p->out_dtype == MRB_F32, (cudaStream_t)stream, residual_up2, (Ho + 1) / 2, (Wo + 1) / 2);
+                     p->relu, p->out_dtype == MRB_F32, (cudaStream_t)stream, residual_up2, (Ho + 1) / 2, (Wo + 1) / 2, grouped);
 }
 
 MRB_API size_t mrb_conv2d_dgrad_workspace_bytes(const mrb_conv_params* p) {
@@ -1189,6 +1238,7 @@ MRB_API int mrb_conv2d_dgrad(const mrb_conv_params* p, const void* grad_output, 
   if (p->batch == 0) return MRB_OK;
   if (!grad_output || !weight || !grad_input || !workspace) return MRB_ERR_BAD_ARG;
   if (p->out_h || p->out_w) return MRB_ERR_UNSUPPORTED;
+  if (p->flags & MRB_CONV_GROUPED64) return MRB_ERR_UNSUPPORTED;   // grouped: use mrb_conv2d_dgrad_prepared
   if (workspace_bytes < mrb_conv2d_dgrad_workspace_bytes(p)) return MRB_ERR_WORKSPACE;
   cudaStream_t stream = (cudaStream_t)stream_;
   const int taps = p->kh * p->kw;
@@ -1210,6 +1260,7 @@ static int conv2d_dgrad_impl(const mrb_conv_params* p, const void* grad_output, 
   // dgrad == forward conv of grad_output [N,Ho,Wo,Cout] with Wd [Cin][taps][Cout], pad' = k - 1 - pad
   ConvPlan pl;
   const long long Ci = p->cin, Co = p->cout;
+  if ((p->flags & MRB_CONV_GROUPED64) && p->stride != 1) return MRB_ERR_UNSUPPORTED;
   if (p->stride == 2) {
     // 1x1 stride 2: grad_input[2h, 2w] = Wd . grad_output[h, w]; every other position is zero
     // `add` must be grad_input itself (accumulate a second stride-2 branch in place, e.g. conv1 + downsample of a
@@ -1241,7 +1292,7 @@ static int conv2d_dgrad_impl(const mrb_conv_params* p, const void* grad_output, 
     if (has_pitch(p->x_pitch)) { pl.out_n = p->x_pitch[0]; pl.out_h = p->x_pitch[1]; pl.out_w = p->x_pitch[2]; }
   }
   return conv_launch(pl, grad_output, wd, p->cout, p->cin, p->kh, p->kw, p->kh - 1 - p->pad, p->kw - 1 - pad_w, nullptr, nullptr, add, relu_mask,
-                     grad_input, 0, p->out_dtype == MRB_F32, stream);
+                     grad_input, 0, p->out_dtype == MRB_F32, stream, 0, 0, 0, (p->flags & MRB_CONV_GROUPED64) != 0);
 }
 
 static int conv_wgrad_impl(const mrb_conv_params* p, const void* input, const void* grad_output, const float* scale,
@@ -1252,7 +1303,9 @@ static int conv_wgrad_impl(const mrb_conv_params* p, const void* input, const vo
   if (!grad_weight) return MRB_ERR_BAD_ARG;
   cudaStream_t stream = (cudaStream_t)stream_;
   const int taps = p->kh * p->kw;
-  if (!accumulate) MRB_CUDA_TRY(cudaMemsetAsync(grad_weight, 0, (size_t)p->cout * taps * p->cin * sizeof(float), stream));
+  const bool grouped = (p->flags & MRB_CONV_GROUPED64) != 0;
+  if (grouped && (p->cin != p->cout || p->cout % 128 || p->stride != 1)) return MRB_ERR_UNSUPPORTED;
+  if (!accumulate) MRB_CUDA_TRY(cudaMemsetAsync(grad_weight, 0, (size_t)p->cout * taps * (grouped ? 128 : p->cin) * sizeof(float), stream));
   if (p->batch == 0) return MRB_OK;
   if (!input || !grad_output) return MRB_ERR_BAD_ARG;
   if (p->cin % 8 || p->cout % 8 || ((uintptr_t)input & 15) || ((uintptr_t)grad_output & 15) || ((uintptr_t)grad_weight & 15))
@@ -1290,7 +1343,9 @@ static int conv_wgrad_impl(const mrb_conv_params* p, const void* input, const vo
   a.cin = p->cin; a.cout = p->cout;
   a.bn = ceil_div(p->cin, 64) * 64;
   if (a.bn > 256) a.bn = 256;
+  a.grouped = grouped ? 1 : 0;
   a.co_tiles = ceil_div(p->cout, 128); a.ci_tiles = ceil_div(p->cin, a.bn);
+  if (grouped) { a.bn = 128; a.ci_tiles = 1; }
   const int out_tiles = a.co_tiles * a.ci_tiles * taps;
   // one wave of equally sized work items (items <= #SMs): every extra split costs a 128 x BN fp32 red.add flush
   int splits = kNumSMs / out_tiles;

@@ -1,13 +1,14 @@
 """Grouped 3x3 convolution (ResNeXt / X-101-32x8d, reference modeling/backbone/resnet.py:283-296 `groups=num_groups`)
-on the dense tcgen05 engine, first (functional, not yet fast) form.
+on the dense tcgen05 engine.
 
 A group of Cg = C / groups <= 64 channels is a diagonal block of a 64 -> 64 "super-group": the layer is C / 64
 independent dense 64 -> 64 convolutions whose weights are block-diagonal (MMA work x 64/Cg, no extra memory traffic:
-the tensor core is not what bounds these layers).  Each super-group is ONE call of the existing kernels on strided
-channel windows of the NHWC tensors (mrb_conv_params.x_pitch / y_pitch), so forward, data gradient and weight
-gradient reuse the validated code paths unchanged.  Status: composed after this round's GPU budget was spent -- the
-weight expansion is pinned on CPU (tests/test_grouped_cpu.py); the GPU test is marked xfail(strict=False) until it
-has run once.  The single-launch form (n_tile doubling as the A-operand channel offset) is DESIGN.md 4b item 4."""
+the tensor core is not what bounds these layers).  Round 1 composed the layer from one call per super-group on strided
+channel windows (kept as MRB_GROUPED=composed); the native form is one launch per direction (include/mrb_b200.h
+MRB_CONV_GROUPED64).  The weight expansion is pinned on CPU (tests/test_grouped_cpu.py), the kernels against fp32
+F.conv2d(groups=...) on the B200 (tests/test_zz_grouped_gpu.py)."""
+import os
+
 import torch
 
 SG = 64      # channels of a super-group = one k-block of the engine
@@ -51,21 +52,35 @@ def _window(t, sg):
 
 
 class GroupedConvFn(torch.autograd.Function):
-    """y = act(grouped_conv(x, w) * scale + shift), stride 1, on the conv engine (bf16 NHWC)."""
+    """y = act(grouped_conv(x, w) * scale + shift) on the conv engine (bf16 NHWC), ONE launch per direction:
+    MRB_CONV_GROUPED64 -- the N tile index doubles as the 64-channel offset of the A operand, the weight operand is the
+    block-diagonal expansion [C, 64, kh, kw].  Stride 2 (`STRIDE_IN_1X1: False`, the first block of res3..res5 only) is
+    computed at stride 1 and subsampled: 3 of ~100 layers pay 4x on a layer class that is not tensor-bound.
+    MRB_GROUPED=composed selects round 1's per-super-group composition (one launch per 64 channels) for A/B runs."""
 
     @staticmethod
-    def forward(ctx, x, weight, scale, shift, groups, pad, relu):
+    def forward(ctx, x, weight, scale, shift, groups, pad, relu, stride=1):
         from mrb_b200 import ops
         c = x.shape[1]
         _, sgs = check_geometry(c, weight.shape[0], groups)
+        if x.dtype != torch.bfloat16:
+            raise RuntimeError("grouped conv: bf16 NHWC input required (cast at the call site)")
         x = x.contiguous(memory_format=torch.channels_last)
         w_exp = expand_group_weights(weight.detach(), groups).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
-        out = torch.empty_like(x)
-        for sg in range(sgs):
-            sl = slice(sg * SG, (sg + 1) * SG)
-            ops.conv2d_fwd(_window(x, sg), w_exp[sl], None if scale is None else scale[sl].contiguous(),
-                           None if shift is None else shift[sl].contiguous(), None, 1, pad, relu, out=_window(out, sg))
-        ctx.cfg = (groups, pad, relu, sgs)
+        composed = os.environ.get("MRB_GROUPED", "native") == "composed"
+        if composed:
+            out = torch.empty_like(x)
+            for sg in range(sgs):
+                sl = slice(sg * SG, (sg + 1) * SG)
+                ops.conv2d_fwd(_window(x, sg), w_exp[sl], None if scale is None else scale[sl].contiguous(),
+                               None if shift is None else shift[sl].contiguous(), None, 1, pad, relu, out=_window(out, sg))
+        else:
+            out = ops.conv2d_fwd(x, w_exp, scale, shift, None, 1, pad, relu, grouped=True)
+        if stride == 2:
+            out = out[:, :, ::2, ::2].contiguous(memory_format=torch.channels_last)
+        elif stride != 1:
+            raise RuntimeError("grouped conv: stride 1 or 2")
+        ctx.cfg = (groups, pad, relu, sgs, stride, composed, tuple(x.shape))
         ctx.save_for_backward(x, w_exp, scale, out if relu else None)
         return out
 
@@ -73,25 +88,39 @@ class GroupedConvFn(torch.autograd.Function):
     def backward(ctx, g):
         from mrb_b200 import ops
         x, w_exp, scale, y = ctx.saved_tensors
-        groups, pad, relu, sgs = ctx.cfg
+        groups, pad, relu, sgs, stride, composed, x_shape = ctx.cfg
         if relu:
             g = torch.where(y > 0, g, torch.zeros((), dtype=g.dtype, device=g.device))
-        g = g.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
-        n, c, h, w = x.shape
-        gx = gw = None
-        if ctx.needs_input_grad[0]:
-            parts = [ops.conv2d_dgrad(_window(g, sg), w_exp[sg * SG:(sg + 1) * SG], (n, SG, h, w),
-                                      None if scale is None else scale[sg * SG:(sg + 1) * SG].contiguous(), None, None, 1, pad)
-                     for sg in range(sgs)]
-            gx = torch.cat(parts, 1).contiguous(memory_format=torch.channels_last)
-        if ctx.needs_input_grad[1]:
+        g = g.to(torch.bfloat16)
+        n, c, h, w = x_shape
+        if stride == 2:
             k = w_exp.shape[2]
-            parts = [ops.conv2d_wgrad(_window(x, sg), _window(g, sg), (SG, SG, k, k), 1, pad,
-                                      None if scale is None else scale[sg * SG:(sg + 1) * SG].contiguous())
-                     for sg in range(sgs)]
-            gw = collapse_group_grads(torch.cat(parts, 0), groups)
-        return gx, gw, None, None, None, None, None
+            hf, wf = h + 2 * pad - k + 1, w + 2 * pad - k + 1
+            gf = torch.zeros((n, c, hf, wf), dtype=torch.bfloat16, device=g.device).contiguous(memory_format=torch.channels_last)
+            gf[:, :, ::2, ::2] = g
+            g = gf
+        g = g.contiguous(memory_format=torch.channels_last)
+        gx = gw = None
+        k = w_exp.shape[2]
+        if ctx.needs_input_grad[0]:
+            if composed:
+                parts = [ops.conv2d_dgrad(_window(g, sg), w_exp[sg * SG:(sg + 1) * SG], (n, SG, h, w),
+                                          None if scale is None else scale[sg * SG:(sg + 1) * SG].contiguous(), None, None, 1, pad)
+                         for sg in range(sgs)]
+                gx = torch.cat(parts, 1).contiguous(memory_format=torch.channels_last)
+            else:
+                gx = ops.conv2d_dgrad_grouped(g, ops.grouped_dgrad_weights(w_exp, scale), x_shape, 1, pad)
+        if ctx.needs_input_grad[1]:
+            if composed or c % 128:
+                parts = [ops.conv2d_wgrad(_window(x, sg), _window(g, sg), (SG, SG, k, k), 1, pad,
+                                          None if scale is None else scale[sg * SG:(sg + 1) * SG].contiguous())
+                         for sg in range(sgs)]
+                gw_exp = torch.cat(parts, 0)
+            else:
+                gw_exp = ops.conv2d_wgrad_grouped(x, g, k, 1, pad, scale)
+            gw = collapse_group_grads(gw_exp, groups)
+        return gx, gw, None, None, None, None, None, None
 
 
-def conv2d_grouped(x, weight, groups, scale=None, shift=None, pad=1, relu=False):
-    return GroupedConvFn.apply(x, weight, scale, shift, groups, pad, relu)
+def conv2d_grouped(x, weight, groups, scale=None, shift=None, pad=1, relu=False, stride=1):
+    return GroupedConvFn.apply(x, weight, scale, shift, groups, pad, relu, stride)

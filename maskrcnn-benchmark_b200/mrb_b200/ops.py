@@ -62,10 +62,16 @@ def _view(t, name):
     return t.contiguous(memory_format=torch.channels_last), None
 
 
-def _params(x_shape, w_shape, stride, pad, relu, out_dtype, out_hw=None, x_pitch=None, y_pitch=None):
+FLAG_PAD_W, FLAG_GROUPED64 = 1, 2          # mrb_conv_params.flags (include/mrb_b200.h)
+
+
+def _params(x_shape, w_shape, stride, pad, relu, out_dtype, out_hw=None, x_pitch=None, y_pitch=None, grouped=False):
     n, c, h, w = x_shape
     co, ci, kh, kw = w_shape
-    if ci != c:
+    if grouped:
+        if ci != 64 or co != c or c % 64:
+            raise RuntimeError("grouped conv2d: expanded weight [C, 64, kh, kw] with C == Cin %% 64 == 0 expected")
+    elif ci != c:
         raise RuntimeError("conv2d: weight expects %d input channels, got %d" % (ci, c))
     ph, pw = (pad, pad) if isinstance(pad, int) else pad
     p = _c.ConvParams()
@@ -73,7 +79,9 @@ def _params(x_shape, w_shape, stride, pad, relu, out_dtype, out_hw=None, x_pitch
     p.cout, p.kh, p.kw = co, kh, kw
     p.stride, p.pad, p.relu, p.out_dtype = stride, ph, int(bool(relu)), _DT[out_dtype]
     if pw != ph:
-        p.pad_w, p.flags = pw, 1          # MRB_CONV_PAD_W
+        p.pad_w, p.flags = pw, FLAG_PAD_W
+    if grouped:
+        p.flags |= FLAG_GROUPED64
     ho = (h + 2 * ph - kh) // stride + 1
     wo = (w + 2 * pw - kw) // stride + 1
     if out_hw is not None:
@@ -86,7 +94,7 @@ def _params(x_shape, w_shape, stride, pad, relu, out_dtype, out_hw=None, x_pitch
 
 
 def conv2d_fwd(x, weight, scale=None, bias=None, residual=None, stride=1, pad=0, relu=False,
-               out_dtype=torch.bfloat16, out_hw=None, residual_up2=False, out=None):
+               out_dtype=torch.bfloat16, out_hw=None, residual_up2=False, out=None, grouped=False):
     """y = act(conv(x, weight) * scale[c] + bias[c] + residual).  x, weight bf16 channels_last.
     residual_up2: `residual` has half the output resolution and is read through a nearest 2x upsample.
     pad: int or (pad_h, pad_w).  x may be a strided NHWC window (see _view); `out` (optional) is a preallocated
@@ -103,7 +111,7 @@ def conv2d_fwd(x, weight, scale=None, bias=None, residual=None, stride=1, pad=0,
         out_dtype = out.dtype
         if residual is not None and y_pitch is not None:
             raise RuntimeError("conv2d_fwd: residual with a strided `out` is not supported")
-    p, ho, wo = _params(x.shape, weight.shape, stride, pad, relu, out_dtype, out_hw, x_pitch, y_pitch)
+    p, ho, wo = _params(x.shape, weight.shape, stride, pad, relu, out_dtype, out_hw, x_pitch, y_pitch, grouped)
     if out is None:
         out = torch.empty((p.batch, p.cout, ho, wo), dtype=out_dtype, device=x.device, memory_format=torch.channels_last)
     elif tuple(out.shape) != (p.batch, p.cout, ho, wo):
@@ -120,8 +128,67 @@ def conv2d_fwd(x, weight, scale=None, bias=None, residual=None, stride=1, pad=0,
         fn = lib.mrb_conv2d_fwd_up2 if residual_up2 else lib.mrb_conv2d_fwd
         _c.check(fn(ctypes.byref(p), _c._ptr(x), _c._ptr(weight), _c._ptr(scale), _c._ptr(bias),
                     _c._ptr(residual), _c._ptr(out), _c._stream()), "mrb_conv2d_fwd")
-    _count(1, ("fwd", p.batch, p.cin, p.height, p.width, p.cout, _kk(p), p.stride, _pp(p)))
+    _count(1, ("fwd", p.batch, p.cin, p.height, p.width, p.cout, _kk(p), p.stride, _pp(p)) + ((p.cin // 64,) if grouped else ()))
     return out
+
+
+# ------------------------------------------------------------------------- grouped conv (block-diagonal super-groups)
+def grouped_dgrad_weights(w_exp, scale=None):
+    """Expanded grouped filter [C, 64, kh, kw] (row co: its filter against the 64 input channels of co's super-group)
+    -> flat bf16 [Cin][kh][kw][64] for the data gradient: entry (ci, tap, k) = w_exp[64*(ci//64) + k, ci % 64, flipped tap]
+    (* scale[co], the frozen-BN scale of the forward epilogue)."""
+    c, sg, kh, kw = w_exp.shape
+    w = w_exp.float().view(c // 64, 64, sg, kh, kw)                   # [B, co_l, ci_l, kh, kw]
+    if scale is not None:
+        w = w * scale.float().view(c // 64, 64, 1, 1, 1)
+    w = w.flip(3, 4).permute(0, 2, 3, 4, 1)                           # [B, ci_l, kh', kw', co_l]
+    return w.reshape(-1).to(torch.bfloat16).contiguous()
+
+
+def conv2d_dgrad_grouped(grad_out, wd_flat, x_shape, stride=1, pad=1, add=None, relu_mask=None):
+    """Data gradient of a grouped (MRB_CONV_GROUPED64) convolution from the prepared weights of grouped_dgrad_weights."""
+    if stride != 1:
+        raise RuntimeError("conv2d_dgrad_grouped: stride 1 only")
+    grad_out = _nhwc(grad_out, "conv2d_dgrad_grouped(grad_out)")
+    n, c, h, w = x_shape
+    k2 = wd_flat.numel() // (c * 64)
+    k = int(round(k2 ** 0.5))
+    p, ho, wo = _params(tuple(x_shape), (c, 64, k, k), 1, pad, False, torch.bfloat16, None, None, None, True)
+    if tuple(grad_out.shape) != (n, c, ho, wo) or grad_out.dtype != torch.bfloat16 or wd_flat.dtype != torch.bfloat16:
+        raise RuntimeError("conv2d_dgrad_grouped: bad grad_out / weights")
+    gx = torch.empty(tuple(x_shape), dtype=torch.bfloat16, device=grad_out.device, memory_format=torch.channels_last)
+    for t in (add, relu_mask):
+        if t is not None and (t.dtype != torch.bfloat16 or tuple(t.shape) != tuple(x_shape)):
+            raise RuntimeError("conv2d_dgrad_grouped: add/relu_mask must be bf16 and shaped like x")
+    add = _nhwc(add, "add") if add is not None else None
+    relu_mask = _nhwc(relu_mask, "relu_mask") if relu_mask is not None else None
+    with torch.cuda.device(grad_out.device):
+        _c.check(lib.mrb_conv2d_dgrad_prepared(ctypes.byref(p), _c._ptr(grad_out), _c._ptr(wd_flat), _c._ptr(add),
+                                               _c._ptr(relu_mask), _c._ptr(gx), _c._stream()), "mrb_conv2d_dgrad_prepared(grouped)")
+    _count(1, ("dgrad", n, c, h, w, c, k, 1, pad, c // 64))
+    return gx
+
+
+def conv2d_wgrad_grouped(x, grad_out, k, stride=1, pad=1, scale=None):
+    """Weight gradient of a grouped convolution as the EXPANDED fp32 [C, 64, k, k] (row co against the 64 input channels
+    of its super-group): the kernel produces each 128-channel Cout tile against its own 128 input channels, the two
+    diagonal 64 x 64 blocks are kept."""
+    if stride != 1:
+        raise RuntimeError("conv2d_wgrad_grouped: stride 1 only")
+    x = _nhwc(x, "conv2d_wgrad_grouped(x)")
+    grad_out = _nhwc(grad_out, "conv2d_wgrad_grouped(grad_out)")
+    n, c, h, w = x.shape
+    p, ho, wo = _params(x.shape, (c, 64, k, k), 1, pad, False, torch.float32, None, None, None, True)
+    if tuple(grad_out.shape) != (n, c, ho, wo) or c % 128:
+        raise RuntimeError("conv2d_wgrad_grouped: grad_out shape mismatch or C %% 128 != 0")
+    gw = torch.empty((c, k * k, 128), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _c.check(lib.mrb_conv2d_wgrad(ctypes.byref(p), _c._ptr(x), _c._ptr(grad_out), _c._ptr(scale), _c._ptr(gw), _c._stream()),
+                 "mrb_conv2d_wgrad(grouped)")
+    _count(1, ("wgrad", n, c, h, w, c, k, 1, pad, c // 64))
+    gw = gw.view(c // 128, 2, 64, k * k, 2, 64)                       # [tile, half, co_l, tap, half', ci_l]
+    diag = torch.stack([gw[:, 0, :, :, 0], gw[:, 1, :, :, 1]], 1)     # [tile, half, co_l, tap, ci_l]
+    return diag.reshape(c, k, k, 64).permute(0, 3, 1, 2)              # logical [C, 64, k, k]
 
 
 def prepare_dgrad_weights(weights, scales, out=None):

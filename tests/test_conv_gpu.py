@@ -297,3 +297,62 @@ def test_conv_full_size_properties(ops):
             got_s = float(dw[:, :, r, q].double().sum())
             scale = float((gs.abs() * xs[:, r:r + h, q:q + w].abs()).sum())
             assert abs(got_s - want_s) <= 1e-5 * scale, (r, q, got_s, want_s)
+
+
+# ---------------------------------------------------------------- tile plans (MRB_CONV_TILE override: th,tw,bn,epi,sets)
+TILE_PLANS = ["10,12,128,1,2", "10,12,128,1,3", "7,18,64,1,2", "5,25,256,0", "3,42,128,1,3", "9,14,128,1,2", "1,128,128,1,3", "4,32,256,0"]
+
+
+@pytest.mark.parametrize("plan", TILE_PLANS)
+def test_conv_tile_plans_fwd_and_dgrad(ops, monkeypatch, plan):
+    """Every tile rectangle (th x tw <= 128 rows of the M = 128 tile), N tile, epilogue mode and buffer-ring depth the
+    planner may choose gives the same result: forward with BN + residual + ReLU, data gradient with add + ReLU mask."""
+    monkeypatch.setenv("MRB_CONV_TILE", plan)
+    n, c, h, w, co = 2, 128, 25, 42, 256
+    x, wt = _mk(n, c, h, w, co, 3, 11)
+    g = torch.Generator().manual_seed(12)
+    scale, bias = torch.rand(co, generator=g) + 0.5, torch.randn(co, generator=g)
+    conv = F.conv2d(x.float(), wt.float(), padding=1)
+    res = torch.randn(conv.shape, generator=g).to(torch.bfloat16)
+    want = torch.relu(conv * scale[None, :, None, None] + bias[None, :, None, None] + res.float())
+    got = ops.conv2d_fwd(x.to(DEV), wt.to(DEV), scale.to(DEV), bias.to(DEV), res.to(DEV), 1, 1, relu=True)
+    _assert_close(got, want, tol=1e-2)
+    go = torch.randn(n, co, h, w, generator=g).to(torch.bfloat16)
+    add = torch.randn(n, c, h, w, generator=g).to(torch.bfloat16)
+    mask = torch.randn(n, c, h, w, generator=g).to(torch.bfloat16)
+    xr = x.float().requires_grad_(True)
+    F.conv2d(xr, wt.float(), padding=1).backward(go.float())
+    want_gx = (xr.grad + add.float()) * (mask.float() > 0)
+    gx = ops.conv2d_dgrad(go.to(DEV), wt.to(DEV), (n, c, h, w), None, add.to(DEV), mask.to(DEV), 1, 1)
+    _assert_close(gx, want_gx, tol=1e-2)
+    if plan.startswith("1,128"):
+        # the flattened 1x1 path with the same plan
+        x1, w1 = _mk(n, c, h, w, co, 1, 13)
+        want1 = torch.relu(F.conv2d(x1.float(), w1.float()) * scale[None, :, None, None] + bias[None, :, None, None] + res.float())
+        got1 = ops.conv2d_fwd(x1.to(DEV), w1.to(DEV), scale.to(DEV), bias.to(DEV), res.to(DEV), 1, 0, relu=True)
+        _assert_close(got1, want1, tol=1e-2)
+
+
+def test_conv_random_weights_full_size_p2(ops):
+    """Random-weight BASELINE-size cases against fp32 F.conv2d computed on the host: 3x3 256->256 and 1x1 64->256 on the
+    2 x 200 x 336 P2 plane (fused BN + ReLU), sampled rows (the full fp32 reference of the 3x3 takes ~20 s of CPU)."""
+    g = torch.Generator().manual_seed(21)
+    for (c, co, k) in ((256, 256, 3), (64, 256, 1)):
+        x = torch.randn(2, c, 200, 336, generator=g).to(torch.bfloat16)
+        wt = (torch.randn(co, c, k, k, generator=g) / (c * k * k) ** 0.5).to(torch.bfloat16)
+        scale, bias = torch.rand(co, generator=g) + 0.5, torch.randn(co, generator=g)
+        got = ops.conv2d_fwd(x.to(DEV), wt.to(DEV), scale.to(DEV), bias.to(DEV), None, 1, k // 2, relu=True,
+                             out_dtype=torch.float32).cpu()
+        for (r0, r1) in ((0, 9), (95, 106), (191, 200)):          # top edge, interior, bottom edge (with halo)
+            lo, hi = max(r0 - k // 2, 0), min(r1 + k // 2, 200)
+            ref = F.conv2d(x[:, :, lo:hi].float(), wt.float(), padding=(0, k // 2))
+            if k == 3:
+                # rows of `ref` are valid convolution rows lo+1 .. hi-2; pad the image borders explicitly
+                xp = F.pad(x[:, :, lo:hi].float(), (0, 0, 1 if lo == 0 else 0, 1 if hi == 200 else 0))
+                ref = F.conv2d(xp, wt.float(), padding=(0, 1))
+                first = lo + 1 - (1 if lo == 0 else 0)
+            else:
+                first = lo
+            ref = torch.relu(ref * scale[None, :, None, None] + bias[None, :, None, None])
+            a, b = max(r0, first), min(r1, first + ref.shape[2])
+            _assert_close(got[:, :, a:b], ref[:, :, a - first:b - first])

@@ -8,20 +8,29 @@ pytestmark = [pytest.mark.gpu, pytest.mark.timeout(120)]
 DEV = "cuda:0"
 
 
-@pytest.mark.parametrize("c,groups,h,w", [(256, 32, 20, 28), (128, 4, 13, 21)])
-def test_grouped_conv_matches_torch(built_lib, c, groups, h, w):
+@pytest.mark.parametrize("mode", ["native", "composed"])
+@pytest.mark.parametrize("c,groups,h,w,stride", [(256, 32, 20, 28, 1), (128, 4, 13, 21, 1), (512, 32, 25, 42, 1), (256, 32, 20, 28, 2),
+                                                 (1024, 32, 13, 21, 1)])
+def test_grouped_conv_matches_torch(built_lib, monkeypatch, mode, c, groups, h, w, stride):
+    """X-101-32x8d layer geometries (reference resnet.py:302-311: groups=32, width 8 * 2^stage => 8/16/32/64 channels per
+    group; stride 2 in the 3x3 of a stage's first block): forward (+BN+ReLU), data and weight gradient vs fp32 F.conv2d."""
     from mrb_b200.grouped import conv2d_grouped
+    if mode == "composed" and (c > 256 or stride == 2):
+        pytest.skip("composed form: covered on the small cases")
+    monkeypatch.setenv("MRB_GROUPED", mode)
     g = torch.Generator().manual_seed(7)
     x = torch.randn(2, c, h, w, generator=g).to(torch.bfloat16)
     wt = (torch.randn(c, c // groups, 3, 3, generator=g) / (9 * c // groups) ** 0.5).to(torch.bfloat16).float()
     scale, shift = torch.rand(c, generator=g) + 0.5, torch.randn(c, generator=g) * 0.1
-    go = torch.randn(2, c, h, w, generator=g).to(torch.bfloat16)
+    ho, wo = (h - 1) // stride + 1, (w - 1) // stride + 1
+    go = torch.randn(2, c, ho, wo, generator=g).to(torch.bfloat16)
     xr, wr = x.float().requires_grad_(True), wt.clone().requires_grad_(True)
-    y = torch.relu(F.conv2d(xr, wr, padding=1, groups=groups) * scale[None, :, None, None] + shift[None, :, None, None])
+    y = torch.relu(F.conv2d(xr, wr, stride=stride, padding=1, groups=groups) * scale[None, :, None, None] + shift[None, :, None, None])
     y.backward(go.float())
     xd = x.to(DEV).contiguous(memory_format=torch.channels_last).requires_grad_(True)
     wd = wt.to(DEV).requires_grad_(True)
-    yd = conv2d_grouped(xd, wd, groups, scale.to(DEV), shift.to(DEV), pad=1, relu=True)
+    yd = conv2d_grouped(xd, wd, groups, scale.to(DEV), shift.to(DEV), pad=1, relu=True, stride=stride)
+    assert yd.shape == y.shape
 
     def rel(a, b):
         a, b = a.float().cpu(), b.float().cpu()
