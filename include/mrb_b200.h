@@ -215,6 +215,24 @@ typedef struct mrb_conv_params {
   long long x_pitch[3];
   long long y_pitch[3];
 } mrb_conv_params;
+/* Deformable convolution on the tensor-core path (NHWC bf16): bilinear sampler producing the GEMM's A operand and its
+ * backward.  Replaces deformable_im2col / col2im / col2im_coord and the modulated twins
+ * (csrc/cuda/deform_conv_kernel_cuda.cu:197-874) for the model's DFConv2d layers (layers/misc.py:114-203); the GEMMs
+ * around them are mrb_conv2d_fwd / _dgrad_prepared / _wgrad over K = kh*kw*C (see csrc/dcn_nhwc.cu).
+ *   input        : [N,H,W,C] bf16 (C % 8 == 0)
+ *   offset_mask  : [N,Ho,Wo,oc_pitch] fp32: channels (2t, 2t+1) = (dh, dw) of tap t; modulated != 0: channel
+ *                  2*kh*kw + t = mask LOGIT of tap t (the sigmoid of DFConv2d.forward is applied inside)
+ *   columns      : [N*Ho*Wo][kh*kw*C] bf16, K ordered (tap, channel) == the KRSC filter's memory order
+ *   grad_input   : [N,H,W,C] fp32, ACCUMULATED into (caller zero-fills; may be NULL)
+ *   grad_offset_mask : like offset_mask, fully written for the channels in use (mask-logit gradient through the sigmoid)
+ * deformable_groups == 1. */
+int mrb_dcn_sample_nhwc(const void* input_bf16, const float* offset_mask, void* columns_bf16, int batch, int height,
+                        int width, int channels, int out_h, int out_w, int kh, int kw, int stride, int pad, int dilation,
+                        int oc_pitch, int modulated, mrb_stream_t stream);
+int mrb_dcn_backward_nhwc(const void* input_bf16, const float* offset_mask, const void* grad_columns_bf16,
+                          float* grad_input_f32, float* grad_offset_mask, int batch, int height, int width, int channels,
+                          int out_h, int out_w, int kh, int kw, int stride, int pad, int dilation, int oc_pitch,
+                          int modulated, mrb_stream_t stream);
 int mrb_conv2d_fwd(const mrb_conv_params* p, const void* input_bf16, const void* weight_bf16,
                    const float* scale, const float* bias, const void* residual, void* output,
                    mrb_stream_t stream);

@@ -53,12 +53,12 @@ class DeformConvFunction(Function):
         geom = (weight.size(3), weight.size(2), ctx.stride[1], ctx.stride[0], ctx.padding[1], ctx.padding[0],
                 ctx.dilation[1], ctx.dilation[0], ctx.groups, ctx.deformable_groups)
         if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
-            grad_input = torch.zeros_like(input)
-            grad_offset = torch.zeros_like(offset)
+            grad_input = torch.zeros_like(input, memory_format=torch.contiguous_format)
+            grad_offset = torch.zeros_like(offset, memory_format=torch.contiguous_format)
             _C.deform_conv_backward_input(input, offset, grad_output, grad_input, grad_offset, weight,
                                           ctx.bufs_[0], *geom, step)
         if ctx.needs_input_grad[2]:
-            grad_weight = torch.zeros_like(weight)
+            grad_weight = torch.zeros_like(weight, memory_format=torch.contiguous_format)
             _C.deform_conv_backward_parameters(input, offset, grad_output, grad_weight, ctx.bufs_[0],
                                                ctx.bufs_[1], *geom, 1, step)
         return grad_input, grad_offset, grad_weight, None, None, None, None, None
@@ -75,6 +75,9 @@ class ModulatedDeformConvFunction(Function):
         ctx.stride, ctx.padding, ctx.dilation = stride, padding, dilation
         ctx.groups, ctx.deformable_groups = groups, deformable_groups
         ctx.with_bias = bias is not None
+        # `_C.modulated_deform_conv_*` insist on NCHW-contiguous input / weight (deform_conv_cuda.cu:504-505).  Every tensor
+        # of the reference is; here the producer may be an engine conv (channels_last), so normalise at the call site
+        input, weight = input.contiguous(), weight.contiguous()
         if not ctx.with_bias:
             bias = input.new_empty(1)  # placeholder, never read
         if weight.requires_grad or mask.requires_grad or offset.requires_grad or input.requires_grad:
@@ -93,10 +96,11 @@ class ModulatedDeformConvFunction(Function):
         if not grad_output.is_cuda:
             raise NotImplementedError
         input, offset, mask, weight, bias = ctx.saved_tensors
-        grad_input = torch.zeros_like(input)
-        grad_offset = torch.zeros_like(offset)
-        grad_mask = torch.zeros_like(mask)
-        grad_weight = torch.zeros_like(weight)
+        cf = torch.contiguous_format
+        grad_input = torch.zeros_like(input, memory_format=cf)
+        grad_offset = torch.zeros_like(offset, memory_format=cf)
+        grad_mask = torch.zeros_like(mask, memory_format=cf)
+        grad_weight = torch.zeros_like(weight, memory_format=cf)
         grad_bias = torch.zeros_like(bias)
         _C.modulated_deform_conv_backward(
             input, weight, bias, ctx._bufs[0], offset, mask, ctx._bufs[1], grad_input, grad_weight, grad_bias,

@@ -11,6 +11,8 @@ of the modules whose bodies are chains the conv engine fuses into one launch eac
   Bottleneck.forward         (conv -> FrozenBN -> relu_) x2,           4 fused launches forward; hand-scheduled
     (backbone/resnet.py:324-344)  conv -> FrozenBN, += identity, relu_  backward with ReLU masks / BN scale /
                                                                         residual join in dgrad epilogues
+    ... with groups=32 3x3 (X-101, resnet.py:302-311)                   grouped tcgen05 conv (block-diagonal super-groups)
+    ... with DFConv2d 3x3 (configs/dcn, resnet.py:286-300)              offset conv + sampler + tcgen05 GEMM (mrb_b200.dcn)
   FPN.forward                inner 1x1 + F.interpolate + add, 3x3,     lateral conv with the 2x-upsampled top-down
     (backbone/fpn.py:43-76)    LastLevelMaxPool                         map read in the epilogue; 3x3; pool
   RPNHead.forward            relu(conv3x3), cls_logits, bbox_pred      3x3+bias+ReLU; ONE 1x1 with Cout = A + 4A
@@ -121,8 +123,13 @@ def _bottleneck_kind(mod, be):
     return None
 
 
+def _stride_of(m):
+    s = m.stride
+    return int(s if isinstance(s, int) else s[0])
+
+
 def _fuse_bottleneck(mod, be, kind):
-    mod.strides = (mod.conv1.stride[0], mod.conv2.stride[0], mod.downsample[0].stride[0] if mod.downsample is not None else 1)
+    mod.strides = (_stride_of(mod.conv1), _stride_of(mod.conv2), _stride_of(mod.downsample[0]) if mod.downsample is not None else 1)
     mod._aff = [FrozenAffine(b) for b in (mod.bn1, mod.bn2, mod.bn3)]
     mod._aff_d = FrozenAffine(mod.downsample[1]) if mod.downsample is not None else None
     mod._g_premasked = False                      # decided by _wire_resnet once the consumers are known

@@ -4,7 +4,7 @@ pass routes every conv (+FrozenBN +ReLU +residual) through Backend.conv as ONE f
 import torch
 from torch import nn
 
-from maskrcnn_benchmark.layers import Conv2d, FrozenBatchNorm2d
+from maskrcnn_benchmark.layers import Conv2d, DFConv2d, FrozenBatchNorm2d
 
 
 def _kaiming_uniform(conv):
@@ -32,9 +32,9 @@ class FrozenAffine:
 
 
 class Bottleneck(nn.Module):
-    """resnet.py:239-344 with STRIDE_IN_1X1, frozen BN, groups = 1."""
+    """resnet.py:239-344, frozen BN; the 3x3 is dense, grouped (ResNeXt) or deformable (DFConv2d)."""
 
-    def __init__(self, cin, mid, cout, stride, stride_in_1x1=True):
+    def __init__(self, cin, mid, cout, stride, stride_in_1x1=True, groups=1, dcn=None):
         super().__init__()
         self.downsample = None
         if cin != cout:
@@ -43,17 +43,25 @@ class Bottleneck(nn.Module):
         s1, s3 = (stride, 1) if stride_in_1x1 else (1, stride)
         self.conv1 = Conv2d(cin, mid, 1, stride=s1, bias=False)
         self.bn1 = FrozenBatchNorm2d(mid)
-        self.conv2 = Conv2d(mid, mid, 3, stride=s3, padding=1, bias=False)
+        if dcn is not None:
+            # resnet.py:286-300 (DFConv2d initialises its own offset conv; the deformable weight keeps its default init)
+            self.conv2 = DFConv2d(mid, mid, with_modulated_dcn=bool(dcn), kernel_size=3, stride=s3, groups=groups, dilation=1,
+                                  deformable_groups=1, bias=False)
+        else:
+            self.conv2 = Conv2d(mid, mid, 3, stride=s3, padding=1, bias=False, groups=groups)
+        self.general = dcn is not None or groups > 1
         self.bn2 = FrozenBatchNorm2d(mid)
         self.conv3 = Conv2d(mid, cout, 1, bias=False)
         self.bn3 = FrozenBatchNorm2d(cout)
-        for c in (self.conv1, self.conv2, self.conv3):
+        for c in (self.conv1, self.conv3) + ((self.conv2,) if dcn is None else ()):
             _kaiming_uniform(c)
         self.strides = (s1, s3, stride)
         self._aff = [FrozenAffine(b) for b in (self.bn1, self.bn2, self.bn3)]
         self._aff_d = FrozenAffine(self.downsample[1]) if self.downsample is not None else None
 
     def run(self, be, x):
+        if getattr(self, "general", False):
+            return be.bottleneck_general(self, x)
         if hasattr(be, "bottleneck") and self.strides[1] == 1:
             # every consumer of a bottleneck output (next block, FPN lateral) pre-masks the gradient it returns
             return be.bottleneck(self, x, g_premasked=getattr(self, "_g_premasked", True))
@@ -89,13 +97,14 @@ class ResNet(nn.Module):
     def __init__(self, cfg):
         super().__init__()
         self.stem = Stem(cfg.stem_out)
-        cin, mid, cout = cfg.stem_out, cfg.width_per_group, cfg.res2_out
+        cin, mid, cout = cfg.stem_out, cfg.width_per_group * cfg.num_groups, cfg.res2_out
         self.stage_names = []
         for i, n in enumerate(cfg.stage_blocks):
             blocks = []
+            dcn = (cfg.with_modulated_dcn if cfg.stage_with_dcn[i] else None)
             for j in range(n):
                 stride = 2 if (i > 0 and j == 0) else 1
-                blocks.append(Bottleneck(cin, mid, cout, stride, cfg.stride_in_1x1))
+                blocks.append(Bottleneck(cin, mid, cout, stride, cfg.stride_in_1x1, cfg.num_groups, dcn))
                 cin = cout
             name = "layer%d" % (i + 1)
             self.add_module(name, nn.Sequential(*blocks))

@@ -444,6 +444,64 @@ class B200Backend(Backend):
         wd = blk.downsample[0].weight if blk.downsample is not None else None
         return _BottleneckFn.apply(x, blk.conv1.weight, blk.conv2.weight, blk.conv3.weight, wd, self, blk, g_premasked)
 
+    # ---------------------------------------------------------------- grouped / deformable 3x3 variants
+    @staticmethod
+    def _grouped_ok(c2):
+        cin, cout, g = c2.in_channels, c2.out_channels, c2.groups
+        return (cin == cout and g > 1 and cin % g == 0 and cin % 64 == 0 and 64 % (cin // g) == 0 and tuple(c2.kernel_size) == (3, 3)
+                and tuple(c2.padding) == (1, 1) and tuple(c2.dilation) == (1, 1) and c2.stride[0] == c2.stride[1] and c2.stride[0] in (1, 2)
+                and c2.padding_mode == "zeros")
+
+    def grouped_conv(self, x, weight, bias, groups, stride, pad, out_fp32=False):
+        """layers.Conv2d(groups > 1) through the engine (ResNeXt geometry only), or None."""
+        from mrb_b200 import grouped
+        ph, pw = (pad, pad) if isinstance(pad, int) else pad
+        co, cg, kh, kw = weight.shape
+        cin = x.shape[1]
+        if not (cin == co and cin % 64 == 0 and cg * groups == cin and 64 % cg == 0 and (kh, kw, ph, pw) == (3, 3, 1, 1) and stride in (1, 2)):
+            return None
+        if bias is not None and bias.requires_grad and torch.is_grad_enabled():
+            return None
+        x16 = x.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        y = grouped.conv2d_grouped(x16, weight, groups, None, None if bias is None else bias.detach().float(), 1, False, stride)
+        return y.float() if out_fp32 else y
+
+    def bottleneck_general_ok(self, mod):
+        """Bottleneck whose 3x3 is grouped (ResNeXt, resnet.py:302-311) or deformable (DFConv2d, resnet.py:286-300)."""
+        c2 = mod.conv2
+        if type(c2).__name__ == "DFConv2d":
+            conv, off = getattr(c2, "conv", None), getattr(c2, "offset", None)
+            if conv is None or off is None or type(conv).__name__ not in ("DeformConv", "ModulatedDeformConv"):
+                return False
+            ks = conv.kernel_size if isinstance(conv.kernel_size, tuple) else (conv.kernel_size,) * 2
+            one = lambda v: (v if isinstance(v, int) else v[0])     # noqa: E731
+            return (tuple(ks) == (3, 3) and conv.groups == 1 and conv.deformable_groups == 1 and one(conv.stride) == 1
+                    and one(conv.padding) == 1 and one(conv.dilation) == 1 and getattr(conv, "bias", None) is None
+                    and conv.in_channels % 8 == 0 and conv.out_channels % 8 == 0 and tuple(off.kernel_size) == (3, 3)
+                    and off.stride[0] == 1 and off.in_channels % 8 == 0)
+        return isinstance(c2, torch.nn.Conv2d) and c2.bias is None and self._grouped_ok(c2)
+
+    def bottleneck_general(self, blk, x):
+        from mrb_b200 import dcn, grouped
+        s1, s3, sd = blk.strides
+        (a1, b1), (a2, b2), (a3, b3) = (a.get() for a in blk._aff)
+        y = self.conv(x, blk.conv1.weight, a1, b1, stride=s1, relu=True)
+        c2 = blk.conv2
+        if type(c2).__name__ == "DFConv2d":
+            # offsets (and mask logits) stay fp32 NHWC, all round-up-to-8 channels kept (the extra ones are zero)
+            om = self.conv(y, c2.offset.weight, bias=c2.offset.bias, pad=1, out_fp32=True, keep_padded=True)
+            w = c2.conv.weight
+            y = dcn.deform_conv_nhwc(y, om, w, self._weight16(w), a2, b2, relu=True, modulated=bool(c2.with_modulated_dcn),
+                                     stride=1, pad=1, be=self, wsink=self.grad_sink(w))
+        else:
+            y = grouped.conv2d_grouped(y, c2.weight, c2.groups, a2, b2, 1, True, s3)
+        if blk.downsample is not None:
+            ad, bd = blk._aff_d.get()
+            idn = self.conv(x, blk.downsample[0].weight, ad, bd, stride=sd)
+        else:
+            idn = x
+        return self.conv(y, blk.conv3.weight, a3, b3, residual=idn, relu=True)
+
     def stem(self, images, weight, scale, shift, relu=True, bias=None, out_fp32=False):
         """7x7/2 conv on 3 channels == 4x4/1 conv on the 2x2 space-to-depth image (12 -> 16 channels):
         out(o) = sum_t w[t] in(2o-3+t); with a leading zero tap t' = t+1 the taps pair up as

@@ -13,7 +13,10 @@ class RCNNConfig:
     stem_out: int = 64
     res2_out: int = 256
     width_per_group: int = 64
+    num_groups: int = 1                       # RESNETS.NUM_GROUPS (32 for X-101-32x8d, with width_per_group 8)
     stride_in_1x1: bool = True
+    stage_with_dcn: Tuple[bool, ...] = (False, False, False, False)   # RESNETS.STAGE_WITH_DCN (configs/dcn: F,T,T,T)
+    with_modulated_dcn: bool = False          # RESNETS.WITH_MODULATED_DCN
     freeze_at: int = 2                        # BACKBONE.FREEZE_CONV_BODY_AT
     fpn_out: int = 256                        # RESNETS.BACKBONE_OUT_CHANNELS
     # RPN: defaults.py:128-175, yaml:9-13

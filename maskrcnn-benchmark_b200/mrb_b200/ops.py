@@ -347,6 +347,51 @@ def sgd_momentum_step(param, grad, momentum_buf, param_bf16, lr, momentum, weigh
     _count(1)
 
 
+# ------------------------------------------------------------------------- deformable conv (NHWC bf16, tensor-core path)
+def _dcn_geom(x, om, k, stride, pad, dil, modulated):
+    n, c, h, w = x.shape
+    ho = (h + 2 * pad - (dil * (k - 1) + 1)) // stride + 1
+    wo = (w + 2 * pad - (dil * (k - 1) + 1)) // stride + 1
+    if om.dtype != torch.float32 or om.dim() != 4 or tuple(om.shape[0:1] + om.shape[2:]) != (n, ho, wo) or \
+            not om.is_contiguous(memory_format=torch.channels_last):
+        raise RuntimeError("dcn: offset/mask tensor must be fp32 channels_last [N, >= %d, %d, %d]" % (k * k * (3 if modulated else 2), ho, wo))
+    if om.shape[1] < k * k * (3 if modulated else 2):
+        raise RuntimeError("dcn: offset/mask tensor has too few channels")
+    return n, c, h, w, ho, wo
+
+
+def dcn_sample_nhwc(x, om, k=3, stride=1, pad=1, dil=1, modulated=False):
+    """Deformable im2col on NHWC bf16: -> cols, logical [N, k*k*C, Ho, Wo] channels_last (memory [pix][tap*C + c]).
+    om: fp32 channels_last [N, OC, Ho, Wo]: channels (2t, 2t+1) = offsets of tap t, (2*k*k + t) = mask logit (v2)."""
+    x = _nhwc(x, "dcn_sample_nhwc(x)")
+    if x.dtype != torch.bfloat16:
+        raise RuntimeError("dcn_sample_nhwc: bf16 input required")
+    n, c, h, w, ho, wo = _dcn_geom(x, om, k, stride, pad, dil, modulated)
+    cols = torch.empty((n, k * k * c, ho, wo), dtype=torch.bfloat16, device=x.device, memory_format=torch.channels_last)
+    with torch.cuda.device(x.device):
+        _c.check(lib.mrb_dcn_sample_nhwc(_c._ptr(x), _c._ptr(om), _c._ptr(cols), n, h, w, c, ho, wo, k, k, stride, pad, dil,
+                                         om.shape[1], int(bool(modulated)), _c._stream()), "mrb_dcn_sample_nhwc")
+    _count(1)
+    return cols
+
+
+def dcn_backward_nhwc(x, om, gcols, k=3, stride=1, pad=1, dil=1, modulated=False, need_grad_x=True):
+    """-> (grad_x fp32 NHWC [N, C, H, W] logical or None, grad_om fp32 channels_last shaped like om; unused channels 0)."""
+    x = _nhwc(x, "dcn_backward_nhwc(x)")
+    gcols = _nhwc(gcols, "dcn_backward_nhwc(gcols)")
+    n, c, h, w, ho, wo = _dcn_geom(x, om, k, stride, pad, dil, modulated)
+    if gcols.dtype != torch.bfloat16 or tuple(gcols.shape) != (n, k * k * c, ho, wo):
+        raise RuntimeError("dcn_backward_nhwc: gcols must be bf16 [N, k*k*C, Ho, Wo]")
+    gx = torch.zeros((n, c, h, w), dtype=torch.float32, device=x.device).contiguous(memory_format=torch.channels_last) if need_grad_x else None
+    gom = torch.zeros_like(om)
+    with torch.cuda.device(x.device):
+        _c.check(lib.mrb_dcn_backward_nhwc(_c._ptr(x), _c._ptr(om), _c._ptr(gcols), _c._ptr(gx), _c._ptr(gom), n, h, w, c, ho, wo,
+                                           k, k, stride, pad, dil, om.shape[1], int(bool(modulated)), _c._stream()),
+                 "mrb_dcn_backward_nhwc")
+    _count(1)
+    return gx, gom
+
+
 # ------------------------------------------------------------------------- fused FPN ROIAlign
 class _RoiAlignFpn(torch.autograd.Function):
     @staticmethod

@@ -54,6 +54,24 @@ class CpuCheckerBackend(Backend):
     def stem(self, images, weight, scale, shift):
         return self._affine(F.conv2d(images, weight, None, 2, 3), scale, shift, None, None, True)
 
+    # grouped (ResNeXt) bottleneck variant: fp32 ATen grouped conv (checker of B200Backend.bottleneck_general)
+    def bottleneck_general_ok(self, mod):
+        c2 = mod.conv2
+        return isinstance(c2, torch.nn.Conv2d) and c2.groups > 1 and c2.bias is None and tuple(c2.kernel_size) == (3, 3)
+
+    def bottleneck_general(self, blk, x):
+        s1, s3, sd = blk.strides
+        (a1, b1), (a2, b2), (a3, b3) = (a.get() for a in blk._aff)
+        y = self.conv(x, blk.conv1.weight, a1, b1, stride=s1, relu=True)
+        c2 = blk.conv2
+        y = self._affine(F.conv2d(y, c2.weight, None, s3, 1, 1, c2.groups), a2, b2, None, None, True)
+        if blk.downsample is not None:
+            ad, bd = blk._aff_d.get()
+            idn = self.conv(x, blk.downsample[0].weight, ad, bd, stride=sd)
+        else:
+            idn = x
+        return self.conv(y, blk.conv3.weight, a3, b3, residual=idn, relu=True)
+
     def max_pool(self, x, k, s, p):
         return F.max_pool2d(x, k, s, p)
 

@@ -1,0 +1,94 @@
+"""Deformable conv at the BASELINE.json config-5 layer shapes (configs/dcn/e2e_mask_rcnn_dconv_R_50_FPN_1x.yaml:13-15,
+STAGE_WITH_DCN (F,T,T,T): res3 4x [2,128,100,168], res4 6x [2,256,50,84], res5 3x [2,512,25,42]; 3x3 s1 p1, dg 1), v1 and v2:
+  * the `_C.deform_conv_*` / `_C.modulated_deform_conv_*` fp32 path through layers (1e-4, north_star tolerance), and
+  * the tensor-core path of the fused model graph (mrb_b200.dcn: bf16 operands, fp32 offsets/accumulation; 1e-2),
+both against torchvision.ops.deform_conv2d on the host in fp32 (the independent implementation SURVEY 8c names for DCN;
+the oracle's C port is pinned to it in tests/test_oracle.py)."""
+import pytest
+import torch
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
+DEV = "cuda:0"
+SHAPES = [(128, 100, 168), (256, 50, 84), (512, 25, 42)]
+
+
+def _inputs(c, h, w, modulated, seed):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(2, c, h, w, generator=g)
+    wt = torch.randn(c, c, 3, 3, generator=g) / (9 * c) ** 0.5
+    off = torch.randn(2, 18, h, w, generator=g) * 2          # offset ~ N(0, 2)
+    mlogit = torch.randn(2, 9, h, w, generator=g) if modulated else None
+    go = torch.randn(2, c, h, w, generator=g)
+    return x, wt, off, mlogit, go
+
+
+def _reference(x, wt, off, mlogit, go):
+    from torchvision.ops import deform_conv2d
+    xr, wr, orq = x.clone().requires_grad_(True), wt.clone().requires_grad_(True), off.clone().requires_grad_(True)
+    mr = mlogit.clone().requires_grad_(True) if mlogit is not None else None
+    y = deform_conv2d(xr, orq, wr, None, stride=1, padding=1, mask=None if mr is None else mr.sigmoid())
+    y.backward(go)
+    return y.detach(), xr.grad, wr.grad, orq.grad, (mr.grad if mr is not None else None)
+
+
+def _rel(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-12))
+
+
+@pytest.mark.parametrize("modulated", [False, True])
+@pytest.mark.parametrize("c,h,w", SHAPES)
+def test_dcn_fp32_C_path_at_baseline_shapes(built_lib, c, h, w, modulated):
+    from maskrcnn_benchmark import layers
+    x, wt, off, mlogit, go = _inputs(c, h, w, modulated, c)
+    y, gx, gw, goff, gm = _reference(x, wt, off, mlogit, go)
+    xd, wd, od = (t.to(DEV).requires_grad_(True) for t in (x, wt, off))
+    if modulated:
+        md = mlogit.to(DEV).requires_grad_(True)
+        yd = layers.modulated_deform_conv(xd, od, md.sigmoid(), wd, None, 1, 1, 1, 1, 1)
+    else:
+        yd = layers.deform_conv(xd, od, wd, 1, 1, 1, 1, 1)
+    yd.backward(go.to(DEV))
+    assert _rel(yd.detach(), y) < 1e-4
+    assert _rel(xd.grad, gx) < 1e-4 and _rel(od.grad, goff) < 1e-4
+    assert _rel(wd.grad, gw) < 2e-4          # K = 2*H*W products per element, fp32 split-K accumulation
+    if modulated:
+        assert _rel(md.grad, gm) < 1e-4
+
+
+@pytest.mark.parametrize("modulated", [False, True])
+@pytest.mark.parametrize("c,h,w", SHAPES)
+def test_dcn_tensor_core_path_at_baseline_shapes(built_lib, c, h, w, modulated):
+    from mrb_b200 import dcn
+    x, wt, off, mlogit, go = _inputs(c, h, w, modulated, 100 + c)
+    # the checker sees the same bf16-rounded activations / weights / incoming gradient
+    xb, wb, gb = x.bfloat16(), wt.bfloat16(), go.bfloat16()
+    g = torch.Generator().manual_seed(5)
+    scale, shift = torch.rand(c, generator=g) + 0.5, torch.randn(c, generator=g) * 0.1
+    from torchvision.ops import deform_conv2d
+    xr, wr, orq = xb.float().requires_grad_(True), wb.float().requires_grad_(True), off.clone().requires_grad_(True)
+    mr = mlogit.clone().requires_grad_(True) if modulated else None
+    conv = deform_conv2d(xr, orq, wr, None, stride=1, padding=1, mask=None if mr is None else mr.sigmoid())
+    y = torch.relu(conv * scale[None, :, None, None] + shift[None, :, None, None])
+    y.backward(gb.float())
+    # product path: NHWC bf16 activations, fp32 NHWC offsets (+ mask logits) padded to a multiple of 8 channels
+    cl = dict(memory_format=torch.channels_last)
+    oc = 32 if modulated else 24
+    om = torch.zeros(2, oc, h, w)
+    om[:, :18] = off
+    if modulated:
+        om[:, 18:27] = mlogit
+    omd = om.to(DEV).contiguous(**cl).requires_grad_(True)
+    xd = xb.to(DEV).contiguous(**cl).requires_grad_(True)
+    wd = wt.to(DEV).contiguous(**cl).requires_grad_(True)
+    w16 = wb.to(DEV).contiguous(**cl)
+    yd = dcn.deform_conv_nhwc(xd, omd, wd, w16, scale.to(DEV), shift.to(DEV), relu=True, modulated=modulated)
+    assert yd.dtype == torch.bfloat16 and yd.shape == y.shape
+    yd.backward(gb.to(DEV))
+    assert _rel(yd.detach(), y.detach()) < 1e-2
+    assert _rel(xd.grad, xr.grad) < 2e-2
+    assert _rel(wd.grad, wr.grad) < 2e-2
+    assert _rel(omd.grad[:, :18], orq.grad) < 2e-2
+    if modulated:
+        assert _rel(omd.grad[:, 18:27], mr.grad) < 2e-2
+    assert float(omd.grad[:, 27 if modulated else 18:].abs().max()) == 0.0

@@ -19,7 +19,7 @@ def _have_ref():
     return refenv.find_reference_root() is not None
 
 
-@pytest.mark.parametrize("cfgname", ["e2e_mask_rcnn_R_50_FPN_1x.yaml"])
+@pytest.mark.parametrize("cfgname", ["e2e_mask_rcnn_R_50_FPN_1x.yaml", "e2e_mask_rcnn_X_101_32x8d_FPN_1x.yaml"])
 def test_fused_reference_graph_equals_reference_train_step(built_lib, oracle_mod, cfgname):
     if not _have_ref():
         pytest.skip("reference checkout absent")
@@ -29,6 +29,6 @@ def test_fused_reference_graph_equals_reference_train_step(built_lib, oracle_mod
     out = json.loads(r.stdout.strip().splitlines()[-1])
     f = out["report"]["fused"]
     assert f.get("stem") == 1 and f.get("fpn") == 1 and f.get("rpn_head") == 1 and f.get("box_head") == 1 and f.get("mask_head") == 1
-    assert sum(v for k, v in f.items() if k.startswith("bottleneck")) == 16
+    assert sum(v for k, v in f.items() if k.startswith("bottleneck")) == (33 if "X_101" in cfgname else 16)
     assert not out["report"]["skipped"]
     assert out["n_grads"] > 60 and out["worst_rel_grad"] < 1e-3

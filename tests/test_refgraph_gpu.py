@@ -13,27 +13,56 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900)]
 
 
-def test_reference_generalized_rcnn_over_layers_on_gpu(built_lib, oracle_mod):
+def _run(cfgname, tag):
     sys.path.insert(0, os.path.join(ROOT, "maskrcnn-benchmark_b200"))
     from mrb_b200 import refenv
     if refenv.find_reference_root() is None:
         pytest.skip("reference mirror absent (baseline/_ref is created by build() where /root/reference exists)")
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "refgraph", "run_gpu.py")],
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "refgraph", "run_gpu.py"), cfgname],
                        capture_output=True, text=True, timeout=850, cwd=os.path.join(ROOT, "tests", "refgraph"))
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     out = json.loads(r.stdout.strip().splitlines()[-1])
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    json.dump(out, open(os.path.join(ROOT, "gpurun_out", "refgraph_gpu.json"), "w"), indent=1)
+    json.dump(out, open(os.path.join(ROOT, "gpurun_out", "refgraph_gpu_%s.json" % tag), "w"), indent=1)
+    return out
+
+
+def _check_numbers(out, tags=("unfused", "fused"), feat_tol=3e-2):
+    for tag in tags:
+        # bf16 operands / activations vs the fp32 checker
+        assert max(out["feat_rel_err"][tag]) < feat_tol, out["feat_rel_err"]
+        lc, lg = out["losses"]["checker"], out["losses"][tag]
+        for k in lc:
+            assert abs(lc[k] - lg[k]) <= 5e-2 * max(1.0, abs(lc[k])), (tag, k, lc[k], lg[k])
+        assert out["grad_rel_err"][tag]["median"] < 5e-2, out["grad_rel_err"][tag]
+
+
+def test_x101_reference_graph_on_gpu(built_lib, oracle_mod):
+    """BASELINE config 4 (e2e_mask_rcnn_X_101_32x8d_FPN_1x: groups 32, stride in the 3x3), width-reduced: every grouped
+    3x3 of the unfused graph reaches the engine through layers.Conv2d; fused = 33 'general' bottlenecks."""
+    out = _run("e2e_mask_rcnn_X_101_32x8d_FPN_1x.yaml", "x101")
+    assert out["aten_fallbacks_unfused"] == 0, out
+    f = out["report"]["fused"]
+    assert f.get("bottleneck[general]") == 33 and not out["report"]["skipped"], out["report"]
+    _check_numbers(out)
+
+
+@pytest.mark.parametrize("cfgname,tag", [("dcn/e2e_mask_rcnn_dconv_R_50_FPN_1x.yaml", "dcn"), ("dcn/e2e_mask_rcnn_mdconv_R_50_FPN_1x.yaml", "mdcn")])
+def test_dcn_reference_graph_on_gpu(built_lib, oracle_mod, cfgname, tag):
+    """BASELINE config 5 (configs/dcn: DFConv2d in res3-res5), width-reduced: the fused graph (offset conv + sampler +
+    tcgen05 GEMM, mrb_b200.dcn) against the unfused graph whose DCN layers run the fp32 `_C.deform_conv_*` kernels."""
+    out = _run(cfgname, tag)
+    f = out["report"]["fused"]
+    assert f.get("bottleneck[general]") == 13 and f.get("bottleneck[fn]") == 3 and not out["report"]["skipped"], out["report"]
+    _check_numbers(out, tags=("fused",))
+
+
+def test_reference_generalized_rcnn_over_layers_on_gpu(built_lib, oracle_mod):
+    out = _run("e2e_mask_rcnn_R_50_FPN_1x.yaml", "r50")
     # every conv of the unfused reference graph reached the engine (the 7x7 stem included), none fell back to ATen
     assert out["engine_calls_unfused"] >= 60 and out["aten_fallbacks_unfused"] == 0, out
     f = out["report"]["fused"]
     assert f.get("stem") == 1 and f.get("fpn") == 1 and f.get("rpn_head") == 1 and f.get("box_head") == 1 and f.get("mask_head") == 1
     assert f.get("bottleneck[fn]") == 16 and not out["report"]["skipped"]
     assert out["libmrb_launches"]["fused"] > 100
-    for tag in ("unfused", "fused"):
-        # bf16 operands / activations vs the fp32 checker
-        assert max(out["feat_rel_err"][tag]) < 3e-2, out["feat_rel_err"]
-        lc, lg = out["losses"]["checker"], out["losses"][tag]
-        for k in lc:
-            assert abs(lc[k] - lg[k]) <= 5e-2 * max(1.0, abs(lc[k])), (tag, k, lc[k], lg[k])
-        assert out["grad_rel_err"][tag]["median"] < 5e-2, out["grad_rel_err"][tag]
+    _check_numbers(out)
