@@ -222,6 +222,12 @@ def ops_metrics(device, peaks):
     hbm = peaks.get("hbm_gbs", 6650.0)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
     out = []
+    # the reference's own CUDA kernels compiled for this GPU (oracle/_ref/cuda, checker build): timed beside ours
+    try:
+        import oracle
+        R = oracle.ref_cuda()
+    except Exception:
+        R = None
 
     def rec(name, alg, t, **kw):
         d = {"op": name, "us": round(t * 1e6, 1), "algorithmic_MB": round(alg / 1e6, 2), "achieved_gbs": round(alg / t / 1e9, 1),
@@ -235,12 +241,29 @@ def ops_metrics(device, peaks):
     r = rois.shape[0]
     foot = min(roi_footprint_elems(rois, 0.25, h, w, c), n * c * h * w)
     rd = rois.to(device)
-    for layout, x in (("NCHW", feat.to(device)), ("NHWC", feat.to(device).contiguous(memory_format=torch.channels_last))):
+    xd = feat.to(device)
+    kw = {}
+    if R is not None:
+        kw["reference_cuda_us"] = round(timed(lambda: R.roi_align_forward(xd, rd, 0.25, 7, 7, 2), flush, reps=5) * 1e6, 1)
+    for layout, x in (("NCHW", xd), ("NHWC", feat.to(device).contiguous(memory_format=torch.channels_last))):
         t = timed(lambda: _C.roi_align_forward(x, rd, 0.25, 7, 7, 2), flush, reps=5)
-        rec("roi_align_forward config1 (1x256x200x336 f32, R=100, 7x7)", 4 * (r * c * 49 + foot + 5 * r), t, layout=layout)
+        rec("roi_align_forward config1 (1x256x200x336 f32, R=100, 7x7)", 4 * (r * c * 49 + foot + 5 * r), t, layout=layout, **kw)
     g = torch.randn(r, c, 7, 7, device=device)
+    kw = {}
+    if R is not None:
+        kw["reference_cuda_us"] = round(timed(lambda: R.roi_align_backward(g, rd, 0.25, 7, 7, n, c, h, w, 2), flush, reps=5) * 1e6, 1)
     t = timed(lambda: _C.roi_align_backward(g, rd, 0.25, 7, 7, n, c, h, w, 2), flush, reps=5)
-    rec("roi_align_backward config1", 4 * (r * c * 49 + 2 * foot + n * c * h * w + 5 * r), t, layout="NCHW")
+    rec("roi_align_backward config1", 4 * (r * c * 49 + 2 * foot + n * c * h * w + 5 * r), t, layout="NCHW", **kw)
+    # box-head sized single-level call (P2 of 2 images, 1024 boxes): ours vs the reference kernel
+    featp2 = _inputs.fpn_features(2, 1)[0].to(device)
+    roisp2 = _inputs.rois_for_level(1024, 2, 31, max_size=128)
+    footp2 = min(roi_footprint_elems(roisp2, 0.25, 200, 336, 256), 2 * 256 * 200 * 336)
+    rp2 = roisp2.to(device)
+    kw = {}
+    if R is not None:
+        kw["reference_cuda_us"] = round(timed(lambda: R.roi_align_forward(featp2, rp2, 0.25, 7, 7, 2), flush, reps=5) * 1e6, 1)
+    t = timed(lambda: _C.roi_align_forward(featp2, rp2, 0.25, 7, 7, 2), flush, reps=5)
+    rec("roi_align_forward P2 (2x256x200x336 f32, R=1024, 7x7)", 4 * (1024 * 256 * 49 + footp2 + 5 * 1024), t, layout="NCHW", **kw)
     # the shapes the train step runs: fused multi-level ROIAlign on bf16 NHWC P2..P5 of 2 images
     feats = [f.to(torch.bfloat16).to(device).contiguous(memory_format=torch.channels_last) for f in _inputs.fpn_features(2, 2)]
     scales = (0.25, 0.125, 0.0625, 0.03125)
@@ -271,17 +294,28 @@ def ops_metrics(device, peaks):
     alg = sum(20 * s + 16 * s * math.ceil(s / 64) for s in sizes)
     rec("nms_batched (10 RPN problems, thr 0.7)", alg, t, us_per_problem=round(t * 1e5, 1), note="latency bound: bytes are tiny")
     b1, s1 = bs[0][0].to(device), bs[0][1].to(device)
+    kw = {}
+    if R is not None:
+        kw["reference_cuda_us"] = round(timed(lambda: R.nms(torch.cat([b1, s1[:, None]], 1), 0.7), flush, reps=5) * 1e6, 1)
     t = timed(lambda: _C.nms(b1, s1, 0.7), flush, reps=5)
-    rec("nms N=2000 through _C (incl. the 4-byte D2H sizing the result)", 20 * 2000 + 16 * 2000 * 32, t, note="latency bound")
+    rec("nms N=2000 through _C (incl. the 4-byte D2H sizing the result)", 20 * 2000 + 16 * 2000 * 32, t, note="latency bound", **kw)
     # focal loss, RetinaNet 800x1344: 201600 anchors x 80
     logits, targets = _inputs.focal_inputs(201600, 80, 0)
     ld, td = logits.to(device), targets.to(device)
+    kw = {}
+    if R is not None:
+        kw["reference_cuda_us"] = round(timed(lambda: R.sigmoid_focalloss_forward(ld, td, 80, 2.0, 0.25), flush, reps=5) * 1e6, 1)
     t = timed(lambda: _C.sigmoid_focalloss_forward(ld, td, 80, 2.0, 0.25), flush, reps=5)
-    rec("sigmoid_focalloss_forward (201600x80)", 4 * 201600 * 80 * 2 + 4 * 201600, t)
+    rec("sigmoid_focalloss_forward (201600x80)", 4 * 201600 * 80 * 2 + 4 * 201600, t, **kw)
     dl = torch.rand_like(ld)
+    kw = {}
+    if R is not None:
+        kw["reference_cuda_us"] = round(timed(lambda: R.sigmoid_focalloss_backward(ld, td, dl, 80, 2.0, 0.25), flush, reps=5) * 1e6, 1)
     t = timed(lambda: _C.sigmoid_focalloss_backward(ld, td, dl, 80, 2.0, 0.25), flush, reps=5)
-    rec("sigmoid_focalloss_backward (201600x80)", 4 * 201600 * 80 * 3 + 4 * 201600, t)
-    return {"peak_hbm_gbs": hbm, "timing": "CUDA events, L2 flushed between launches, median of 5", "rows": out}
+    rec("sigmoid_focalloss_backward (201600x80)", 4 * 201600 * 80 * 3 + 4 * 201600, t, **kw)
+    return {"peak_hbm_gbs": hbm, "timing": "CUDA events, L2 flushed between launches, median of 5",
+            "reference_cuda": "the reference's csrc/cuda kernels compiled unmodified for sm_100a (oracle/build_ref.py::build_cuda), same "
+                              "inputs, same timing" if R is not None else "not built on this box", "rows": out}
 
 
 # =========================================================================================== CPU reference arm

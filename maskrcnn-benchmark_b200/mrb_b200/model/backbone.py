@@ -120,7 +120,10 @@ class ResNet(nn.Module):
     def run(self, be, images):
         x = self.stem.run(be, images)
         outs = []
+        sb = getattr(be, "stage_boundary", None)
         for name in self.stage_names:
+            if sb is not None and x.requires_grad:
+                x = sb([x], "backbone.body.%s." % name)[0]     # backward reaching x <=> this stage's gradients are issued
             for blk in getattr(self, name):
                 x = blk.run(be, x)
             outs.append(x)
@@ -165,4 +168,8 @@ class Backbone(nn.Module):
         self.out_channels = cfg.fpn_out
 
     def run(self, be, images):
-        return self.fpn.run(be, self.body.run(be, images))
+        feats = self.body.run(be, images)
+        sb = getattr(be, "stage_boundary", None)
+        if sb is not None and self.training:
+            feats = sb(feats, "backbone.fpn.")       # backward reaching C2..C5 <=> the FPN's gradients are issued
+        return self.fpn.run(be, feats)

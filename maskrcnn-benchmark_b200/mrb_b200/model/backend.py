@@ -90,6 +90,22 @@ class _ConvFn(Function):
         return (gx, gw, gb, gres) + (None,) * 14
 
 
+class _BucketBoundaryFn(Function):
+    """Identity whose backward tells the arena that every gradient kernel of bucket `name` (everything downstream of these
+    tensors up to the next boundary) has been issued: its all-reduce starts now and overlaps the rest of backward."""
+
+    @staticmethod
+    def forward(ctx, be, name, *xs):
+        ctx.be, ctx.name = be, name
+        return tuple(x.view_as(x) for x in xs)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        if ctx.be.arena is not None:
+            ctx.be.arena.reduce_bucket(ctx.name)
+        return (None, None) + grads
+
+
 class _HeadsBoundaryFn(Function):
     """Identity on the FPN outputs whose backward runs exactly when every consumer downstream (RPN head, both ROI
     heads) has issued its backward -- the moment the gradients of all their parameters are complete.  The backend uses
@@ -363,6 +379,12 @@ class B200Backend(Backend):
             return feats
         return list(_HeadsBoundaryFn.apply(self, *feats))
 
+    def stage_boundary(self, xs, bucket):
+        """Mark `xs` as the inputs of everything belonging to gradient bucket `bucket` (data-parallel runs only)."""
+        if self.arena is None or self.arena.world <= 1 or not any(x.requires_grad for x in xs):
+            return xs
+        return list(_BucketBoundaryFn.apply(self, bucket, *xs))
+
     def heads_grads_ready(self):
         if self.arena is not None:
             self.arena.early_reduce()
@@ -606,6 +628,8 @@ class B200Backend(Backend):
         """ConvTranspose2d(k=2, s=2), weight [Cin, Cout, 2, 2]: see _Deconv2x2Fn (two strided 1x1 convs, no shuffle)."""
         if weight.shape[1] % 8 or x.shape[1] % 8:
             raise RuntimeError("deconv2x2: channel counts must be multiples of 8")
+        if x.shape[0] == 0:      # no ROIs (e.g. an image without detections at test time)
+            return x.new_zeros((0, weight.shape[1], 2 * x.shape[2], 2 * x.shape[3]), dtype=torch.bfloat16)
         return _Deconv2x2Fn.apply(x.to(torch.bfloat16), weight, bias, relu, premask_x, gy_premasked)
 
     def roi_align_fpn(self, feats, rois, scales, pooled, sampling_ratio, nhwc):

@@ -2,7 +2,8 @@
 
 `oracle` is the CPU restatement (mrb_oracle*.c, built by oracle/Makefile) of the
 reference's csrc hot path plus, when available, `oracle/_ref` (the reference's
-own csrc/cpu sources compiled in place by oracle/build_ref.py).  Only tests/,
+own csrc/cpu sources AND its csrc/cuda kernels compiled in place by
+oracle/build_ref.py; the CUDA ones are the GPU-side checker).  Only tests/,
 bench.py (cpu_baseline / --impl reference) and __graft_entry__.smoke() import
 this package, and only as the checker.  Nothing under maskrcnn-benchmark_b200/
 may import it.
@@ -26,6 +27,7 @@ def build():
     if os.path.isdir(os.environ.get("MRB_REFERENCE", "/root/reference")):
         from . import build_ref
         build_ref.build()
+        build_ref.build_cuda()
 
 
 def lib():
@@ -51,6 +53,27 @@ def ref():
         spec.loader.exec_module(mod)
         _REF = mod
     return _REF
+
+
+_REF_CUDA = None
+
+
+def ref_cuda():
+    """The reference's own CUDA kernels (csrc/cuda/*.cu compiled for sm_100a by build_ref.build_cuda): module with the 14
+    `_C` names in their *_cuda forms, or None if never built / not loadable.  GPU-side checker only."""
+    global _REF_CUDA
+    if _REF_CUDA is None:
+        path = os.path.join(_HERE, "_ref", "cuda", "mrb_ref_cuda.so")
+        if not os.path.exists(path):
+            return None
+        try:
+            spec = importlib.util.spec_from_file_location("mrb_ref_cuda", path)
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+        except Exception:
+            return None
+        _REF_CUDA = mod
+    return _REF_CUDA
 
 
 def _f32(t):

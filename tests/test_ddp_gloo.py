@@ -62,8 +62,14 @@ sum(model(imgs, sizes, tg).values()).backward()    # autograd accumulates into t
 for p, g_local in zip([q for q in model.parameters() if q.requires_grad], local[rank]):
     torch.testing.assert_close(p.grad, g_local, rtol=1e-5, atol=1e-7)
     assert p.grad.data_ptr() >= arena.grad.data_ptr()
-arena.early_reduce()
+assert list(arena.buckets) == ["backbone.body.layer2.", "backbone.body.layer3.", "backbone.body.layer4.", "backbone.fpn.", "heads", "bias"]
+# the order in which the boundary nodes of the B200 backend fire during backward: heads, FPN (+ biases), layer4, layer3;
+# the first trainable stage (layer2) is left for sync()
+for name in ("heads", "backbone.fpn.", "backbone.body.layer4.", "backbone.body.layer3."):
+    arena.reduce_bucket(name)
+assert set(arena._pending) == {"heads", "backbone.fpn.", "bias", "backbone.body.layer4.", "backbone.body.layer3."}
 arena.sync()
+assert not arena._pending
 for p, b in zip([q for q in model.parameters() if q.requires_grad], want):
     torch.testing.assert_close(p.grad, b * world, rtol=1e-4, atol=1e-6)      # sum; step() folds in the 1/world
 flat = torch.cat([g.reshape(-1) for g in got])
