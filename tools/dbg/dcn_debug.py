@@ -45,3 +45,32 @@ for (c, h, w, mod) in ((128, 100, 168, False), (128, 100, 168, True), (256, 50, 
     gw = ops.conv2d_wgrad(cols, gyd, (64, 9 * c, 1, 1), 1, 0)
     gw_ref = torch.einsum("nohw,nkhw->ok", gy.bfloat16().float(), cols.float().cpu())
     print("   engine wgrad", rel(gw.view(64, 9 * c), gw_ref))
+
+print("---- full function, Cout = C, scale/shift/relu")
+from mrb_b200 import dcn
+for (c, h, w, mod) in ((128, 100, 168, False), (256, 50, 84, False), (256, 50, 84, True), (512, 25, 42, False)):
+    g = torch.Generator().manual_seed(100 + c)
+    x = torch.randn(2, c, h, w, generator=g); wt = torch.randn(c, c, 3, 3, generator=g) / (9 * c) ** 0.5
+    off = torch.randn(2, 18, h, w, generator=g) * 2
+    ml = torch.randn(2, 9, h, w, generator=g) if mod else None
+    go = torch.randn(2, c, h, w, generator=g)
+    xb, wb, gb = x.bfloat16(), wt.bfloat16(), go.bfloat16()
+    g2 = torch.Generator().manual_seed(5)
+    scale, shift = torch.rand(c, generator=g2) + 0.5, torch.randn(c, generator=g2) * 0.1
+    for relu in (False, True):
+        xr, wr, orq = xb.float().requires_grad_(True), wb.float().requires_grad_(True), off.clone().requires_grad_(True)
+        mr = ml.clone().requires_grad_(True) if mod else None
+        conv = deform_conv2d(xr, orq, wr, None, stride=1, padding=1, mask=None if mr is None else mr.sigmoid())
+        y = conv * scale[None, :, None, None] + shift[None, :, None, None]
+        if relu: y = torch.relu(y)
+        y.backward(gb.float())
+        oc = 32 if mod else 24
+        om = torch.zeros(2, oc, h, w); om[:, :18] = off
+        if mod: om[:, 18:27] = ml
+        cl = dict(memory_format=torch.channels_last)
+        omd = om.to(DEV).contiguous(**cl).requires_grad_(True)
+        xd = xb.to(DEV).contiguous(**cl).requires_grad_(True)
+        wd = wt.to(DEV).contiguous(**cl).requires_grad_(True)
+        yd = dcn.deform_conv_nhwc(xd, omd, wd, wb.to(DEV).contiguous(**cl), scale.to(DEV), shift.to(DEV), relu=relu, modulated=mod)
+        yd.backward(gb.to(DEV))
+        print(c, mod, "relu" if relu else "lin", "y", rel(yd.detach(), y.detach()), "gx", rel(xd.grad, xr.grad), "gw", rel(wd.grad, wr.grad), "goff", rel(omd.grad[:, :18], orq.grad))
