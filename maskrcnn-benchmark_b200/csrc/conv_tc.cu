@@ -1000,10 +1000,13 @@ static int conv_launch(const ConvPlan& pl, const void* x, const void* w, int cin
           const double waves = (double)ceil_div(tiles, kNumSMs);
           const double mma = k_blocks_tile * (cand >= 256 ? 520.0 : cand >= 128 ? 270.0 : cand >= 64 ? 200.0 : 160.0);
           const double load = k_blocks_tile * (rows * 128.0 * (0.5 + 0.5 * halo) + cand * 128.0) / 96.0;
-          const double epi = mode == 1 ? 500.0 + 4.0 * cand + (residual || relu_mask ? 300.0 : 0.0) : 600.0 + 9.0 * cand;
+          const double epi = mode == 1 ? 500.0 + 4.0 * cand + (residual || relu_mask ? 300.0 : 0.0)
+                                       : 600.0 + 9.0 * cand + (residual || relu_mask ? 4.0 * cand : 0.0);
           double t_tile = mma > load ? mma : load;
           if (epi > t_tile) t_tile = epi;
-          const double cost = waves * (t_tile + 150.0) * (1.0 + 0.02 * (halo - 1.0));
+          // partially filled tiles waste MMA rows and L2->smem bytes: mild preference for full 128-row rectangles
+          // (profiles/sweep_conv_r2_b.json: 8x16 beats 10x12 on the 200x336 planes at equal wave count)
+          const double cost = waves * (t_tile + 150.0) * (1.0 + 0.02 * (halo - 1.0)) * (1.0 + 0.10 * (128 - rows) / 128.0);
           if (best_cost < 0 || cost < best_cost * 0.995) { best_cost = cost; th = t_h; tw = t_w; bn = cand; tma_epi = mode == 1; }
         }
       }

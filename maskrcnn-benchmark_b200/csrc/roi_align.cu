@@ -132,6 +132,21 @@ roi_align_fwd_nchw_kernel(const float* __restrict__ input, const float* __restri
       const int c = o / PP, bin = o - c * PP;
       const float* __restrict__ src = src0 + (size_t)c * plane;
       float acc = 0.f;
+      if (S2 == 4) {
+        // the 16 taps first (memory-level parallelism), then the reference's summation order
+        float v[16], wt[16];
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+          const int i = s * PP + bin;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) { v[4 * s + k] = __ldg(src + t_off[k * ns + i]); wt[4 * s + k] = t_w[k * ns + i]; }
+        }
+#pragma unroll
+        for (int s = 0; s < 4; ++s)
+          acc = __fadd_rn(acc, tap_sum(wt[4 * s], v[4 * s], wt[4 * s + 1], v[4 * s + 1], wt[4 * s + 2], v[4 * s + 2], wt[4 * s + 3], v[4 * s + 3]));
+        dst0[o] = __fdiv_rn(acc, g.count);
+        continue;
+      }
       for (int s = 0; s < S2; ++s) {
         const int i = s * PP + bin;
         const float v1 = __ldg(src + t_off[i]), v2 = __ldg(src + t_off[ns + i]);
@@ -205,6 +220,34 @@ roi_align_fwd_nhwc_kernel(const float* __restrict__ input, const float* __restri
     float acc[VEC];
 #pragma unroll
     for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
+    if (g.gh == 2 && g.gw == 2) {
+      // sampling_ratio 2 (every reference config): request the 16 taps of the bin first, then reduce them in the
+      // reference's order (sample (0,0), (0,1), (1,0), (1,1); w1 v1 + w2 v2 + w3 v3 + w4 v4 within a sample) -- the same
+      // arithmetic, bit for bit, with 16 requests in flight per warp instead of 4.
+      Sample sm[4];
+      float v[16][VEC];
+#pragma unroll
+      for (int s2 = 0; s2 < 4; ++s2) {
+        const float y = sample_coord(g.sh, ph, g.bin_h, s2 >> 1, 2);
+        const float x = sample_coord(g.sw, pw, g.bin_w, s2 & 1, 2);
+        sm[s2] = make_sample(H, W, y, x);
+        const bool ok = sm[s2].valid && c_ok;
+        const size_t o1 = ok ? ((size_t)sm[s2].yl * W + sm[s2].xl) * C : 0, o2 = ok ? ((size_t)sm[s2].yl * W + sm[s2].xh) * C : 0;
+        const size_t o3 = ok ? ((size_t)sm[s2].yh * W + sm[s2].xl) * C : 0, o4 = ok ? ((size_t)sm[s2].yh * W + sm[s2].xh) * C : 0;
+        vec_load<VEC>(src + o1, v[4 * s2]);
+        vec_load<VEC>(src + o2, v[4 * s2 + 1]);
+        vec_load<VEC>(src + o3, v[4 * s2 + 2]);
+        vec_load<VEC>(src + o4, v[4 * s2 + 3]);
+      }
+#pragma unroll
+      for (int s2 = 0; s2 < 4; ++s2) {
+        if (!sm[s2].valid || !c_ok) continue;
+#pragma unroll
+        for (int k = 0; k < VEC; ++k)
+          acc[k] = __fadd_rn(acc[k], tap_sum(sm[s2].w1, v[4 * s2][k], sm[s2].w2, v[4 * s2 + 1][k], sm[s2].w3, v[4 * s2 + 2][k],
+                                             sm[s2].w4, v[4 * s2 + 3][k]));
+      }
+    } else
     for (int iy = 0; iy < g.gh; ++iy) {
       const float y = sample_coord(g.sh, ph, g.bin_h, iy, g.gh);
       for (int ix = 0; ix < g.gw; ++ix) {

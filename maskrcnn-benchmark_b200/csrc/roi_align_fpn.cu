@@ -160,20 +160,28 @@ roi_align_fpn_fwd_kernel(FpnArgs a, const float* __restrict__ rois, T* __restric
       Axis2 ay, ax;
       axis2(H, fpn_coord(g.sh, ph, g.bin_h, 0, 2), fpn_coord(g.sh, ph, g.bin_h, 1, 2), ay);
       axis2(W, fpn_coord(g.sw, pw, g.bin_w, 0, 2), fpn_coord(g.sw, pw, g.bin_w, 1, 2), ax);
-      if (c_ok) {
+      // All (row, column) taps of the bin are requested before the first one is consumed: the gather is latency bound
+      // (a load -> fma chain per tap kept ONE 256-byte request in flight per warp), so memory-level parallelism is what
+      // buys bandwidth.  Zero-weight taps are predicated off (no traffic).
+      uint2 raw[16];
+      float wg[16];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          if (ay.w[i] == 0.f) continue;
+      for (int i = 0; i < 4; ++i) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float wgt = ay.w[i] * ax.w[j];
-            if (wgt == 0.f) continue;
-            float v[4];
-            load4<T>(src + ((size_t)ay.r[i] * W + ax.r[j]) * C, v);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) acc[k] = fmaf(wgt, v[k], acc[k]);
-          }
+        for (int j = 0; j < 4; ++j) {
+          const float wgt = ay.w[i] * ax.w[j];
+          wg[i * 4 + j] = wgt;
+          raw[i * 4 + j] = make_uint2(0u, 0u);
+          if (c_ok && wgt != 0.f)
+            raw[i * 4 + j] = __ldg(reinterpret_cast<const uint2*>(src + ((size_t)ay.r[i] * W + ax.r[j]) * C));
         }
+      }
+#pragma unroll
+      for (int t = 0; t < 16; ++t) {
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw[t]);
+        const float2 lo = __bfloat1622float2(h2[0]), hi = __bfloat1622float2(h2[1]);
+        acc[0] = fmaf(wg[t], lo.x, acc[0]); acc[1] = fmaf(wg[t], lo.y, acc[1]);
+        acc[2] = fmaf(wg[t], hi.x, acc[2]); acc[3] = fmaf(wg[t], hi.y, acc[3]);
       }
     } else
     for (int iy = 0; iy < g.gh; ++iy) {
