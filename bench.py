@@ -51,7 +51,7 @@ CONFIGS = {
 }
 
 
-HARNESS_CONFIGS = ("mask_r50", "faster_fwd")     # configs the from-scratch harness model covers
+HARNESS_CONFIGS = ("mask_r50", "faster_fwd", "x101", "dcn")     # configs the from-scratch harness model covers
 
 
 def synth_batch(n, seed, device="cpu", pin=False):

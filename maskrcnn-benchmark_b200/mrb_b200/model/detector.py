@@ -53,7 +53,7 @@ class GeneralizedRCNN(nn.Module):
             tgt = mask.mask_targets(gt_sel, rois_sel[:, 1:], res)
             bce = torch.nn.functional.binary_cross_entropy_with_logits(sel_logits.float(), tgt,
                                                                        reduction="none").mean((1, 2))
-            return (bce * wsel).sum() / wsel.sum().clamp(min=1)
+            return torch.where(wsel > 0, bce, torch.zeros((), dtype=bce.dtype, device=bce.device)).sum() / wsel.sum().clamp(min=1)
         lab = labels.reshape(-1)
         pos = (lab > 0).nonzero().squeeze(1)             # keep_only_positive_boxes (mask_head.py:11-32)
         rois_pos = rois[pos]

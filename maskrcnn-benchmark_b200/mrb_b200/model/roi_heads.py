@@ -102,9 +102,13 @@ class BoxHead(nn.Module):
         pos = labels > 0
         idx = (4 * labels.clamp(min=0))[:, None] + torch.arange(4, device=labels.device)[None, :]
         pred = torch.gather(box_regression.float(), 1, idx)
-        diff = torch.abs(pred - reg_targets)
+        # The reference INDEXES the positive rows (loss.py:150-160); this fixed-shape form must select, not multiply:
+        # a degenerate proposal (exp(dw) underflows with random-init RPN deltas -> width 0) encodes to an infinite
+        # target, harmless in a row that is never positive but inf * 0 = NaN under a multiplicative mask.
+        zero = torch.zeros((), dtype=pred.dtype, device=pred.device)
+        diff = torch.abs(torch.where(pos[:, None], pred - reg_targets, zero))
         l1 = torch.where(diff < 1.0, 0.5 * diff * diff, diff - 0.5)
-        box_loss = (l1 * pos[:, None]).sum() / (labels >= 0).sum().clamp(min=1)
+        box_loss = torch.where(pos[:, None], l1, zero).sum() / (labels >= 0).sum().clamp(min=1)
         return cls_loss, box_loss
 
     @torch.no_grad()

@@ -223,11 +223,12 @@ class RPN(nn.Module):
         beta = 1.0 / 9
         for i, (pos_idx, pos_ok, reg_t, sel, sel_lab, sel_w) in enumerate(prepared):
             num_sampled = num_sampled + sel_w.sum()
-            diff = torch.abs(reg[i][pos_idx].float() - reg_t)
+            zero = torch.zeros((), dtype=torch.float32, device=reg_t.device)
+            diff = torch.abs(torch.where(pos_ok[:, None], reg[i][pos_idx].float() - reg_t, zero))     # select, never inf * 0
             l1 = torch.where(diff < beta, 0.5 * diff * diff / beta, diff - 0.5 * beta)
-            box_sum = box_sum + (l1 * pos_ok[:, None]).sum()
+            box_sum = box_sum + torch.where(pos_ok[:, None], l1, zero).sum()
             bce = F.binary_cross_entropy_with_logits(obj[i][sel].float(), sel_lab, reduction="none")
-            obj_sum = obj_sum + (bce * sel_w).sum()
+            obj_sum = obj_sum + torch.where(sel_w > 0, bce, zero).sum()
         num_sampled = num_sampled.clamp(min=1)
         return obj_sum / num_sampled, box_sum / num_sampled
 
