@@ -215,6 +215,17 @@ typedef struct mrb_conv_params {
   long long x_pitch[3];
   long long y_pitch[3];
 } mrb_conv_params;
+/* Operand preparation for MRB_CONV_GROUPED64 (csrc/grouped_prep.cu).  weight: the grouped filter [C][taps][C/groups] bf16
+ * (KRSC).  w_exp / wd_exp: [C][taps][64] bf16 -- the forward operand and the (flipped, per-Cout scaled) data-gradient operand
+ * of mrb_conv2d_fwd / mrb_conv2d_dgrad_prepared; either may be NULL.  mrb_grouped_collapse_wgrad folds the [C][taps][128]
+ * fp32 result of mrb_conv2d_wgrad(MRB_CONV_GROUPED64) back into the grouped layout [C, C/groups, kh, kw] given by its
+ * element strides (co, cg, tap), overwriting or accumulating. */
+int mrb_grouped_expand_weights(const void* weight_bf16, const float* scale, void* w_exp_bf16, void* wd_exp_bf16,
+                               int channels, int taps, int groups, mrb_stream_t stream);
+int mrb_grouped_collapse_wgrad(const float* grad_expanded128, float* grad_weight, int channels, int taps, int groups,
+                               long long stride_co, long long stride_cg, long long stride_tap, int accumulate,
+                               mrb_stream_t stream);
+
 /* Deformable convolution on the tensor-core path (NHWC bf16): bilinear sampler producing the GEMM's A operand and its
  * backward.  Replaces deformable_im2col / col2im / col2im_coord and the modulated twins
  * (csrc/cuda/deform_conv_kernel_cuda.cu:197-874) for the model's DFConv2d layers (layers/misc.py:114-203); the GEMMs

@@ -59,49 +59,55 @@ class GroupedConvFn(torch.autograd.Function):
     MRB_GROUPED=composed selects round 1's per-super-group composition (one launch per 64 channels) for A/B runs."""
 
     @staticmethod
-    def forward(ctx, x, weight, scale, shift, groups, pad, relu, stride=1):
+    def forward(ctx, x, weight, scale, shift, groups, pad, relu, stride=1, w16=None, wsink=None):
         from mrb_b200 import ops
         c = x.shape[1]
         _, sgs = check_geometry(c, weight.shape[0], groups)
         if x.dtype != torch.bfloat16:
             raise RuntimeError("grouped conv: bf16 NHWC input required (cast at the call site)")
         x = x.contiguous(memory_format=torch.channels_last)
-        w_exp = expand_group_weights(weight.detach(), groups).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        if w16 is None:
+            w16 = weight.detach().to(torch.bfloat16)
+        w16 = w16.contiguous(memory_format=torch.channels_last)
         composed = os.environ.get("MRB_GROUPED", "native") == "composed"
         if composed:
+            w_exp = expand_group_weights(w16, groups).contiguous(memory_format=torch.channels_last)
             out = torch.empty_like(x)
             for sg in range(sgs):
                 sl = slice(sg * SG, (sg + 1) * SG)
                 ops.conv2d_fwd(_window(x, sg), w_exp[sl], None if scale is None else scale[sl].contiguous(),
                                None if shift is None else shift[sl].contiguous(), None, 1, pad, relu, out=_window(out, sg))
         else:
+            w_exp, _ = ops.grouped_expand_weights(w16, groups, None, True, False)      # one launch (csrc/grouped_prep.cu)
             out = ops.conv2d_fwd(x, w_exp, scale, shift, None, 1, pad, relu, grouped=True)
         if stride == 2:
             out = out[:, :, ::2, ::2].contiguous(memory_format=torch.channels_last)
         elif stride != 1:
             raise RuntimeError("grouped conv: stride 1 or 2")
-        ctx.cfg = (groups, pad, relu, sgs, stride, composed, tuple(x.shape))
-        ctx.save_for_backward(x, w_exp, scale, out if relu else None)
+        ctx.cfg = (groups, pad, relu, sgs, stride, composed, tuple(x.shape), tuple(weight.shape))
+        ctx.wsink = wsink
+        ctx.save_for_backward(x, w16, scale, out if relu else None)
         return out
 
     @staticmethod
     def backward(ctx, g):
         from mrb_b200 import ops
-        x, w_exp, scale, y = ctx.saved_tensors
-        groups, pad, relu, sgs, stride, composed, x_shape = ctx.cfg
+        x, w16, scale, y = ctx.saved_tensors
+        groups, pad, relu, sgs, stride, composed, x_shape, w_shape = ctx.cfg
         if relu:
             g = torch.where(y > 0, g, torch.zeros((), dtype=g.dtype, device=g.device))
         g = g.to(torch.bfloat16)
         n, c, h, w = x_shape
+        k = w_shape[2]
         if stride == 2:
-            k = w_exp.shape[2]
             hf, wf = h + 2 * pad - k + 1, w + 2 * pad - k + 1
             gf = torch.zeros((n, c, hf, wf), dtype=torch.bfloat16, device=g.device).contiguous(memory_format=torch.channels_last)
             gf[:, :, ::2, ::2] = g
             g = gf
         g = g.contiguous(memory_format=torch.channels_last)
         gx = gw = None
-        k = w_exp.shape[2]
+        if composed:
+            w_exp = expand_group_weights(w16, groups).contiguous(memory_format=torch.channels_last)
         if ctx.needs_input_grad[0]:
             if composed:
                 parts = [ops.conv2d_dgrad(_window(g, sg), w_exp[sg * SG:(sg + 1) * SG], (n, SG, h, w),
@@ -109,18 +115,26 @@ class GroupedConvFn(torch.autograd.Function):
                          for sg in range(sgs)]
                 gx = torch.cat(parts, 1).contiguous(memory_format=torch.channels_last)
             else:
-                gx = ops.conv2d_dgrad_grouped(g, ops.grouped_dgrad_weights(w_exp, scale), x_shape, 1, pad)
+                _, wd = ops.grouped_expand_weights(w16, groups, scale, False, True)
+                gx = ops.conv2d_dgrad_grouped(g, wd, x_shape, 1, pad)
         if ctx.needs_input_grad[1]:
             if composed or c % 128:
+                if not composed:
+                    w_exp = expand_group_weights(w16, groups).contiguous(memory_format=torch.channels_last)
                 parts = [ops.conv2d_wgrad(_window(x, sg), _window(g, sg), (SG, SG, k, k), 1, pad,
                                           None if scale is None else scale[sg * SG:(sg + 1) * SG].contiguous())
                          for sg in range(sgs)]
-                gw_exp = torch.cat(parts, 0)
+                gw = collapse_group_grads(torch.cat(parts, 0), groups)
             else:
-                gw_exp = ops.conv2d_wgrad_grouped(x, g, k, 1, pad, scale)
-            gw = collapse_group_grads(gw_exp, groups)
-        return gx, gw, None, None, None, None, None, None
+                gw128 = ops.conv2d_wgrad_grouped(x, g, k, 1, pad, scale, raw=True)
+                if ctx.wsink is not None:
+                    ops.grouped_collapse_wgrad(gw128, w_shape, groups, accumulate_into=ctx.wsink)   # straight into the arena
+                else:
+                    gw = ops.grouped_collapse_wgrad(gw128, w_shape, groups)
+        return gx, gw, None, None, None, None, None, None, None, None
 
 
-def conv2d_grouped(x, weight, groups, scale=None, shift=None, pad=1, relu=False, stride=1):
-    return GroupedConvFn.apply(x, weight, scale, shift, groups, pad, relu, stride)
+def conv2d_grouped(x, weight, groups, scale=None, shift=None, pad=1, relu=False, stride=1, w16=None, wsink=None):
+    """w16: a current bf16 copy of `weight` (e.g. the optimizer arena's); wsink: persistent fp32 gradient accumulator of `weight`
+    (then the weight gradient is ADDED there and None is returned to autograd)."""
+    return GroupedConvFn.apply(x, weight, scale, shift, groups, pad, relu, stride, w16, wsink)

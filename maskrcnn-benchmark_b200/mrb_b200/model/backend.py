@@ -516,7 +516,8 @@ class B200Backend(Backend):
             y = dcn.deform_conv_nhwc(y, om, w, self._weight16(w), a2, b2, relu=True, modulated=bool(c2.with_modulated_dcn),
                                      stride=1, pad=1, be=self, wsink=self.grad_sink(w))
         else:
-            y = grouped.conv2d_grouped(y, c2.weight, c2.groups, a2, b2, 1, True, s3)
+            y = grouped.conv2d_grouped(y, c2.weight, c2.groups, a2, b2, 1, True, s3, w16=self._weight16(c2.weight),
+                                       wsink=self.grad_sink(c2.weight))
         if blk.downsample is not None:
             ad, bd = blk._aff_d.get()
             idn = self.conv(x, blk.downsample[0].weight, ad, bd, stride=sd)

@@ -145,6 +145,44 @@ def grouped_dgrad_weights(w_exp, scale=None):
     return w.reshape(-1).to(torch.bfloat16).contiguous()
 
 
+def grouped_expand_weights(w16, groups, scale=None, fwd=True, dgrad=False):
+    """One launch: the block-diagonal expansions of a grouped filter.  w16: bf16 [C, C/groups, kh, kw] channels_last (KRSC).
+    -> (w_exp [C, 64, kh, kw] channels_last bf16 or None, wd_flat bf16 [C*kh*kw*64] or None); see csrc/grouped_prep.cu."""
+    w16 = _nhwc(w16, "grouped_expand_weights(w16)")
+    if w16.dtype != torch.bfloat16:
+        raise RuntimeError("grouped_expand_weights: bf16 weight required")
+    c, cg, kh, kw = w16.shape
+    w_exp = torch.empty((c, 64, kh, kw), dtype=torch.bfloat16, device=w16.device).contiguous(memory_format=torch.channels_last) if fwd else None
+    wd = torch.empty(c * kh * kw * 64, dtype=torch.bfloat16, device=w16.device) if dgrad else None
+    with torch.cuda.device(w16.device):
+        _c.check(lib.mrb_grouped_expand_weights(_c._ptr(w16), _c._ptr(scale), _c._ptr(w_exp), _c._ptr(wd), c, kh * kw, groups,
+                                                _c._stream()), "mrb_grouped_expand_weights")
+    _count(1)
+    return w_exp, wd
+
+
+def grouped_collapse_wgrad(gw128, w_shape, groups, accumulate_into=None):
+    """Expanded weight gradient [C, taps, 128] fp32 (conv2d_wgrad_grouped_raw) -> the grouped layout [C, C/groups, kh, kw]
+    (channels_last memory), or ADDED into `accumulate_into` (any dense layout of that shape)."""
+    c, cg, kh, kw = w_shape
+    if accumulate_into is not None:
+        out, acc = accumulate_into, 1
+        if out.dtype != torch.float32 or tuple(out.shape) != tuple(w_shape):
+            raise RuntimeError("grouped_collapse_wgrad: accumulate_into must be fp32 shaped like the weight")
+    else:
+        out, acc = torch.empty(tuple(w_shape), dtype=torch.float32, device=gw128.device).contiguous(memory_format=torch.channels_last), 0
+    s = out.stride()
+    with torch.cuda.device(gw128.device):
+        # tap stride: taps are enumerated (r, q) row-major; a dense [.., kh, kw] block has stride(q) = s[3], stride(r) = s[2] = kw * s[3]
+        if s[2] != kw * s[3]:
+            raise RuntimeError("grouped_collapse_wgrad: unsupported weight layout")
+        _c.check(lib.mrb_grouped_collapse_wgrad(_c._ptr(gw128), _c._ptr(out), c, kh * kw, groups, ctypes.c_longlong(s[0]),
+                                                ctypes.c_longlong(s[1]), ctypes.c_longlong(s[3]), acc, _c._stream()),
+                 "mrb_grouped_collapse_wgrad")
+    _count(1)
+    return out
+
+
 def conv2d_dgrad_grouped(grad_out, wd_flat, x_shape, stride=1, pad=1, add=None, relu_mask=None):
     """Data gradient of a grouped (MRB_CONV_GROUPED64) convolution from the prepared weights of grouped_dgrad_weights."""
     if stride != 1:
@@ -169,10 +207,10 @@ def conv2d_dgrad_grouped(grad_out, wd_flat, x_shape, stride=1, pad=1, add=None, 
     return gx
 
 
-def conv2d_wgrad_grouped(x, grad_out, k, stride=1, pad=1, scale=None):
+def conv2d_wgrad_grouped(x, grad_out, k, stride=1, pad=1, scale=None, raw=False):
     """Weight gradient of a grouped convolution as the EXPANDED fp32 [C, 64, k, k] (row co against the 64 input channels
     of its super-group): the kernel produces each 128-channel Cout tile against its own 128 input channels, the two
-    diagonal 64 x 64 blocks are kept."""
+    diagonal 64 x 64 blocks are kept.  raw=True returns the kernel's [C, k*k, 128] buffer (for grouped_collapse_wgrad)."""
     if stride != 1:
         raise RuntimeError("conv2d_wgrad_grouped: stride 1 only")
     x = _nhwc(x, "conv2d_wgrad_grouped(x)")
@@ -186,6 +224,8 @@ def conv2d_wgrad_grouped(x, grad_out, k, stride=1, pad=1, scale=None):
         _c.check(lib.mrb_conv2d_wgrad(ctypes.byref(p), _c._ptr(x), _c._ptr(grad_out), _c._ptr(scale), _c._ptr(gw), _c._stream()),
                  "mrb_conv2d_wgrad(grouped)")
     _count(1, ("wgrad", n, c, h, w, c, k, 1, pad, c // 64))
+    if raw:
+        return gw
     gw = gw.view(c // 128, 2, 64, k * k, 2, 64)                       # [tile, half, co_l, tap, half', ci_l]
     diag = torch.stack([gw[:, 0, :, :, 0], gw[:, 1, :, :, 1]], 1)     # [tile, half, co_l, tap, ci_l]
     return diag.reshape(c, k, k, 64).permute(0, 3, 1, 2)              # logical [C, 64, k, k]

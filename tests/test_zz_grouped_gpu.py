@@ -39,3 +39,28 @@ def test_grouped_conv_matches_torch(built_lib, monkeypatch, mode, c, groups, h, 
     yd.backward(go.to(DEV))
     assert rel(xd.grad, xr.grad) < 2e-2
     assert rel(wd.grad, wr.grad) < 2e-2
+
+
+@pytest.mark.parametrize("c,groups", [(256, 32), (512, 32), (128, 4), (2048, 32)])
+def test_grouped_prep_kernels_match_the_python_expansion(built_lib, c, groups):
+    """csrc/grouped_prep.cu (one launch each) == the torch composition pinned on CPU by tests/test_grouped_cpu.py."""
+    from mrb_b200 import ops
+    from mrb_b200.grouped import collapse_group_grads, expand_group_weights
+    g = torch.Generator().manual_seed(c + groups)
+    cg = c // groups
+    w16 = torch.randn(c, cg, 3, 3, generator=g).bfloat16().to(DEV).contiguous(memory_format=torch.channels_last)
+    scale = (torch.rand(c, generator=g) + 0.5).to(DEV)
+    w_exp, wd = ops.grouped_expand_weights(w16, groups, scale, True, True)
+    want_exp = expand_group_weights(w16, groups)
+    assert torch.equal(w_exp, want_exp)
+    want_wd = ops.grouped_dgrad_weights(want_exp, scale)
+    assert float((wd.float() - want_wd.float()).abs().max()) <= 1e-2 * float(want_wd.float().abs().max())     # bf16(w * scale) either way
+    if c % 128 == 0:
+        gw128 = torch.randn(c, 9, 128, generator=g).to(DEV)
+        got = ops.grouped_collapse_wgrad(gw128, (c, cg, 3, 3), groups)
+        v = gw128.view(c // 128, 2, 64, 9, 2, 64)
+        diag = torch.stack([v[:, 0, :, :, 0], v[:, 1, :, :, 1]], 1).reshape(c, 3, 3, 64).permute(0, 3, 1, 2)
+        assert torch.equal(got, collapse_group_grads(diag, groups))
+        acc = torch.ones(c, cg, 3, 3, device=DEV)                       # NCHW-contiguous destination, accumulate
+        ops.grouped_collapse_wgrad(gw128, (c, cg, 3, 3), groups, accumulate_into=acc)
+        assert torch.equal(acc, got + 1)
