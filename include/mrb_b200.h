@@ -215,6 +215,13 @@ typedef struct mrb_conv_params {
   long long x_pitch[3];
   long long y_pitch[3];
 } mrb_conv_params;
+/* Mask-head training targets from polygon segmentations: project_masks_on_boxes (modeling/roi_heads/mask_head/loss.py:11-42,
+ * the host-side per-proposal crop/resize/rasterise loop) as one launch.  polys_xy: packed (x, y) vertices, image
+ * coordinates; poly_start[num_polys + 1], inst_start[num_instances + 1]: CSR ranges (instance = union of its polygons);
+ * rois [R,4] xyxy; inst_of_roi [R]; out [R, M, M] fp32 in {0,1}.  Cell-centre, even-odd rule (see csrc/mask_targets.cu). */
+int mrb_mask_targets_polygons(const float* polys_xy, const int* poly_start, const int* inst_start, const float* rois,
+                              const int* inst_of_roi, float* out, int num_rois, int mask_size, mrb_stream_t stream);
+
 /* Operand preparation for MRB_CONV_GROUPED64 (csrc/grouped_prep.cu).  weight: the grouped filter [C][taps][C/groups] bf16
  * (KRSC).  w_exp / wd_exp: [C][taps][64] bf16 -- the forward operand and the (flipped, per-Cout scaled) data-gradient operand
  * of mrb_conv2d_fwd / mrb_conv2d_dgrad_prepared; either may be NULL.  mrb_grouped_collapse_wgrad folds the [C][taps][128]

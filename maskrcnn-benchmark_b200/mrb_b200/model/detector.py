@@ -41,6 +41,20 @@ class GeneralizedRCNN(nn.Module):
         n, s = labels.shape
         res = self.cfg.mask_resolution
         gt_all = torch.stack([t["boxes"][gidx[i]] for i, t in enumerate(targets)])          # [n, s, 4]
+        # polygon segmentations ("polygons": per instance, a list of flat [x0, y0, x1, y1, ...] sequences -- the reference's
+        # SegmentationMask(mode="poly")): rasterised on the GPU, one launch (ops.mask_targets_polygons); without them the
+        # instance mask of a ground-truth box is its rectangle
+        polyset = inst_all = None
+        if all("polygons" in t for t in targets):
+            from mrb_b200 import ops
+            polyset = targets[0].get("_polyset")
+            if polyset is None:
+                polyset = ops.PolygonSet([p for t in targets for p in t["polygons"]], labels.device)
+            off, acc = [], 0
+            for t in targets:
+                off.append(acc)
+                acc += len(t["polygons"])
+            inst_all = gidx + torch.tensor(off, device=gidx.device, dtype=gidx.dtype)[:, None]   # [n, s] global instance index
         m = self.cfg.mask_rois_per_image
         if m > 0:
             posm = labels > 0
@@ -50,7 +64,10 @@ class GeneralizedRCNN(nn.Module):
             lab_sel = torch.gather(labels, 1, order).reshape(-1).clamp(min=0)
             gt_sel = torch.gather(gt_all, 1, order[..., None].expand(-1, -1, 4)).reshape(-1, 4)
             sel_logits = mask.run(be, feats, rois_sel, select=lab_sel)
-            tgt = mask.mask_targets(gt_sel, rois_sel[:, 1:], res)
+            if polyset is not None:
+                tgt = ops.mask_targets_polygons(polyset, rois_sel[:, 1:], torch.gather(inst_all, 1, order).reshape(-1), res)
+            else:
+                tgt = mask.mask_targets(gt_sel, rois_sel[:, 1:], res)
             bce = torch.nn.functional.binary_cross_entropy_with_logits(sel_logits.float(), tgt,
                                                                        reduction="none").mean((1, 2))
             return torch.where(wsel > 0, bce, torch.zeros((), dtype=bce.dtype, device=bce.device)).sum() / wsel.sum().clamp(min=1)
@@ -58,7 +75,10 @@ class GeneralizedRCNN(nn.Module):
         pos = (lab > 0).nonzero().squeeze(1)             # keep_only_positive_boxes (mask_head.py:11-32)
         rois_pos = rois[pos]
         logits = mask.run(be, feats, rois_pos)
-        tgt = mask.mask_targets(gt_all.reshape(n * s, 4)[pos], rois_pos[:, 1:], res)
+        if polyset is not None:
+            tgt = ops.mask_targets_polygons(polyset, rois_pos[:, 1:], inst_all.reshape(-1)[pos], res)
+        else:
+            tgt = mask.mask_targets(gt_all.reshape(n * s, 4)[pos], rois_pos[:, 1:], res)
         return mask.loss(logits, lab[pos], tgt)
 
     def forward(self, images, image_sizes, targets=None, generator=None):

@@ -432,6 +432,44 @@ def dcn_backward_nhwc(x, om, gcols, k=3, stride=1, pad=1, dil=1, modulated=False
     return gx, gom
 
 
+# ------------------------------------------------------------------------- mask targets from polygons
+class PolygonSet:
+    """Polygon segmentations of the instances of a batch, packed for mrb_mask_targets_polygons.
+    instances: list (one entry per instance) of lists of flat [x0, y0, x1, y1, ...] coordinate sequences."""
+
+    def __init__(self, instances, device):
+        xy, pstart, istart = [], [0], [0]
+        for polys in instances:
+            for p in polys:
+                p = [float(v) for v in p]
+                if len(p) % 2:
+                    raise RuntimeError("PolygonSet: odd number of coordinates")
+                xy.extend(p)
+                pstart.append(len(xy) // 2)
+            istart.append(len(pstart) - 1)
+        self.xy = torch.tensor(xy if xy else [0.0, 0.0], dtype=torch.float32, device=device)
+        self.poly_start = torch.tensor(pstart, dtype=torch.int32, device=device)
+        self.inst_start = torch.tensor(istart, dtype=torch.int32, device=device)
+        self.num_instances = len(instances)
+
+
+def mask_targets_polygons(polyset, rois, inst_of_roi, m):
+    """[R, m, m] fp32 {0,1}: instance inst_of_roi[r] rasterised on the m x m grid of box rois[r] (xyxy)."""
+    rois = rois.float().contiguous()
+    idx = inst_of_roi.to(torch.int32).contiguous()
+    if not rois.is_cuda:
+        raise RuntimeError("mask_targets_polygons: expected CUDA tensors (no CPU path)")
+    r = rois.shape[0]
+    out = torch.empty((r, m, m), dtype=torch.float32, device=rois.device)
+    if r:
+        with torch.cuda.device(rois.device):
+            _c.check(lib.mrb_mask_targets_polygons(_c._ptr(polyset.xy), _c._ptr(polyset.poly_start), _c._ptr(polyset.inst_start),
+                                                   _c._ptr(rois), _c._ptr(idx), _c._ptr(out), r, m, _c._stream()),
+                     "mrb_mask_targets_polygons")
+        _count(1)
+    return out
+
+
 # ------------------------------------------------------------------------- fused FPN ROIAlign
 class _RoiAlignFpn(torch.autograd.Function):
     @staticmethod
