@@ -1033,7 +1033,7 @@ static int conv_launch(const ConvPlan& pl, const void* x, const void* w, int cin
     const size_t set_b = (size_t)tile_bufs * ceil_div(bn, 64) * kABytes;
     auto stages_with = [&](int sets) { return (int)(((long long)227 * 1024 - (long long)fixed0 - (long long)(sets * set_b)) / (kABytes + bn * 128)); };
     if ((residual || relu_mask) && stages_with(3) >= 3) tile_sets = 3;
-    if (sets_req == 2 || sets_req == 3) tile_sets = sets_req;
+    if (sets_req >= 1 && sets_req <= 3) tile_sets = sets_req;
     if (stages_with(tile_sets) < 2) {
       if (tile_sets == 3 && stages_with(2) >= 2) tile_sets = 2;
       else { tma_epi = false; tile_bufs = 1; }

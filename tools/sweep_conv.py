@@ -18,17 +18,17 @@ DEV = "cuda:0"
 # (kind, n, cin, h, w, cout, k, res, [plans])
 S33 = ["8,16,256,0", "8,16,128,1,2", "8,16,128,1,3", "4,32,256,0", "4,32,128,1,2"]
 SHAPES = [
-    ("fwd", 2, 256, 50, 84, 256, 3, False, ["4,32,256,0", "4,32,128,1,2", "10,12,128,1,2", "10,12,256,0", "7,18,128,1,2", "5,25,128,1,2", "10,12,64,1,2"]),
+    ("fwd", 2, 256, 50, 84, 256, 3, False, ["4,32,256,0", "4,32,128,1,2", "10,12,128,1,2", "10,12,256,0", "10,12,128,0", "10,12,128,1,1", "10,12,64,1,1", "10,12,64,0"]),
     ("dgrad", 2, 256, 50, 84, 256, 3, False, ["4,32,128,1,2", "10,12,128,1,2", "10,12,128,1,3", "10,12,256,0"]),
-    ("fwd", 2, 512, 25, 42, 512, 3, False, ["8,16,128,1,2", "9,14,128,1,2", "4,21,128,1,2", "9,14,64,1,2", "5,21,64,1,2", "5,21,128,1,2", "9,14,256,0"]),
-    ("fwd", 2, 128, 100, 168, 128, 3, False, ["8,16,128,1,2", "10,12,128,1,2", "9,14,128,1,2", "8,16,64,1,2"]),
+    ("fwd", 2, 512, 25, 42, 512, 3, False, ["9,14,128,1,2", "9,14,64,1,2", "9,14,256,0", "9,14,128,0", "9,14,128,1,1", "9,14,64,0", "9,14,64,1,1"]),
+    ("fwd", 2, 128, 100, 168, 128, 3, False, ["8,16,128,1,2", "8,16,128,0", "8,16,128,1,1"]),
     ("fwd", 2, 64, 200, 336, 64, 3, False, ["8,16,64,1,2", "10,12,64,1,2", "8,16,64,0"]),
     ("fwd", 2, 256, 200, 336, 256, 3, False, S33),
     ("fwd", 2, 64, 200, 336, 256, 1, False, ["1,128,128,1,2", "1,128,128,1,3", "1,128,256,0", "1,128,64,1,2", "1,128,64,1,3"]),
     ("fwd", 2, 64, 200, 336, 256, 1, True, ["1,128,128,1,2", "1,128,128,1,3", "1,128,64,1,3"]),
     ("fwd", 2, 256, 200, 336, 64, 1, False, ["1,128,64,1,2", "1,128,64,1,3", "1,128,64,0"]),
     ("fwd", 2, 256, 50, 84, 1024, 1, True, ["1,128,128,1,2", "1,128,128,1,3", "1,128,256,0", "1,114,128,1,3"]),
-    ("fwd", 2, 1024, 50, 84, 256, 1, False, ["1,128,128,1,2", "1,128,256,0", "1,128,64,1,2", "1,114,128,1,2"]),
+    ("fwd", 2, 1024, 50, 84, 256, 1, False, ["1,128,128,1,2", "1,128,256,0", "1,128,128,0", "1,128,128,1,1", "1,128,64,0"]),
     ("fwd", 2, 512, 25, 42, 2048, 1, True, ["1,128,128,1,2", "1,128,128,1,3", "1,128,256,0"]),
     ("fwd", 2, 2048, 25, 42, 512, 1, False, ["1,128,128,1,2", "1,128,256,0", "1,128,64,1,2"]),
     ("fwd", 256, 256, 14, 14, 256, 3, False, ["8,16,256,0", "9,14,256,0", "7,14,256,0", "9,14,128,1,2"]),
