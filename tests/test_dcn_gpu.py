@@ -56,9 +56,19 @@ def test_dcn_fp32_C_path_at_baseline_shapes(built_lib, c, h, w, modulated):
         assert _rel(md.grad, gm) < 1e-4
 
 
+def _rel2(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-12))
+
+
+@pytest.mark.parametrize("relu", [False, True])
 @pytest.mark.parametrize("modulated", [False, True])
 @pytest.mark.parametrize("c,h,w", SHAPES)
-def test_dcn_tensor_core_path_at_baseline_shapes(built_lib, c, h, w, modulated):
+def test_dcn_tensor_core_path_at_baseline_shapes(built_lib, c, h, w, modulated, relu):
+    """relu=False: max-norm comparison of every output (2e-2 of the tensor's scale: bf16 operands).  relu=True adds the fused
+    FrozenBN + ReLU epilogue: a pre-activation within bf16 rounding of 0 can land on the other side of the ReLU than in the fp32
+    checker, which switches that output's whole back-propagated contribution on or off -- isolated O(1) deviations by
+    construction -- so the gradients are compared in relative L2 norm there."""
     from mrb_b200 import dcn
     x, wt, off, mlogit, go = _inputs(c, h, w, modulated, 100 + c)
     # the checker sees the same bf16-rounded activations / weights / incoming gradient
@@ -69,7 +79,9 @@ def test_dcn_tensor_core_path_at_baseline_shapes(built_lib, c, h, w, modulated):
     xr, wr, orq = xb.float().requires_grad_(True), wb.float().requires_grad_(True), off.clone().requires_grad_(True)
     mr = mlogit.clone().requires_grad_(True) if modulated else None
     conv = deform_conv2d(xr, orq, wr, None, stride=1, padding=1, mask=None if mr is None else mr.sigmoid())
-    y = torch.relu(conv * scale[None, :, None, None] + shift[None, :, None, None])
+    y = conv * scale[None, :, None, None] + shift[None, :, None, None]
+    if relu:
+        y = torch.relu(y)
     y.backward(gb.float())
     # product path: NHWC bf16 activations, fp32 NHWC offsets (+ mask logits) padded to a multiple of 8 channels
     cl = dict(memory_format=torch.channels_last)
@@ -82,13 +94,14 @@ def test_dcn_tensor_core_path_at_baseline_shapes(built_lib, c, h, w, modulated):
     xd = xb.to(DEV).contiguous(**cl).requires_grad_(True)
     wd = wt.to(DEV).contiguous(**cl).requires_grad_(True)
     w16 = wb.to(DEV).contiguous(**cl)
-    yd = dcn.deform_conv_nhwc(xd, omd, wd, w16, scale.to(DEV), shift.to(DEV), relu=True, modulated=modulated)
+    yd = dcn.deform_conv_nhwc(xd, omd, wd, w16, scale.to(DEV), shift.to(DEV), relu=relu, modulated=modulated)
     assert yd.dtype == torch.bfloat16 and yd.shape == y.shape
     yd.backward(gb.to(DEV))
     assert _rel(yd.detach(), y.detach()) < 1e-2
-    assert _rel(xd.grad, xr.grad) < 2e-2
-    assert _rel(wd.grad, wr.grad) < 2e-2
-    assert _rel(omd.grad[:, :18], orq.grad) < 2e-2
+    err = _rel2 if relu else _rel
+    assert err(xd.grad, xr.grad) < 2e-2
+    assert err(wd.grad, wr.grad) < 2e-2
+    assert err(omd.grad[:, :18], orq.grad) < 2e-2
     if modulated:
-        assert _rel(omd.grad[:, 18:27], mr.grad) < 2e-2
+        assert err(omd.grad[:, 18:27], mr.grad) < 2e-2
     assert float(omd.grad[:, 27 if modulated else 18:].abs().max()) == 0.0
