@@ -133,6 +133,9 @@ class ParamArena:
         # A/B switch.  Must be identical on every rank (collective order): pass `early_reduce` explicitly from rank-0
         # config in multi-rank programs; the environment variable is only the single-launcher default.
         self.early = (os.environ.get("MRB_EARLY_REDUCE", "1") != "0") if early_reduce is None else bool(early_reduce)
+        # per-stage buckets (FPN, layer4, layer3 ...) on top of the heads bucket; MRB_BUCKETED_REDUCE=0 keeps round 1's two-way
+        # split (heads early, everything else at sync) for A/B runs.  Same on every rank.
+        self.bucketed = os.environ.get("MRB_BUCKETED_REDUCE", "1") != "0"
         self.sinks, self.views16 = {}, {}
         off = 0
         with torch.no_grad():
@@ -163,6 +166,8 @@ class ParamArena:
         nodes) once every gradient kernel of the bucket has been issued, so that it overlaps the rest of the backward pass.
         "backbone.fpn." also carries the bias region.  No-op for a single rank / unknown or already reduced buckets."""
         if self.world <= 1 or not self.early or name not in self.buckets or name in self._pending:
+            return
+        if not self.bucketed and name != "heads":
             return
         import torch.distributed as dist
         lo, hi = self.buckets[name]
