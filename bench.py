@@ -313,6 +313,34 @@ def ops_metrics(device, peaks):
         kw["reference_cuda_us"] = round(timed(lambda: R.sigmoid_focalloss_backward(ld, td, dl, 80, 2.0, 0.25), flush, reps=5) * 1e6, 1)
     t = timed(lambda: _C.sigmoid_focalloss_backward(ld, td, dl, 80, 2.0, 0.25), flush, reps=5)
     rec("sigmoid_focalloss_backward (201600x80)", 4 * 201600 * 80 * 3 + 4 * 201600, t, **kw)
+    # deformable conv v2 3x3 on the three BASELINE config-5 layer shapes: tensor-core path of the model graph (mrb_b200.dcn) vs the
+    # fp32 `_C` path vs the reference's own CUDA implementation (im2col + cuBLAS)
+    try:
+        from maskrcnn_benchmark import layers
+        from mrb_b200 import dcn
+        for (c, h, w) in ((128, 100, 168), (256, 50, 84), (512, 25, 42)):
+            g = torch.Generator().manual_seed(c)
+            x = torch.randn(2, c, h, w, generator=g).to(device)
+            wt = (torch.randn(c, c, 3, 3, generator=g) / (3 * c ** 0.5)).to(device)
+            om = torch.zeros(2, 32, h, w)
+            om[:, :18] = torch.randn(2, 18, h, w, generator=g) * 2
+            om[:, 18:27] = torch.randn(2, 9, h, w, generator=g)
+            omd = om.to(device).contiguous(memory_format=torch.channels_last)
+            x16 = x.bfloat16().contiguous(memory_format=torch.channels_last)
+            w16 = wt.bfloat16().contiguous(memory_format=torch.channels_last)
+            flops = 2.0 * 2 * h * w * c * c * 9
+            t_tc = timed(lambda: dcn.deform_conv_nhwc(x16, omd, wt, w16, None, None, relu=True, modulated=True), flush, reps=5)
+            off, msk = omd[:, :18].contiguous(), omd[:, 18:27].sigmoid().contiguous()
+            t_f32 = timed(lambda: layers.modulated_deform_conv(x, off, msk, wt, None, 1, 1, 1, 1, 1), flush, reps=3)
+            d = {"op": "modulated deform conv 3x3 fwd, 2x%dx%dx%d" % (c, h, w), "us": round(t_tc * 1e6, 1), "path": "tensor-core (sampler + tcgen05 GEMM)",
+                 "tflops": round(flops / t_tc / 1e12, 1), "fp32_C_path_us": round(t_f32 * 1e6, 1)}
+            if R is not None:
+                out_r, bias0 = x.new_empty(2, c, h, w), x.new_zeros(c)
+                d["reference_cuda_us"] = round(timed(lambda: R.modulated_deform_conv_forward(
+                    x, wt, bias0, x.new_empty(0), off, msk, out_r, x.new_empty(0), 3, 3, 1, 1, 1, 1, 1, 1, 1, 1, False), flush, reps=3) * 1e6, 1)
+            out.append(d)
+    except Exception as e:
+        out.append({"op": "modulated deform conv", "error": repr(e)[:200]})
     return {"peak_hbm_gbs": hbm, "timing": "CUDA events, L2 flushed between launches, median of 5",
             "reference_cuda": "the reference's csrc/cuda kernels compiled unmodified for sm_100a (oracle/build_ref.py::build_cuda), same "
                               "inputs, same timing" if R is not None else "not built on this box", "rows": out}
