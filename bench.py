@@ -399,8 +399,9 @@ def _ref_inputs(n, seed, device, with_masks=True):
     return il, targets
 
 
-def cpu_reference_step(cfg_name, n_images, threads):
-    """One step of the reference's own GeneralizedRCNN on the host cores (fp32): -> (images/s, seconds, kind)."""
+def cpu_reference_steps(cfg_name, n_images, threads, warmup, steps):
+    """The reference's own GeneralizedRCNN on the host cores (fp32), model built once, `steps` timed steps after `warmup`:
+    -> ([(images/s, seconds)], kind) or None without a reference mirror."""
     root, kind = _pure_reference_package()
     if root is None:
         return None
@@ -415,16 +416,21 @@ def cpu_reference_step(cfg_name, n_images, threads):
     torch.manual_seed(0)
     model = build_detection_model(cfg)
     model.train(train)
-    il, targets = _ref_inputs(n_images, 0, "cpu", with_masks=cfg.MODEL.MASK_ON)
-    t0 = time.perf_counter()
-    if train:
-        losses = model(il, targets)
-        sum(losses.values()).backward()
-    else:
-        with torch.no_grad():
-            model(il)
-    dt = time.perf_counter() - t0
-    return n_images / dt, dt, kind
+    out = []
+    for i in range(warmup + steps):
+        il, targets = _ref_inputs(n_images, i, "cpu", with_masks=cfg.MODEL.MASK_ON)
+        t0 = time.perf_counter()
+        if train:
+            model.zero_grad()
+            losses = model(il, targets)
+            sum(losses.values()).backward()
+        else:
+            with torch.no_grad():
+                model(il)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            out.append((n_images / dt, dt))
+    return out, kind
 
 
 def run_reference(args, rank, world):
@@ -436,15 +442,11 @@ def run_reference(args, rank, world):
     # process may use (all 128 hardware threads of the GPU box oversubscribe the ATen CPU convs: measured 88 s/image vs 6.5 s)
     avail = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     cores = int(os.environ.get("MRB_CPU_THREADS", 0)) or (max(1, avail // 2) if avail >= 16 else avail)
-    vals, kind = [], "port"
-    for i in range(args.warmup + args.steps):
-        r = cpu_reference_step(args.config, 1, cores)
-        if r is None:
-            print(json.dumps({"impl": "reference", "unavailable": "no reference mirror (baseline/_ref) on this box"}))
-            return
-        v, dt, kind = r
-        if i >= args.warmup:
-            vals.append((v, dt))
+    r = cpu_reference_steps(args.config, 1, cores, args.warmup, args.steps)
+    if r is None:
+        print(json.dumps({"impl": "reference", "unavailable": "no reference mirror (baseline/_ref) on this box"}))
+        return
+    vals, kind = r
     v = sum(x for x, _ in vals) / len(vals)
     ms = sum(d for _, d in vals) / len(vals) * 1e3
     sample = ("1 image (800x1333 padded to 800x1344) per step: the reference's own GeneralizedRCNN (%s), fp32 ATen CPU convs, "
