@@ -1012,6 +1012,11 @@ static int conv_launch(const ConvPlan& pl, const void* x, const void* w, int cin
       }
     }
   }
+  // Long-K narrow tiles without epilogue inputs: the per-thread epilogue needs 16 KB of staging instead of 64 KB of tile
+  // buffers, i.e. 6 ring stages instead of 4, and the main loop of these tiles is bound by (operand latency) / (ring depth):
+  // measured 17.3 vs 19.4 us (res4 3x3), 10.6 vs 12.2 us (1x1 1024->256), profiles/sweep_conv_r2_e.json.  With a residual or
+  // a ReLU mask to stage the TMA epilogue stays (per-thread loads of those were the 1.4 TB/s case of round 1).
+  if (tma_epi && bn <= 128 && !residual && !relu_mask && k_blocks_tile >= 8 && !grouped) tma_epi = false;
   int sets_req = 0;
   if (const char* e = getenv("MRB_CONV_TILE")) {     // "th,tw,bn,epi[,sets]": measurement override (tools/bench_conv.py sweeps)
     int v[5] = {0, 0, 0, -1, 0};

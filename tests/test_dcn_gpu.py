@@ -65,10 +65,8 @@ def _rel2(a, b):
 @pytest.mark.parametrize("modulated", [False, True])
 @pytest.mark.parametrize("c,h,w", SHAPES)
 def test_dcn_tensor_core_path_at_baseline_shapes(built_lib, c, h, w, modulated, relu):
-    """relu=False: max-norm comparison of every output (2e-2 of the tensor's scale: bf16 operands).  relu=True adds the fused
-    FrozenBN + ReLU epilogue: a pre-activation within bf16 rounding of 0 can land on the other side of the ReLU than in the fp32
-    checker, which switches that output's whole back-propagated contribution on or off -- isolated O(1) deviations by
-    construction -- so the gradients are compared in relative L2 norm there."""
+    """Forward (+ fused FrozenBN scale/shift, optionally ReLU) and all four gradients in max norm, 2e-2 of each tensor's scale
+    (bf16 operands)."""
     from mrb_b200 import dcn
     x, wt, off, mlogit, go = _inputs(c, h, w, modulated, 100 + c)
     # the checker sees the same bf16-rounded activations / weights / incoming gradient
@@ -79,10 +77,7 @@ def test_dcn_tensor_core_path_at_baseline_shapes(built_lib, c, h, w, modulated, 
     xr, wr, orq = xb.float().requires_grad_(True), wb.float().requires_grad_(True), off.clone().requires_grad_(True)
     mr = mlogit.clone().requires_grad_(True) if modulated else None
     conv = deform_conv2d(xr, orq, wr, None, stride=1, padding=1, mask=None if mr is None else mr.sigmoid())
-    y = conv * scale[None, :, None, None] + shift[None, :, None, None]
-    if relu:
-        y = torch.relu(y)
-    y.backward(gb.float())
+    y_lin = conv * scale[None, :, None, None] + shift[None, :, None, None]
     # product path: NHWC bf16 activations, fp32 NHWC offsets (+ mask logits) padded to a multiple of 8 channels
     cl = dict(memory_format=torch.channels_last)
     oc = 32 if modulated else 24
@@ -95,13 +90,21 @@ def test_dcn_tensor_core_path_at_baseline_shapes(built_lib, c, h, w, modulated, 
     wd = wt.to(DEV).contiguous(**cl).requires_grad_(True)
     w16 = wb.to(DEV).contiguous(**cl)
     yd = dcn.deform_conv_nhwc(xd, omd, wd, w16, scale.to(DEV), shift.to(DEV), relu=relu, modulated=modulated)
-    assert yd.dtype == torch.bfloat16 and yd.shape == y.shape
+    assert yd.dtype == torch.bfloat16 and yd.shape == y_lin.shape
     yd.backward(gb.to(DEV))
+    if relu:
+        # the checker takes the ReLU decision of the product's (bf16) output: a pre-activation within bf16 rounding of 0 would
+        # otherwise switch that output's whole back-propagated contribution on in one implementation and off in the other
+        # (measured without this: 3 % relative L2 on the gradients, isolated O(1) deviations; tools/dbg/dcn_debug.py)
+        keep = (yd.detach().float().cpu() > 0)
+        y = y_lin * keep
+    else:
+        y = y_lin
+    y.backward(gb.float())
     assert _rel(yd.detach(), y.detach()) < 1e-2
-    err = _rel2 if relu else _rel
-    assert err(xd.grad, xr.grad) < 2e-2
-    assert err(wd.grad, wr.grad) < 2e-2
-    assert err(omd.grad[:, :18], orq.grad) < 2e-2
+    assert _rel(xd.grad, xr.grad) < 2e-2
+    assert _rel(wd.grad, wr.grad) < 2e-2
+    assert _rel(omd.grad[:, :18], orq.grad) < 2e-2
     if modulated:
-        assert err(omd.grad[:, 18:27], mr.grad) < 2e-2
+        assert _rel(omd.grad[:, 18:27], mr.grad) < 2e-2
     assert float(omd.grad[:, 27 if modulated else 18:].abs().max()) == 0.0

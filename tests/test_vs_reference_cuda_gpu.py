@@ -110,18 +110,26 @@ def test_deform_conv_v1_baseline_shapes(C, R, c, h, w):
     off = (torch.randn(2, 18, h, w, generator=g) * 2).to(DEV)
     go = torch.randn(2, c, h, w, generator=g).to(DEV)
     geom = (3, 3, 1, 1, 1, 1, 1, 1, 1, 1)          # kW kH dW dH padW padH dilW dilH group deformable_group
-    outs = []
-    for M in (R, C):
-        out, cols, ones = x.new_empty(2, c, h, w), x.new_empty(0), x.new_empty(0)
-        # im2col_step 1: the reference's batched-step reshapes (deform_conv_cuda.cu:226-236 `.view` of a transposed
-        # buffer) no longer run on a current PyTorch; its per-image path is intact
-        M.deform_conv_forward(x, wt, off, out, cols, ones, *geom, 1)
-        gi, goff, gw = torch.zeros_like(x), torch.zeros_like(off), torch.zeros_like(wt)
-        M.deform_conv_backward_input(x, off, go, gi, goff, wt, x.new_empty(0), *geom, 1)
-        M.deform_conv_backward_parameters(x, off, go, gw, x.new_empty(0), x.new_empty(0), *geom, 1.0, 1)
-        outs.append((out, gi, goff, gw))
-    for a, b, tol in zip(outs[1], outs[0], (1e-4, 1e-4, 1e-4, 2e-4)):
-        assert _rel(a, b) < tol
+    # ours: the whole batch, im2col_step = batch (what layers/dcn/deform_conv_func.py passes)
+    out, gi, goff, gw = x.new_empty(2, c, h, w), torch.zeros_like(x), torch.zeros_like(off), torch.zeros_like(wt)
+    C.deform_conv_forward(x, wt, off, out, x.new_empty(0), x.new_empty(0), *geom, 2)
+    C.deform_conv_backward_input(x, off, go, gi, goff, wt, x.new_empty(0), *geom, 2)
+    C.deform_conv_backward_parameters(x, off, go, gw, x.new_empty(0), x.new_empty(0), *geom, 1.0, 2)
+    # reference: ONE IMAGE PER CALL.  Its v1 host code re-views `columns` / `weight` inside the per-step loop
+    # (deform_conv_cuda.cu:226-229) and views a transposed buffer (:240-246); with more than one step, or a step of more than
+    # one image, those views throw on a current PyTorch.  The kernels are the same either way; dW accumulates across calls.
+    r_out, r_gi, r_goff, r_gw = [], [], [], torch.zeros_like(wt)
+    for i in range(2):
+        xi, oi, gi_ = x[i:i + 1].contiguous(), off[i:i + 1].contiguous(), go[i:i + 1].contiguous()
+        o = x.new_empty(1, c, h, w)
+        R.deform_conv_forward(xi, wt, oi, o, x.new_empty(0), x.new_empty(0), *geom, 1)
+        a, b = torch.zeros_like(xi), torch.zeros_like(oi)
+        R.deform_conv_backward_input(xi, oi, gi_, a, b, wt, x.new_empty(0), *geom, 1)
+        R.deform_conv_backward_parameters(xi, oi, gi_, r_gw, x.new_empty(0), x.new_empty(0), *geom, 1.0, 1)
+        r_out.append(o); r_gi.append(a); r_goff.append(b)
+    want = (torch.cat(r_out), torch.cat(r_gi), torch.cat(r_goff), r_gw)
+    for got, ref, tol in zip((out, gi, goff, gw), want, (1e-4, 1e-4, 1e-4, 2e-4)):
+        assert _rel(got, ref) < tol
 
 
 @pytest.mark.parametrize("c,h,w", DCN_SHAPES)
