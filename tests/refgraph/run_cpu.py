@@ -15,6 +15,10 @@ model, cfg = common.build(cfgname)
 model.train()
 il, targets = common.inputs()
 l0, g0 = common.train_step(model, il, targets, reseed)
+model.eval()
+with torch.no_grad():
+    dets0 = model(il)
+model.train()
 from oracle.cpu_backend import CpuCheckerBackend  # noqa: E402
 from mrb_b200.fuse import fuse_model  # noqa: E402
 rep = fuse_model(model, CpuCheckerBackend())
@@ -31,4 +35,13 @@ for n in g0:
 model.eval()
 with torch.no_grad():
     dets = model(il)
+# eval mode: the fused graph returns the same detections (boxes, scores, labels[, masks]) as the unfused reference forward
+for a, b in zip(dets0, dets):
+    assert len(a) == len(b), (len(a), len(b))
+    if len(a):
+        torch.testing.assert_close(a.bbox, b.bbox, rtol=1e-4, atol=1e-3)
+        torch.testing.assert_close(a.get_field("scores"), b.get_field("scores"), rtol=1e-4, atol=1e-5)
+        assert torch.equal(a.get_field("labels"), b.get_field("labels"))
+        if a.has_field("mask"):
+            torch.testing.assert_close(a.get_field("mask"), b.get_field("mask"), rtol=1e-3, atol=1e-4)
 print(json.dumps({"report": rep, "losses": l1, "worst_rel_grad": worst, "n_grads": len(g0), "dets": [len(d) for d in dets]}))

@@ -19,7 +19,8 @@ def _have_ref():
     return refenv.find_reference_root() is not None
 
 
-@pytest.mark.parametrize("cfgname", ["e2e_mask_rcnn_R_50_FPN_1x.yaml", "e2e_mask_rcnn_X_101_32x8d_FPN_1x.yaml"])
+@pytest.mark.parametrize("cfgname", ["e2e_mask_rcnn_R_50_FPN_1x.yaml", "e2e_mask_rcnn_X_101_32x8d_FPN_1x.yaml",
+                                     "e2e_faster_rcnn_R_50_FPN_1x.yaml"])
 def test_fused_reference_graph_equals_reference_train_step(built_lib, oracle_mod, cfgname):
     if not _have_ref():
         pytest.skip("reference checkout absent")
@@ -28,7 +29,8 @@ def test_fused_reference_graph_equals_reference_train_step(built_lib, oracle_mod
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     out = json.loads(r.stdout.strip().splitlines()[-1])
     f = out["report"]["fused"]
-    assert f.get("stem") == 1 and f.get("fpn") == 1 and f.get("rpn_head") == 1 and f.get("box_head") == 1 and f.get("mask_head") == 1
+    assert f.get("stem") == 1 and f.get("fpn") == 1 and f.get("rpn_head") == 1 and f.get("box_head") == 1
+    assert f.get("mask_head", 0) == (0 if "faster" in cfgname else 1)
     assert sum(v for k, v in f.items() if k.startswith("bottleneck")) == (33 if "X_101" in cfgname else 16)
     assert not out["report"]["skipped"]
     assert out["n_grads"] > 60 and out["worst_rel_grad"] < 1e-3
