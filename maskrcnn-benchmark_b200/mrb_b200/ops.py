@@ -65,7 +65,20 @@ def _view(t, name):
 FLAG_PAD_W, FLAG_GROUPED64 = 1, 2          # mrb_conv_params.flags (include/mrb_b200.h)
 
 
+_PARAMS = {}
+
+
 def _params(x_shape, w_shape, stride, pad, relu, out_dtype, out_hw=None, x_pitch=None, y_pitch=None, grouped=False):
+    """mrb_conv_params of a launch (+ output size); memoised per geometry -- the structs are never mutated after creation."""
+    key = (tuple(x_shape), tuple(w_shape), stride, pad, bool(relu), out_dtype, None if out_hw is None else tuple(out_hw),
+           x_pitch, y_pitch, grouped)
+    hit = _PARAMS.get(key)
+    if hit is None:
+        hit = _PARAMS[key] = _make_params(x_shape, w_shape, stride, pad, relu, out_dtype, out_hw, x_pitch, y_pitch, grouped)
+    return hit
+
+
+def _make_params(x_shape, w_shape, stride, pad, relu, out_dtype, out_hw=None, x_pitch=None, y_pitch=None, grouped=False):
     n, c, h, w = x_shape
     co, ci, kh, kw = w_shape
     if grouped:
@@ -124,7 +137,7 @@ def conv2d_fwd(x, weight, scale=None, bias=None, residual=None, stride=1, pad=0,
     for v in (scale, bias):
         if v is not None and (v.dtype != torch.float32 or v.numel() != p.cout or not v.is_contiguous()):
             raise RuntimeError("conv2d_fwd: scale/bias must be contiguous fp32 [Cout]")
-    with torch.cuda.device(x.device):
+    with _c.on_device(x.device):
         fn = lib.mrb_conv2d_fwd_up2 if residual_up2 else lib.mrb_conv2d_fwd
         _c.check(fn(ctypes.byref(p), _c._ptr(x), _c._ptr(weight), _c._ptr(scale), _c._ptr(bias),
                     _c._ptr(residual), _c._ptr(out), _c._stream()), "mrb_conv2d_fwd")
@@ -154,7 +167,7 @@ def grouped_expand_weights(w16, groups, scale=None, fwd=True, dgrad=False):
     c, cg, kh, kw = w16.shape
     w_exp = torch.empty((c, 64, kh, kw), dtype=torch.bfloat16, device=w16.device).contiguous(memory_format=torch.channels_last) if fwd else None
     wd = torch.empty(c * kh * kw * 64, dtype=torch.bfloat16, device=w16.device) if dgrad else None
-    with torch.cuda.device(w16.device):
+    with _c.on_device(w16.device):
         _c.check(lib.mrb_grouped_expand_weights(_c._ptr(w16), _c._ptr(scale), _c._ptr(w_exp), _c._ptr(wd), c, kh * kw, groups,
                                                 _c._stream()), "mrb_grouped_expand_weights")
     _count(1)
@@ -172,7 +185,7 @@ def grouped_collapse_wgrad(gw128, w_shape, groups, accumulate_into=None):
     else:
         out, acc = torch.empty(tuple(w_shape), dtype=torch.float32, device=gw128.device).contiguous(memory_format=torch.channels_last), 0
     s = out.stride()
-    with torch.cuda.device(gw128.device):
+    with _c.on_device(gw128.device):
         # tap stride: taps are enumerated (r, q) row-major; a dense [.., kh, kw] block has stride(q) = s[3], stride(r) = s[2] = kw * s[3]
         if s[2] != kw * s[3]:
             raise RuntimeError("grouped_collapse_wgrad: unsupported weight layout")
@@ -200,7 +213,7 @@ def conv2d_dgrad_grouped(grad_out, wd_flat, x_shape, stride=1, pad=1, add=None, 
             raise RuntimeError("conv2d_dgrad_grouped: add/relu_mask must be bf16 and shaped like x")
     add = _nhwc(add, "add") if add is not None else None
     relu_mask = _nhwc(relu_mask, "relu_mask") if relu_mask is not None else None
-    with torch.cuda.device(grad_out.device):
+    with _c.on_device(grad_out.device):
         _c.check(lib.mrb_conv2d_dgrad_prepared(ctypes.byref(p), _c._ptr(grad_out), _c._ptr(wd_flat), _c._ptr(add),
                                                _c._ptr(relu_mask), _c._ptr(gx), _c._stream()), "mrb_conv2d_dgrad_prepared(grouped)")
     _count(1, ("dgrad", n, c, h, w, c, k, 1, pad, c // 64))
@@ -220,7 +233,7 @@ def conv2d_wgrad_grouped(x, grad_out, k, stride=1, pad=1, scale=None, raw=False)
     if tuple(grad_out.shape) != (n, c, ho, wo) or c % 128:
         raise RuntimeError("conv2d_wgrad_grouped: grad_out shape mismatch or C %% 128 != 0")
     gw = torch.empty((c, k * k, 128), dtype=torch.float32, device=x.device)
-    with torch.cuda.device(x.device):
+    with _c.on_device(x.device):
         _c.check(lib.mrb_conv2d_wgrad(ctypes.byref(p), _c._ptr(x), _c._ptr(grad_out), _c._ptr(scale), _c._ptr(gw), _c._stream()),
                  "mrb_conv2d_wgrad(grouped)")
     _count(1, ("wgrad", n, c, h, w, c, k, 1, pad, c // 64))
@@ -247,7 +260,7 @@ def prepare_dgrad_weights(weights, scales, out=None):
     co = (ctypes.c_int * n)(*[w.shape[0] for w in ws])
     tp = (ctypes.c_int * n)(*[w.shape[2] * w.shape[3] for w in ws])
     ci = (ctypes.c_int * n)(*[w.shape[1] for w in ws])
-    with torch.cuda.device(ws[0].device):
+    with _c.on_device(ws[0].device):
         _c.check(lib.mrb_conv2d_prepare_dgrad_weights(n, wp, sp, op, co, tp, ci, _c._stream()), "mrb_conv2d_prepare_dgrad_weights")
     _count((n + 39) // 40)
     return out
@@ -281,7 +294,7 @@ def conv2d_dgrad(grad_out, weight, x_shape, scale=None, add=None, relu_mask=None
     if add is not None and add is not gx:
         add = _nhwc(add, "add")
     relu_mask = _nhwc(relu_mask, "relu_mask") if relu_mask is not None else None
-    with torch.cuda.device(grad_out.device):
+    with _c.on_device(grad_out.device):
         if prepared is not None:
             # `prepared` already holds the flipped/transposed/scaled weights (prepare_dgrad_weights)
             _c.check(lib.mrb_conv2d_dgrad_prepared(ctypes.byref(p), _c._ptr(grad_out), _c._ptr(prepared), _c._ptr(add),
@@ -318,7 +331,7 @@ def conv2d_wgrad(x, grad_out, w_shape, stride=1, pad=0, scale=None, accumulate_i
     else:
         gw = torch.empty(tuple(w_shape), dtype=torch.float32, device=x.device).contiguous(memory_format=torch.channels_last)
         fn = lib.mrb_conv2d_wgrad
-    with torch.cuda.device(x.device):
+    with _c.on_device(x.device):
         _c.check(fn(ctypes.byref(p), _c._ptr(x), _c._ptr(grad_out), _c._ptr(scale), _c._ptr(gw), _c._stream()),
                  "mrb_conv2d_wgrad")
     _count(1, ("wgrad", p.batch, p.cin, p.height, p.width, p.cout, _kk(p), p.stride, _pp(p)))
@@ -337,7 +350,7 @@ def bias_grad(grad_out, accumulate_into=None):
             raise RuntimeError("bias_grad: accumulate_into must be contiguous fp32 [C]")
     else:
         out, fn = torch.empty(c, dtype=torch.float32, device=grad_out.device), lib.mrb_bias_grad
-    with torch.cuda.device(grad_out.device):
+    with _c.on_device(grad_out.device):
         _c.check(fn(_c._ptr(grad_out), _c._ptr(out), ctypes.c_longlong(n * h * w), c, _c._stream()), "mrb_bias_grad")
     _count(1)
     return out
@@ -351,7 +364,7 @@ def max_pool_nhwc(x, kernel, stride, pad):
     n, c, h, w = x.shape
     ho, wo = (h + 2 * pad - kernel) // stride + 1, (w + 2 * pad - kernel) // stride + 1
     out = torch.empty((n, c, ho, wo), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
-    with torch.cuda.device(x.device):
+    with _c.on_device(x.device):
         _c.check(lib.mrb_max_pool_nhwc(_c._ptr(x), _c._ptr(out), n, h, w, c, kernel, stride, pad, _c._stream()), "mrb_max_pool_nhwc")
     _count(1)
     return out
@@ -364,7 +377,7 @@ def sum_pool2x2_nhwc(g):
         raise RuntimeError("sum_pool2x2_nhwc: bf16 input required")
     n, c, h, w = g.shape
     out = torch.empty((n, c, (h + 1) // 2, (w + 1) // 2), dtype=g.dtype, device=g.device, memory_format=torch.channels_last)
-    with torch.cuda.device(g.device):
+    with _c.on_device(g.device):
         _c.check(lib.mrb_sum_pool2x2_nhwc(_c._ptr(g), _c._ptr(out), n, h, w, c, _c._stream()), "mrb_sum_pool2x2_nhwc")
     _count(1)
     return out
@@ -379,7 +392,7 @@ def sgd_momentum_step(param, grad, momentum_buf, param_bf16, lr, momentum, weigh
             raise RuntimeError("sgd_momentum_step: param/grad/momentum_buf must be contiguous fp32 CUDA tensors of one size")
     if param_bf16 is not None and (param_bf16.dtype != torch.bfloat16 or param_bf16.numel() != n or not param_bf16.is_contiguous()):
         raise RuntimeError("sgd_momentum_step: param_bf16 must be a contiguous bf16 tensor of the same size")
-    with torch.cuda.device(param.device):
+    with _c.on_device(param.device):
         _c.check(lib.mrb_sgd_momentum_step(_c._ptr(param), _c._ptr(grad), _c._ptr(momentum_buf), _c._ptr(param_bf16),
                                            ctypes.c_longlong(n), ctypes.c_float(lr), ctypes.c_float(momentum),
                                            ctypes.c_float(weight_decay), ctypes.c_float(grad_scale), int(bool(zero_grad)),
@@ -408,7 +421,7 @@ def dcn_sample_nhwc(x, om, k=3, stride=1, pad=1, dil=1, modulated=False):
         raise RuntimeError("dcn_sample_nhwc: bf16 input required")
     n, c, h, w, ho, wo = _dcn_geom(x, om, k, stride, pad, dil, modulated)
     cols = torch.empty((n, k * k * c, ho, wo), dtype=torch.bfloat16, device=x.device, memory_format=torch.channels_last)
-    with torch.cuda.device(x.device):
+    with _c.on_device(x.device):
         _c.check(lib.mrb_dcn_sample_nhwc(_c._ptr(x), _c._ptr(om), _c._ptr(cols), n, h, w, c, ho, wo, k, k, stride, pad, dil,
                                          om.shape[1], int(bool(modulated)), _c._stream()), "mrb_dcn_sample_nhwc")
     _count(1)
@@ -424,7 +437,7 @@ def dcn_backward_nhwc(x, om, gcols, k=3, stride=1, pad=1, dil=1, modulated=False
         raise RuntimeError("dcn_backward_nhwc: gcols must be bf16 [N, k*k*C, Ho, Wo]")
     gx = torch.zeros((n, c, h, w), dtype=torch.float32, device=x.device).contiguous(memory_format=torch.channels_last) if need_grad_x else None
     gom = torch.zeros_like(om)
-    with torch.cuda.device(x.device):
+    with _c.on_device(x.device):
         _c.check(lib.mrb_dcn_backward_nhwc(_c._ptr(x), _c._ptr(om), _c._ptr(gcols), _c._ptr(gx), _c._ptr(gom), n, h, w, c, ho, wo,
                                            k, k, stride, pad, dil, om.shape[1], int(bool(modulated)), _c._stream()),
                  "mrb_dcn_backward_nhwc")
@@ -462,7 +475,7 @@ def mask_targets_polygons(polyset, rois, inst_of_roi, m):
     r = rois.shape[0]
     out = torch.empty((r, m, m), dtype=torch.float32, device=rois.device)
     if r:
-        with torch.cuda.device(rois.device):
+        with _c.on_device(rois.device):
             _c.check(lib.mrb_mask_targets_polygons(_c._ptr(polyset.xy), _c._ptr(polyset.poly_start), _c._ptr(polyset.inst_start),
                                                    _c._ptr(rois), _c._ptr(idx), _c._ptr(out), r, m, _c._stream()),
                      "mrb_mask_targets_polygons")
@@ -489,7 +502,7 @@ class _RoiAlignFpn(torch.autograd.Function):
         ptrs = (ctypes.c_void_p * L)(*[f.data_ptr() for f in feats])
         geom = (L, n, c, pooled, sampling_ratio, k_min, k_max, float(s0), lvl0, _DT[dt], int(bool(out_nhwc)))
         if r > 0:
-            with torch.cuda.device(rois.device):
+            with _c.on_device(rois.device):
                 _c.check(lib.mrb_roi_align_fpn_fwd(ptrs, hs, ws, sc, L, _c._ptr(rois), _c._ptr(out), r, n, c, pooled,
                                                    sampling_ratio, k_min, k_max, ctypes.c_float(s0), lvl0, _DT[dt],
                                                    int(bool(out_nhwc)), _c._stream()), "mrb_roi_align_fpn_fwd")
@@ -518,7 +531,7 @@ class _RoiAlignFpn(torch.autograd.Function):
             ws = (ctypes.c_int * L)(*[s[3] for s in ctx.shapes])
             sc = (ctypes.c_float * L)(*ctx.scales)
             ptrs = (ctypes.c_void_p * L)(*[g.data_ptr() for g in grads])
-            with torch.cuda.device(rois.device):
+            with _c.on_device(rois.device):
                 _c.check(lib.mrb_roi_align_fpn_bwd(_c._ptr(gout), ptrs, hs, ws, sc, L, _c._ptr(rois), r, n, c, pooled, sr,
                                                    k_min, k_max, ctypes.c_float(s0), lvl0, dtc, out_nhwc, _c._stream()),
                          "mrb_roi_align_fpn_bwd")
@@ -554,7 +567,7 @@ def nms_batched(boxes, scores, sizes, threshold):
     offs_c = (ctypes.c_int * (p + 1))(*offs)
     keep = torch.empty(max(offs[-1], 1), dtype=torch.int64, device=boxes.device)
     counts = torch.zeros(max(p, 1), dtype=torch.int32, device=boxes.device)
-    with torch.cuda.device(boxes.device):
+    with _c.on_device(boxes.device):
         nbytes = lib.mrb_nms_batched_workspace_bytes(offs_c, p)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=boxes.device)
         _c.check(lib.mrb_nms_batched(_c._ptr(boxes), _c._ptr(scores), offs_c, p, ctypes.c_float(threshold), _c._ptr(keep),
