@@ -222,6 +222,57 @@ typedef struct mrb_conv_params {
 int mrb_mask_targets_polygons(const float* polys_xy, const int* poly_start, const int* inst_start, const float* rois,
                               const int* inst_of_roi, float* out, int num_rois, int mask_size, mrb_stream_t stream);
 
+/* ------------------------------------------------------------- detection glue (csrc/detect_glue.cu)
+ * The stages between the tensor-core phases of a train step that the reference runs as Python over BoxList objects
+ * (hundreds of small launches, several host synchronisations): one launch each, fixed shapes, no host sync.
+ *
+ * mrb_rpn_decode: RPNPostProcessor.forward_for_single_feature_map after its top-k (modeling/rpn/inference.py:91-111) for one
+ * level: gathers the k selected anchors' deltas, BoxCoder.decode (modeling/box_coder.py:52-95), clip_to_image
+ * (structures/bounding_box.py:198-212) and the sigmoid of the k logits.  logits [N, A], deltas [N, A, 4], anchors [A, 4],
+ * topk_idx [N, k] int64, image_w / image_h [N] fp32 -> boxes [N, k, 4], scores [N, k].  weights_host: 4 floats. */
+int mrb_rpn_decode(const float* logits, const float* deltas, const float* anchors, const int64_t* topk_idx, const float* image_w,
+                   const float* image_h, float* boxes, float* scores, int num_images, int num_anchors, int k,
+                   const float* weights_host, float xform_clip, mrb_stream_t stream);
+/* mrb_rpn_collect: what follows the NMS (inference.py:116-123, select_over_all_levels :154-181, add_gt_proposals :53-74).
+ * boxes / scores / keep: the (level-major, image-minor) problems of mrb_nms_batched back to back, level l holding
+ * num_images x k_per_level[l] rows; num_keep [num_levels * num_images].  Per image the candidates are the first
+ * min(num_keep, post_nms_top_n) survivors of every level; of those the fpn_post_nms_top_n best are kept -- over the whole
+ * batch (per_batch, training: original order preserved) or per image (sorted by score).  Output rows [N, W + gmax] with
+ * W = mrb_rpn_collect_width(...): the kept boxes, then zero rows (valid = 0, score = -1), then the gmax ground-truth slots
+ * (score 1, valid for the first gt_count[i]); gmax = 0 appends nothing.  Ties at the cut are taken in (image, slot) order. */
+int mrb_rpn_collect(const float* boxes, const float* scores, const int64_t* keep, const int32_t* num_keep,
+                    const int* k_per_level_host, int num_levels, int num_images, int post_nms_top_n, int fpn_post_nms_top_n,
+                    int per_batch, int sorted, const float* gt_boxes, const int32_t* gt_count, int gmax, float* out_boxes,
+                    float* out_scores, uint8_t* out_valid, mrb_stream_t stream);
+int mrb_rpn_collect_width(const int* k_per_level_host, int num_levels, int num_images, int post_nms_top_n,
+                          int fpn_post_nms_top_n, int per_batch);
+/* mrb_roi_assign_sample: FastRCNNLossComputation.subsample (modeling/roi_heads/box_head/loss.py:41-118) for the batch: IoU
+ * with the ground truth (structures/boxlist_ops.py:53-89), Matcher without the low-quality pass (modeling/matcher.py:42-81),
+ * labels, BalancedPositiveNegativeSampler (balanced_positive_negative_sampler.py:19-68) driven by rand_keys [N, P] (iid
+ * uniform: the int(batch * fraction) smallest keys among the positives, the rest from the negatives == randperm[:n]),
+ * BoxCoder.encode (box_coder.py:22-50).  boxes [N, P, 4], valid [N, P] u8, gt_boxes [N, gmax, 4], gt_labels [N, gmax] int64,
+ * gt_count [N].  Outputs, S = batch_size_per_image rows per image, sampled rows first in proposal order, then unsampled
+ * rows as padding with label -1: out_rois [N*S, 5] (image index, box), out_labels [N*S] int64, out_reg_targets [N*S, 4],
+ * out_gt_index [N*S] int64.  With mask_rois_per_image = M > 0 also the mask branch's list (keep_only_positive_boxes,
+ * mask_head/mask_head.py:11-32, at fixed width): the positives among the S rows first: mask_rois [N*M, 5], mask_labels
+ * [N*M] int64 (0 on padding), mask_weight [N*M] (1 / 0), mask_gt_index [N*M] int64. */
+int mrb_roi_assign_sample(const float* boxes, const uint8_t* valid, const float* rand_keys, const float* gt_boxes,
+                          const int64_t* gt_labels, const int32_t* gt_count, int num_images, int num_proposals, int gmax,
+                          int batch_size_per_image, float positive_fraction, float fg_iou, float bg_iou,
+                          const float* weights_host, int mask_rois_per_image, float* out_rois, int64_t* out_labels,
+                          float* out_reg_targets, int64_t* out_gt_index, float* mask_rois, int64_t* mask_labels,
+                          float* mask_weight, int64_t* mask_gt_index, mrb_stream_t stream);
+/* mrb_rpn_anchor_match: RPNLossComputation.match_targets_to_anchors + the labelling of prepare_targets
+ * (modeling/rpn/loss.py:40-90): IoU of every anchor with the ground truth, Matcher with allow_low_quality_matches
+ * (matcher.py:42-112), label 1 / 0 / -1 (between thresholds, or outside the image by more than straddle_thresh;
+ * straddle_thresh < 0 disables the visibility test, anchor_generator.py:100-116).  anchors [A, 4] (shared by the images),
+ * labels [N, A] fp32, matched_gt [N, A] int32 (arg-max ground truth of every anchor). */
+size_t mrb_rpn_anchor_match_workspace_bytes(int num_images, int num_anchors, int gmax);
+int mrb_rpn_anchor_match(const float* anchors, const float* gt_boxes, const int32_t* gt_count, const float* image_w,
+                         const float* image_h, int num_images, int num_anchors, int gmax, float fg_iou, float bg_iou,
+                         float straddle_thresh, float* labels, int32_t* matched_gt, void* workspace, size_t workspace_bytes,
+                         mrb_stream_t stream);
+
 /* Operand preparation for MRB_CONV_GROUPED64 (csrc/grouped_prep.cu).  weight: the grouped filter [C][taps][C/groups] bf16
  * (KRSC).  w_exp / wd_exp: [C][taps][64] bf16 -- the forward operand and the (flipped, per-Cout scaled) data-gradient operand
  * of mrb_conv2d_fwd / mrb_conv2d_dgrad_prepared; either may be NULL.  mrb_grouped_collapse_wgrad folds the [C][taps][128]

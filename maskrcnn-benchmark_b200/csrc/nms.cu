@@ -7,9 +7,10 @@
 //     sub/add/mul/div and no FMA, in the CPU kernel's operation order (nms_cpu.cpp:49-60), so
 //     the kept set is bit-exact with the CPU reference (the reference CUDA kernel uses `>` and
 //     lets nvcc contract, nms.cu:13-21,60);
-//   * no blocking D2H copy of the N x N/64 mask and no host scan (nms.cu:100-123): the scan runs
-//     in one CTA per problem, a warp resolving the 64x64 diagonal tile with ballots/shuffles and
-//     the whole CTA OR-ing the kept rows into the running "removed" bit-vector held in smem;
+//   * no blocking D2H copy of the N x N/64 mask and no host scan (nms.cu:100-123): one CTA per
+//     problem resolves the greedy walk as a fixed point over kept / removed bit sets in smem (a box
+//     is removed once a suppressor is known kept, kept once all its suppressors are known removed);
+//     same unique result as the serial walk in a handful of rounds instead of n/64 dependent steps;
 //   * only the upper triangle of mask tiles is computed (the reference computes and ships all);
 //   * the descending-score order is produced on device by a rank (counting) sort on a total-order
 //     integer key with index tie-break == a stable descending sort;
@@ -115,39 +116,46 @@ __device__ __forceinline__ bool suppresses(const float4 a, float a_area, const f
 
 __global__ void __launch_bounds__(64)
 nms_mask_kernel(NmsBatch nb, unsigned char* __restrict__ ws_base, float thr) {
+  // Suppressor matrix: word (c, row_b) of `mask` holds, for the box of rank c, the boxes r of rank block row_b with r < c
+  // that suppress it (IoU >= thr).  suppresses() is symmetric bit for bit (max/min and a commutative sum), so the tile is
+  // evaluated from the column box's side; only tiles on or above the diagonal exist.
   const int p = blockIdx.z;
   const int n = nb.off[p + 1] - nb.off[p];
   const int col_blocks = (n + 63) >> 6;
   const int row_b = blockIdx.y, col_b = blockIdx.x;
   if (row_b >= col_blocks || col_b >= col_blocks || col_b < row_b) return;
   const NmsWs w = nms_ws_carve(ws_base + nb.ws[p], n);
-  __shared__ float4 cb[64];
-  __shared__ float ca[64];
+  __shared__ float4 rb[64];
+  __shared__ float ra[64];
   const int col_size = min(n - col_b * 64, 64);
   const int row_size = min(n - row_b * 64, 64);
-  if ((int)threadIdx.x < col_size) {
-    cb[threadIdx.x] = w.boxes[col_b * 64 + threadIdx.x];
-    ca[threadIdx.x] = w.areas[col_b * 64 + threadIdx.x];
+  if ((int)threadIdx.x < row_size) {
+    rb[threadIdx.x] = w.boxes[row_b * 64 + threadIdx.x];
+    ra[threadIdx.x] = w.areas[row_b * 64 + threadIdx.x];
   }
   __syncthreads();
-  if ((int)threadIdx.x < row_size) {
-    const int r = row_b * 64 + threadIdx.x;
-    const float4 a = w.boxes[r];
-    const float aa = w.areas[r];
+  if ((int)threadIdx.x < col_size) {
+    const int c = col_b * 64 + threadIdx.x;
+    const float4 a = w.boxes[c];
+    const float aa = w.areas[c];
     unsigned long long t = 0;
-    const int start = (row_b == col_b) ? threadIdx.x + 1 : 0;
-    for (int i = start; i < col_size; ++i)
-      if (suppresses(a, aa, cb[i], ca[i], thr)) t |= 1ull << i;
-    w.mask[(size_t)r * col_blocks + col_b] = t;
+    const int end = (row_b == col_b) ? (int)threadIdx.x : row_size;   // rows of lower rank only
+    for (int i = 0; i < end; ++i)
+      if (suppresses(rb[i], ra[i], a, aa, thr)) t |= 1ull << i;
+    w.mask[(size_t)c * col_blocks + row_b] = t;
   }
 }
 
-// --- 3. greedy scan + ascending compaction, one CTA per problem ------------------------------
+// --- 3. greedy resolution + ascending compaction, one CTA per problem --------------------------
+// The greedy scan "walk the boxes by descending score, keep a box unless a kept one suppresses it" has a unique
+// solution, reached here as a fixed point instead of a serial walk: a box is REMOVED as soon as one of its suppressors is
+// known kept, KEPT as soon as all of its suppressors are known removed (a box without suppressors at once).  Every round
+// decides at least the undecided box of lowest rank, typical inputs need a handful of rounds (the length of the longest
+// keep/remove dependency chain), and a round costs one L2 latency instead of the serial walk's two per 64 boxes.
 __global__ void __launch_bounds__(kScanThreads)
 nms_scan_kernel(NmsBatch nb, unsigned char* __restrict__ ws_base, long long* __restrict__ keep,
                 int* __restrict__ num_keep) {
-  extern __shared__ unsigned long long remv[];  // [col_blocks]
-  __shared__ unsigned long long s_kept;
+  extern __shared__ unsigned long long sm_scan[];  // kept[col_blocks], removed[col_blocks], nz[n] (col_blocks <= 64)
   __shared__ int s_warp_tot[kScanThreads / 32];
   __shared__ int s_base;
   const int p = blockIdx.x;
@@ -155,45 +163,68 @@ nms_scan_kernel(NmsBatch nb, unsigned char* __restrict__ ws_base, long long* __r
   const int col_blocks = (n + 63) >> 6;
   const NmsWs w = nms_ws_carve(ws_base + nb.ws[p], n);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int t = tid; t < col_blocks; t += kScanThreads) remv[t] = 0;
+  unsigned long long* kept = sm_scan;
+  unsigned long long* removed = sm_scan + col_blocks;
+  unsigned long long* nz = sm_scan + 2 * col_blocks;
+  const bool use_nz = col_blocks <= 64;
+  // the bit sets only grow (atomicOr) while a round reads them: any mix of old and new words yields decisions that are valid
+  volatile unsigned long long* vkept = kept;
+  volatile unsigned long long* vremoved = removed;
+  for (int t = tid; t < 2 * col_blocks; t += kScanThreads) sm_scan[t] = 0;
   __syncthreads();
-
-  for (int b = 0; b < col_blocks; ++b) {
-    const int rows = min(64, n - b * 64);
-    if (warp == 0) {
-      const unsigned long long* diag = w.mask + (size_t)(b * 64) * col_blocks + b;
-      const unsigned long long d0 = (lane < rows) ? diag[(size_t)lane * col_blocks] : 0ull;
-      const unsigned long long d1 = (lane + 32 < rows) ? diag[(size_t)(lane + 32) * col_blocks] : 0ull;
-      const unsigned long long valid = (rows == 64) ? ~0ull : ((1ull << rows) - 1ull);
-      unsigned long long cand = ~remv[b] & valid;
-      unsigned long long kept = 0;
-      while (cand) {  // warp-uniform: every lane holds the same cand
-        const int i = __ffsll((long long)cand) - 1;
-        kept |= 1ull << i;
-        const unsigned long long lo = __shfl_sync(0xffffffffu, d0, i & 31);
-        const unsigned long long hi = __shfl_sync(0xffffffffu, d1, i & 31);
-        cand &= ~((i < 32) ? lo : hi);
-        cand &= ~(1ull << i);
+  // round 0: which suppressor words of every box are non-zero; boxes without suppressors are kept
+  for (int i = tid; i < n; i += kScanThreads) {
+    const int wd_end = (i >> 6) + 1;
+    const unsigned long long* row = w.mask + (size_t)i * col_blocks;
+    unsigned long long m = 0;
+    bool any = false;
+#pragma unroll 4
+    for (int wd = 0; wd < wd_end; ++wd) {
+      const unsigned long long t = row[wd];
+      if (t) {
+        any = true;
+        if (use_nz) m |= 1ull << wd;
       }
-      if (lane == 0) s_kept = kept;
     }
-    __syncthreads();
-    const unsigned long long kept = s_kept;
-    if (tid < rows && ((kept >> tid) & 1ull)) w.flags[w.order[b * 64 + tid]] = 1;
-    // OR the kept rows of block b into the running "removed" words of the later column blocks.
-    // One warp per column block; lane l fetches rows l and l+32 (all 64 loads of a column in flight
-    // at once -- a per-thread loop over the kept rows serialises on L2 latency), OR-reduced with redux.
-    const unsigned long long* base = w.mask + (size_t)(b * 64) * col_blocks;
-    for (int t = b + 1 + warp; t < col_blocks; t += kScanThreads / 32) {
-      unsigned long long v = 0;
-      if ((kept >> lane) & 1ull) v = base[(size_t)lane * col_blocks + t];
-      if ((kept >> (lane + 32)) & 1ull) v |= base[(size_t)(lane + 32) * col_blocks + t];
-      const unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)v);
-      const unsigned hi = __reduce_or_sync(0xffffffffu, (unsigned)(v >> 32));
-      if (lane == 0) remv[t] |= ((unsigned long long)hi << 32) | lo;
-    }
-    __syncthreads();
+    if (use_nz) nz[i] = m;
+    if (!any) atomicOr(&kept[i >> 6], 1ull << (i & 63));
   }
+  for (;;) {
+    __syncthreads();
+    int undecided = 0;
+    for (int i = tid; i < n; i += kScanThreads) {
+      const int word = i >> 6;
+      const unsigned long long bit = 1ull << (i & 63);
+      if ((vkept[word] | vremoved[word]) & bit) continue;
+      const unsigned long long* row = w.mask + (size_t)i * col_blocks;
+      bool any_kept = false, any_open = false;
+      if (use_nz) {
+        unsigned long long m = nz[i];
+        while (m) {
+          const int wd = __ffsll((long long)m) - 1;
+          m &= m - 1;
+          const unsigned long long t = row[wd];
+          const unsigned long long k = vkept[wd], r = vremoved[wd];
+          any_kept |= (t & k) != 0;
+          any_open |= (t & ~k & ~r) != 0;
+        }
+      } else {
+        for (int wd = 0; wd <= word; ++wd) {
+          const unsigned long long t = row[wd];
+          const unsigned long long k = vkept[wd], r = vremoved[wd];
+          any_kept |= (t & k) != 0;
+          any_open |= (t & ~k & ~r) != 0;
+        }
+      }
+      if (any_kept) atomicOr(&removed[word], bit);
+      else if (!any_open) atomicOr(&kept[word], bit);
+      else ++undecided;
+    }
+    if (__syncthreads_count(undecided) == 0) break;
+  }
+  for (int i = tid; i < n; i += kScanThreads)
+    if ((kept[i >> 6] >> (i & 63)) & 1ull) w.flags[w.order[i]] = 1;
+  __syncthreads();
 
   // ascending-index compaction of flags[0..n)
   if (tid == 0) s_base = 0;
@@ -229,7 +260,7 @@ static int nms_run(const float* boxes, const float* scores, const NmsBatch& nb, 
     return (int)cudaMemsetAsync(num_keep, 0, sizeof(int) * nb.num, stream);
   }
   const int max_cb = (max_n + 63) / 64;
-  if ((size_t)max_cb * 8 > 160 * 1024) return MRB_ERR_UNSUPPORTED;
+  if ((size_t)max_cb * 16 > 160 * 1024) return MRB_ERR_UNSUPPORTED;
   {
     dim3 grid(ceil_div(max_n, kRankThreads), nb.num);
     nms_rank_kernel<<<grid, kRankThreads, 0, stream>>>(boxes, scores, nb, (unsigned char*)ws);
@@ -242,7 +273,7 @@ static int nms_run(const float* boxes, const float* scores, const NmsBatch& nb, 
     MRB_LAUNCH_CHECK();
   }
   {
-    const size_t smem = (size_t)max_cb * 8;
+    const size_t smem = (size_t)max_cb * 16 + (max_cb <= 64 ? (size_t)max_n * 8 : 0);
     if (smem > 48 * 1024)
       MRB_CUDA_TRY(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     nms_scan_kernel<<<nb.num, kScanThreads, smem, stream>>>(nb, (unsigned char*)ws, keep, num_keep);

@@ -288,6 +288,9 @@ class B200Backend(Backend):
     act_dtype = torch.bfloat16
     channels_last = True
     stride2_3x3 = False       # 3x3 stride-2 convs (STRIDE_IN_1X1: False) on the engine
+    # proposal selection / target assignment / sampling as the launches of csrc/detect_glue.cu (MRB_FUSED_GLUE=0: the
+    # PyTorch formulation, kept as the A/B arm and as what the CPU checker backend runs)
+    fused_glue = __import__("os").environ.get("MRB_FUSED_GLUE", "1") != "0"
 
     def __init__(self, wgrad="tc"):
         self._w16 = {}

@@ -141,14 +141,16 @@ def sample_pos_neg_idx(labels, batch_size, positive_fraction, generator=None):
     return pos_idx, pos_ok, neg_idx, neg_ok
 
 
-def sample_pos_neg(labels, batch_size, positive_fraction, generator=None):
-    """The same sample as boolean masks (pos, neg) over the elements of `labels`."""
+def sample_pos_neg(labels, batch_size, positive_fraction, generator=None, key=None):
+    """The same sample as boolean masks (pos, neg) over the elements of `labels`.  `key`: the iid uniform keys to use
+    (n <= 4096 only) instead of drawing them."""
     n = labels.numel()
-    if n <= 4096:
+    if n <= 4096 or key is not None:
         # few candidates (the <= ~2000 proposals of an image): rank every element among the masked ones by pairwise
         # key comparison -- two n x n passes instead of two single-block top-k launches
         cap = min(int(batch_size * positive_fraction), n)
-        key = torch.rand(n, device=labels.device, generator=generator)
+        if key is None:
+            key = torch.rand(n, device=labels.device, generator=generator)
         pos, neg = labels >= 1, labels == 0
         # lt[i, j]: element j precedes element i.  Ties (float32 rand has 2^24 values: ~10% of 2000-element calls
         # contain one) are broken by index, so the counts are exact as with the reference's randperm[:num]

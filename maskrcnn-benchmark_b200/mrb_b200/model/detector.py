@@ -36,11 +36,12 @@ class GeneralizedRCNN(nn.Module):
             batch[i, :, :im.shape[1], :im.shape[2]] = im
         return batch, sizes
 
-    def _mask_loss(self, be, feats, rois, labels, gidx, targets):
+    def _mask_loss(self, be, feats, rois, labels, gidx, targets, sm=None, gtp=None):
         mask = self.roi_heads.mask
         n, s = labels.shape
         res = self.cfg.mask_resolution
-        gt_all = torch.stack([t["boxes"][gidx[i]] for i, t in enumerate(targets)])          # [n, s, 4]
+        fused = sm is not None and "mask_rois" in sm
+        gt_all = None if fused else torch.stack([t["boxes"][gidx[i]] for i, t in enumerate(targets)])          # [n, s, 4]
         # polygon segmentations ("polygons": per instance, a list of flat [x0, y0, x1, y1, ...] sequences -- the reference's
         # SegmentationMask(mode="poly")): rasterised on the GPU, one launch (ops.mask_targets_polygons); without them the
         # instance mask of a ground-truth box is its rectangle
@@ -54,8 +55,25 @@ class GeneralizedRCNN(nn.Module):
             for t in targets:
                 off.append(acc)
                 acc += len(t["polygons"])
-            inst_all = gidx + torch.tensor(off, device=gidx.device, dtype=gidx.dtype)[:, None]   # [n, s] global instance index
+            if fused:
+                inst_off = targets[0].get("_inst_off")
+                if inst_off is None:
+                    inst_off = torch.tensor(off, device=gidx.device, dtype=gidx.dtype)[:, None]
+            else:
+                inst_all = gidx + torch.tensor(off, device=gidx.device, dtype=gidx.dtype)[:, None]   # [n, s] global instance index
         m = self.cfg.mask_rois_per_image
+        if fused:
+            # the positives-first list came out of the assign-and-sample launch
+            rois_sel, lab_sel, wsel, mg = sm["mask_rois"], sm["mask_labels"], sm["mask_weight"], sm["mask_gt_index"]
+            sel_logits = mask.run(be, feats, rois_sel, select=lab_sel)
+            if polyset is not None:
+                tgt = ops.mask_targets_polygons(polyset, rois_sel[:, 1:], (mg + inst_off).reshape(-1), res)
+            else:
+                gt_sel = torch.gather(gtp[0], 1, mg[..., None].expand(-1, -1, 4)).reshape(-1, 4)
+                tgt = mask.mask_targets(gt_sel, rois_sel[:, 1:], res)
+            bce = torch.nn.functional.binary_cross_entropy_with_logits(sel_logits.float(), tgt,
+                                                                       reduction="none").mean((1, 2))
+            return torch.where(wsel > 0, bce, torch.zeros((), dtype=bce.dtype, device=bce.device)).sum() / wsel.sum().clamp(min=1)
         if m > 0:
             posm = labels > 0
             order = torch.sort((~posm).to(torch.int8), dim=1, stable=True)[1][:, :m]        # positives first
@@ -87,14 +105,23 @@ class GeneralizedRCNN(nn.Module):
         be = self.be
         if self.training and targets is None:
             raise ValueError("In training mode, targets should be passed")
+        gtp = sm = None
+        if self.training and getattr(be, "fused_glue", False):
+            from mrb_b200 import ops
+            gtp = ops.pad_targets(targets, images.device)      # ground truth as fixed-shape tensors for the glue kernels
         feats = self.backbone.run(be, images)
         if self.training and hasattr(be, "heads_boundary"):
             feats = be.heads_boundary(feats)        # data-parallel runs: marks where the heads' gradients are complete
-        proposals, losses = self.rpn.run(be, feats, image_sizes, targets, self.training, generator)
+        proposals, losses = self.rpn.run(be, feats, image_sizes, targets, self.training, generator, gtp=gtp)
         box = self.roi_heads.box
         if self.training:
-            boxes, labels, reg_t, gidx = box.subsample(proposals, targets, generator, be)
-            rois = _to_rois(boxes)
+            if gtp is not None and proposals[0].shape[1] <= 8192:
+                mm = self.cfg.mask_rois_per_image if self.cfg.mask_on else 0
+                sm = box.subsample_fused(proposals, gtp, generator, mm)
+                rois, labels, reg_t, gidx = sm["rois"], sm["labels"], sm["reg_targets"], sm["gt_index"]
+            else:
+                boxes, labels, reg_t, gidx = box.subsample(proposals, targets, generator, be)
+                rois = _to_rois(boxes)
             if self.cfg.mask_on:
                 # The mask branch needs only the sampled boxes/labels and the FPN features.  With a backend that offers
                 # stream lanes it is issued on its own stream, BEFORE the box branch: autograd replays every node on the
@@ -105,10 +132,10 @@ class GeneralizedRCNN(nn.Module):
                 if st is not None:
                     cur = torch.cuda.current_stream()
                     st.wait_stream(cur)
-                    for t in list(feats) + [rois, labels, gidx]:
+                    for t in list(feats) + [rois, labels, gidx] + (list(sm.values()) + list(gtp) if sm is not None else []):
                         t.record_stream(st)
                     with torch.cuda.stream(st):
-                        loss_mask = self._mask_loss(be, feats, rois, labels, gidx, targets)
+                        loss_mask = self._mask_loss(be, feats, rois, labels, gidx, targets, sm, gtp)
                     loss_mask.record_stream(cur)
                 else:
                     loss_mask = None
@@ -120,7 +147,7 @@ class GeneralizedRCNN(nn.Module):
                 if st is not None:
                     torch.cuda.current_stream().wait_stream(st)
                 else:
-                    loss_mask = self._mask_loss(be, feats, rois, labels, gidx, targets)
+                    loss_mask = self._mask_loss(be, feats, rois, labels, gidx, targets, sm, gtp)
                 losses["loss_mask"] = loss_mask
             return losses
         boxes, _, valid = proposals

@@ -43,7 +43,7 @@ class BoxHead(nn.Module):
         self.matcher = box_ops.Matcher(cfg.roi_fg_iou, cfg.roi_bg_iou, allow_low_quality_matches=False)
 
     @torch.no_grad()
-    def subsample(self, proposals, targets, generator=None, be=None):
+    def subsample(self, proposals, targets, generator=None, be=None, keys=None):
         """box_head/loss.py:41-118: match, label, sample 512 per image (25 % positive).
         -> boxes [N, S, 4], labels [N, S] (-1 = padding), reg targets [N, S, 4], matched gt [N, S]"""
         cfg = self.cfg
@@ -58,7 +58,8 @@ class BoxHead(nn.Module):
             lab = torch.where(midx == box_ops.Matcher.BELOW_LOW, torch.zeros_like(lab), lab)
             lab = torch.where(midx == box_ops.Matcher.BETWEEN, -torch.ones_like(lab), lab)
             lab = torch.where(valid[i], lab, -torch.ones_like(lab))
-            pos, neg = box_ops.sample_pos_neg(lab, S, cfg.roi_positive_fraction, generator)
+            pos, neg = box_ops.sample_pos_neg(lab, S, cfg.roi_positive_fraction, generator,
+                                              key=None if keys is None else keys[i])
             sel = pos | neg
             # fixed-size gather: selected rows first, in index order (== nonzero(pos | neg))
             order = torch.sort((~sel).to(torch.int8), stable=True)[1][:S]
@@ -77,6 +78,19 @@ class BoxHead(nn.Module):
                 outs = [image(i) for i in range(n)]
         ob, ol, ot, og = zip(*outs)
         return torch.stack(ob), torch.stack(ol), torch.stack(ot), torch.stack(og)
+
+    @torch.no_grad()
+    def subsample_fused(self, proposals, gtp, generator=None, mask_rois_per_image=0, keys=None):
+        """subsample (+ the mask branch's positives-first list) as one launch: mrb_roi_assign_sample (csrc/detect_glue.cu).
+        -> dict(rois [N*S, 5], labels [N, S], reg_targets [N, S, 4], gt_index [N, S], mask_*)."""
+        from mrb_b200 import ops
+        cfg = self.cfg
+        boxes, _, valid = proposals
+        if keys is None:
+            keys = torch.rand(boxes.shape[:2], device=boxes.device, generator=generator)
+        return ops.roi_assign_sample(boxes, valid, keys, gtp[0], gtp[1], gtp[2], cfg.roi_batch_size, cfg.roi_positive_fraction,
+                                     cfg.roi_fg_iou, cfg.roi_bg_iou, cfg.bbox_reg_weights,
+                                     min(int(mask_rois_per_image), cfg.roi_batch_size))
 
     def features(self, be, feats, rois):
         cfg = self.cfg

@@ -96,21 +96,68 @@ class RPN(nn.Module):
         self._size_cache = {}
 
     # ------------------------------------------------------------------ proposals (no_grad)
+    def _sizes(self, image_sizes, dev):
+        """(widths [N], heights [N]) fp32 on the device, cached: host -> device copies must not sit inside a captured step"""
+        key = (tuple(tuple(s) for s in image_sizes), str(dev))
+        if key not in self._size_cache:
+            self._size_cache[key] = (torch.tensor([s[1] for s in image_sizes], device=dev, dtype=torch.float32),
+                                     torch.tensor([s[0] for s in image_sizes], device=dev, dtype=torch.float32))
+        return self._size_cache[key]
+
     @torch.no_grad()
-    def select_proposals(self, be, anchors, logits, deltas, image_sizes, targets, training):
-        """-> (boxes [N, P, 4], scores [N, P], valid [N, P] bool).  P is fixed; invalid rows hold
-        zero boxes / -1 scores."""
+    def _select_proposals_fused(self, be, anchors, logits, deltas, image_sizes, gtp, training):
+        """select_proposals as 5 top-k + 5 decode launches (one lane per level), the batched NMS and ONE collect launch
+        (csrc/detect_glue.cu); same contract.  The top-k runs on the logits (sigmoid is monotone; the k sigmoids are taken
+        in the decode kernel)."""
+        from mrb_b200 import ops
         cfg = self.cfg
         n = logits[0].shape[0]
         dev = logits[0].device
         pre_n = cfg.pre_nms_top_n_train if training else cfg.pre_nms_top_n_test
         post_n = cfg.post_nms_top_n_train if training else cfg.post_nms_top_n_test
         fpn_post_n = cfg.fpn_post_nms_top_n_train if training else cfg.fpn_post_nms_top_n_test
-        key = (tuple(tuple(s) for s in image_sizes), str(dev))
-        if key not in self._size_cache:     # host -> device copies must not sit inside a captured step
-            self._size_cache[key] = (torch.tensor([s[1] for s in image_sizes], device=dev, dtype=torch.float32),
-                                     torch.tensor([s[0] for s in image_sizes], device=dev, dtype=torch.float32))
-        widths, heights = self._size_cache[key]
+        widths, heights = self._sizes(image_sizes, dev)
+        ks = [min(pre_n, lg.shape[1]) for lg in logits]
+        tot = n * sum(ks)
+        boxes = torch.empty((tot, 4), dtype=torch.float32, device=dev)
+        scores = torch.empty((tot,), dtype=torch.float32, device=dev)
+        fork = getattr(be, "fork", None)
+        handles, off = [], 0
+        for li, (anc, lg, dl, k) in enumerate(zip(anchors, logits, deltas, ks)):
+            bo, so = boxes[off:off + n * k], scores[off:off + n * k]
+
+            def level(anc=anc, lg=lg, dl=dl, k=k, bo=bo, so=so):
+                idx = lg.topk(k, dim=1, sorted=True)[1]                                   # inference.py:91-95
+                ops.rpn_decode(lg, dl, anc, idx, widths, heights, bo, so, self.box_coder.weights, self.box_coder.clip)
+                return bo
+            if fork is not None:
+                handles.append(fork((anc, lg, dl, widths, heights, boxes, scores), level, lane=li))
+            else:
+                level()
+            off += n * k
+        for h in handles:
+            be.join(h)
+        sizes = [k for k in ks for _ in range(n)]
+        keep, counts = be.nms_batched(boxes, scores, sizes, cfg.rpn_nms_thresh)
+        per_batch = bool(training and cfg.fpn_post_nms_per_batch)
+        add_gt = training and gtp is not None
+        return ops.rpn_collect(boxes, scores, keep, counts, ks, n, post_n, fpn_post_n, per_batch,
+                               gtp[0] if add_gt else None, gtp[2] if add_gt else None)
+
+    @torch.no_grad()
+    def select_proposals(self, be, anchors, logits, deltas, image_sizes, targets, training, gtp=None):
+        """-> (boxes [N, P, 4], scores [N, P], valid [N, P] bool).  P is fixed; invalid rows hold
+        zero boxes / -1 scores."""
+        cfg = self.cfg
+        n = logits[0].shape[0]
+        dev = logits[0].device
+        if getattr(be, "fused_glue", False) and (not training or targets is None or gtp is not None) and \
+                not (training and cfg.fpn_post_nms_per_batch and n > 8):
+            return self._select_proposals_fused(be, anchors, logits, deltas, image_sizes, gtp, training)
+        pre_n = cfg.pre_nms_top_n_train if training else cfg.pre_nms_top_n_test
+        post_n = cfg.post_nms_top_n_train if training else cfg.post_nms_top_n_test
+        fpn_post_n = cfg.fpn_post_nms_top_n_train if training else cfg.fpn_post_nms_top_n_test
+        widths, heights = self._sizes(image_sizes, dev)
         def level(anc, lg, dl):
             k = min(pre_n, lg.shape[1])
             sc, idx = lg.sigmoid().topk(k, dim=1, sorted=True)                       # inference.py:91-95
@@ -190,6 +237,27 @@ class RPN(nn.Module):
 
     # ------------------------------------------------------------------ loss
     @torch.no_grad()
+    def loss_targets_fused(self, anchors_all, image_sizes, targets, gtp, generator=None):
+        """loss_targets with the IoU / Matcher / labelling of all anchors of the batch as one launch pair
+        (mrb_rpn_anchor_match); the sampling and the encoding of the sampled rows as in loss_targets."""
+        from mrb_b200 import ops
+        cfg = self.cfg
+        widths, heights = self._sizes(image_sizes, anchors_all.device)
+        labels, matched = ops.rpn_anchor_match(anchors_all, gtp[0], gtp[2], widths, heights, cfg.rpn_fg_iou, cfg.rpn_bg_iou,
+                                               float(self.anchor_generator.straddle_thresh))
+        out = []
+        for i, t in enumerate(targets):
+            pos_idx, pos_ok, neg_idx, neg_ok = box_ops.sample_pos_neg_idx(labels[i], cfg.rpn_batch_size,
+                                                                            cfg.rpn_positive_fraction, generator)
+            gt = t["boxes"][matched[i][pos_idx].long()]
+            reg_t = self.box_coder.encode(gt, anchors_all[pos_idx])
+            sel = torch.cat([pos_idx, neg_idx])
+            sel_lab = torch.cat([torch.ones_like(pos_ok, dtype=torch.float32), torch.zeros_like(neg_ok, dtype=torch.float32)])
+            sel_w = torch.cat([pos_ok, neg_ok]).float()
+            out.append((pos_idx, pos_ok, reg_t, sel, sel_lab, sel_w))
+        return out
+
+    @torch.no_grad()
     def loss_targets(self, anchors_all, visibility, targets, generator=None):
         """Anchor labelling + sampling + regression targets (loss.py:40-131, no gradients, independent of the
         network outputs): matching and labelling run over all ~268k anchors, everything after the sampling touches
@@ -232,26 +300,37 @@ class RPN(nn.Module):
         num_sampled = num_sampled.clamp(min=1)
         return obj_sum / num_sampled, box_sum / num_sampled
 
-    def run(self, be, feats, image_sizes, targets, training, generator=None):
+    def run(self, be, feats, image_sizes, targets, training, generator=None, gtp=None):
         grid_sizes = [f.shape[-2:] for f in feats]
         anchors = self.anchor_generator.grid(grid_sizes, feats[0].device)
         prepared = None
+        fused = getattr(be, "fused_glue", False) and gtp is not None
         if training:
-            anchors_all = torch.cat(anchors, 0)
-            vis = torch.stack([self.anchor_generator.visibility(anchors_all, w, h) for (h, w) in image_sizes])
+            akey = (tuple(tuple(g) for g in grid_sizes), str(feats[0].device))
+            if getattr(self, "_anchors_all", (None,))[0] != akey:
+                self._anchors_all = (akey, torch.cat(anchors, 0))
+            anchors_all = self._anchors_all[1]
+            vis = None if fused else torch.stack([self.anchor_generator.visibility(anchors_all, w, h) for (h, w) in image_sizes])
             # the target assignment needs nothing from the network: with a backend that offers a second stream it runs
             # there, concurrently with the RPN head convolutions and the proposal selection (a few hundred tiny kernels
             # that would otherwise sit on the critical path between two tensor-core phases)
             fork = getattr(be, "fork", None)
-            if fork is not None:
-                prepared = fork((anchors_all, vis) + tuple(t["boxes"] for t in targets),
-                                lambda: self.loss_targets(anchors_all, vis, targets, generator))
+            if fused:
+                tfn = lambda: self.loss_targets_fused(anchors_all, image_sizes, targets, gtp, generator)
+            else:
+                tfn = lambda: self.loss_targets(anchors_all, vis, targets, generator)
+            forked = fork is not None
+            if forked:
+                ins = (anchors_all,) + tuple(t["boxes"] for t in targets) + (tuple(gtp) if fused else (vis,))
+                prepared = fork(ins, tfn)
+            elif fused:
+                prepared = tfn()
         logits, deltas = self.head.run(be, feats)
         proposals = self.select_proposals(be, anchors, [l.detach() for l in logits], [d.detach() for d in deltas],
-                                          image_sizes, targets, training)
+                                          image_sizes, targets, training, gtp=gtp)
         losses = {}
         if training:
-            if prepared is not None:
+            if prepared is not None and forked:
                 prepared = be.join(prepared)
             lo, lb = self.loss(anchors_all, vis, logits, deltas, targets, generator, prepared)
             losses = {"loss_objectness": lo, "loss_rpn_box_reg": lb}

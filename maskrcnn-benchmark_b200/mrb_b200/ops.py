@@ -575,3 +575,131 @@ def nms_batched(boxes, scores, sizes, threshold):
                  "mrb_nms_batched")
     _count(3)
     return keep[:offs[-1]], counts[:p]
+
+
+# --------------------------------------------------------------------------------- detection glue (csrc/detect_glue.cu)
+lib.mrb_rpn_anchor_match_workspace_bytes.restype = ctypes.c_size_t
+
+
+def _f32c(t, name):
+    if not t.is_cuda:
+        raise RuntimeError("%s: expected CUDA tensors (no CPU path)" % name)
+    if t.dtype != torch.float32 or not t.is_contiguous():
+        t = t.float().contiguous()
+    return t
+
+
+def rpn_decode(logits, deltas, anchors, topk_idx, image_w, image_h, boxes_out, scores_out, weights=(1.0, 1.0, 1.0, 1.0),
+               xform_clip=None):
+    """One level of RPNPostProcessor.forward_for_single_feature_map after its top-k (rpn/inference.py:91-111): decode
+    (box_coder.py:52-95) + clip_to_image + sigmoid of the k selected anchors of every image, one launch.
+    logits [N, A], deltas [N, A, 4], anchors [A, 4], topk_idx [N, k] int64 -> boxes_out [N, k, 4], scores_out [N, k]
+    (caller-allocated, contiguous fp32: slices of the buffers the batched NMS reads)."""
+    import math
+    n, a = logits.shape
+    k = topk_idx.shape[1]
+    logits, deltas, anchors = _f32c(logits, "rpn_decode"), _f32c(deltas, "rpn_decode"), _f32c(anchors, "rpn_decode")
+    if topk_idx.dtype != torch.int64 or not topk_idx.is_contiguous():
+        topk_idx = topk_idx.long().contiguous()
+    if not (boxes_out.is_contiguous() and scores_out.is_contiguous() and boxes_out.dtype == torch.float32
+            and scores_out.dtype == torch.float32 and boxes_out.numel() == n * k * 4 and scores_out.numel() == n * k):
+        raise RuntimeError("rpn_decode: outputs must be contiguous fp32 [N, k, 4] / [N, k]")
+    w = (ctypes.c_float * 4)(*[float(x) for x in weights])
+    clip = math.log(1000.0 / 16) if xform_clip is None else float(xform_clip)
+    with _c.on_device(logits.device):
+        _c.check(lib.mrb_rpn_decode(_c._ptr(logits), _c._ptr(deltas), _c._ptr(anchors), _c._ptr(topk_idx), _c._ptr(image_w),
+                                    _c._ptr(image_h), _c._ptr(boxes_out), _c._ptr(scores_out), n, a, k, w,
+                                    ctypes.c_float(clip), _c._stream()), "mrb_rpn_decode")
+    _count(1)
+
+
+def rpn_collect(boxes, scores, keep, counts, ks, num_images, post_nms_top_n, fpn_post_nms_top_n, per_batch, gt_boxes=None,
+                gt_count=None):
+    """Everything RPNPostProcessor does after the NMS (inference.py:116-123, :154-181, :53-74) in one launch.
+    boxes / scores / keep / counts: the (level-major, image-minor) problems of nms_batched, level l = num_images x ks[l] rows.
+    -> (boxes [N, W + gmax, 4], scores [N, W + gmax], valid [N, W + gmax] bool)."""
+    boxes, scores = _f32c(boxes, "rpn_collect"), _f32c(scores, "rpn_collect")
+    L = len(ks)
+    kc = (ctypes.c_int * L)(*[int(k) for k in ks])
+    w = lib.mrb_rpn_collect_width(kc, L, num_images, post_nms_top_n, fpn_post_nms_top_n, int(bool(per_batch)))
+    gmax = 0 if gt_boxes is None else gt_boxes.shape[1]
+    dev = boxes.device
+    ob = torch.empty((num_images, w + gmax, 4), dtype=torch.float32, device=dev)
+    os_ = torch.empty((num_images, w + gmax), dtype=torch.float32, device=dev)
+    ov = torch.empty((num_images, w + gmax), dtype=torch.bool, device=dev)
+    with _c.on_device(dev):
+        _c.check(lib.mrb_rpn_collect(_c._ptr(boxes), _c._ptr(scores), _c._ptr(keep), _c._ptr(counts), kc, L, num_images,
+                                     post_nms_top_n, fpn_post_nms_top_n, int(bool(per_batch)), int(not per_batch),
+                                     _c._ptr(gt_boxes), _c._ptr(gt_count), gmax, _c._ptr(ob), _c._ptr(os_), _c._ptr(ov),
+                                     _c._stream()), "mrb_rpn_collect")
+    _count(1)
+    return ob, os_, ov
+
+
+def pad_targets(targets, device):
+    """Ground truth of a batch as fixed-shape tensors: boxes [N, Gmax, 4] fp32, labels [N, Gmax] int64, count [N] int32."""
+    n = len(targets)
+    gmax = max(1, max(int(t["boxes"].shape[0]) for t in targets))
+    gb = torch.zeros((n, gmax, 4), dtype=torch.float32, device=device)
+    gl = torch.zeros((n, gmax), dtype=torch.int64, device=device)
+    for i, t in enumerate(targets):
+        g = int(t["boxes"].shape[0])
+        if g:
+            gb[i, :g] = t["boxes"]
+            gl[i, :g] = t["labels"]
+    cnt = torch.zeros((n,), dtype=torch.int32, device=device)
+    for i, t in enumerate(targets):          # scalar fills, not a host -> device copy: the step may be under graph capture
+        cnt[i:i + 1].fill_(int(t["boxes"].shape[0]))
+    return gb, gl, cnt
+
+
+def roi_assign_sample(boxes, valid, rand_keys, gt_boxes, gt_labels, gt_count, batch_size_per_image, positive_fraction, fg_iou,
+                      bg_iou, weights, mask_rois_per_image=0):
+    """FastRCNNLossComputation.subsample (box_head/loss.py:41-118) + the mask branch's positives-first list, one launch.
+    -> dict(rois [N*S, 5], labels [N, S], reg_targets [N, S, 4], gt_index [N, S]) (+ mask_rois [N*M, 5], mask_labels [N*M],
+    mask_weight [N*M], mask_gt_index [N, M] when mask_rois_per_image = M > 0)."""
+    boxes, rand_keys, gt_boxes = _f32c(boxes, "roi_assign_sample"), _f32c(rand_keys, "roi_assign_sample"), _f32c(gt_boxes, "roi_assign_sample")
+    n, p, _ = boxes.shape
+    if valid.dtype != torch.bool or not valid.is_contiguous():
+        valid = valid.bool().contiguous()
+    s, m = int(batch_size_per_image), int(mask_rois_per_image)
+    dev = boxes.device
+    out = {"rois": torch.empty((n * s, 5), dtype=torch.float32, device=dev),
+           "labels": torch.empty((n, s), dtype=torch.int64, device=dev),
+           "reg_targets": torch.empty((n, s, 4), dtype=torch.float32, device=dev),
+           "gt_index": torch.empty((n, s), dtype=torch.int64, device=dev)}
+    if m > 0:
+        out.update({"mask_rois": torch.empty((n * m, 5), dtype=torch.float32, device=dev),
+                    "mask_labels": torch.empty((n * m,), dtype=torch.int64, device=dev),
+                    "mask_weight": torch.empty((n * m,), dtype=torch.float32, device=dev),
+                    "mask_gt_index": torch.empty((n, m), dtype=torch.int64, device=dev)})
+    w = (ctypes.c_float * 4)(*[float(x) for x in weights])
+    with _c.on_device(dev):
+        _c.check(lib.mrb_roi_assign_sample(
+            _c._ptr(boxes), _c._ptr(valid), _c._ptr(rand_keys), _c._ptr(gt_boxes), _c._ptr(gt_labels), _c._ptr(gt_count), n, p,
+            gt_boxes.shape[1], s, ctypes.c_float(positive_fraction), ctypes.c_float(fg_iou), ctypes.c_float(bg_iou), w, m,
+            _c._ptr(out["rois"]), _c._ptr(out["labels"]), _c._ptr(out["reg_targets"]), _c._ptr(out["gt_index"]),
+            _c._ptr(out.get("mask_rois")), _c._ptr(out.get("mask_labels")), _c._ptr(out.get("mask_weight")),
+            _c._ptr(out.get("mask_gt_index")), _c._stream()), "mrb_roi_assign_sample")
+    _count(1)
+    return out
+
+
+def rpn_anchor_match(anchors, gt_boxes, gt_count, image_w, image_h, fg_iou, bg_iou, straddle_thresh):
+    """RPN anchor labelling (rpn/loss.py:40-90, matcher.py:42-112 with low-quality matches) for the batch: two launches.
+    -> labels [N, A] fp32 (1 / 0 / -1), matched_gt [N, A] int32."""
+    anchors, gt_boxes = _f32c(anchors, "rpn_anchor_match"), _f32c(gt_boxes, "rpn_anchor_match")
+    n, gmax, _ = gt_boxes.shape
+    a = anchors.shape[0]
+    dev = anchors.device
+    labels = torch.empty((n, a), dtype=torch.float32, device=dev)
+    matched = torch.empty((n, a), dtype=torch.int32, device=dev)
+    with _c.on_device(dev):
+        nbytes = lib.mrb_rpn_anchor_match_workspace_bytes(n, a, gmax)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        _c.check(lib.mrb_rpn_anchor_match(_c._ptr(anchors), _c._ptr(gt_boxes), _c._ptr(gt_count), _c._ptr(image_w), _c._ptr(image_h),
+                                          n, a, gmax, ctypes.c_float(fg_iou), ctypes.c_float(bg_iou),
+                                          ctypes.c_float(straddle_thresh), _c._ptr(labels), _c._ptr(matched), _c._ptr(ws),
+                                          ctypes.c_size_t(nbytes), _c._stream()), "mrb_rpn_anchor_match")
+    _count(3)
+    return labels, matched
