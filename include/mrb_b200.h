@@ -273,6 +273,48 @@ int mrb_rpn_anchor_match(const float* anchors, const float* gt_boxes, const int3
                          float straddle_thresh, float* labels, int32_t* matched_gt, void* workspace, size_t workspace_bytes,
                          mrb_stream_t stream);
 
+/* ------------------------------------------------------------- loss stages (csrc/loss_glue.cu)
+ * Forward + backward of the three loss computations of the train step, each a launch or two, deterministic reductions.
+ * `result` buffers are small fp32 device arrays written by the forward and read by the backward; grad_* are the upstream
+ * gradients of the scalar losses as DEVICE scalars.
+ *
+ * RPN (modeling/rpn/loss.py:92-131): head_outputs_host[l] = level l's head output [N, locations[l], pixel_stride] fp32 (A
+ * logits, then 4A deltas, then padding up to pixel_stride per location: the NHWC output of the fused cls+bbox 1x1 conv).  sel_* [N, num_sel]: the sampled anchors
+ * (index into the concatenated anchor list, label 1/0, weight 1 / 0 = padding); pos_* [N, num_pos]: the sampled positives
+ * with their regression targets.  result[3] = {objectness loss, box loss (smooth-L1 beta), #sampled}.  The backward writes
+ * ONLY the sampled entries of grad_outputs_host[l] (same shapes), which the caller has zeroed. */
+int mrb_rpn_loss_fwd(void* const* head_outputs_host, const int* locations_host, int num_levels, int num_images,
+                     int anchors_per_location, int pixel_stride, const int64_t* sel_idx, const float* sel_label, const float* sel_weight, int num_sel,
+                     const int64_t* pos_idx, const uint8_t* pos_ok, const float* reg_targets, int num_pos, float beta,
+                     float* result, mrb_stream_t stream);
+int mrb_rpn_loss_bwd(void* const* head_outputs_host, void* const* grad_outputs_host, const int* locations_host, int num_levels,
+                     int num_images, int anchors_per_location, int pixel_stride, const int64_t* sel_idx, const float* sel_label,
+                     const float* sel_weight, int num_sel, const int64_t* pos_idx, const uint8_t* pos_ok, const float* reg_targets,
+                     int num_pos, float beta, const float* result, const float* grad_objectness, const float* grad_box,
+                     mrb_stream_t stream);
+/* Box head (modeling/roi_heads/box_head/loss.py:120-167): outputs [R, ld] fp32 = class logits in columns [0, C), box
+ * regression in [C + 4c, C + 4c + 4); labels [R] int64 (-1 = row not sampled), reg_targets [R, 4].
+ * result[3] = {cross-entropy (mean over sampled rows), smooth-L1(beta 1) sum over positives / #sampled, #sampled}.
+ * The backward writes the whole [R, ld] gradient. */
+int mrb_box_loss_fwd(const float* outputs, int ld, int num_classes, const int64_t* labels, const float* reg_targets, int num_rois,
+                     float* result, mrb_stream_t stream);
+int mrb_box_loss_bwd(const float* outputs, int ld, int num_classes, const int64_t* labels, const float* reg_targets, int num_rois,
+                     const float* result, const float* grad_cls, const float* grad_box, float* grad_outputs, mrb_stream_t stream);
+/* Mask head (modeling/roi_heads/mask_head/loss.py:100-133): logits [R, mask_pixels, channels] bf16 (NHWC), labels [R] int64
+ * (class whose plane is read, loss.py:120-126), targets [R, mask_pixels] fp32, weights [R] (1 positive / 0 padding).
+ * row_losses [R] scratch; result[2] = {sum_r w_r mean_pix BCE / max(sum w, 1), max(sum w, 1)}.  The backward writes the whole
+ * bf16 gradient [R, mask_pixels, channels] (channels % 8 == 0). */
+int mrb_mask_loss_fwd(const void* logits_bf16, int channels, int mask_pixels, const int64_t* labels, const float* targets,
+                      const float* weights, int num_rois, float* row_losses, float* result, mrb_stream_t stream);
+int mrb_mask_loss_bwd(const void* logits_bf16, int channels, int mask_pixels, const int64_t* labels, const float* targets,
+                      const float* weights, int num_rois, const float* result, const float* grad_loss, void* grad_logits_bf16,
+                      mrb_stream_t stream);
+/* mrb_rpn_decode reading logits and deltas in place from the head output [N, locations, A + 4A] (see mrb_rpn_loss_fwd). */
+int mrb_rpn_decode_packed(const float* head_output, int anchors_per_location, int pixel_stride, const float* anchors,
+                          const int64_t* topk_idx,
+                          const float* image_w, const float* image_h, float* boxes, float* scores, int num_images,
+                          int num_anchors, int k, const float* weights_host, float xform_clip, mrb_stream_t stream);
+
 /* Operand preparation for MRB_CONV_GROUPED64 (csrc/grouped_prep.cu).  weight: the grouped filter [C][taps][C/groups] bf16
  * (KRSC).  w_exp / wd_exp: [C][taps][64] bf16 -- the forward operand and the (flipped, per-Cout scaled) data-gradient operand
  * of mrb_conv2d_fwd / mrb_conv2d_dgrad_prepared; either may be NULL.  mrb_grouped_collapse_wgrad folds the [C][taps][128]

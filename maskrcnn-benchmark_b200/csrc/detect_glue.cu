@@ -132,13 +132,25 @@ __global__ void __launch_bounds__(256)
 rpn_decode_kernel(const float* __restrict__ logits, const float4* __restrict__ deltas, const float4* __restrict__ anchors,
                   const int64_t* __restrict__ idx, const float* __restrict__ im_w, const float* __restrict__ im_h,
                   float4* __restrict__ boxes, float* __restrict__ scores, int N, int A, int k, float wx, float wy, float ww,
-                  float wh, float clip) {   // wx..wh: RECIPROCALS of the box-coder weights
+                  float wh, float clip, int packed_apl, int packed_ld) {   // wx..wh: RECIPROCALS of the box-coder weights
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= N * k) return;
   const int i = t / k;
   int64_t a = idx[t];
   a = a < 0 ? 0 : (a >= A ? A - 1 : a);
-  const float4 d = deltas[(size_t)i * A + a];
+  float4 d;
+  float z;
+  if (packed_apl > 0) {
+    // head output [N, A / apl locations, apl logits + 4 apl deltas] read in place (`logits` is its base)
+    const int pix = (int)(a / packed_apl), q = (int)(a - (int64_t)pix * packed_apl);
+    const float* row = logits + ((size_t)i * (A / packed_apl) + pix) * (size_t)packed_ld;
+    z = row[q];
+    const float* dp = row + packed_apl + 4 * q;
+    d = make_float4(dp[0], dp[1], dp[2], dp[3]);
+  } else {
+    d = deltas[(size_t)i * A + a];
+    z = logits[(size_t)i * A + a];
+  }
   const float4 an = anchors[a];
   // box_coder.py:62-93 (TO_REMOVE = 1)
   const float w = __fadd_rn(__fsub_rn(an.z, an.x), 1.f), h = __fadd_rn(__fsub_rn(an.w, an.y), 1.f);
@@ -157,7 +169,6 @@ rpn_decode_kernel(const float* __restrict__ logits, const float4* __restrict__ d
   x2 = fminf(fmaxf(x2, 0.f), lx);
   y2 = fminf(fmaxf(y2, 0.f), ly);
   boxes[t] = make_float4(x1, y1, x2, y2);
-  const float z = logits[(size_t)i * A + a];
   scores[t] = __fdiv_rn(1.f, __fadd_rn(1.f, expf(-z)));   // inference.py:88 (.sigmoid())
 }
 
@@ -584,7 +595,25 @@ MRB_API int mrb_rpn_decode(const float* logits, const float* deltas, const float
   const int total = num_images * k;
   rpn_decode_kernel<<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(
       logits, (const float4*)deltas, (const float4*)anchors, topk_idx, image_w, image_h, (float4*)boxes, scores, num_images,
-      num_anchors, k, 1.f / weights_host[0], 1.f / weights_host[1], 1.f / weights_host[2], 1.f / weights_host[3], xform_clip);
+      num_anchors, k, 1.f / weights_host[0], 1.f / weights_host[1], 1.f / weights_host[2], 1.f / weights_host[3], xform_clip, 0, 0);
+  MRB_LAUNCH_CHECK();
+  return MRB_OK;
+}
+
+MRB_API int mrb_rpn_decode_packed(const float* head_output, int anchors_per_location, int pixel_stride, const float* anchors,
+                                  const int64_t* topk_idx,
+                                  const float* image_w, const float* image_h, float* boxes, float* scores, int num_images,
+                                  int num_anchors, int k, const float* weights_host, float xform_clip, mrb_stream_t stream) {
+  if (num_images < 0 || num_anchors <= 0 || k < 0 || !weights_host || anchors_per_location <= 0 ||
+      num_anchors % anchors_per_location || pixel_stride < 5 * anchors_per_location)
+    return MRB_ERR_BAD_ARG;
+  if (num_images == 0 || k == 0) return MRB_OK;
+  if (!head_output || !anchors || !topk_idx || !image_w || !image_h || !boxes || !scores) return MRB_ERR_BAD_ARG;
+  if (((uintptr_t)anchors & 15) || ((uintptr_t)boxes & 15)) return MRB_ERR_BAD_ARG;
+  const int total = num_images * k;
+  rpn_decode_kernel<<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      head_output, nullptr, (const float4*)anchors, topk_idx, image_w, image_h, (float4*)boxes, scores, num_images, num_anchors, k,
+      1.f / weights_host[0], 1.f / weights_host[1], 1.f / weights_host[2], 1.f / weights_host[3], xform_clip, anchors_per_location, pixel_stride);
   MRB_LAUNCH_CHECK();
   return MRB_OK;
 }

@@ -291,6 +291,8 @@ class B200Backend(Backend):
     # proposal selection / target assignment / sampling as the launches of csrc/detect_glue.cu (MRB_FUSED_GLUE=0: the
     # PyTorch formulation, kept as the A/B arm and as what the CPU checker backend runs)
     fused_glue = __import__("os").environ.get("MRB_FUSED_GLUE", "1") != "0"
+    # the three loss stages as the fused forward / backward launches of csrc/loss_glue.cu (MRB_FUSED_LOSSES=0: PyTorch ops)
+    fused_losses = __import__("os").environ.get("MRB_FUSED_LOSSES", "1") != "0"
 
     def __init__(self, wgrad="tc"):
         self._w16 = {}
@@ -618,15 +620,16 @@ class B200Backend(Backend):
             for e in stale:
                 e[2] = e[0]._version
 
-    def linear(self, x, weight, bias, relu=False, out_fp32=False, premask_x=False, gy_premasked=False):
-        """Fully connected layer on the conv engine: [R, K] x [Cout, K]^T as a 1x1 conv over R "pixels"."""
+    def linear(self, x, weight, bias, relu=False, out_fp32=False, premask_x=False, gy_premasked=False, keep_padded=False):
+        """Fully connected layer on the conv engine: [R, K] x [Cout, K]^T as a 1x1 conv over R "pixels".
+        keep_padded: return the round-up-to-8 output columns (the extra ones are exactly zero)."""
         r, k = x.shape
         co = weight.shape[0]
         w16 = self._weight16(weight).view(co, k, 1, 1)
         y = self.conv(x.to(torch.bfloat16).reshape(r, k, 1, 1), weight.view(co, k, 1, 1), bias=bias, relu=relu,
                       out_fp32=out_fp32, w16=w16, premask_x=premask_x, gy_premasked=gy_premasked,
-                      wparam=weight if isinstance(weight, torch.nn.Parameter) else None)
-        return y.reshape(r, co)
+                      wparam=weight if isinstance(weight, torch.nn.Parameter) else None, keep_padded=keep_padded)
+        return y.reshape(r, y.shape[1])
 
     def deconv2x2(self, x, weight, bias, relu=False, premask_x=False, gy_premasked=False):
         """ConvTranspose2d(k=2, s=2), weight [Cin, Cout, 2, 2]: see _Deconv2x2Fn (two strided 1x1 convs, no shuffle)."""

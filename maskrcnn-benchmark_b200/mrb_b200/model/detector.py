@@ -65,12 +65,15 @@ class GeneralizedRCNN(nn.Module):
         if fused:
             # the positives-first list came out of the assign-and-sample launch
             rois_sel, lab_sel, wsel, mg = sm["mask_rois"], sm["mask_labels"], sm["mask_weight"], sm["mask_gt_index"]
-            sel_logits = mask.run(be, feats, rois_sel, select=lab_sel)
             if polyset is not None:
                 tgt = ops.mask_targets_polygons(polyset, rois_sel[:, 1:], (mg + inst_off).reshape(-1), res)
             else:
                 gt_sel = torch.gather(gtp[0], 1, mg[..., None].expand(-1, -1, 4)).reshape(-1, 4)
                 tgt = mask.mask_targets(gt_sel, rois_sel[:, 1:], res)
+            if getattr(be, "fused_losses", False):
+                from mrb_b200 import ops as _ops
+                return _ops.mask_head_loss(mask.run(be, feats, rois_sel, padded_logits=True), lab_sel, tgt, wsel)
+            sel_logits = mask.run(be, feats, rois_sel, select=lab_sel)
             bce = torch.nn.functional.binary_cross_entropy_with_logits(sel_logits.float(), tgt,
                                                                        reduction="none").mean((1, 2))
             return torch.where(wsel > 0, bce, torch.zeros((), dtype=bce.dtype, device=bce.device)).sum() / wsel.sum().clamp(min=1)
@@ -140,8 +143,12 @@ class GeneralizedRCNN(nn.Module):
                 else:
                     loss_mask = None
             x = box.features(be, feats, rois)
-            cls, reg = box.predict(be, x)
-            lc, lb = box.loss(cls, reg, labels, reg_t)
+            if getattr(be, "fused_losses", False):
+                from mrb_b200 import ops
+                lc, lb = ops.box_head_loss(box.predict_packed(be, x), labels, reg_t, self.cfg.num_classes)
+            else:
+                cls, reg = box.predict(be, x)
+                lc, lb = box.loss(cls, reg, labels, reg_t)
             losses.update({"loss_classifier": lc, "loss_box_reg": lb})
             if self.cfg.mask_on:
                 if st is not None:

@@ -108,6 +108,13 @@ class BoxHead(nn.Module):
         nc = self.cfg.num_classes
         return o[:, :nc], o[:, nc:]
 
+    def predict_packed(self, be, x):
+        """cls_score and bbox_pred as one GEMM, the padded [R, ld >= 5 C] fp32 result as it comes out of the engine"""
+        pr = self.predictor
+        w = torch.cat([pr.cls_score.weight, pr.bbox_pred.weight], 0)
+        b = torch.cat([pr.cls_score.bias, pr.bbox_pred.bias], 0)
+        return be.linear(x, w, b, relu=False, out_fp32=True, premask_x=True, keep_padded=True)
+
     def loss(self, class_logits, box_regression, labels, reg_targets):
         """box_head/loss.py:120-167"""
         labels = labels.reshape(-1)
@@ -190,9 +197,10 @@ class MaskHead(nn.Module):
                 nn.init.kaiming_normal_(p, mode="fan_out", nonlinearity="relu")
         self.predictor = pr
 
-    def run(self, be, feats, rois, select=None):
+    def run(self, be, feats, rois, select=None, padded_logits=False):
         """Mask logits [R, num_classes, M, M]; with `select` (class index per ROI, training) only the selected class
-        plane of each ROI, [R, M, M] (mask_head/loss.py:120-126)."""
+        plane of each ROI, [R, M, M] (mask_head/loss.py:120-126).  padded_logits: the logit conv's bf16 NHWC output with
+        its channels rounded up to 8, for ops.mask_head_loss."""
         cfg = self.cfg
         x = be.roi_align_fpn(feats[:4], rois, cfg.pooler_scales, cfg.mask_resolution_pool, cfg.mask_sampling_ratio,
                              nhwc=True)
@@ -201,6 +209,9 @@ class MaskHead(nn.Module):
             c = getattr(fe, name)
             x = be.conv(x, c.weight, bias=c.bias, pad=1, relu=True, premask_x=i > 0, gy_premasked=True)
         x = be.deconv2x2(x, pr.conv5_mask.weight, pr.conv5_mask.bias, relu=True, premask_x=True, gy_premasked=True)
+        if padded_logits:
+            return be.conv(x, pr.mask_fcn_logits.weight, bias=pr.mask_fcn_logits.bias, out_fp32=False, premask_x=True,
+                           keep_padded=True)
         if select is not None and hasattr(be, "conv_select"):
             return be.conv_select(x, pr.mask_fcn_logits.weight, pr.mask_fcn_logits.bias, select, premask_x=True)
         logits = be.conv(x, pr.mask_fcn_logits.weight, bias=pr.mask_fcn_logits.bias, out_fp32=True, premask_x=True)

@@ -84,6 +84,18 @@ class RPNHead(nn.Module):
             deltas.append(o[..., a:].reshape(n, h * ww * a, 4))
         return logits, deltas
 
+    def run_packed(self, be, feats):
+        """The head outputs as they leave the engine: per level one NHWC fp32 tensor [N, H, W, ld] holding, per location,
+        A logits, 4A deltas and zero padding up to ld = roundup8(5A) -- read in place by the decode / loss launches."""
+        w = torch.cat([self.cls_logits.weight, self.bbox_pred.weight], 0)
+        b = torch.cat([self.cls_logits.bias, self.bbox_pred.bias], 0)
+        outs = []
+        for f in feats:
+            t = be.conv(f, self.conv.weight, bias=self.conv.bias, pad=1, relu=True, gy_premasked=True)
+            o = be.conv(t, w, bias=b, out_fp32=True, premask_x=True, keep_padded=True)   # [N, ld, H, W] channels_last
+            outs.append(o.permute(0, 2, 3, 1))
+        return outs
+
 
 class RPN(nn.Module):
     def __init__(self, cfg, in_channels):
@@ -105,19 +117,25 @@ class RPN(nn.Module):
         return self._size_cache[key]
 
     @torch.no_grad()
-    def _select_proposals_fused(self, be, anchors, logits, deltas, image_sizes, gtp, training):
+    def _select_proposals_fused(self, be, anchors, logits, deltas, image_sizes, gtp, training, outs=None):
         """select_proposals as 5 top-k + 5 decode launches (one lane per level), the batched NMS and ONE collect launch
         (csrc/detect_glue.cu); same contract.  The top-k runs on the logits (sigmoid is monotone; the k sigmoids are taken
         in the decode kernel)."""
         from mrb_b200 import ops
         cfg = self.cfg
-        n = logits[0].shape[0]
-        dev = logits[0].device
         pre_n = cfg.pre_nms_top_n_train if training else cfg.pre_nms_top_n_test
         post_n = cfg.post_nms_top_n_train if training else cfg.post_nms_top_n_test
         fpn_post_n = cfg.fpn_post_nms_top_n_train if training else cfg.fpn_post_nms_top_n_test
+        apl = self.head.num_anchors
+        if outs is not None:         # head outputs [N, H, W, ld] read in place (RPNHead.run_packed)
+            outs = [o.detach() for o in outs]
+            logits, deltas = outs, outs
+            ks = [min(pre_n, o.shape[1] * o.shape[2] * apl) for o in outs]
+        else:
+            ks = [min(pre_n, lg.shape[1]) for lg in logits]
+        n = logits[0].shape[0]
+        dev = logits[0].device
         widths, heights = self._sizes(image_sizes, dev)
-        ks = [min(pre_n, lg.shape[1]) for lg in logits]
         tot = n * sum(ks)
         boxes = torch.empty((tot, 4), dtype=torch.float32, device=dev)
         scores = torch.empty((tot,), dtype=torch.float32, device=dev)
@@ -127,6 +145,10 @@ class RPN(nn.Module):
             bo, so = boxes[off:off + n * k], scores[off:off + n * k]
 
             def level(anc=anc, lg=lg, dl=dl, k=k, bo=bo, so=so):
+                if outs is not None:
+                    idx = lg[..., :apl].reshape(n, -1).topk(k, dim=1, sorted=True)[1]
+                    ops.rpn_decode_packed(lg, apl, anc, idx, widths, heights, bo, so, self.box_coder.weights, self.box_coder.clip)
+                    return bo
                 idx = lg.topk(k, dim=1, sorted=True)[1]                                   # inference.py:91-95
                 ops.rpn_decode(lg, dl, anc, idx, widths, heights, bo, so, self.box_coder.weights, self.box_coder.clip)
                 return bo
@@ -237,7 +259,7 @@ class RPN(nn.Module):
 
     # ------------------------------------------------------------------ loss
     @torch.no_grad()
-    def loss_targets_fused(self, anchors_all, image_sizes, targets, gtp, generator=None):
+    def loss_targets_fused(self, anchors_all, image_sizes, targets, gtp, generator=None, stacked=False):
         """loss_targets with the IoU / Matcher / labelling of all anchors of the batch as one launch pair
         (mrb_rpn_anchor_match); the sampling and the encoding of the sampled rows as in loss_targets."""
         from mrb_b200 import ops
@@ -255,6 +277,8 @@ class RPN(nn.Module):
             sel_lab = torch.cat([torch.ones_like(pos_ok, dtype=torch.float32), torch.zeros_like(neg_ok, dtype=torch.float32)])
             sel_w = torch.cat([pos_ok, neg_ok]).float()
             out.append((pos_idx, pos_ok, reg_t, sel, sel_lab, sel_w))
+        if stacked:
+            return tuple(torch.stack([o[j] for o in out]) for j in range(6))
         return out
 
     @torch.no_grad()
@@ -315,8 +339,9 @@ class RPN(nn.Module):
             # there, concurrently with the RPN head convolutions and the proposal selection (a few hundred tiny kernels
             # that would otherwise sit on the critical path between two tensor-core phases)
             fork = getattr(be, "fork", None)
+            packed = fused and getattr(be, "fused_losses", False)
             if fused:
-                tfn = lambda: self.loss_targets_fused(anchors_all, image_sizes, targets, gtp, generator)
+                tfn = lambda: self.loss_targets_fused(anchors_all, image_sizes, targets, gtp, generator, stacked=packed)
             else:
                 tfn = lambda: self.loss_targets(anchors_all, vis, targets, generator)
             forked = fork is not None
@@ -325,6 +350,16 @@ class RPN(nn.Module):
                 prepared = fork(ins, tfn)
             elif fused:
                 prepared = tfn()
+        if training and packed:
+            # fused losses: the head outputs stay in the engine's layout, read in place by decode and loss launches
+            from mrb_b200 import ops
+            outs = self.head.run_packed(be, feats)
+            proposals = self._select_proposals_fused(be, anchors, None, None, image_sizes, gtp, training, outs=outs)
+            if forked:
+                prepared = be.join(prepared)
+            pos_idx, pos_ok, reg_t, sel, sel_lab, sel_w = prepared
+            lo, lb = ops.rpn_loss(outs, self.head.num_anchors, sel, sel_lab, sel_w, pos_idx, pos_ok, reg_t)
+            return proposals, {"loss_objectness": lo, "loss_rpn_box_reg": lb}
         logits, deltas = self.head.run(be, feats)
         proposals = self.select_proposals(be, anchors, [l.detach() for l in logits], [d.detach() for d in deltas],
                                           image_sizes, targets, training, gtp=gtp)

@@ -703,3 +703,159 @@ def rpn_anchor_match(anchors, gt_boxes, gt_count, image_w, image_h, fg_iou, bg_i
                                           ctypes.c_size_t(nbytes), _c._stream()), "mrb_rpn_anchor_match")
     _count(3)
     return labels, matched
+
+
+def rpn_decode_packed(head_out, apl, anchors, topk_idx, image_w, image_h, boxes_out, scores_out, weights=(1.0, 1.0, 1.0, 1.0),
+                      xform_clip=None):
+    """rpn_decode reading logits and deltas in place from the RPN head's NHWC output `head_out` [N, H, W, ld] fp32 (apl logits,
+    4 apl deltas, padding per location)."""
+    import math
+    if not (head_out.is_cuda and head_out.dtype == torch.float32 and head_out.is_contiguous() and head_out.dim() == 4):
+        raise RuntimeError("rpn_decode_packed: head output must be a contiguous fp32 CUDA tensor [N, H, W, ld]")
+    n, h, w_, ld = head_out.shape
+    a = h * w_ * apl
+    k = topk_idx.shape[1]
+    anchors = _f32c(anchors, "rpn_decode_packed")
+    if topk_idx.dtype != torch.int64 or not topk_idx.is_contiguous():
+        topk_idx = topk_idx.long().contiguous()
+    w = (ctypes.c_float * 4)(*[float(x) for x in weights])
+    clip = math.log(1000.0 / 16) if xform_clip is None else float(xform_clip)
+    with _c.on_device(head_out.device):
+        _c.check(lib.mrb_rpn_decode_packed(_c._ptr(head_out), apl, ld, _c._ptr(anchors), _c._ptr(topk_idx), _c._ptr(image_w),
+                                           _c._ptr(image_h), _c._ptr(boxes_out), _c._ptr(scores_out), n, a, k, w,
+                                           ctypes.c_float(clip), _c._stream()), "mrb_rpn_decode_packed")
+    _count(1)
+
+
+# --------------------------------------------------------------------------------- fused losses (csrc/loss_glue.cu)
+def _gscalar(g, like):
+    if g is None:
+        return torch.zeros((), dtype=torch.float32, device=like.device)
+    return g.detach().to(torch.float32).contiguous()
+
+
+class _RpnLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, sel_idx, sel_label, sel_weight, pos_idx, pos_ok, reg_t, apl, beta, *outs):
+        outs = [o if o.is_contiguous() else o.contiguous() for o in outs]
+        n, ld = outs[0].shape[0], outs[0].shape[3]
+        L = len(outs)
+        hw = (ctypes.c_int * L)(*[o.shape[1] * o.shape[2] for o in outs])
+        ptrs = (ctypes.c_void_p * L)(*[o.data_ptr() for o in outs])
+        result = torch.empty(3, dtype=torch.float32, device=outs[0].device)
+        with _c.on_device(outs[0].device):
+            _c.check(lib.mrb_rpn_loss_fwd(ptrs, hw, L, n, apl, ld, _c._ptr(sel_idx), _c._ptr(sel_label), _c._ptr(sel_weight),
+                                          sel_idx.shape[1], _c._ptr(pos_idx), _c._ptr(pos_ok), _c._ptr(reg_t), pos_idx.shape[1],
+                                          ctypes.c_float(beta), _c._ptr(result), _c._stream()), "mrb_rpn_loss_fwd")
+        _count(1)
+        ctx.save_for_backward(sel_idx, sel_label, sel_weight, pos_idx, pos_ok, reg_t, result, *outs)
+        ctx.geom = (apl, beta)
+        return result[0], result[1]
+
+    @staticmethod
+    def backward(ctx, g_obj, g_box):
+        sel_idx, sel_label, sel_weight, pos_idx, pos_ok, reg_t, result = ctx.saved_tensors[:7]
+        outs = ctx.saved_tensors[7:]
+        apl, beta = ctx.geom
+        n, ld = outs[0].shape[0], outs[0].shape[3]
+        L = len(outs)
+        flat = torch.zeros(sum(o.numel() for o in outs), dtype=torch.float32, device=outs[0].device)
+        grads, off = [], 0
+        for o in outs:
+            grads.append(flat[off:off + o.numel()].view(o.shape))
+            off += o.numel()
+        hw = (ctypes.c_int * L)(*[o.shape[1] * o.shape[2] for o in outs])
+        ptrs = (ctypes.c_void_p * L)(*[o.data_ptr() for o in outs])
+        gptrs = (ctypes.c_void_p * L)(*[g.data_ptr() for g in grads])
+        go, gb = _gscalar(g_obj, flat), _gscalar(g_box, flat)
+        with _c.on_device(flat.device):
+            _c.check(lib.mrb_rpn_loss_bwd(ptrs, gptrs, hw, L, n, apl, ld, _c._ptr(sel_idx), _c._ptr(sel_label), _c._ptr(sel_weight),
+                                          sel_idx.shape[1], _c._ptr(pos_idx), _c._ptr(pos_ok), _c._ptr(reg_t), pos_idx.shape[1],
+                                          ctypes.c_float(beta), _c._ptr(result), _c._ptr(go), _c._ptr(gb), _c._stream()),
+                     "mrb_rpn_loss_bwd")
+        _count(1)
+        return (None,) * 8 + tuple(grads)
+
+
+def rpn_loss(outs, apl, sel_idx, sel_label, sel_weight, pos_idx, pos_ok, reg_targets, beta=1.0 / 9):
+    """RPNLossComputation.__call__ (rpn/loss.py:92-131) on the head's NHWC outputs `outs` (one [N, H, W, ld] fp32 tensor per
+    level: apl logits, 4 apl deltas, padding): -> (loss_objectness, loss_rpn_box_reg).  sel_* [N, S], pos_* [N, P]."""
+    sel_idx = sel_idx.long().contiguous()
+    pos_idx = pos_idx.long().contiguous()
+    pos_ok = pos_ok.bool().contiguous()
+    return _RpnLossFn.apply(sel_idx, sel_label.float().contiguous(), sel_weight.float().contiguous(), pos_idx, pos_ok,
+                            reg_targets.float().contiguous(), int(apl), float(beta), *outs)
+
+
+class _BoxLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, o, labels, reg_t, num_classes):
+        if not o.is_contiguous():
+            o = o.contiguous()
+        r, ld = o.shape
+        result = torch.empty(3, dtype=torch.float32, device=o.device)
+        with _c.on_device(o.device):
+            _c.check(lib.mrb_box_loss_fwd(_c._ptr(o), ld, num_classes, _c._ptr(labels), _c._ptr(reg_t), r, _c._ptr(result),
+                                          _c._stream()), "mrb_box_loss_fwd")
+        _count(1)
+        ctx.save_for_backward(o, labels, reg_t, result)
+        ctx.nc = num_classes
+        return result[0], result[1]
+
+    @staticmethod
+    def backward(ctx, g_cls, g_box):
+        o, labels, reg_t, result = ctx.saved_tensors
+        r, ld = o.shape
+        d_o = torch.empty_like(o)
+        gc, gb = _gscalar(g_cls, o), _gscalar(g_box, o)
+        with _c.on_device(o.device):
+            _c.check(lib.mrb_box_loss_bwd(_c._ptr(o), ld, ctx.nc, _c._ptr(labels), _c._ptr(reg_t), r, _c._ptr(result), _c._ptr(gc),
+                                          _c._ptr(gb), _c._ptr(d_o), _c._stream()), "mrb_box_loss_bwd")
+        _count(1)
+        return d_o, None, None, None
+
+
+def box_head_loss(outputs, labels, reg_targets, num_classes):
+    """FastRCNNLossComputation.__call__ (box_head/loss.py:120-167) on the predictor output [R, ld >= 5 C] fp32 (C class logits,
+    then 4 C regression outputs): -> (loss_classifier, loss_box_reg).  labels [R] int64 (-1 = not sampled)."""
+    if outputs.dtype != torch.float32 or not outputs.is_cuda:
+        raise RuntimeError("box_head_loss: expected a fp32 CUDA tensor (no CPU path)")
+    return _BoxLossFn.apply(outputs, labels.reshape(-1).long().contiguous(), reg_targets.reshape(-1, 4).float().contiguous(),
+                            int(num_classes))
+
+
+class _MaskLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, y, labels, targets, weights):
+        r, c, h, w = y.shape
+        if y.dtype != torch.bfloat16 or not y.is_contiguous(memory_format=torch.channels_last):
+            y = y.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        rows = torch.empty(r, dtype=torch.float32, device=y.device)
+        result = torch.empty(2, dtype=torch.float32, device=y.device)
+        with _c.on_device(y.device):
+            _c.check(lib.mrb_mask_loss_fwd(_c._ptr(y), c, h * w, _c._ptr(labels), _c._ptr(targets), _c._ptr(weights), r,
+                                           _c._ptr(rows), _c._ptr(result), _c._stream()), "mrb_mask_loss_fwd")
+        _count(2)
+        ctx.save_for_backward(y, labels, targets, weights, result)
+        return result[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        y, labels, targets, weights, result = ctx.saved_tensors
+        r, c, h, w = y.shape
+        gy = torch.empty_like(y, memory_format=torch.channels_last)
+        gg = _gscalar(g, y)
+        with _c.on_device(y.device):
+            _c.check(lib.mrb_mask_loss_bwd(_c._ptr(y), c, h * w, _c._ptr(labels), _c._ptr(targets), _c._ptr(weights), r,
+                                           _c._ptr(result), _c._ptr(gg), _c._ptr(gy), _c._stream()), "mrb_mask_loss_bwd")
+        _count(1)
+        return gy, None, None, None
+
+
+def mask_head_loss(logits_nhwc, labels, targets, weights):
+    """MaskRCNNLossComputation.__call__ (mask_head/loss.py:100-133), fixed-shape form: logits [R, C, M, M] bf16 channels_last
+    (C % 8 == 0), labels [R] (class plane read per ROI), targets [R, M, M] fp32, weights [R] -> weighted mean of the per-ROI
+    mean BCE-with-logits."""
+    if logits_nhwc.shape[1] % 8:
+        raise RuntimeError("mask_head_loss: channel count must be a multiple of 8")
+    return _MaskLossFn.apply(logits_nhwc, labels.long().contiguous(), targets.float().contiguous(), weights.float().contiguous())

@@ -401,3 +401,129 @@ def test_harness_step_fused_glue_runs_and_matches_unfused_losses(built_lib):
     # the RPN losses do not depend on the ROI sampling keys' layout (same anchors, same generator draws per image)
     for k in ("loss_objectness", "loss_rpn_box_reg"):
         assert abs(out[True][k] - out[False][k]) <= 2e-2 * max(1.0, abs(out[False][k])), (k, out)
+
+
+# ------------------------------------------------------------------------------------------ 5. fused losses (csrc/loss_glue.cu)
+def test_rpn_loss_fused_equals_torch_formulation(built_lib):
+    from mrb_b200 import ops
+    from mrb_b200.model import box_ops
+    from mrb_b200.model.rpn import RPN
+    cfg = _cfg()
+    rpn = RPN(cfg, 256).to(DEV)
+    g = torch.Generator().manual_seed(21)
+    n, A, ld = 2, 3, 16
+    grids = [(100, 168), (50, 84), (25, 42), (13, 21), (7, 11)]
+    anchors_all = torch.cat(rpn.anchor_generator.grid(grids, DEV), 0)
+    outs = []
+    for h, w in grids:
+        o = torch.randn(n, h, w, ld, generator=g)
+        o[..., 5 * A:] = 0
+        outs.append(o.to(DEV).requires_grad_(True))
+    sizes = [(800, 1333), (768, 1216)]
+    targets = [{"boxes": _rand_boxes(g, 6, 1333, 800, 30, 400).to(DEV), "labels": torch.ones(6, dtype=torch.int64, device=DEV)},
+               {"boxes": _rand_boxes(g, 2, 1216, 768, 30, 400).to(DEV), "labels": torch.ones(2, dtype=torch.int64, device=DEV)}]
+    gtp = ops.pad_targets(targets, DEV)
+    gen = torch.Generator(device=DEV).manual_seed(3)
+    prepared = rpn.loss_targets_fused(anchors_all, sizes, targets, gtp, gen)
+    assert sum(int(p[1].sum()) for p in prepared) > 0          # some positives
+    # PyTorch formulation on the same numbers
+    logits = [o[..., :A].reshape(n, -1) for o in outs]
+    deltas = [o[..., A:5 * A].reshape(n, -1, 4) for o in outs]
+    lo, lb = rpn.loss(anchors_all, None, logits, deltas, targets, None, prepared)
+    (lo * 1.5 + lb * 0.7).backward()
+    want_g = [o.grad.clone() for o in outs]
+    for o in outs:
+        o.grad = None
+    st = tuple(torch.stack([p[j] for p in prepared]) for j in range(6))
+    flo, flb = ops.rpn_loss(outs, A, st[3], st[4], st[5], st[0], st[1], st[2])
+    (flo * 1.5 + flb * 0.7).backward()
+    torch.testing.assert_close(flo, lo, rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(flb, lb, rtol=1e-5, atol=1e-7)
+    for o, wg in zip(outs, want_g):
+        torch.testing.assert_close(o.grad, wg, rtol=1e-4, atol=1e-8)
+        assert not o.grad[..., 5 * A:].any()
+
+
+def test_box_head_loss_fused_equals_torch_formulation(built_lib):
+    from mrb_b200 import ops
+    from mrb_b200.model.roi_heads import BoxHead
+    cfg = _cfg()
+    head = BoxHead(cfg, 256)
+    g = torch.Generator().manual_seed(22)
+    r, nc, ld = 1024, cfg.num_classes, 408
+    o = torch.randn(r, ld, generator=g) * 2
+    o[:, 5 * nc:] = 0
+    o = o.to(DEV).requires_grad_(True)
+    labels = torch.randint(-1, nc, (r,), generator=g)
+    labels[torch.rand(r, generator=g) < 0.6] = 0
+    labels = labels.to(DEV)
+    reg_t = torch.randn(r, 4, generator=g).to(DEV)
+    lc, lb = head.loss(o[:, :nc], o[:, nc:5 * nc], labels, reg_t)
+    (lc * 0.9 + lb * 1.3).backward()
+    want = o.grad.clone()
+    o.grad = None
+    flc, flb = ops.box_head_loss(o, labels, reg_t, nc)
+    (flc * 0.9 + flb * 1.3).backward()
+    torch.testing.assert_close(flc, lc, rtol=2e-5, atol=1e-7)
+    torch.testing.assert_close(flb, lb, rtol=2e-5, atol=1e-7)
+    torch.testing.assert_close(o.grad, want, rtol=1e-4, atol=1e-9)
+
+
+def test_mask_head_loss_fused_equals_torch_formulation(built_lib):
+    from mrb_b200 import ops
+    g = torch.Generator().manual_seed(23)
+    r, c, m = 256, 88, 28
+    y0 = (torch.randn(r, c, m, m, generator=g) * 2).to(DEV).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    y = y0.clone().requires_grad_(True)
+    labels = torch.randint(0, 81, (r,), generator=g).to(DEV)
+    tgt = (torch.rand(r, m, m, generator=g) < 0.4).float().to(DEV)
+    w = (torch.rand(r, generator=g) < 0.3).float().to(DEV)
+    # PyTorch formulation (detector._mask_loss): pick the class plane, per-ROI mean BCE, weighted mean
+    sel = torch.gather(y.permute(0, 2, 3, 1), 3, labels.view(r, 1, 1, 1).expand(r, m, m, 1)).squeeze(3).float()
+    bce = torch.nn.functional.binary_cross_entropy_with_logits(sel, tgt, reduction="none").mean((1, 2))
+    want = torch.where(w > 0, bce, torch.zeros((), device=DEV)).sum() / w.sum().clamp(min=1)
+    (want * 2.0).backward()
+    want_g = y.grad.float().clone()
+    y2 = y0.clone().requires_grad_(True)
+    got = ops.mask_head_loss(y2, labels, tgt, w)
+    (got * 2.0).backward()
+    torch.testing.assert_close(got, want, rtol=1e-5, atol=1e-7)
+    assert y2.grad.dtype == torch.bfloat16 and y2.grad.is_contiguous(memory_format=torch.channels_last)
+    torch.testing.assert_close(y2.grad.float(), want_g, rtol=1.6e-2, atol=1e-9)      # bf16 rounding of the gradient
+
+
+def test_harness_step_fused_losses_match_unfused(built_lib):
+    """the harness train step with fused glue + fused losses vs the PyTorch loss ops on the same assignment (same keys):
+    all five losses, and the gradient reaching the backbone output"""
+    from mrb_b200.model import build_model
+    from mrb_b200.model.backend import B200Backend
+    from mrb_b200.model.config import RCNNConfig
+    torch.manual_seed(0)
+    cfg = RCNNConfig(mask_rois_per_image=64)
+    be = B200Backend()
+    model = build_model(cfg, be, DEV).train()
+    g = torch.Generator().manual_seed(1)
+    images = torch.randn(2, 3, 320, 448, generator=g).to(DEV)
+    sizes = [(320, 448), (300, 400)]
+    targets = [{"boxes": _rand_boxes(g, 6, 448, 320, 20, 200).to(DEV), "labels": torch.randint(1, 81, (6,), generator=g).to(DEV)},
+               {"boxes": _rand_boxes(g, 3, 400, 300, 20, 200).to(DEV), "labels": torch.randint(1, 81, (3,), generator=g).to(DEV)}]
+    out, grads = {}, {}
+    be.fused_glue = True
+    for fused in (True, False):
+        be.fused_losses = fused
+        model.zero_grad(set_to_none=True)
+        gen = torch.Generator(device=DEV).manual_seed(5)
+        losses = model(images, sizes, targets, generator=gen)
+        sum(losses.values()).backward()
+        out[fused] = {k: float(v.detach()) for k, v in losses.items()}
+        grads[fused] = {k: p.grad.detach().float().clone() for k, p in model.named_parameters() if p.grad is not None}
+        assert all(np.isfinite(v) for v in out[fused].values()), out[fused]
+    for k in out[True]:
+        assert abs(out[True][k] - out[False][k]) <= 5e-3 * max(1.0, abs(out[False][k])), (k, out)
+    assert set(grads[True]) == set(grads[False])
+    worst = 0.0
+    for k in grads[True]:
+        a, b = grads[True][k], grads[False][k]
+        den = float(b.norm()) + 1e-12
+        worst = max(worst, float((a - b).norm()) / den if den > 1e-9 else 0.0)
+    assert worst < 5e-2, worst      # bf16 operands on both sides; the loss gradients themselves agree to 1e-4 (tests above)
