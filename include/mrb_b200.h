@@ -297,7 +297,7 @@ int mrb_rpn_loss_bwd(void* const* head_outputs_host, void* const* grad_outputs_h
  * result[3] = {cross-entropy (mean over sampled rows), smooth-L1(beta 1) sum over positives / #sampled, #sampled}.
  * The backward writes the whole [R, ld] gradient. */
 int mrb_box_loss_fwd(const float* outputs, int ld, int num_classes, const int64_t* labels, const float* reg_targets, int num_rois,
-                     float* result, mrb_stream_t stream);
+                     float* row_scratch /* [3 R] */, float* result, mrb_stream_t stream);
 int mrb_box_loss_bwd(const float* outputs, int ld, int num_classes, const int64_t* labels, const float* reg_targets, int num_rois,
                      const float* result, const float* grad_cls, const float* grad_box, float* grad_outputs, mrb_stream_t stream);
 /* Mask head (modeling/roi_heads/mask_head/loss.py:100-133): logits [R, mask_pixels, channels] bf16 (NHWC), labels [R] int64

@@ -232,28 +232,35 @@ rpn_collect_kernel(const float4* __restrict__ boxes, const float* __restrict__ s
   float4* ob = out_b + (size_t)i * out_w;
   float* os = out_s + (size_t)i * out_w;
   unsigned char* ov = out_v + (size_t)i * out_w;
-  int n_sel = 0, tie_base = ties_before;
-  for (int c0 = 0; c0 < a.C; c0 += blockDim.x) {
-    const int c = c0 + threadIdx.x;
-    const unsigned key = c < a.C ? keys[c] : 0u;
-    const int is_tie = (key != 0 && key == T);
-    int tie_tot;
-    const int tie_rank = tie_base + block_excl_scan(is_tie, &tie_tot, scan_ws);
-    const int sel = key != 0 && (key > T || (is_tie && tie_rank < quota));
-    int sel_tot;
-    const int pos = n_sel + block_excl_scan(sel, &sel_tot, scan_ws);
-    if (sel) {
-      if (a.sorted) {
-        sortbuf[pos] = ((unsigned long long)key << 32) | (unsigned)(0x7fffffff - c);   // descending: key, then ascending slot
-      } else {
-        const int row = rows[c];
-        ob[pos] = boxes[row];
-        os[pos] = scores[row];
-        ov[pos] = 1;
-      }
+  // every thread owns a contiguous run of slots (slot order == output order): two CTA-wide scans in total
+  const int per = (a.C + (int)blockDim.x - 1) / (int)blockDim.x;
+  const int c_lo = min((int)threadIdx.x * per, a.C), c_hi = min(c_lo + per, a.C);
+  int my_ties = 0;
+  for (int c = c_lo; c < c_hi; ++c) my_ties += (keys[c] != 0 && keys[c] == T);
+  int tie_tot;
+  int tie_rank = ties_before + block_excl_scan(my_ties, &tie_tot, scan_ws);
+  int my_sel = 0;
+  for (int c = c_lo; c < c_hi; ++c) {
+    const unsigned key = keys[c];
+    const bool is_tie = key != 0 && key == T;
+    const bool sel = key != 0 && (key > T || (is_tie && tie_rank < quota));
+    tie_rank += is_tie;
+    my_sel += sel;
+    rows[c] = sel ? rows[c] : -1;       // rows doubles as the selection flag from here on
+  }
+  int n_sel;
+  int pos = block_excl_scan(my_sel, &n_sel, scan_ws);
+  for (int c = c_lo; c < c_hi; ++c) {
+    const int row = rows[c];
+    if (row < 0) continue;
+    if (a.sorted) {
+      sortbuf[pos] = ((unsigned long long)keys[c] << 32) | (unsigned)(0x7fffffff - c);   // descending: key, then ascending slot
+    } else {
+      ob[pos] = boxes[row];
+      os[pos] = scores[row];
+      ov[pos] = 1;
     }
-    n_sel += sel_tot;
-    tie_base += tie_tot;
+    ++pos;
   }
   if (a.sorted) {
     int p2 = 1;
@@ -363,21 +370,25 @@ roi_assign_sample_kernel(const float4* __restrict__ boxes, const unsigned char* 
     auto key_of = [&](int p, unsigned* k) { *k = keys[p]; return lab[p] > 0; };
     radix_select(key_of, a.P, a.pos_cap, &Tp, &qp, hist, ghist, sh);
   }
-  int n_pos = 0, tie_base = 0;
-  // mark the selection in bit 30 of lab's companion: reuse sel flags through a second pass below
-  // first pass: count selected positives
-  for (int p0 = 0; p0 < a.P; p0 += blockDim.x) {
-    const int p = p0 + threadIdx.x;
-    const bool is_pos = p < a.P && lab[p] > 0;
-    const int is_tie = is_pos && keys[p] == Tp;
+  // every thread owns a contiguous run of proposals (index order == output order): one CTA-wide scan per quantity
+  const int per = (a.P + (int)blockDim.x - 1) / (int)blockDim.x;
+  const int p_lo = min((int)threadIdx.x * per, a.P), p_hi = min(p_lo + per, a.P);
+  int n_pos;
+  {
+    int my_ties = 0;
+    for (int p = p_lo; p < p_hi; ++p) my_ties += (lab[p] > 0 && keys[p] == Tp);
     int tie_tot;
-    const int tr = tie_base + block_excl_scan(is_tie, &tie_tot, scan_ws);
-    const int sel = is_pos && (keys[p] > Tp || (is_tie && tr < qp));
-    int tot;
-    block_excl_scan(sel, &tot, scan_ws);
-    if (p < a.P && is_pos && !sel) lab[p] = -2 - lab[p];     // unsampled positive: remember the class as -(2 + class)
-    n_pos += tot;
-    tie_base += tie_tot;
+    int tr = block_excl_scan(my_ties, &tie_tot, scan_ws);
+    int my_sel = 0;
+    for (int p = p_lo; p < p_hi; ++p) {
+      if (lab[p] <= 0) continue;
+      const bool is_tie = keys[p] == Tp;
+      const bool sel = keys[p] > Tp || (is_tie && tr < qp);
+      tr += is_tie;
+      if (sel) ++my_sel;
+      else lab[p] = -2 - lab[p];     // unsampled positive: remember the class as -(2 + class)
+    }
+    block_excl_scan(my_sel, &n_pos, scan_ws);
   }
   __syncthreads();
   const int neg_want = a.S - n_pos;
@@ -386,42 +397,35 @@ roi_assign_sample_kernel(const float4* __restrict__ boxes, const unsigned char* 
     radix_select(key_of, a.P, neg_want > 0 ? neg_want : 1, &Tn, &qn, hist, ghist, sh);
   }
   // two-way partition in index order: sampled rows first, then the rest; the first S rows are the output
-  int n_sel = 0, n_rest = 0;
-  tie_base = 0;
-  // pass A: count sampled rows (needed to place the rest)
-  int total_sel = 0;
   {
-    int tb = 0;
-    for (int p0 = 0; p0 < a.P; p0 += blockDim.x) {
-      const int p = p0 + threadIdx.x;
-      const int l = p < a.P ? lab[p] : -1;
-      const int is_tie = (l == 0) && keys[p] == Tn;
-      int tie_tot;
-      const int tr = tb + block_excl_scan(is_tie, &tie_tot, scan_ws);
-      const int sel = (l > 0) || (neg_want > 0 && l == 0 && (keys[p] > Tn || (is_tie && tr < qn)));
-      int tot;
-      block_excl_scan(sel, &tot, scan_ws);
-      total_sel += tot;
-      tb += tie_tot;
-    }
-  }
-  for (int p0 = 0; p0 < a.P; p0 += blockDim.x) {
-    const int p = p0 + threadIdx.x;
-    const int l = p < a.P ? lab[p] : -1;
-    const int is_tie = (l == 0) && keys[p] == Tn;
+    int my_ties = 0;
+    for (int p = p_lo; p < p_hi; ++p) my_ties += (lab[p] == 0 && keys[p] == Tn);
     int tie_tot;
-    const int tr = tie_base + block_excl_scan(is_tie, &tie_tot, scan_ws);
-    const int sel = (l > 0) || (neg_want > 0 && l == 0 && (keys[p] > Tn || (is_tie && tr < qn)));
-    int tot, rtot;
-    const int ps = n_sel + block_excl_scan(sel, &tot, scan_ws);
-    const int pr = total_sel + n_rest + block_excl_scan((p < a.P) && !sel, &rtot, scan_ws);
-    if (p < a.P) {
-      const int slot = sel ? ps : pr;
+    int tr = block_excl_scan(my_ties, &tie_tot, scan_ws);
+    int my_sel = 0;
+    unsigned selbits = 0;            // per <= 32 checked on the host
+    for (int p = p_lo; p < p_hi; ++p) {
+      const int l = lab[p];
+      bool sel = l > 0;
+      if (l == 0) {
+        const bool is_tie = keys[p] == Tn;
+        sel = neg_want > 0 && (keys[p] > Tn || (is_tie && tr < qn));
+        tr += is_tie;
+      }
+      if (sel) {
+        ++my_sel;
+        selbits |= 1u << (p - p_lo);
+      }
+    }
+    int packed_tot;                  // low 16 bits: sampled rows, high 16 bits: the rest
+    const int packed = block_excl_scan(my_sel | ((p_hi - p_lo - my_sel) << 16), &packed_tot, scan_ws);
+    const int total_sel = packed_tot & 0xffff;
+    int ps = packed & 0xffff, pr = total_sel + (packed >> 16);
+    for (int p = p_lo; p < p_hi; ++p) {
+      const bool sel = (selbits >> (p - p_lo)) & 1u;
+      const int slot = sel ? ps++ : pr++;
       if (slot < a.S) sel_of[slot] = sel ? p : -1 - p;
     }
-    n_sel += tot;
-    n_rest += rtot;
-    tie_base += tie_tot;
   }
   __syncthreads();
   // emit the S rows (fewer than S proposals: the tail repeats row 0 as padding with label -1)
@@ -456,46 +460,34 @@ roi_assign_sample_kernel(const float4* __restrict__ boxes, const unsigned char* 
   // mask branch: the positives among the S rows first (mask_head.py:11-32), fixed width mask_m
   if (a.mask_m > 0) {
     __syncthreads();
-    int base_pos = 0, base_rest = 0, total_pos = 0;
-    for (int s0 = 0; s0 < a.S; s0 += blockDim.x) {
-      const int s = s0 + threadIdx.x;
-      int isp = 0;
-      if (s < a.S && s < a.P) {
-        const int p = sel_of[s];
-        isp = p >= 0 && lab[p] > 0;
-      }
-      int tot;
-      block_excl_scan(isp, &tot, scan_ws);
-      total_pos += tot;
+    const int sper = (a.S + (int)blockDim.x - 1) / (int)blockDim.x;
+    const int s_lo = min((int)threadIdx.x * sper, a.S), s_hi = min(s_lo + sper, a.S);
+    int my_pos = 0;
+    for (int sidx = s_lo; sidx < s_hi; ++sidx) {
+      const int p = sidx < a.P ? sel_of[sidx] : -1;
+      my_pos += (p >= 0 && lab[p] > 0);
     }
-    for (int s0 = 0; s0 < a.S; s0 += blockDim.x) {
-      const int s = s0 + threadIdx.x;
-      int p = -1, isp = 0;
-      if (s < a.S) {
-        p = s < a.P ? sel_of[s] : -1;
-        isp = p >= 0 && lab[p] > 0;
-        if (p < 0) p = -1 - p;
+    int packed_tot;
+    const int packed = block_excl_scan(my_pos | ((s_hi - s_lo - my_pos) << 16), &packed_tot, scan_ws);
+    const int total_pos = packed_tot & 0xffff;
+    int pp = packed & 0xffff, pr = total_pos + (packed >> 16);
+    for (int sidx = s_lo; sidx < s_hi; ++sidx) {
+      int p = sidx < a.P ? sel_of[sidx] : -1;
+      const bool isp = p >= 0 && lab[p] > 0;
+      if (p < 0) p = -1 - p;
+      const int slot = isp ? pp++ : pr++;
+      if (slot < a.mask_m) {
+        const float4 b = bx[p];
+        const size_t o = (size_t)i * a.mask_m + slot;
+        m_rois[o * 5 + 0] = (float)i;
+        m_rois[o * 5 + 1] = b.x;
+        m_rois[o * 5 + 2] = b.y;
+        m_rois[o * 5 + 3] = b.z;
+        m_rois[o * 5 + 4] = b.w;
+        m_labels[o] = isp ? (int64_t)lab[p] : (int64_t)0;
+        m_w[o] = isp ? 1.f : 0.f;
+        m_gidx[o] = mid[p];
       }
-      int tot, rtot;
-      const int pp = base_pos + block_excl_scan(isp, &tot, scan_ws);
-      const int pr = total_pos + base_rest + block_excl_scan((s < a.S) && !isp, &rtot, scan_ws);
-      if (s < a.S) {
-        const int slot = isp ? pp : pr;
-        if (slot < a.mask_m) {
-          const float4 b = bx[p];
-          const size_t o = (size_t)i * a.mask_m + slot;
-          m_rois[o * 5 + 0] = (float)i;
-          m_rois[o * 5 + 1] = b.x;
-          m_rois[o * 5 + 2] = b.y;
-          m_rois[o * 5 + 3] = b.z;
-          m_rois[o * 5 + 4] = b.w;
-          m_labels[o] = isp ? (int64_t)lab[p] : (int64_t)0;
-          m_w[o] = isp ? 1.f : 0.f;
-          m_gidx[o] = mid[p];
-        }
-      }
-      base_pos += tot;
-      base_rest += rtot;
     }
   }
 }
@@ -653,7 +645,7 @@ MRB_API int mrb_rpn_collect(const float* boxes, const float* scores, const int64
   int p2 = 1;
   while (p2 < a.W) p2 <<= 1;
   const size_t smem = (size_t)a.C * 8 + (a.sorted ? (size_t)p2 * 8 : 0);
-  if (smem > 200 * 1024) return MRB_ERR_UNSUPPORTED;
+  if (smem > 200 * 1024 || a.C >= 65536) return MRB_ERR_UNSUPPORTED;
   MRB_CUDA_TRY(cudaFuncSetAttribute(rpn_collect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(num_images);
@@ -709,7 +701,7 @@ MRB_API int mrb_roi_assign_sample(const float* boxes, const uint8_t* valid, cons
   a.ww = weights_host[2];
   a.wh = weights_host[3];
   const size_t smem = (size_t)a.P * 12 + (size_t)a.S * 4;
-  if (smem > 200 * 1024) return MRB_ERR_UNSUPPORTED;
+  if (smem > 200 * 1024 || num_proposals > 32 * kGlueThreads || num_proposals >= 65536) return MRB_ERR_UNSUPPORTED;
   MRB_CUDA_TRY(cudaFuncSetAttribute(roi_assign_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(num_images);

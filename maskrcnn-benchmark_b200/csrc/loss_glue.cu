@@ -156,15 +156,15 @@ rpn_loss_bwd_kernel(RpnLevels fw, RpnLevels gr, const int64_t* __restrict__ sel_
 // ------------------------------------------------------------------------------------------ box head loss
 // o [R, ld]: class logits in columns [0, C), regression outputs in [C + 4 c, C + 4 c + 4); labels [R] (-1 = not sampled)
 // result: {classification loss, box loss, number of sampled rows}
-__global__ void __launch_bounds__(kLossThreads)
-box_loss_fwd_kernel(const float* __restrict__ o, int ld, int C, const int64_t* __restrict__ labels,
-                    const float4* __restrict__ reg_t, int R, float* __restrict__ result) {
-  __shared__ float ws[32];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-  float cls = 0.f, box = 0.f, cnt = 0.f;   // lane 0 of every warp accumulates its rows
-  for (int r = warp; r < R; r += nwarp) {
-    const int64_t lab = labels[r];
-    if (lab < 0) continue;
+__global__ void __launch_bounds__(256)
+box_loss_rows_kernel(const float* __restrict__ o, int ld, int C, const int64_t* __restrict__ labels,
+                     const float4* __restrict__ reg_t, int R, float* __restrict__ rows) {   // rows [R][3]: cls, box, sampled
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= R) return;
+  const int64_t lab = labels[r];
+  float cls = 0.f, box = 0.f, cnt = 0.f;
+  if (lab >= 0) {
     const float* row = o + (size_t)r * ld;
     float m = -INFINITY;
     for (int c = lane; c < C; c += 32) m = fmaxf(m, row[c]);
@@ -173,30 +173,36 @@ box_loss_fwd_kernel(const float* __restrict__ o, int ld, int C, const int64_t* _
     for (int c = lane; c < C; c += 32) s += expf(row[c] - m);
     s = warp_sum(s);
     if (lane == 0) {
-      cls += (m + logf(s)) - row[lab];
-      cnt += 1.f;
+      cls = (m + logf(s)) - row[lab];
+      cnt = 1.f;
       if (lab > 0) {
         const float* p = row + C + 4 * lab;
         const float4 tg = reg_t[r];
-        box += smooth_l1(p[0] - tg.x, 1.f) + smooth_l1(p[1] - tg.y, 1.f) + smooth_l1(p[2] - tg.z, 1.f) +
-               smooth_l1(p[3] - tg.w, 1.f);
+        box = smooth_l1(p[0] - tg.x, 1.f) + smooth_l1(p[1] - tg.y, 1.f) + smooth_l1(p[2] - tg.z, 1.f) +
+              smooth_l1(p[3] - tg.w, 1.f);
       }
     }
   }
-  __syncthreads();
-  if (lane == 0) ws[warp] = cls;
-  __syncthreads();
-  float sc = 0.f, sb = 0.f, sn = 0.f;
-  if (threadIdx.x == 0) for (int w = 0; w < nwarp; ++w) sc += ws[w];
-  __syncthreads();
-  if (lane == 0) ws[warp] = box;
-  __syncthreads();
-  if (threadIdx.x == 0) for (int w = 0; w < nwarp; ++w) sb += ws[w];
-  __syncthreads();
-  if (lane == 0) ws[warp] = cnt;
-  __syncthreads();
+  if (lane == 0) {
+    rows[(size_t)r * 3 + 0] = cls;
+    rows[(size_t)r * 3 + 1] = box;
+    rows[(size_t)r * 3 + 2] = cnt;
+  }
+}
+
+__global__ void __launch_bounds__(kLossThreads)
+box_loss_sum_kernel(const float* __restrict__ rows, int R, float* __restrict__ result) {
+  __shared__ float ws[32];
+  float c = 0.f, b = 0.f, n = 0.f;
+  for (int r = threadIdx.x; r < R; r += blockDim.x) {
+    c += rows[(size_t)r * 3 + 0];
+    b += rows[(size_t)r * 3 + 1];
+    n += rows[(size_t)r * 3 + 2];
+  }
+  const float sc = block_sum_fixed(c, ws);
+  const float sb = block_sum_fixed(b, ws);
+  const float sn = block_sum_fixed(n, ws);
   if (threadIdx.x == 0) {
-    for (int w = 0; w < nwarp; ++w) sn += ws[w];
     result[0] = sc / sn;                 // F.cross_entropy(ignore_index=-1): mean over the sampled rows
     result[1] = sb / fmaxf(sn, 1.f);     // loss.py:160-165: / labels.numel() (here: the sampled rows)
     result[2] = sn;
@@ -364,12 +370,14 @@ MRB_API int mrb_rpn_loss_bwd(void* const* head_outputs_host, void* const* grad_o
 }
 
 MRB_API int mrb_box_loss_fwd(const float* outputs, int ld, int num_classes, const int64_t* labels, const float* reg_targets,
-                             int num_rois, float* result, mrb_stream_t stream) {
-  if (!outputs || !labels || !reg_targets || !result || num_rois <= 0 || num_classes <= 0 || ld < 5 * num_classes)
+                             int num_rois, float* row_scratch, float* result, mrb_stream_t stream) {
+  if (!outputs || !labels || !reg_targets || !row_scratch || !result || num_rois <= 0 || num_classes <= 0 || ld < 5 * num_classes)
     return MRB_ERR_BAD_ARG;
   if ((uintptr_t)reg_targets & 15) return MRB_ERR_BAD_ARG;
-  box_loss_fwd_kernel<<<1, kLossThreads, 0, (cudaStream_t)stream>>>(outputs, ld, num_classes, labels, (const float4*)reg_targets,
-                                                                     num_rois, result);
+  box_loss_rows_kernel<<<ceil_div(num_rois, 8), 256, 0, (cudaStream_t)stream>>>(outputs, ld, num_classes, labels,
+                                                                                 (const float4*)reg_targets, num_rois, row_scratch);
+  MRB_LAUNCH_CHECK();
+  box_loss_sum_kernel<<<1, kLossThreads, 0, (cudaStream_t)stream>>>(row_scratch, num_rois, result);
   MRB_LAUNCH_CHECK();
   return MRB_OK;
 }

@@ -12,6 +12,8 @@
 // Sampling arithmetic is the reference's (see roi_align.cu) in fp32 with the same operation order.
 #include <cuda_bf16.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace mrb {
@@ -232,6 +234,89 @@ roi_align_fpn_fwd_kernel(FpnArgs a, const float* __restrict__ rois, T* __restric
   }
 }
 
+// ---- forward, second form (bf16 features, sampling_ratio 2, C % 8 == 0): one CTA per ROI, a lane owns 8 consecutive channels
+// (16-byte loads: a warp request covers 256 channels = 512 B), the taps of a bin go out one row (4 columns) at a time and rows
+// of zero weight are skipped, which keeps the kernel at 4 CTAs per SM (the first form holds all 16 taps of 8 B + 16 weights
+// per lane: 80 registers, 3 CTAs per SM, twice the load instructions per byte).  Same taps and weights as the first form's
+// separable path; a zero-weight tap contributes an exact +0, so skipping it does not change the sum.
+constexpr int kV2Lane = 8;
+__global__ void __launch_bounds__(kFpnThreads, 4)
+roi_align_fpn_fwd_v2_kernel(FpnArgs a, const float* __restrict__ rois, __nv_bfloat16* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int n = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const RoiGeomF g = fpn_geom(rois + (size_t)n * 5, a);
+  const int H = a.H[g.level], W = a.W[g.level], C = a.C, PP = a.P * a.P, PPS = PP | 1;
+  float* tile = reinterpret_cast<float*>(smem_raw);  // [256][PPS], NCHW-order output only
+  __shared__ Axis2 s_ay[kMaxP], s_ax[kMaxP];
+  if ((int)threadIdx.x < a.P)
+    axis2(H, fpn_coord(g.sh, threadIdx.x, g.bin_h, 0, 2), fpn_coord(g.sh, threadIdx.x, g.bin_h, 1, 2), s_ay[threadIdx.x]);
+  else if ((int)threadIdx.x < 2 * a.P)
+    axis2(W, fpn_coord(g.sw, threadIdx.x - a.P, g.bin_w, 0, 2), fpn_coord(g.sw, threadIdx.x - a.P, g.bin_w, 1, 2), s_ax[threadIdx.x - a.P]);
+  __syncthreads();
+  const __nv_bfloat16* __restrict__ base = reinterpret_cast<const __nv_bfloat16*>(a.feat[g.level]) + (size_t)g.b * H * W * C;
+  for (int c0 = 0; c0 < C; c0 += 32 * kV2Lane) {
+    const int cl = c0 + lane * kV2Lane;
+    const bool c_ok = cl < C;
+    const __nv_bfloat16* __restrict__ src = base + (c_ok ? cl : 0);
+    for (int bin = warp; bin < PP; bin += kFpnThreads / 32) {
+      const int ph = bin / a.P, pw = bin - ph * a.P;
+      const Axis2 ay = s_ay[ph], ax = s_ax[pw];
+      float acc[kV2Lane];
+#pragma unroll
+      for (int k = 0; k < kV2Lane; ++k) acc[k] = 0.f;
+      const size_t co0 = (size_t)ax.r[0] * C, co1 = (size_t)ax.r[1] * C, co2 = (size_t)ax.r[2] * C, co3 = (size_t)ax.r[3] * C;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {          // one row of taps (4 columns) in flight per batch
+        if (ay.w[i] == 0.f) continue;        // warp-uniform
+        const __nv_bfloat16* rp = src + (size_t)ay.r[i] * W * C;
+        uint4 raw[4];
+        float wg[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float wgt = ay.w[i] * ax.w[j];
+          wg[j] = wgt;
+          raw[j] = make_uint4(0u, 0u, 0u, 0u);
+          if (c_ok && wgt != 0.f)
+            raw[j] = __ldg(reinterpret_cast<const uint4*>(rp + (j == 0 ? co0 : (j == 1 ? co1 : (j == 2 ? co2 : co3)))));
+        }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw[t]);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float2 f = __bfloat1622float2(h2[q]);
+            acc[2 * q] = fmaf(wg[t], f.x, acc[2 * q]);
+            acc[2 * q + 1] = fmaf(wg[t], f.y, acc[2 * q + 1]);
+          }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < kV2Lane; ++k) acc[k] = __fdiv_rn(acc[k], g.count);
+      if (a.out_nhwc) {
+        if (c_ok) {
+          uint4 o;
+          __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) oh[q] = __floats2bfloat162_rn(acc[2 * q], acc[2 * q + 1]);
+          *reinterpret_cast<uint4*>(out + ((size_t)n * PP + bin) * C + cl) = o;
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < kV2Lane; ++k) tile[(lane * kV2Lane + k) * PPS + bin] = acc[k];
+      }
+    }
+    if (!a.out_nhwc) {
+      __syncthreads();
+      const int cn = min(32 * kV2Lane, C - c0);
+      __nv_bfloat16* __restrict__ dst = out + ((size_t)n * C + c0) * PP;
+      for (int c = warp; c < cn; c += kFpnThreads / 32)
+        for (int bin = lane; bin < PP; bin += 32) dst[(size_t)c * PP + bin] = __float2bfloat16_rn(tile[c * PPS + bin]);
+      __syncthreads();
+    }
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kFpnThreads)
 roi_align_fpn_bwd_kernel(FpnArgs a, const float* __restrict__ rois, const T* __restrict__ gout) {
@@ -350,7 +435,13 @@ MRB_API int mrb_roi_align_fpn_fwd(const void* const* feats_host, const int* heig
   const size_t smem = out_nhwc ? 0 : (size_t)kFpnSlab * ((pooled * pooled) | 1) * sizeof(float);
   if (smem > 200 * 1024) return MRB_ERR_UNSUPPORTED;
   dim3 grid(num_rois, ceil_div(channels, kFpnSlab));
-  if (dtype == MRB_BF16) {
+  static const bool no_v2 = [] { const char* e = getenv("MRB_ROIALIGN_FPN_V2"); return e && e[0] == '0'; }();
+  const size_t smem2 = out_nhwc ? 0 : (size_t)(32 * kV2Lane) * ((pooled * pooled) | 1) * sizeof(float);
+  if (dtype == MRB_BF16 && !no_v2 && sampling_ratio == 2 && channels % kV2Lane == 0 && pooled <= kMaxP && smem2 <= 72 * 1024) {
+    // (adaptive sampling grids, other channel counts and large NCHW tiles take the first form)
+    if (smem2 > 48 * 1024) MRB_CUDA_TRY(cudaFuncSetAttribute(roi_align_fpn_fwd_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    roi_align_fpn_fwd_v2_kernel<<<num_rois, kFpnThreads, smem2, (cudaStream_t)stream>>>(a, rois, (__nv_bfloat16*)output);
+  } else if (dtype == MRB_BF16) {
     if (smem > 48 * 1024) MRB_CUDA_TRY(cudaFuncSetAttribute(roi_align_fpn_fwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     roi_align_fpn_fwd_kernel<__nv_bfloat16><<<grid, kFpnThreads, smem, (cudaStream_t)stream>>>(a, rois, (__nv_bfloat16*)output);
   } else if (dtype == MRB_F32) {

@@ -28,8 +28,13 @@ of the modules whose bodies are chains the conv engine fuses into one launch eac
   MaskRCNNC4Predictor        relu(conv5_mask), mask_fcn_logits         deconv as two strided 1x1 convs, 1x1 fp32
     (mask_head/roi_mask_predictors.py:29-32)
 
+  RPNPostProcessor.forward   per (level, image): top-k, decode, clip,      per level top-k + decode launch, ONE batched NMS,
+    (rpn/inference.py:76-181)  NMS (sync), BoxList ops; top-k over levels    ONE selection launch, one sync (detect_glue.cu)
+  project_masks_on_boxes     host loop: crop, resize, rasterise, upload    one launch on the polygon vertices
+    (mask_head/loss.py:11-42)                                               (the last two only with backend.fused_glue)
+
 Nothing else changes: module classes, parameters, buffers and state_dict keys are the reference's; the anchor
-generator, proposal selection, matcher/sampler, box coder and all losses are the reference's own Python.
+generator, matcher/sampler, box coder and all losses are the reference's own Python.
 Modules are recognised by structure (attribute names / layer types), not by import, so the pass needs no reference
 checkout; anything that does not match exactly is left alone (it still reaches the engine per conv through
 layers.Conv2d, unfused).  Activations between fused modules travel as bf16 NHWC (`channels_last`); tensors
@@ -321,6 +326,122 @@ def _fuse_mask_head(fe, pr, be):
 
 
 # ---------------------------------------------------------------------------------- the pass
+# ---------------------------------------------------------------------------------- detection glue (opt-in with the backend)
+def _fuse_rpn_postprocessor(mod, be):
+    """RPNPostProcessor.forward (rpn/inference.py:125-181): per level one top-k + one decode launch, ONE batched NMS launch
+    sequence for all (image, level) problems and ONE selection launch (csrc/detect_glue.cu), then a single host
+    synchronisation to size the returned BoxLists -- instead of a Python loop over levels x images with an NMS-sizing
+    synchronisation and a dozen BoxList operations each.  Same proposals (ties between equal scores aside)."""
+    need = ("pre_nms_top_n", "post_nms_top_n", "nms_thresh", "min_size", "box_coder", "fpn_post_nms_top_n", "fpn_post_nms_per_batch")
+    if type(mod).__name__ != "RPNPostProcessor" or not all(hasattr(mod, n) for n in need):
+        return False
+    if not (hasattr(mod.box_coder, "weights") and hasattr(mod.box_coder, "bbox_xform_clip")):
+        return False
+    orig = mod.forward
+    cache = {}
+
+    def forward(self, anchors, objectness, box_regression, targets=None):
+        from mrb_b200 import ops
+        n, L = len(anchors), len(objectness)
+        dev = objectness[0].device
+        per_batch = bool(self.training and self.fpn_post_nms_per_batch)
+        if self.min_size != 0 or dev.type != "cuda" or not (1 < L <= 8) or (per_batch and n > 8) or \
+                (self.training and targets is None):
+            return orig(anchors, objectness, box_regression, targets)
+        with torch.no_grad():
+            sizes = tuple(tuple(a[0].size) for a in anchors)                  # (width, height) of every image
+            key = (sizes, str(dev))
+            if key not in cache:
+                cache[key] = (torch.tensor([float(s[0]) for s in sizes], device=dev), torch.tensor([float(s[1]) for s in sizes], device=dev))
+            widths, heights = cache[key]
+            lgs, dls, ks = [], [], []
+            for o, r in zip(objectness, box_regression):
+                _, a, h, w = o.shape
+                lgs.append(o.detach().float().permute(0, 2, 3, 1).reshape(n, -1))                             # rpn/utils.py:11-15
+                dls.append(r.detach().float().view(n, a, 4, h, w).permute(0, 3, 4, 1, 2).reshape(n, -1, 4))
+                ks.append(min(int(self.pre_nms_top_n), a * h * w))
+            boxes = torch.empty((n * sum(ks), 4), dtype=torch.float32, device=dev)
+            scores = torch.empty((n * sum(ks),), dtype=torch.float32, device=dev)
+            off = 0
+            for l in range(L):
+                k = ks[l]
+                idx = lgs[l].topk(k, dim=1, sorted=True)[1]                                                   # inference.py:91-95
+                ops.rpn_decode(lgs[l], dls[l], anchors[0][l].bbox, idx, widths, heights, boxes[off:off + n * k],
+                               scores[off:off + n * k], self.box_coder.weights, self.box_coder.bbox_xform_clip)
+                off += n * k
+            keep, counts = ops.nms_batched(boxes, scores, [k for k in ks for _ in range(n)], float(self.nms_thresh))
+            gb = gc = None
+            gs = [0] * n
+            if self.training and targets is not None:                                                          # add_gt_proposals
+                gs = [len(t) for t in targets]
+                gmax = max(1, max(gs))
+                gb = torch.zeros((n, gmax, 4), dtype=torch.float32, device=dev)
+                for i, t in enumerate(targets):
+                    if gs[i]:
+                        gb[i, :gs[i]] = t.convert("xyxy").bbox
+                gc = torch.zeros((n,), dtype=torch.int32, device=dev)
+                for i in range(n):                 # scalar fills: a pageable host -> device copy would block until the stream drains
+                    gc[i:i + 1].fill_(gs[i])
+            b, s, v = ops.rpn_collect(boxes, scores, keep, counts, ks, n, int(self.post_nms_top_n), int(self.fpn_post_nms_top_n),
+                                      per_batch, gb, gc)
+            wcols = b.shape[1] - (gb.shape[1] if gb is not None else 0)
+            nv = v[:, :wcols].sum(1).tolist()                     # the one host synchronisation of the proposal stage
+            box_cls = type(anchors[0][0])
+            out = []
+            for i in range(n):
+                bb, ss = b[i, :nv[i]], s[i, :nv[i]]
+                if gs[i]:
+                    bb = torch.cat([bb, b[i, wcols:wcols + gs[i]]])
+                    ss = torch.cat([ss, s[i, wcols:wcols + gs[i]]])
+                bl = box_cls(bb, anchors[i][0].size, mode="xyxy")
+                bl.add_field("objectness", ss)
+                out.append(bl)
+            return out
+    _bind(mod, forward)
+    return True
+
+
+def _fuse_mask_targets(be, rep):
+    """project_masks_on_boxes (roi_heads/mask_head/loss.py:11-42): the per-proposal crop / resize / rasterise loop on the
+    HOST (flagged as a bottleneck at loss.py:31-32) becomes one launch on the polygons' vertices (csrc/mask_targets.cu).
+    Module-level function: rebinding it affects every MaskRCNNLossComputation of the process (opt-in, idempotent).
+    Cell-centre even-odd rule; pycocotools' rleFrPoly samples a 5x upsampled boundary instead and can differ on cells the
+    polygon boundary passes through."""
+    import sys
+    m = sys.modules.get("maskrcnn_benchmark.modeling.roi_heads.mask_head.loss")
+    if m is None or not hasattr(m, "project_masks_on_boxes"):
+        return False
+    orig = m.project_masks_on_boxes
+    if getattr(orig, "_mrb_fused", False):
+        return True
+
+    def project_masks_on_boxes(segmentation_masks, proposals, discretization_size):
+        from mrb_b200 import ops
+        dev = proposals.bbox.device
+        inst = getattr(segmentation_masks, "instances", None)
+        polys = getattr(inst, "polygons", None)
+        if dev.type != "cuda" or getattr(segmentation_masks, "mode", None) != "poly" or polys is None:
+            return orig(segmentation_masks, proposals, discretization_size)
+        r = len(polys)
+        if r == 0:
+            return torch.empty(0, dtype=torch.float32, device=dev)
+        pset = ops.PolygonSet([[p.tolist() for p in pi.polygons] for pi in polys], dev)
+        bx = proposals.convert("xyxy").bbox.float()
+        w, h = segmentation_masks.size
+        # PolygonInstance.crop (structures/segmentation_mask.py:270-292): the box is clamped to the image, at least 1 x 1
+        x1 = bx[:, 0].clamp(min=0, max=w - 1)
+        y1 = bx[:, 1].clamp(min=0, max=h - 1)
+        x2 = torch.maximum(bx[:, 2].clamp(min=0, max=w), x1 + 1)
+        y2 = torch.maximum(bx[:, 3].clamp(min=0, max=h), y1 + 1)
+        rois = torch.stack([x1, y1, x2, y2], 1)
+        return ops.mask_targets_polygons(pset, rois, torch.arange(r, device=dev, dtype=torch.int32), int(discretization_size))
+    project_masks_on_boxes._mrb_fused = True
+    project_masks_on_boxes._mrb_orig = orig
+    m.project_masks_on_boxes = project_masks_on_boxes
+    rep["fused"]["mask_targets"] = 1
+    return True
+
+
 def fuse_model(model, backend=None, channels_last_weights=True):
     """Rebind the forwards listed in the module docstring, in place.  Returns a report
     {"fused": {kind: count}, "skipped": [reasons]}.  Idempotent."""
@@ -378,6 +499,11 @@ def fuse_model(model, backend=None, channels_last_weights=True):
         if not getattr(mod, "_mrb_fused", False) and _pooler_ok(mod):
             _fuse_pooler(mod, be)
             bump("pooler")
+    if getattr(be, "fused_glue", False):
+        for name, mod in model.named_modules():
+            if not getattr(mod, "_mrb_fused", False) and _fuse_rpn_postprocessor(mod, be):
+                bump("rpn_postprocessor")
+        _fuse_mask_targets(be, rep)
     _wire_resnet(model, be)
     model._mrb_backend = be
     return rep

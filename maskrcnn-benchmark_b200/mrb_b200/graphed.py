@@ -20,14 +20,16 @@ def _sig(tensors):
 
 
 class GraphedModule:
-    def __init__(self, mod, sample_args, backend=None, arena=None, warmup=3, pool=None):
+    def __init__(self, mod, sample_args, backend=None, arena=None, warmup=3, pool=None, share_inputs=False):
         self.mod, self.be, self.arena = mod, backend, arena
         self.eager_forward = mod.forward
         self.training_state = mod.training
         flat_in, self.in_spec = tree_flatten(tuple(sample_args))
         if not all(isinstance(t, torch.Tensor) for t in flat_in):
             raise ValueError("graph_module: sample arguments must be (nested lists/tuples of) tensors")
-        self.static_in = [t.detach().clone().requires_grad_(t.requires_grad) for t in flat_in]
+        # share_inputs: the sample tensors ARE the static inputs (e.g. the static outputs of the segment upstream: the replay
+        # then finds its inputs in place and copies nothing)
+        self.static_in = [(t.detach() if share_inputs else t.detach().clone()).requires_grad_(t.requires_grad) for t in flat_in]
         self.sig = _sig(self.static_in)
         self.params = [p for p in mod.parameters() if p.requires_grad]
         surface = [t for t in self.static_in if t.requires_grad] + self.params
@@ -94,10 +96,11 @@ class GraphedModule:
         self._fn = _Replay
         self.replays = 0
         self.fallbacks = 0
+        self.bypass = False         # True: run the eager forward (launch accounting / A-B runs)
 
     def __call__(self, *args):
         flat, _ = tree_flatten(tuple(args))
-        if self.mod.training != self.training_state or not torch.is_grad_enabled() or _sig(flat) != self.sig:
+        if self.bypass or self.mod.training != self.training_state or not torch.is_grad_enabled() or _sig(flat) != self.sig:
             self.fallbacks += 1
             return self.eager_forward(*args)
         self.replays += 1
@@ -105,10 +108,10 @@ class GraphedModule:
         return tree_unflatten(list(out), self.out_spec)
 
 
-def graph_module(mod, sample_args, backend=None, arena=None, warmup=3, pool=None):
+def graph_module(mod, sample_args, backend=None, arena=None, warmup=3, pool=None, share_inputs=False):
     """Capture `mod` (an nn.Module whose forward takes tensors / lists of tensors of FIXED shape) and rebind its forward.
-    Returns the GraphedModule (counters `replays` / `fallbacks`; `mod.forward` is the eager one again after `.release()`)."""
-    seg = GraphedModule(mod, sample_args, backend, arena, warmup, pool)
+    Returns the GraphedModule (counters `replays` / `fallbacks`; `.bypass = True` runs the eager forward again)."""
+    seg = GraphedModule(mod, sample_args, backend, arena, warmup, pool, share_inputs)
     mod.forward = seg.__call__
     mod._mrb_graphed = seg
     return seg

@@ -460,9 +460,18 @@ class PolygonSet:
                 xy.extend(p)
                 pstart.append(len(xy) // 2)
             istart.append(len(pstart) - 1)
-        self.xy = torch.tensor(xy if xy else [0.0, 0.0], dtype=torch.float32, device=device)
-        self.poly_start = torch.tensor(pstart, dtype=torch.int32, device=device)
-        self.inst_start = torch.tensor(istart, dtype=torch.int32, device=device)
+        if not xy:
+            xy = [0.0, 0.0]
+        # ONE pinned, asynchronous host -> device copy (a pageable torch.tensor(..., device=cuda) blocks the host until the
+        # stream has drained): vertices, then the two CSR arrays bit-cast into the same fp32 buffer
+        host = torch.empty(len(xy) + len(pstart) + len(istart), dtype=torch.float32).pin_memory() if torch.device(device).type == "cuda" \
+            else torch.empty(len(xy) + len(pstart) + len(istart), dtype=torch.float32)
+        host[:len(xy)] = torch.tensor(xy, dtype=torch.float32)
+        host[len(xy):].view(torch.int32).copy_(torch.tensor(pstart + istart, dtype=torch.int32))
+        dev = host.to(device, non_blocking=True)
+        self.xy = dev[:len(xy)]
+        self.poly_start = dev[len(xy):len(xy) + len(pstart)].view(torch.int32)
+        self.inst_start = dev[len(xy) + len(pstart):].view(torch.int32)
         self.num_instances = len(instances)
 
 
@@ -794,10 +803,11 @@ class _BoxLossFn(torch.autograd.Function):
             o = o.contiguous()
         r, ld = o.shape
         result = torch.empty(3, dtype=torch.float32, device=o.device)
+        rows = torch.empty(3 * r, dtype=torch.float32, device=o.device)
         with _c.on_device(o.device):
-            _c.check(lib.mrb_box_loss_fwd(_c._ptr(o), ld, num_classes, _c._ptr(labels), _c._ptr(reg_t), r, _c._ptr(result),
-                                          _c._stream()), "mrb_box_loss_fwd")
-        _count(1)
+            _c.check(lib.mrb_box_loss_fwd(_c._ptr(o), ld, num_classes, _c._ptr(labels), _c._ptr(reg_t), r, _c._ptr(rows),
+                                          _c._ptr(result), _c._stream()), "mrb_box_loss_fwd")
+        _count(2)
         ctx.save_for_backward(o, labels, reg_t, result)
         ctx.nc = num_classes
         return result[0], result[1]

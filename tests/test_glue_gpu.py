@@ -527,3 +527,77 @@ def test_harness_step_fused_losses_match_unfused(built_lib):
         den = float(b.norm()) + 1e-12
         worst = max(worst, float((a - b).norm()) / den if den > 1e-9 else 0.0)
     assert worst < 5e-2, worst      # bf16 operands on both sides; the loss gradients themselves agree to 1e-4 (tests above)
+
+
+# ------------------------------------------------------------------------------------------ 6. the same launches behind the reference's own classes
+def test_fused_reference_postprocessor_and_mask_targets(built_lib):
+    """mrb_b200.fuse rebinds RPNPostProcessor.forward and project_masks_on_boxes of the UNMODIFIED reference: same BoxLists /
+    same mask targets as the reference's Python on the same inputs"""
+    from mrb_b200 import fuse, refenv
+    if refenv.activate() is None:
+        pytest.skip("reference checkout absent")
+    from maskrcnn_benchmark.modeling.box_coder import BoxCoder
+    from maskrcnn_benchmark.modeling.roi_heads.mask_head import loss as mask_loss_mod
+    from maskrcnn_benchmark.modeling.rpn.inference import RPNPostProcessor
+    from maskrcnn_benchmark.structures.bounding_box import BoxList
+    from maskrcnn_benchmark.structures.segmentation_mask import SegmentationMask
+    from mrb_b200.model.backend import B200Backend
+    from mrb_b200.model.rpn import RPN
+    cfg = _cfg()
+    rpn = RPN(cfg, 256).to(DEV)
+    g = torch.Generator().manual_seed(31)
+    n, A = 2, 3
+    grids = [(100, 168), (50, 84), (25, 42), (13, 21), (7, 11)]
+    anchors = rpn.anchor_generator.grid(grids, DEV)
+    obj = [torch.randn(n, A, h, w, generator=g).to(DEV) for h, w in grids]
+    reg = [(torch.randn(n, 4 * A, h, w, generator=g) * 0.3).to(DEV) for h, w in grids]
+    sizes = [(800, 1333), (768, 1216)]
+    targets = [BoxList(_rand_boxes(g, 5, 1333, 800).to(DEV), (1333, 800), mode="xyxy"),
+               BoxList(_rand_boxes(g, 2, 1216, 768).to(DEV), (1216, 768), mode="xyxy")]
+    anchor_lists = [[BoxList(a, (s[1], s[0]), mode="xyxy") for a in anchors] for s in sizes]
+    be = B200Backend()
+    for training in (True, False):
+        pre, post, fpn_post = (2000, 2000, 2000) if training else (1000, 1000, 1000)
+        ref = RPNPostProcessor(pre, post, 0.7, 0, BoxCoder((1.0, 1.0, 1.0, 1.0)), fpn_post_nms_top_n=fpn_post, fpn_post_nms_per_batch=True)
+        fus = RPNPostProcessor(pre, post, 0.7, 0, BoxCoder((1.0, 1.0, 1.0, 1.0)), fpn_post_nms_top_n=fpn_post, fpn_post_nms_per_batch=True)
+        ref.train(training)
+        fus.train(training)
+        assert fuse._fuse_rpn_postprocessor(fus, be)
+        want = ref(anchor_lists, obj, reg, targets if training else None)
+        got = fus(anchor_lists, obj, reg, targets if training else None)
+        for i in range(n):
+            assert got[i].size == want[i].size and got[i].mode == want[i].mode
+            r = torch.cat([want[i].bbox, want[i].get_field("objectness")[:, None]], 1)
+            f = torch.cat([got[i].bbox, got[i].get_field("objectness")[:, None]], 1)
+            assert r.shape == f.shape, (training, i, r.shape, f.shape)
+            same = (np.abs(_canon(r) - _canon(f)).max(1) <= 1e-4).mean()
+            assert same > 0.995, (training, i, same)
+    # mask targets: polygons (rectangles, triangles, two-part instances) on random proposals
+    rep = {"fused": {}, "skipped": []}
+    orig = getattr(mask_loss_mod.project_masks_on_boxes, "_mrb_orig", mask_loss_mod.project_masks_on_boxes)
+    assert fuse._fuse_mask_targets(be, rep)
+    fused_fn = mask_loss_mod.project_masks_on_boxes
+    try:
+        polys = []
+        props = _rand_boxes(g, 24, 1333, 800, 20, 300)
+        for j in range(24):
+            x1, y1, x2, y2 = [float(v) for v in _rand_boxes(g, 1, 1333, 800, 30, 400)[0]]
+            if j % 3 == 0:
+                polys.append([[x1, y1, x2, y1, x2, y2, x1, y2]])
+            elif j % 3 == 1:
+                polys.append([[x1, y1, x2, (y1 + y2) / 2, x1, y2]])
+            else:
+                polys.append([[x1, y1, (x1 + x2) / 2, y1, (x1 + x2) / 2, y2, x1, y2], [(x1 + x2) / 2 + 3, y1, x2, y1, x2, y2]])
+            if j % 2:
+                props[j] = torch.tensor([x1 - 7.3, y1 + 2.1, x2 + 4.9, y2 - 3.3])       # overlapping its instance
+        props[:, 0::2] = props[:, 0::2].clamp(0, 1332)
+        props[:, 1::2] = props[:, 1::2].clamp(0, 799)
+        seg = SegmentationMask(polys, (1333, 800), mode="poly")
+        pl = BoxList(props.to(DEV), (1333, 800), mode="xyxy")
+        want = orig(seg, pl, 28)
+        got = fused_fn(seg, pl, 28)
+        assert got.shape == want.shape == (24, 28, 28) and got.device == want.device
+        assert float((got != want).float().mean()) < 2e-3           # cells whose centre lies on an edge, in fp32 vs fp64
+        assert float(got.mean()) > 0.02
+    finally:
+        mask_loss_mod.project_masks_on_boxes = orig

@@ -69,3 +69,26 @@ def test_reference_generalized_rcnn_over_layers_on_gpu(built_lib, oracle_mod):
     assert f.get("bottleneck[fn]") == 16 and not out["report"]["skipped"]
     assert out["libmrb_launches"]["fused"] > 100
     _check_numbers(out)
+
+
+def test_graphed_segments_equal_eager(built_lib):
+    """mrb_b200.graphed: backbone + FPN and the RPN head of the fused reference graph as CUDA-graph replays == the eager pass"""
+    sys.path.insert(0, os.path.join(ROOT, "maskrcnn-benchmark_b200"))
+    from mrb_b200 import refenv
+    if refenv.find_reference_root() is None:
+        pytest.skip("reference mirror absent")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "refgraph", "run_gpu_graphed.py")],
+                       capture_output=True, text=True, timeout=600, cwd=os.path.join(ROOT, "tests", "refgraph"))
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    out = json.loads(r.stdout.strip().splitlines()[-1])
+    json.dump(out, open(os.path.join(ROOT, "gpurun_out", "refgraph_gpu_graphed.json"), "w"), indent=1)
+    assert out["replays"][0] >= 4 and out["replays"][1] >= 3 and out["fallbacks"] == [0, 0], out
+    for le, lg in zip(out["losses_eager"] + [out["losses_eager"][0]], out["losses_graphed"]):
+        for k in le:
+            assert abs(le[k] - lg[k]) <= 1e-3 * max(1.0, abs(le[k])), (k, le, lg)
+    for w in out["worst_grad_rel_err"]:
+        assert w[0][0] < 2e-2, w           # same kernels; atomics' order and the ROI sampling's tie noise only
+    assert out["param_moved"] > 0
+    a, b = out["losses_after_step"]["graphed"], out["losses_after_step"]["eager"]
+    for k in a:
+        assert abs(a[k] - b[k]) <= 1e-3 * max(1.0, abs(b[k])), (k, a, b)

@@ -20,6 +20,10 @@ fuse_model(model, be)
 opt = ParamArena(model.named_parameters(), be, lr=1e-4, momentum=0.9, weight_decay=1e-4)
 be.enable_overlap(True)
 data = [bench._ref_inputs(2, i, dev) for i in range(4)]
+if os.environ.get("MRB_REFGRAPH_SEGMENTS", "1") != "0":
+    from mrb_b200.graphed import graph_module
+    graph_module(model.backbone, (data[0][0].tensors,), backend=be, arena=opt)
+    graph_module(model.rpn.head, (list(model.backbone(data[0][0].tensors)),), backend=be, arena=opt, share_inputs=True)
 def step(i):
     il, tg = data[i % 4]
     losses = model(il, tg)
@@ -35,5 +39,5 @@ for i in range(5):
 torch.cuda.synchronize()
 pr.disable()
 s = io.StringIO()
-pstats.Stats(pr, stream=s).sort_stats("cumulative").print_stats(60)
-print(s.getvalue()[:12000])
+pstats.Stats(pr, stream=s).sort_stats("cumulative").print_stats(90)
+print(s.getvalue()[:20000])
