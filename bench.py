@@ -576,6 +576,10 @@ def arm_reference_graph(args, cfg_name, device, rank, world, timer, aten=False):
             from mrb_b200.graphed import graph_module
             seg = graph_module(model.backbone, (dev_batches[0][0].tensors,), backend=be, arena=opt)
             graphed = {"enabled": "segment", "segment": "model.backbone (body + fpn), forward and backward", "_seg": seg}
+            if world > 1:
+                # every gradient downstream of the backbone is complete when its backward starts: reduce that bucket while the
+                # backbone's backward graph replays (ParamArena.sync() reduces the rest and waits)
+                seg.pre_backward_hook = lambda: opt.reduce_bucket("heads")
             head = getattr(getattr(model, "rpn", None), "head", None)
             if head is not None and os.environ.get("MRB_REFGRAPH_SEGMENTS", "1") == "1":
                 feats = model.backbone(dev_batches[0][0].tensors)        # a replay: the segment's static outputs
@@ -723,7 +727,8 @@ def arm_harness(args, cfg_name, device, rank, world, timer, sustained_s=0.0):
     from mrb_b200.optim import FlatSGD, ParamArena
     yaml, per_gpu, train, metric, workload = CONFIGS[cfg_name]
     torch.manual_seed(0)
-    use_graph = args.graph in ("on", "auto") and train
+    # eval: the fused glue's post-processing is fixed-shape and sync-free, so the forward pass is capturable too
+    use_graph = args.graph in ("on", "auto") and (train or os.environ.get("MRB_FUSED_GLUE", "1") != "0")
     kw = {}
     if cfg_name == "faster_fwd":
         kw = dict(mask_on=False)
@@ -732,7 +737,7 @@ def arm_harness(args, cfg_name, device, rank, world, timer, sustained_s=0.0):
     elif cfg_name == "dcn":
         kw = dict(stage_with_dcn=(False, True, True, True))
     # graph capture needs a step without host synchronisation: fixed-shape mask head (see RCNNConfig)
-    cfg = RCNNConfig(mask_rois_per_image=128 if use_graph else 0,
+    cfg = RCNNConfig(mask_rois_per_image=128 if (use_graph and train) else 0,
                      parallel_heads=(args.parallel_heads == "on" and args.overlap == "on" and args.optim == "arena"), **kw)
     be = B200Backend(wgrad=args.wgrad)
     model = build_model(cfg, backend=be, device=device)
@@ -757,6 +762,9 @@ def arm_harness(args, cfg_name, device, rank, world, timer, sustained_s=0.0):
     n_batches = 4
     host = [synth_batch(per_gpu, 100 * rank + i, pin=True) for i in range(n_batches)]
     dev = [tuple(t.to(device) for t in b) for b in host]
+    defer_prep = bool(train and args.optim == "arena" and os.environ.get("MRB_DEFER_DGRAD_PREP", "1") != "0")
+    if defer_prep:
+        opt.defer_dgrad_prepare = True
 
     def eager_step(batch):
         images, boxes, labels = batch
@@ -764,9 +772,13 @@ def arm_harness(args, cfg_name, device, rank, world, timer, sustained_s=0.0):
             with torch.no_grad():
                 dets = model(images, sizes)
             return sum(d["boxes"].sum() for d in dets)
+        if defer_prep:
+            model.be.prepare_async()       # data-gradient weights of the updated parameters: side stream, needed by backward only
         losses = model(images, sizes, targets_of(boxes, labels))
         loss = sum(losses.values())
         opt.zero_grad()
+        if defer_prep:
+            model.be.join_prepare()
         loss.backward()
         if grad_sync is not None:
             grad_sync.sync()               # NCCL all-reduce of one flat fp32 gradient buffer (mean over ranks)
@@ -790,7 +802,8 @@ def arm_harness(args, cfg_name, device, rank, world, timer, sustained_s=0.0):
                     eager_step(static)
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
-            opt.zero_grad()
+            if opt is not None:
+                opt.zero_grad()
             ops.STATS["launches"] = 0
             ops.STATS["conv_calls"] = []
             graph = torch.cuda.CUDAGraph()
@@ -980,12 +993,14 @@ def main():
            "result_last_step": head["result_last_step"]}
     if args.impl == "aten":
         out["impl"] = "aten"
-    conv_calls = None
+    conv_calls = conv_from = None
     arms_out = {}
     for a in arms:
         cc = a.pop("conv_calls", None)
-        if conv_calls is None and cc:
-            conv_calls = cc
+        # the conv roofline is taken over the harness arm's launches when it ran (fixed-shape mask head: the same launch list
+        # every step, and the list the in-step profile refers to), else over the first arm's
+        if cc and (conv_calls is None or a["arm"] == "harness"):
+            conv_calls, conv_from = cc, a["arm"]
         arms_out[a["arm"]] = a
     out["arms"] = arms_out
     for a in arms:
@@ -1006,7 +1021,7 @@ def main():
             if flop_img:
                 # conv-FLOP roofline of the whole step (~1631 GFLOP/image fwd+bwd upper bound)
                 rf["step_conv_flop_roofline_frac"] = round(head["value"] / (peaks.get("bf16_tflops", 1590.0) * 1e3 / flop_img) / world, 4)
-            rf["conv_calls_from"] = [a["arm"] for a in arms][0] if arms else None
+            rf["conv_calls_from"] = conv_from
             ins = arms_out.get("harness", {}).get("in_step")
             if ins and "conv_tflops_in_step" in ins:
                 rf["in_step"] = {"achieved": ins["conv_tflops_in_step"], "frac": round(ins["conv_tflops_in_step"] / rf["peak"], 4),

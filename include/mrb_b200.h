@@ -233,6 +233,12 @@ int mrb_mask_targets_polygons(const float* polys_xy, const int* poly_start, cons
 int mrb_rpn_decode(const float* logits, const float* deltas, const float* anchors, const int64_t* topk_idx, const float* image_w,
                    const float* image_h, float* boxes, float* scores, int num_images, int num_anchors, int k,
                    const float* weights_host, float xform_clip, mrb_stream_t stream);
+/* mrb_rpn_topk_decode: objectness.topk(pre_nms_top_n, sorted=True) (inference.py:91-95) AND mrb_rpn_decode_packed in one
+ * launch: one thread-block cluster per image selects the k largest logits of the level (radix select across the cluster's
+ * CTAs), sorts them (descending logit, ascending anchor among equals) and decodes.  boxes [N, k, 4], scores [N, k]. */
+int mrb_rpn_topk_decode(const float* head_output, int anchors_per_location, int pixel_stride, const float* anchors,
+                        const float* image_w, const float* image_h, float* boxes, float* scores, int num_images, int num_anchors,
+                        int k, const float* weights_host, float xform_clip, mrb_stream_t stream);
 /* mrb_rpn_collect: what follows the NMS (inference.py:116-123, select_over_all_levels :154-181, add_gt_proposals :53-74).
  * boxes / scores / keep: the (level-major, image-minor) problems of mrb_nms_batched back to back, level l holding
  * num_images x k_per_level[l] rows; num_keep [num_levels * num_images].  Per image the candidates are the first
@@ -262,6 +268,18 @@ int mrb_roi_assign_sample(const float* boxes, const uint8_t* valid, const float*
                           const float* weights_host, int mask_rois_per_image, float* out_rois, int64_t* out_labels,
                           float* out_reg_targets, int64_t* out_gt_index, float* mask_rois, int64_t* mask_labels,
                           float* mask_weight, int64_t* mask_gt_index, mrb_stream_t stream);
+/* Box-head post-processing (PostProcessor.forward, modeling/roi_heads/box_head/inference.py:45-149), fixed shapes, no host
+ * synchronisation.  mrb_box_post_decode: softmax over the C class logits of `outputs` [N*P, ld] (C logits, then 4C regression
+ * outputs per row), per-class BoxCoder.decode of `proposals` [N*P, 4] + clip_to_image, score threshold -> one NMS problem per
+ * (image, class > 0): boxes / scores [(N * (C-1)) * P] in the layout of mrb_nms_batched (score -1 = no candidate).
+ * mrb_box_post_select, after that NMS: the detections_per_img best survivors of every image over all classes, in (class,
+ * proposal) order -> out_boxes [N, D, 4], out_scores [N, D], out_labels [N, D] int64, out_count [N] (rows beyond are zero). */
+int mrb_box_post_decode(const float* outputs, int ld, int num_classes, const float* proposals, const uint8_t* valid,
+                        const float* image_w, const float* image_h, int num_images, int proposals_per_image, float score_thresh,
+                        const float* weights_host, float xform_clip, float* boxes, float* scores, mrb_stream_t stream);
+int mrb_box_post_select(const float* boxes, const float* scores, const int64_t* keep, const int32_t* num_keep, int num_images,
+                        int proposals_per_image, int num_classes, int detections_per_img, float* out_boxes, float* out_scores,
+                        int64_t* out_labels, int32_t* out_count, mrb_stream_t stream);
 /* mrb_rpn_anchor_match: RPNLossComputation.match_targets_to_anchors + the labelling of prepare_targets
  * (modeling/rpn/loss.py:40-90): IoU of every anchor with the ground truth, Matcher with allow_low_quality_matches
  * (matcher.py:42-112), label 1 / 0 / -1 (between thresholds, or outside the image by more than straddle_thresh;

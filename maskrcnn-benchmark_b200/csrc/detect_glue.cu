@@ -172,6 +172,130 @@ rpn_decode_kernel(const float* __restrict__ logits, const float4* __restrict__ d
   scores[t] = __fdiv_rn(1.f, __fadd_rn(1.f, expf(-z)));   // inference.py:88 (.sigmoid())
 }
 
+// ------------------------------------------------------------------------------------------ 1b. top-k + decode in one launch
+// objectness.topk(pre_nms_top_n, sorted=True) (inference.py:91-95) fused with the decode: one thread-block cluster per image
+// (its CTAs split the level's anchors), keys cached in shared memory, radix select of the k-th logit over the cluster
+// (histograms summed through distributed shared memory), the k selected (key, anchor) pairs gathered into the leader CTA's
+// shared memory in slice order, sorted there (bitonic, descending score, ascending anchor among equal logits) and decoded.
+struct TopkArgs {
+  int N, A, k, apl, ld, slice;      // images, anchors of the level, k, anchors per location, floats per location, anchors per CTA
+  float wx, wy, ww, wh, clip;       // reciprocals of the box-coder weights
+};
+
+__device__ __forceinline__ void decode_one(const float4 d, const float4 an, float lx, float ly, const TopkArgs& a, float4* out) {
+  const float w = __fadd_rn(__fsub_rn(an.z, an.x), 1.f), h = __fadd_rn(__fsub_rn(an.w, an.y), 1.f);
+  const float cx = __fadd_rn(an.x, __fmul_rn(0.5f, w)), cy = __fadd_rn(an.y, __fmul_rn(0.5f, h));
+  const float dx = __fmul_rn(d.x, a.wx), dy = __fmul_rn(d.y, a.wy);
+  const float dw = fminf(__fmul_rn(d.z, a.ww), a.clip), dh = fminf(__fmul_rn(d.w, a.wh), a.clip);
+  const float pcx = __fadd_rn(__fmul_rn(dx, w), cx), pcy = __fadd_rn(__fmul_rn(dy, h), cy);
+  const float pw = __fmul_rn(expf(dw), w), ph = __fmul_rn(expf(dh), h);
+  float x1 = __fsub_rn(pcx, __fmul_rn(0.5f, pw)), y1 = __fsub_rn(pcy, __fmul_rn(0.5f, ph));
+  float x2 = __fsub_rn(__fadd_rn(pcx, __fmul_rn(0.5f, pw)), 1.f), y2 = __fsub_rn(__fadd_rn(pcy, __fmul_rn(0.5f, ph)), 1.f);
+  x1 = fminf(fmaxf(x1, 0.f), lx);
+  y1 = fminf(fmaxf(y1, 0.f), ly);
+  x2 = fminf(fmaxf(x2, 0.f), lx);
+  y2 = fminf(fmaxf(y2, 0.f), ly);
+  *out = make_float4(x1, y1, x2, y2);
+}
+
+__global__ void __launch_bounds__(kGlueThreads)
+rpn_topk_decode_kernel(const float* __restrict__ head_out, const float4* __restrict__ anchors, const float* __restrict__ im_w,
+                       const float* __restrict__ im_h, float4* __restrict__ boxes, float* __restrict__ scores, TopkArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ int hist[256], ghist[256], sh[4], scan_ws[33], cnt_sh[2];
+  cg::cluster_group cluster = cg::this_cluster();
+  const unsigned cs = cluster.num_blocks(), rank = cluster.block_rank();
+  const int i = blockIdx.x / cs;                                   // image
+  unsigned* keys = (unsigned*)smem_raw;                            // [slice]
+  int p2 = 1;
+  while (p2 < a.k) p2 <<= 1;
+  unsigned long long* sortbuf = (unsigned long long*)(smem_raw + (((size_t)a.slice * 4 + 15) & ~(size_t)15));   // [p2], used in the leader
+  const int a_lo = min((int)rank * a.slice, a.A), a_hi = min(a_lo + a.slice, a.A), n = a_hi - a_lo;
+  const float* __restrict__ img = head_out + (size_t)i * (a.A / a.apl) * a.ld;
+  for (int t = threadIdx.x; t < n; t += blockDim.x) {
+    const int g = a_lo + t, pix = g / a.apl, q = g - pix * a.apl;
+    unsigned key = glue_key(img[(size_t)pix * a.ld + q]);
+    keys[t] = key == 0 ? 1u : key;
+  }
+  __syncthreads();
+  unsigned T;
+  int quota;
+  auto key_of = [&](int t, unsigned* k) { *k = keys[t]; return true; };
+  radix_select(key_of, n, a.k, &T, &quota, hist, ghist, sh);
+  // selected elements of this slice, in anchor order; ties at the cut are taken in (slice, anchor) order
+  const int per = (n + (int)blockDim.x - 1) / (int)blockDim.x;
+  const int t_lo = min((int)threadIdx.x * per, n), t_hi = min(t_lo + per, n);
+  int my_ties = 0;
+  for (int t = t_lo; t < t_hi; ++t) my_ties += (keys[t] == T);
+  int tie_tot;
+  int tr = block_excl_scan(my_ties, &tie_tot, scan_ws);
+  if (threadIdx.x == 0) cnt_sh[0] = tie_tot;
+  cluster.sync();
+  int ties_before = 0;
+  for (unsigned r = 0; r < rank; ++r) ties_before += cluster.map_shared_rank(cnt_sh, r)[0];
+  tr += ties_before;
+  int my_sel = 0;
+  for (int t = t_lo; t < t_hi; ++t) {
+    const bool is_tie = keys[t] == T;
+    const bool sel = keys[t] > T || (is_tie && tr < quota);
+    tr += is_tie;
+    my_sel += sel;
+    if (!sel) keys[t] = 0;          // 0 = not selected from here on
+  }
+  int sel_tot;
+  int pos = block_excl_scan(my_sel, &sel_tot, scan_ws);
+  if (threadIdx.x == 0) cnt_sh[1] = sel_tot;
+  cluster.sync();
+  int base = 0;
+  for (unsigned r = 0; r < rank; ++r) base += cluster.map_shared_rank(cnt_sh, r)[1];
+  unsigned long long* lead = cluster.map_shared_rank(sortbuf, 0);
+  pos += base;
+  for (int t = t_lo; t < t_hi; ++t)
+    if (keys[t]) {
+      if (pos < p2) lead[pos] = ((unsigned long long)keys[t] << 32) | (unsigned)(0x7fffffff - (a_lo + t));
+      ++pos;
+    }
+  if (rank == 0) {
+    int total = 0;      // == min(k, A)
+    for (unsigned r = 0; r < cs; ++r) total += cluster.map_shared_rank(cnt_sh, r)[1];
+    if (threadIdx.x == 0) sh[3] = total;
+  }
+  cluster.sync();       // all pairs have landed in the leader's shared memory
+  if (rank != 0) return;
+  const int total = sh[3];
+  for (int t = total + threadIdx.x; t < p2; t += blockDim.x) sortbuf[t] = 0ull;
+  __syncthreads();
+  for (int size = 2; size <= p2; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = threadIdx.x; t < (p2 >> 1); t += blockDim.x) {
+        const int lo = (t / stride) * (stride << 1) + (t % stride), hi = lo + stride;
+        const bool desc = ((lo & size) == 0);
+        const unsigned long long x = sortbuf[lo], y = sortbuf[hi];
+        if ((x < y) == desc) {
+          sortbuf[lo] = y;
+          sortbuf[hi] = x;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  const float lx = __fsub_rn(im_w[i], 1.f), ly = __fsub_rn(im_h[i], 1.f);
+  for (int t = threadIdx.x; t < a.k; t += blockDim.x) {
+    float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
+    float sc = -1.f;
+    if (t < total) {
+      const int g = 0x7fffffff - (int)(unsigned)(sortbuf[t] & 0xffffffffull);
+      const int pix = g / a.apl, q = g - pix * a.apl;
+      const float* row = img + (size_t)pix * a.ld;
+      const float* dp = row + a.apl + 4 * q;
+      decode_one(make_float4(dp[0], dp[1], dp[2], dp[3]), anchors[g], lx, ly, a, &bx);
+      sc = __fdiv_rn(1.f, __fadd_rn(1.f, expf(-row[q])));
+    }
+    boxes[(size_t)i * a.k + t] = bx;
+    scores[(size_t)i * a.k + t] = sc;
+  }
+}
+
 // ------------------------------------------------------------------------------------------ 2. post-NMS selection
 struct CollectArgs {
   int L, N, C, post_n, topn, W, gmax, per_batch, sorted;
@@ -492,6 +616,145 @@ roi_assign_sample_kernel(const float4* __restrict__ boxes, const unsigned char* 
   }
 }
 
+// ------------------------------------------------------------------------------------------ 3b. box-head post-processing
+// PostProcessor.forward (modeling/roi_heads/box_head/inference.py:45-149): softmax, per-class BoxCoder.decode
+// (box_coder.py:52-95), clip_to_image, score threshold -> one NMS problem per (image, class > 0) in the layout of
+// mrb_nms_batched (P rows each, rows below the threshold / invalid proposals carry score -1 and an empty box) ...
+struct PostArgs {
+  int N, P, C, ld;                    // images, proposals per image, classes (incl. background), floats per row of `outputs`
+  float thresh, wx, wy, ww, wh, clip;   // wx..wh: reciprocals of the box-coder weights
+};
+
+__global__ void __launch_bounds__(256)
+box_post_decode_kernel(const float* __restrict__ outputs, const float4* __restrict__ proposals, const unsigned char* __restrict__ valid,
+                       const float* __restrict__ im_w, const float* __restrict__ im_h, float4* __restrict__ boxes,
+                       float* __restrict__ scores, PostArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);      // row = image * P + proposal
+  if (r >= a.N * a.P) return;
+  const int i = r / a.P, p = r - i * a.P;
+  const float* row = outputs + (size_t)r * a.ld;
+  float m = -INFINITY;
+  for (int c = lane; c < a.C; c += 32) m = fmaxf(m, row[c]);
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
+  float ssum = 0.f;
+  for (int c = lane; c < a.C; c += 32) ssum += expf(row[c] - m);
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) ssum += __shfl_xor_sync(0xffffffffu, ssum, d);
+  const bool ok = valid[r] != 0;
+  const float4 an = proposals[r];
+  const float w = __fadd_rn(__fsub_rn(an.z, an.x), 1.f), h = __fadd_rn(__fsub_rn(an.w, an.y), 1.f);
+  const float cx = __fadd_rn(an.x, __fmul_rn(0.5f, w)), cy = __fadd_rn(an.y, __fmul_rn(0.5f, h));
+  const float lx = __fsub_rn(im_w[i], 1.f), ly = __fsub_rn(im_h[i], 1.f);
+  for (int c = 1 + lane; c < a.C; c += 32) {
+    const float prob = expf(row[c] - m) / ssum;
+    const size_t o = ((size_t)(i * (a.C - 1) + (c - 1))) * a.P + p;
+    if (ok && prob > a.thresh) {                                          // inference.py:108 (scores > score_thresh)
+      const float* d = row + a.C + 4 * c;
+      const float dx = __fmul_rn(d[0], a.wx), dy = __fmul_rn(d[1], a.wy);
+      const float dw = fminf(__fmul_rn(d[2], a.ww), a.clip), dh = fminf(__fmul_rn(d[3], a.wh), a.clip);
+      const float pcx = __fadd_rn(__fmul_rn(dx, w), cx), pcy = __fadd_rn(__fmul_rn(dy, h), cy);
+      const float pw = __fmul_rn(expf(dw), w), ph = __fmul_rn(expf(dh), h);
+      float x1 = __fsub_rn(pcx, __fmul_rn(0.5f, pw)), y1 = __fsub_rn(pcy, __fmul_rn(0.5f, ph));
+      float x2 = __fsub_rn(__fadd_rn(pcx, __fmul_rn(0.5f, pw)), 1.f), y2 = __fsub_rn(__fadd_rn(pcy, __fmul_rn(0.5f, ph)), 1.f);
+      boxes[o] = make_float4(fminf(fmaxf(x1, 0.f), lx), fminf(fmaxf(y1, 0.f), ly), fminf(fmaxf(x2, 0.f), lx), fminf(fmaxf(y2, 0.f), ly));
+      scores[o] = prob;
+    } else {
+      boxes[o] = make_float4(0.f, 0.f, 0.f, 0.f);
+      scores[o] = -1.f;
+    }
+  }
+}
+
+// ... and, after the NMS of those problems, the detections_per_img best survivors of every image over all classes
+// (inference.py:131-147), in (class, proposal) order.  One cluster per image, the classes split over its CTAs.
+// Ties at the cut are taken in (class, proposal) order (the reference keeps every score >= the k-th value).
+struct DetArgs {
+  int N, P, C, max_det, cls_per_cta;
+};
+
+__global__ void __launch_bounds__(kGlueThreads)
+box_post_select_kernel(const float4* __restrict__ boxes, const float* __restrict__ scores, const int64_t* __restrict__ keep,
+                       const int32_t* __restrict__ counts, float4* __restrict__ out_b, float* __restrict__ out_s,
+                       int64_t* __restrict__ out_l, int32_t* __restrict__ out_n, DetArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ int hist[256], ghist[256], sh[4], scan_ws[33], cnt_sh[2];
+  cg::cluster_group cluster = cg::this_cluster();
+  const unsigned cs = cluster.num_blocks(), rank = cluster.block_rank();
+  const int i = blockIdx.x / cs;
+  unsigned* keys = (unsigned*)smem_raw;                 // [cls_per_cta * P]  0 = no candidate in the slot
+  const int c_lo = min(1 + (int)rank * a.cls_per_cta, a.C), c_hi = min(c_lo + a.cls_per_cta, a.C);
+  const int n = (c_hi - c_lo) * a.P;
+  for (int t = threadIdx.x; t < n; t += blockDim.x) {
+    const int c = c_lo + t / a.P, q = t - (t / a.P) * a.P;
+    const int prob = i * (a.C - 1) + (c - 1);
+    unsigned key = 0;
+    if (q < counts[prob]) {
+      const int64_t rr = keep[(size_t)prob * a.P + q];
+      const float sc = scores[(size_t)prob * a.P + (rr < 0 ? 0 : (rr >= a.P ? a.P - 1 : rr))];
+      if (sc > 0.f) key = glue_key(sc);
+    }
+    keys[t] = key;
+  }
+  __syncthreads();
+  unsigned T;
+  int quota;
+  auto key_of = [&](int t, unsigned* k) { *k = keys[t]; return *k != 0; };
+  radix_select(key_of, n, a.max_det, &T, &quota, hist, ghist, sh);
+  const int per = (n + (int)blockDim.x - 1) / (int)blockDim.x;
+  const int t_lo = min((int)threadIdx.x * per, n), t_hi = min(t_lo + per, n);
+  int my_ties = 0;
+  for (int t = t_lo; t < t_hi; ++t) my_ties += (keys[t] != 0 && keys[t] == T);
+  int tie_tot;
+  int tr = block_excl_scan(my_ties, &tie_tot, scan_ws);
+  if (threadIdx.x == 0) cnt_sh[0] = tie_tot;
+  cluster.sync();
+  for (unsigned r = 0; r < rank; ++r) tr += cluster.map_shared_rank(cnt_sh, r)[0];
+  int my_sel = 0;
+  for (int t = t_lo; t < t_hi; ++t) {
+    const unsigned key = keys[t];
+    const bool is_tie = key != 0 && key == T;
+    const bool sel = key != 0 && (key > T || (is_tie && tr < quota));
+    tr += is_tie;
+    my_sel += sel;
+    if (!sel) keys[t] = 0;
+  }
+  int sel_tot;
+  int pos = block_excl_scan(my_sel, &sel_tot, scan_ws);
+  if (threadIdx.x == 0) cnt_sh[1] = sel_tot;
+  cluster.sync();
+  int total = 0;
+  for (unsigned r = 0; r < cs; ++r) {
+    const int c = cluster.map_shared_rank(cnt_sh, r)[1];
+    if (r < rank) pos += c;
+    total += c;
+  }
+  for (int t = t_lo; t < t_hi; ++t)
+    if (keys[t]) {
+      const int c = c_lo + t / a.P, q = t - (t / a.P) * a.P;
+      const int prob = i * (a.C - 1) + (c - 1);
+      const size_t row = (size_t)prob * a.P + keep[(size_t)prob * a.P + q];
+      if (pos < a.max_det) {
+        const size_t o = (size_t)i * a.max_det + pos;
+        out_b[o] = boxes[row];
+        out_s[o] = scores[row];
+        out_l[o] = c;
+      }
+      ++pos;
+    }
+  if (rank == 0) {
+    for (int t = total + threadIdx.x; t < a.max_det; t += blockDim.x) {
+      const size_t o = (size_t)i * a.max_det + t;
+      out_b[o] = make_float4(0.f, 0.f, 0.f, 0.f);
+      out_s[o] = 0.f;
+      out_l[o] = 0;
+    }
+    if (threadIdx.x == 0) out_n[i] = total < a.max_det ? total : a.max_det;
+  }
+  cluster.sync();      // nobody leaves while its counters may still be read
+}
+
 // ------------------------------------------------------------------------------------------ 4. RPN anchor labelling
 // pass 1: per anchor best IoU / argmax; per ground-truth box the best IoU over all anchors (atomicMax on the bit pattern of
 // a non-negative float).  pass 2: labels.
@@ -610,6 +873,46 @@ MRB_API int mrb_rpn_decode_packed(const float* head_output, int anchors_per_loca
   return MRB_OK;
 }
 
+MRB_API int mrb_rpn_topk_decode(const float* head_output, int anchors_per_location, int pixel_stride, const float* anchors,
+                                const float* image_w, const float* image_h, float* boxes, float* scores, int num_images, int num_anchors,
+                                int k, const float* weights_host, float xform_clip, mrb_stream_t stream) {
+  if (num_images <= 0 || num_anchors <= 0 || k <= 0 || k > num_anchors || !weights_host || anchors_per_location <= 0 ||
+      num_anchors % anchors_per_location || pixel_stride < 5 * anchors_per_location)
+    return MRB_ERR_BAD_ARG;
+  if (!head_output || !anchors || !image_w || !image_h || !boxes || !scores) return MRB_ERR_BAD_ARG;
+  if (((uintptr_t)anchors & 15) || ((uintptr_t)boxes & 15)) return MRB_ERR_BAD_ARG;
+  if (k > 8192) return MRB_ERR_UNSUPPORTED;
+  // CTAs per image: the fewest (1, 2, 4, 8) that keep a slice's keys within ~100 KB of shared memory
+  int cs = 1;
+  while (cs < 8 && (num_anchors + cs - 1) / cs > 25600) cs <<= 1;
+  TopkArgs a;
+  a.N = num_images; a.A = num_anchors; a.k = k; a.apl = anchors_per_location; a.ld = pixel_stride;
+  a.slice = (num_anchors + cs - 1) / cs;
+  if (a.slice > 50000) return MRB_ERR_UNSUPPORTED;
+  a.wx = 1.f / weights_host[0]; a.wy = 1.f / weights_host[1]; a.ww = 1.f / weights_host[2]; a.wh = 1.f / weights_host[3];
+  a.clip = xform_clip;
+  int p2 = 1;
+  while (p2 < k) p2 <<= 1;
+  const size_t smem = (((size_t)a.slice * 4 + 15) & ~(size_t)15) + (size_t)p2 * 8;
+  if (smem > 220 * 1024) return MRB_ERR_UNSUPPORTED;
+  MRB_CUDA_TRY(cudaFuncSetAttribute(rpn_topk_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(num_images * cs);
+  cfg.blockDim = dim3(kGlueThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cs;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  MRB_CUDA_TRY(cudaLaunchKernelEx(&cfg, rpn_topk_decode_kernel, head_output, (const float4*)anchors, image_w, image_h, (float4*)boxes,
+                                  scores, a));
+  return MRB_OK;
+}
+
 MRB_API int mrb_rpn_collect(const float* boxes, const float* scores, const int64_t* keep, const int32_t* num_keep,
                             const int* k_per_level_host, int num_levels, int num_images, int post_nms_top_n, int fpn_post_nms_top_n,
                             int per_batch, int sorted, const float* gt_boxes, const int32_t* gt_count, int gmax, float* out_boxes,
@@ -718,6 +1021,56 @@ MRB_API int mrb_roi_assign_sample(const float* boxes, const uint8_t* valid, cons
   MRB_CUDA_TRY(cudaLaunchKernelEx(&cfg, roi_assign_sample_kernel, (const float4*)boxes, (const unsigned char*)valid, rand_keys,
                                   (const float4*)gt_boxes, gt_labels, gt_count, out_rois, out_labels, (float4*)out_reg_targets,
                                   out_gt_index, mask_rois, mask_labels, mask_weight, mask_gt_index, a));
+  return MRB_OK;
+}
+
+MRB_API int mrb_box_post_decode(const float* outputs, int ld, int num_classes, const float* proposals, const uint8_t* valid,
+                                const float* image_w, const float* image_h, int num_images, int proposals_per_image,
+                                float score_thresh, const float* weights_host, float xform_clip, float* boxes, float* scores,
+                                mrb_stream_t stream) {
+  if (!outputs || !proposals || !valid || !image_w || !image_h || !weights_host || !boxes || !scores || num_images <= 0 ||
+      proposals_per_image <= 0 || num_classes < 2 || ld < 5 * num_classes)
+    return MRB_ERR_BAD_ARG;
+  if (((uintptr_t)proposals & 15) || ((uintptr_t)boxes & 15)) return MRB_ERR_BAD_ARG;
+  PostArgs a;
+  a.N = num_images; a.P = proposals_per_image; a.C = num_classes; a.ld = ld; a.thresh = score_thresh;
+  a.wx = 1.f / weights_host[0]; a.wy = 1.f / weights_host[1]; a.ww = 1.f / weights_host[2]; a.wh = 1.f / weights_host[3];
+  a.clip = xform_clip;
+  box_post_decode_kernel<<<ceil_div((int64_t)num_images * proposals_per_image, 8), 256, 0, (cudaStream_t)stream>>>(
+      outputs, (const float4*)proposals, (const unsigned char*)valid, image_w, image_h, (float4*)boxes, scores, a);
+  MRB_LAUNCH_CHECK();
+  return MRB_OK;
+}
+
+MRB_API int mrb_box_post_select(const float* boxes, const float* scores, const int64_t* keep, const int32_t* num_keep, int num_images,
+                                int proposals_per_image, int num_classes, int detections_per_img, float* out_boxes, float* out_scores,
+                                int64_t* out_labels, int32_t* out_count, mrb_stream_t stream) {
+  if (!boxes || !scores || !keep || !num_keep || !out_boxes || !out_scores || !out_labels || !out_count || num_images <= 0 ||
+      proposals_per_image <= 0 || num_classes < 2 || detections_per_img <= 0)
+    return MRB_ERR_BAD_ARG;
+  if (((uintptr_t)boxes & 15) || ((uintptr_t)out_boxes & 15)) return MRB_ERR_BAD_ARG;
+  DetArgs a;
+  a.N = num_images; a.P = proposals_per_image; a.C = num_classes; a.max_det = detections_per_img;
+  int cs = 1;
+  while (cs < 8 && (size_t)((num_classes - 1 + cs - 1) / cs) * proposals_per_image * 4 > 96 * 1024) cs <<= 1;
+  a.cls_per_cta = (num_classes - 1 + cs - 1) / cs;
+  const size_t smem = (size_t)a.cls_per_cta * proposals_per_image * 4;
+  if (smem > 200 * 1024) return MRB_ERR_UNSUPPORTED;
+  MRB_CUDA_TRY(cudaFuncSetAttribute(box_post_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(num_images * cs);
+  cfg.blockDim = dim3(kGlueThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cs;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  MRB_CUDA_TRY(cudaLaunchKernelEx(&cfg, box_post_select_kernel, (const float4*)boxes, scores, keep, num_keep, (float4*)out_boxes,
+                                  out_scores, out_labels, out_count, a));
   return MRB_OK;
 }
 

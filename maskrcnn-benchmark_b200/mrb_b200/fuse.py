@@ -30,8 +30,10 @@ of the modules whose bodies are chains the conv engine fuses into one launch eac
 
   RPNPostProcessor.forward   per (level, image): top-k, decode, clip,      per level top-k + decode launch, ONE batched NMS,
     (rpn/inference.py:76-181)  NMS (sync), BoxList ops; top-k over levels    ONE selection launch, one sync (detect_glue.cu)
+  PostProcessor.forward      per (image, class): nonzero, decode, NMS      softmax+decode+threshold launch, ONE batched NMS
+    (box_head/inference.py:45-149)  (sync), cat, kthvalue on the host         over images x classes, top-k launch, one sync
   project_masks_on_boxes     host loop: crop, resize, rasterise, upload    one launch on the polygon vertices
-    (mask_head/loss.py:11-42)                                               (the last two only with backend.fused_glue)
+    (mask_head/loss.py:11-42)                                               (the last three only with backend.fused_glue)
 
 Nothing else changes: module classes, parameters, buffers and state_dict keys are the reference's; the anchor
 generator, matcher/sampler, box coder and all losses are the reference's own Python.
@@ -401,6 +403,67 @@ def _fuse_rpn_postprocessor(mod, be):
     return True
 
 
+def _fuse_box_postprocessor(mod, be):
+    """PostProcessor.forward (roi_heads/box_head/inference.py:45-149): softmax + per-class decode + clip + threshold in one
+    launch, ONE batched NMS over the images x classes problems, one top-detections launch, one host synchronisation to size
+    the returned BoxLists -- instead of a Python loop over images x 80 classes with a `nonzero` and an NMS-sizing
+    synchronisation each.  Same detections (exact ties at the detections_per_img cut aside: the reference keeps all of them)."""
+    need = ("score_thresh", "nms", "detections_per_img", "box_coder", "cls_agnostic_bbox_reg")
+    if type(mod).__name__ != "PostProcessor" or not all(hasattr(mod, n) for n in need):
+        return False
+    if not (hasattr(mod.box_coder, "weights") and hasattr(mod.box_coder, "bbox_xform_clip")):
+        return False
+    orig = mod.forward
+    cache = {}
+
+    def forward(self, x, boxes):
+        from mrb_b200 import ops
+        class_logits, box_regression = x
+        dev = class_logits.device
+        n = len(boxes)
+        counts = [len(b) for b in boxes]
+        p = max(counts) if counts else 0
+        c = class_logits.shape[1]
+        if dev.type != "cuda" or self.cls_agnostic_bbox_reg or getattr(self, "bbox_aug_enabled", False) or p == 0 or \
+                self.detections_per_img <= 0 or box_regression.shape[1] != 4 * c or n * (c - 1) * p >= 2 ** 24:
+            return orig(x, boxes)
+        with torch.no_grad():
+            packed = torch.cat([class_logits.float(), box_regression.float()], 1)                # [R, 5C]
+            if all(k == p for k in counts):
+                outputs = packed
+                props = torch.stack([b.convert("xyxy").bbox for b in boxes]).float()
+                valid = torch.ones((n, p), dtype=torch.bool, device=dev)
+            else:
+                outputs = packed.new_zeros((n * p, packed.shape[1]))
+                props = packed.new_zeros((n, p, 4))
+                valid = torch.zeros((n, p), dtype=torch.bool, device=dev)
+                off = 0
+                for i, (b, k) in enumerate(zip(boxes, counts)):
+                    outputs[i * p:i * p + k] = packed[off:off + k]
+                    props[i, :k] = b.convert("xyxy").bbox
+                    valid[i, :k] = True
+                    off += k
+            sizes = tuple(tuple(b.size) for b in boxes)
+            key = (sizes, str(dev))
+            if key not in cache:
+                cache[key] = (torch.tensor([float(s[0]) for s in sizes], device=dev), torch.tensor([float(s[1]) for s in sizes], device=dev))
+            widths, heights = cache[key]
+            bb, ss, ll, cc = ops.box_postprocess(outputs.contiguous(), c, props, valid, widths, heights, float(self.score_thresh),
+                                                 self.box_coder.weights, float(self.nms), int(self.detections_per_img),
+                                                 self.box_coder.bbox_xform_clip)
+            ks = cc.tolist()                                # the one host synchronisation of the post-processing
+            box_cls = type(boxes[0])
+            out = []
+            for i in range(n):
+                bl = box_cls(bb[i, :ks[i]], boxes[i].size, mode="xyxy")
+                bl.add_field("scores", ss[i, :ks[i]])
+                bl.add_field("labels", ll[i, :ks[i]])
+                out.append(bl)
+            return out
+    _bind(mod, forward)
+    return True
+
+
 def _fuse_mask_targets(be, rep):
     """project_masks_on_boxes (roi_heads/mask_head/loss.py:11-42): the per-proposal crop / resize / rasterise loop on the
     HOST (flagged as a bottleneck at loss.py:31-32) becomes one launch on the polygons' vertices (csrc/mask_targets.cu).
@@ -503,6 +566,8 @@ def fuse_model(model, backend=None, channels_last_weights=True):
         for name, mod in model.named_modules():
             if not getattr(mod, "_mrb_fused", False) and _fuse_rpn_postprocessor(mod, be):
                 bump("rpn_postprocessor")
+            elif not getattr(mod, "_mrb_fused", False) and _fuse_box_postprocessor(mod, be):
+                bump("box_postprocessor")
         _fuse_mask_targets(be, rep)
     _wire_resnet(model, be)
     model._mrb_backend = be

@@ -90,6 +90,8 @@ class GraphedModule:
                         s.copy_(g_)
                     elif s is not None and g_ is None:
                         s.zero_()
+                if seg.pre_backward_hook is not None:
+                    seg.pre_backward_hook()          # e.g. start the all-reduce of everything downstream of this segment
                 seg.g_bwd.replay()
                 return tuple(None if x is None else x.detach() for x in seg.static_gin + seg.static_gparam)
 
@@ -97,6 +99,7 @@ class GraphedModule:
         self.replays = 0
         self.fallbacks = 0
         self.bypass = False         # True: run the eager forward (launch accounting / A-B runs)
+        self.pre_backward_hook = None
 
     def __call__(self, *args):
         flat, _ = tree_flatten(tuple(args))

@@ -293,6 +293,8 @@ class B200Backend(Backend):
     fused_glue = __import__("os").environ.get("MRB_FUSED_GLUE", "1") != "0"
     # the three loss stages as the fused forward / backward launches of csrc/loss_glue.cu (MRB_FUSED_LOSSES=0: PyTorch ops)
     fused_losses = __import__("os").environ.get("MRB_FUSED_LOSSES", "1") != "0"
+    # RPN top-k + decode as one cluster launch per level (mrb_rpn_topk_decode) instead of torch.topk + mrb_rpn_decode_packed
+    fused_topk = __import__("os").environ.get("MRB_FUSED_TOPK", "1") != "0"
 
     def __init__(self, wgrad="tc"):
         self._w16 = {}
@@ -323,6 +325,24 @@ class B200Backend(Backend):
         if stale:
             from mrb_b200 import ops
             ops.prepare_dgrad_weights([e[3] for e in stale], [e[1] for e in stale], [e[4] for e in stale])
+
+    def prepare_async(self):
+        """Issue arena_updated() on its own stream (start of a step, with ParamArena.defer_dgrad_prepare); join_prepare() before
+        the first data-gradient launch (i.e. before backward)."""
+        if self.arena is None:
+            return
+        if getattr(self, "_prep_stream", None) is None:
+            self._prep_stream = torch.cuda.Stream()
+        cur = torch.cuda.current_stream()
+        self._prep_stream.wait_stream(cur)
+        with torch.cuda.stream(self._prep_stream):
+            self.arena_updated()
+        self._prep_pending = True
+
+    def join_prepare(self):
+        if getattr(self, "_prep_pending", False):
+            torch.cuda.current_stream().wait_stream(self._prep_stream)
+            self._prep_pending = False
 
     def enable_overlap(self, on=True):
         """Run the weight-/bias-gradient kernels that accumulate into arena sinks on a second stream: nothing in the

@@ -160,6 +160,10 @@ class GeneralizedRCNN(nn.Module):
         boxes, _, valid = proposals
         rois = _to_rois(boxes)
         x = box.features(be, feats, rois)
+        if getattr(be, "fused_glue", False) and self.cfg.detections_per_img > 0 and boxes.shape[1] * (self.cfg.num_classes - 1) < 2 ** 20:
+            # fixed-shape, sync-free post-processing (padded detections): the whole eval forward is CUDA-graph capturable
+            widths, heights = self.rpn._sizes(image_sizes, boxes.device)
+            return box.postprocess_fused(box.predict_packed(be, x), proposals, widths, heights)
         cls, reg = box.predict(be, x)
         return box.postprocess(be, cls, reg, proposals, image_sizes)
 

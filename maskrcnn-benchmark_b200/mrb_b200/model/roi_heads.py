@@ -133,6 +133,18 @@ class BoxHead(nn.Module):
         return cls_loss, box_loss
 
     @torch.no_grad()
+    def postprocess_fused(self, outputs, proposals, widths, heights):
+        """postprocess on the packed predictor output, three launches + one batched NMS, fixed shapes and no host
+        synchronisation (ops.box_postprocess): a list of {"boxes" [D, 4], "scores" [D], "labels" [D], "count" []} per image,
+        rows beyond `count` zero."""
+        from mrb_b200 import ops
+        cfg = self.cfg
+        boxes, _, valid = proposals
+        b, s, l, c = ops.box_postprocess(outputs, cfg.num_classes, boxes, valid, widths, heights, cfg.score_thresh,
+                                         cfg.bbox_reg_weights, cfg.roi_nms, cfg.detections_per_img)
+        return [{"boxes": b[i], "scores": s[i], "labels": l[i], "count": c[i]} for i in range(b.shape[0])]
+
+    @torch.no_grad()
     def postprocess(self, be, class_logits, box_regression, proposals, image_sizes):
         """box_head/inference.py:45-149: softmax, decode, clip, per-class NMS, top-100."""
         cfg = self.cfg

@@ -146,6 +146,9 @@ class RPN(nn.Module):
 
             def level(anc=anc, lg=lg, dl=dl, k=k, bo=bo, so=so):
                 if outs is not None:
+                    if getattr(be, "fused_topk", False) and k <= 8192 and lg.shape[1] * lg.shape[2] * apl <= 8 * 50000:
+                        ops.rpn_topk_decode(lg, apl, anc, k, widths, heights, bo, so, self.box_coder.weights, self.box_coder.clip)
+                        return bo
                     idx = lg[..., :apl].reshape(n, -1).topk(k, dim=1, sorted=True)[1]
                     ops.rpn_decode_packed(lg, apl, anc, idx, widths, heights, bo, so, self.box_coder.weights, self.box_coder.clip)
                     return bo
@@ -350,6 +353,9 @@ class RPN(nn.Module):
                 prepared = fork(ins, tfn)
             elif fused:
                 prepared = tfn()
+        if (not training) and getattr(be, "fused_glue", False) and getattr(be, "fused_losses", False):
+            outs = self.head.run_packed(be, feats)
+            return self._select_proposals_fused(be, anchors, None, None, image_sizes, None, False, outs=outs), {}
         if training and packed:
             # fused losses: the head outputs stay in the engine's layout, read in place by decode and loss launches
             from mrb_b200 import ops

@@ -736,6 +736,62 @@ def rpn_decode_packed(head_out, apl, anchors, topk_idx, image_w, image_h, boxes_
     _count(1)
 
 
+def rpn_topk_decode(head_out, apl, anchors, k, image_w, image_h, boxes_out, scores_out, weights=(1.0, 1.0, 1.0, 1.0), xform_clip=None):
+    """objectness.topk(k, sorted=True) + rpn_decode_packed in ONE launch (a thread-block cluster per image): the k best anchors of
+    the level by logit, descending (ascending anchor index among equal logits), decoded and clipped, with their sigmoids."""
+    import math
+    if not (head_out.is_cuda and head_out.dtype == torch.float32 and head_out.is_contiguous() and head_out.dim() == 4):
+        raise RuntimeError("rpn_topk_decode: head output must be a contiguous fp32 CUDA tensor [N, H, W, ld]")
+    n, h, w_, ld = head_out.shape
+    a = h * w_ * apl
+    anchors = _f32c(anchors, "rpn_topk_decode")
+    w = (ctypes.c_float * 4)(*[float(x) for x in weights])
+    clip = math.log(1000.0 / 16) if xform_clip is None else float(xform_clip)
+    with _c.on_device(head_out.device):
+        _c.check(lib.mrb_rpn_topk_decode(_c._ptr(head_out), apl, ld, _c._ptr(anchors), _c._ptr(image_w), _c._ptr(image_h),
+                                         _c._ptr(boxes_out), _c._ptr(scores_out), n, a, int(k), w, ctypes.c_float(clip), _c._stream()),
+                 "mrb_rpn_topk_decode")
+    _count(1)
+
+
+def box_postprocess(outputs, num_classes, proposals, valid, image_w, image_h, score_thresh, weights, nms_thresh, detections_per_img,
+                    xform_clip=None):
+    """PostProcessor.forward (box_head/inference.py:45-149) without host synchronisation: softmax + per-class decode + clip +
+    score threshold (one launch), one batched NMS over the N x (C-1) (image, class) problems, top detections_per_img per image
+    (one cluster launch).  outputs [N*P, ld >= 5C] fp32 (C logits, 4C regression outputs), proposals [N, P, 4], valid [N, P].
+    -> (boxes [N, D, 4], scores [N, D], labels [N, D] int64, count [N] int32); rows beyond count are zero."""
+    import math
+    if not (outputs.is_cuda and outputs.dtype == torch.float32 and outputs.is_contiguous()):
+        raise RuntimeError("box_postprocess: outputs must be a contiguous fp32 CUDA tensor (no CPU path)")
+    n, p, _ = proposals.shape
+    proposals = _f32c(proposals, "box_postprocess")
+    if valid.dtype != torch.bool or not valid.is_contiguous():
+        valid = valid.bool().contiguous()
+    ld = outputs.shape[1]
+    dev = outputs.device
+    nprob = n * (num_classes - 1)
+    boxes = torch.empty((nprob * p, 4), dtype=torch.float32, device=dev)
+    scores = torch.empty((nprob * p,), dtype=torch.float32, device=dev)
+    w = (ctypes.c_float * 4)(*[float(x) for x in weights])
+    clip = math.log(1000.0 / 16) if xform_clip is None else float(xform_clip)
+    with _c.on_device(dev):
+        _c.check(lib.mrb_box_post_decode(_c._ptr(outputs), ld, num_classes, _c._ptr(proposals), _c._ptr(valid), _c._ptr(image_w),
+                                         _c._ptr(image_h), n, p, ctypes.c_float(score_thresh), w, ctypes.c_float(clip),
+                                         _c._ptr(boxes), _c._ptr(scores), _c._stream()), "mrb_box_post_decode")
+    _count(1)
+    keep, counts = nms_batched(boxes, scores, [p] * nprob, nms_thresh)
+    d = int(detections_per_img)
+    ob = torch.empty((n, d, 4), dtype=torch.float32, device=dev)
+    os_ = torch.empty((n, d), dtype=torch.float32, device=dev)
+    ol = torch.empty((n, d), dtype=torch.int64, device=dev)
+    on = torch.empty((n,), dtype=torch.int32, device=dev)
+    with _c.on_device(dev):
+        _c.check(lib.mrb_box_post_select(_c._ptr(boxes), _c._ptr(scores), _c._ptr(keep), _c._ptr(counts), n, p, num_classes, d,
+                                         _c._ptr(ob), _c._ptr(os_), _c._ptr(ol), _c._ptr(on), _c._stream()), "mrb_box_post_select")
+    _count(1)
+    return ob, os_, ol, on
+
+
 # --------------------------------------------------------------------------------- fused losses (csrc/loss_glue.cu)
 def _gscalar(g, like):
     if g is None:

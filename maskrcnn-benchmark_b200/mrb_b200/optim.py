@@ -128,6 +128,10 @@ class ParamArena:
             self.buckets["bias"] = [n_w, total]
         self.split = self.buckets["heads"][0] if "heads" in self.buckets else n_w      # [0, split) = the backbone
         self._pending = {}        # bucket name -> async work handle of this step
+        # True: step() leaves the re-derivation of the data-gradient weights to the caller, who issues it at the START of the
+        # next step on a side stream (B200Backend.prepare_async / join_prepare): they are needed only by the backward pass, so
+        # the ~150 us of transposes overlap the forward pass instead of sitting at the end of the step
+        self.defer_dgrad_prepare = False
         self._comm = None
         import os
         # A/B switch.  Must be identical on every rank (collective order): pass `early_reduce` explicitly from rank-0
@@ -230,5 +234,5 @@ class ParamArena:
         for lo, hi, lr, wd in self.groups:
             ops.sgd_momentum_step(self.param[lo:hi], self.grad[lo:hi], self.mom[lo:hi], self.param16[lo:hi], lr,
                                   self.momentum, wd, 1.0 / self.world, True)
-        if self.backend is not None:
+        if self.backend is not None and not self.defer_dgrad_prepare:
             self.backend.arena_updated()

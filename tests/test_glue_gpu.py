@@ -601,3 +601,110 @@ def test_fused_reference_postprocessor_and_mask_targets(built_lib):
         assert float(got.mean()) > 0.02
     finally:
         mask_loss_mod.project_masks_on_boxes = orig
+
+
+@pytest.mark.parametrize("grid,k", [((200, 336), 2000), ((50, 84), 2000), ((25, 42), 2000), ((13, 21), 2000), ((100, 168), 1000)])
+def test_rpn_topk_decode_equals_topk_then_decode(built_lib, grid, k):
+    """mrb_rpn_topk_decode (cluster radix select + sort + decode) == torch.topk(sorted) on the logits + mrb_rpn_decode_packed"""
+    from mrb_b200 import ops
+    from mrb_b200.model import box_ops
+    gh, gw = grid
+    n, apl, ld = 2, 3, 16
+    g = torch.Generator().manual_seed(gh * 7 + k)
+    stride = max(4, 800 // gh)
+    anc = box_ops.grid_anchors(box_ops.cell_anchors(stride, (stride * 8,), (0.5, 1.0, 2.0)), stride, gh, gw, DEV)
+    o = torch.randn(n, gh, gw, ld, generator=g)
+    o[..., 5 * apl:] = 0
+    o[0, 0, :7, 0] = 5.5                       # equal logits among the best: taken in anchor order
+    o = o.to(DEV)
+    a = gh * gw * apl
+    kk = min(k, a)
+    widths = torch.tensor([1333.0, 1201.0], device=DEV)
+    heights = torch.tensor([800.0, 777.0], device=DEV)
+    b1, s1 = torch.empty((n, kk, 4), device=DEV), torch.empty((n, kk), device=DEV)
+    ops.rpn_topk_decode(o, apl, anc, kk, widths, heights, b1, s1)
+    lg = o[..., :apl].reshape(n, -1)
+    # reference order: descending logit, ascending anchor index among equal logits (a stable descending sort)
+    idx = torch.sort(lg, dim=1, descending=True, stable=True)[1][:, :kk].contiguous()
+    b2, s2 = torch.empty((n, kk, 4), device=DEV), torch.empty((n, kk), device=DEV)
+    ops.rpn_decode_packed(o, apl, anc, idx, widths, heights, b2, s2)
+    assert torch.equal(s1, s2), (s1 - s2).abs().max().item()
+    assert torch.equal(b1, b2), (b1 - b2).abs().max().item()
+
+
+def test_box_postprocess_fused_equals_torch_formulation(built_lib):
+    """ops.box_postprocess (softmax + decode + threshold, batched NMS over image x class, top-100; no host sync) vs the harness's
+    PyTorch formulation of PostProcessor.forward (box_head/inference.py:45-149)"""
+    from mrb_b200 import ops
+    from mrb_b200.model.backend import B200Backend
+    from mrb_b200.model.roi_heads import BoxHead
+    cfg = _cfg()
+    head = BoxHead(cfg, 256)
+    be = B200Backend()
+    g = torch.Generator().manual_seed(41)
+    n, p, nc, ld = 2, 1000, cfg.num_classes, 408
+    o = torch.zeros(n * p, ld)
+    o[:, :nc] = torch.randn(n * p, nc, generator=g) * 2.0
+    o[:, 0] += 1.0
+    hot = torch.randint(1, nc, (n * p,), generator=g)
+    o[torch.arange(n * p), hot] += torch.rand(n * p, generator=g) * 6.0          # a few confident classes per row
+    o[:, nc:5 * nc] = torch.randn(n * p, 4 * nc, generator=g) * 0.5
+    o = o.to(DEV)
+    boxes = torch.stack([_rand_boxes(g, p, 1333, 800, 16, 300), _rand_boxes(g, p, 1216, 768, 16, 300)]).to(DEV)
+    valid = torch.ones(n, p, dtype=torch.bool)
+    valid[1, -37:] = False
+    valid = valid.to(DEV)
+    sizes = [(800, 1333), (768, 1216)]
+    widths = torch.tensor([1333.0, 1216.0], device=DEV)
+    heights = torch.tensor([800.0, 768.0], device=DEV)
+    b, s, l, c = ops.box_postprocess(o, nc, boxes, valid, widths, heights, cfg.score_thresh, cfg.bbox_reg_weights, cfg.roi_nms,
+                                     cfg.detections_per_img)
+    want = head.postprocess(be, o[:, :nc], o[:, nc:5 * nc], (boxes, None, valid), sizes)
+    for i in range(n):
+        k = int(c[i])
+        wi = want[i]
+        assert k == min(cfg.detections_per_img, wi["scores"].numel()) or abs(k - wi["scores"].numel()) <= 1, (k, wi["scores"].numel())
+        got = torch.cat([b[i, :k], s[i, :k, None], l[i, :k, None].float()], 1)
+        ref = torch.cat([wi["boxes"], wi["scores"][:, None], wi["labels"][:, None].float()], 1)
+        assert not b[i, k:].any() and not s[i, k:].any()
+        cg_, cr = _canon(got), _canon(ref)
+        if cg_.shape == cr.shape:
+            same = (np.abs(cg_ - cr).max(1) <= 1e-4).mean()
+            assert same > 0.97, (i, same)
+        # class-major order, scores above the threshold
+        assert (l[i, :k][1:] >= l[i, :k][:-1]).all() and float(s[i, :k].min()) > cfg.score_thresh
+
+
+def test_fused_reference_box_postprocessor(built_lib):
+    """mrb_b200.fuse rebinds the reference's box-head PostProcessor.forward: same detections as the reference's Python"""
+    from mrb_b200 import fuse, refenv
+    if refenv.activate() is None:
+        pytest.skip("reference checkout absent")
+    from maskrcnn_benchmark.modeling.box_coder import BoxCoder
+    from maskrcnn_benchmark.modeling.roi_heads.box_head.inference import PostProcessor
+    from maskrcnn_benchmark.structures.bounding_box import BoxList
+    from mrb_b200.model.backend import B200Backend
+    g = torch.Generator().manual_seed(43)
+    nc = 81
+    counts = [1000, 873]
+    r = sum(counts)
+    logits = torch.randn(r, nc, generator=g) * 2.0
+    logits[:, 0] += 1.0
+    hot = torch.randint(1, nc, (r,), generator=g)
+    logits[torch.arange(r), hot] += torch.rand(r, generator=g) * 6.0
+    reg = torch.randn(r, 4 * nc, generator=g) * 0.5
+    boxes = [BoxList(_rand_boxes(g, counts[0], 1333, 800, 16, 300).to(DEV), (1333, 800), mode="xyxy"),
+             BoxList(_rand_boxes(g, counts[1], 1216, 768, 16, 300).to(DEV), (1216, 768), mode="xyxy")]
+    x = (logits.to(DEV), reg.to(DEV))
+    ref = PostProcessor(0.05, 0.5, 100, BoxCoder((10.0, 10.0, 5.0, 5.0)))
+    fus = PostProcessor(0.05, 0.5, 100, BoxCoder((10.0, 10.0, 5.0, 5.0)))
+    assert fuse._fuse_box_postprocessor(fus, B200Backend())
+    want = ref(x, boxes)
+    got = fus(x, boxes)
+    for w, gt in zip(want, got):
+        assert gt.size == w.size and abs(len(gt) - len(w)) <= 1, (len(gt), len(w))
+        a = torch.cat([w.bbox, w.get_field("scores")[:, None], w.get_field("labels")[:, None].float()], 1)
+        b = torch.cat([gt.bbox, gt.get_field("scores")[:, None], gt.get_field("labels")[:, None].float()], 1)
+        if a.shape == b.shape:
+            same = (np.abs(_canon(a) - _canon(b)).max(1) <= 1e-4).mean()
+            assert same > 0.97, same
