@@ -286,6 +286,15 @@ int mrb_box_post_select(const float* boxes, const float* scores, const int64_t* 
  * straddle_thresh < 0 disables the visibility test, anchor_generator.py:100-116).  anchors [A, 4] (shared by the images),
  * labels [N, A] fp32, matched_gt [N, A] int32 (arg-max ground truth of every anchor). */
 size_t mrb_rpn_anchor_match_workspace_bytes(int num_images, int num_anchors, int gmax);
+/* mrb_rpn_sample: BalancedPositiveNegativeSampler over the labelled anchors of every image (balanced_positive_negative_sampler.py:
+ * 19-68; "n random elements" = the n smallest of the iid rand_keys [N, A]) + BoxCoder.encode of the sampled positives against
+ * their matched ground truth (rpn/loss.py:86-90), one launch (a cluster of CTAs per image).  P = int(batch * fraction).
+ * pos_idx / pos_ok / reg_targets [N, P]; sel_idx / sel_label / sel_weight [N, P + batch]: the P positive slots, then the
+ * negative slots (weight 0 = unused slot) -- the inputs of mrb_rpn_loss_fwd. */
+int mrb_rpn_sample(const float* labels, const int32_t* matched_gt, const float* rand_keys, const float* anchors,
+                   const float* gt_boxes, int num_images, int num_anchors, int gmax, int batch_size_per_image,
+                   float positive_fraction, const float* weights_host, int64_t* pos_idx, uint8_t* pos_ok, float* reg_targets,
+                   int64_t* sel_idx, float* sel_label, float* sel_weight, mrb_stream_t stream);
 int mrb_rpn_anchor_match(const float* anchors, const float* gt_boxes, const int32_t* gt_count, const float* image_w,
                          const float* image_h, int num_images, int num_anchors, int gmax, float fg_iou, float bg_iou,
                          float straddle_thresh, float* labels, int32_t* matched_gt, void* workspace, size_t workspace_bytes,
@@ -332,6 +341,11 @@ int mrb_rpn_decode_packed(const float* head_output, int anchors_per_location, in
                           const int64_t* topk_idx,
                           const float* image_w, const float* image_h, float* boxes, float* scores, int num_images,
                           int num_anchors, int k, const float* weights_host, float xform_clip, mrb_stream_t stream);
+
+/* The same for rectangle instances (matched ground-truth box per ROI): gt_boxes [R, 4], rois [R, roi_stride >= 4] with the box
+ * in its first four floats... see csrc/mask_targets.cu.  out [R, M, M] fp32 in {0,1}. */
+int mrb_mask_targets_rect(const float* gt_boxes, const float* rois, int roi_stride, float* out, int num_rois, int mask_size,
+                          mrb_stream_t stream);
 
 /* Operand preparation for MRB_CONV_GROUPED64 (csrc/grouped_prep.cu).  weight: the grouped filter [C][taps][C/groups] bf16
  * (KRSC).  w_exp / wd_exp: [C][taps][64] bf16 -- the forward operand and the (flipped, per-Cout scaled) data-gradient operand

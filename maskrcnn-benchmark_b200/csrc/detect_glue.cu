@@ -73,10 +73,10 @@ __device__ __forceinline__ int block_excl_scan(int v, int* total, int* ws) {
 // finds the threshold T such that taking every key > T and the first `quota` keys == T (in slice-major, index order)
 // yields the `want` largest.  If fewer than `want` keys are present, T = 0 and quota = 0 with everything present > T
 // (keys of present elements must be > 0).  `hist`, `ghist`: 256 ints of smem each; `sh`: 4 ints.
-template <class F>
+template <bool kCluster = true, class F>
 __device__ void radix_select(F key_of, int n, int want, unsigned* T_out, int* quota_out, int* hist, int* ghist, int* sh) {
   cg::cluster_group cluster = cg::this_cluster();
-  const unsigned nranks = cluster.num_blocks();
+  const unsigned nranks = kCluster ? cluster.num_blocks() : 1u;
   unsigned prefix = 0, mask = 0;
   int remaining = want;
   bool short_of = false;
@@ -87,13 +87,19 @@ __device__ void radix_select(F key_of, int n, int want, unsigned* T_out, int* qu
       unsigned k;
       if (key_of(i, &k) && (k & mask) == prefix) atomicAdd(&hist[(k >> shift) & 255u], 1);
     }
-    cluster.sync();
-    for (int t = threadIdx.x; t < 256; t += blockDim.x) {
-      int s = 0;
-      for (unsigned r = 0; r < nranks; ++r) s += cluster.map_shared_rank(hist, r)[t];
-      ghist[t] = s;
+    if (kCluster) {
+      cluster.sync();
+      for (int t = threadIdx.x; t < 256; t += blockDim.x) {
+        int s = 0;
+        for (unsigned r = 0; r < nranks; ++r) s += cluster.map_shared_rank(hist, r)[t];
+        ghist[t] = s;
+      }
+      cluster.sync();  // everybody has read every hist before the next pass clears it; also orders ghist for thread 0
+    } else {           // single CTA: the local histogram is the global one
+      __syncthreads();
+      for (int t = threadIdx.x; t < 256; t += blockDim.x) ghist[t] = hist[t];
+      __syncthreads();
     }
-    cluster.sync();  // everybody has read every hist before the next pass clears it; also orders ghist for thread 0
     if (threadIdx.x == 0) {
       int acc = 0, b = 255;
       for (; b >= 0; --b) {
@@ -492,7 +498,7 @@ roi_assign_sample_kernel(const float4* __restrict__ boxes, const unsigned char* 
   int qp, qn;
   {
     auto key_of = [&](int p, unsigned* k) { *k = keys[p]; return lab[p] > 0; };
-    radix_select(key_of, a.P, a.pos_cap, &Tp, &qp, hist, ghist, sh);
+    radix_select<false>(key_of, a.P, a.pos_cap, &Tp, &qp, hist, ghist, sh);
   }
   // every thread owns a contiguous run of proposals (index order == output order): one CTA-wide scan per quantity
   const int per = (a.P + (int)blockDim.x - 1) / (int)blockDim.x;
@@ -518,7 +524,7 @@ roi_assign_sample_kernel(const float4* __restrict__ boxes, const unsigned char* 
   const int neg_want = a.S - n_pos;
   {
     auto key_of = [&](int p, unsigned* k) { *k = keys[p]; return lab[p] == 0; };
-    radix_select(key_of, a.P, neg_want > 0 ? neg_want : 1, &Tn, &qn, hist, ghist, sh);
+    radix_select<false>(key_of, a.P, neg_want > 0 ? neg_want : 1, &Tn, &qn, hist, ghist, sh);
   }
   // two-way partition in index order: sampled rows first, then the rest; the first S rows are the output
   {
@@ -837,6 +843,139 @@ rpn_anchor_label_kernel(const float4* __restrict__ anchors, const float4* __rest
   }
 }
 
+// ------------------------------------------------------------------------------------------ 5. RPN anchor sampling + encode
+// BalancedPositiveNegativeSampler over the anchors of an image (balanced_positive_negative_sampler.py:19-68: up to
+// batch * fraction random positives, the rest random negatives) and BoxCoder.encode of the sampled positives
+// (rpn/loss.py:86-90, box_coder.py:22-50), for the whole batch in one launch.  One cluster of CTAs per image splits the
+// ~268 k anchors; "n random elements" = the n smallest of caller-supplied iid keys (== randperm[:n]), found by a radix
+// select across the cluster; the sampled anchors are emitted in anchor order.
+struct SampleArgs {
+  int N, A, slice, gmax, P, B;       // images, anchors, anchors per CTA, gt slots, positive cap, batch size per image
+  float wx, wy, ww, wh;
+};
+
+__global__ void __launch_bounds__(kGlueThreads)
+rpn_sample_kernel(const float* __restrict__ labels, const int32_t* __restrict__ matched, const float* __restrict__ rnd,
+                  const float4* __restrict__ anchors, const float4* __restrict__ gt, int64_t* __restrict__ pos_idx,
+                  unsigned char* __restrict__ pos_ok, float4* __restrict__ reg_t, int64_t* __restrict__ sel_idx,
+                  float* __restrict__ sel_label, float* __restrict__ sel_w, SampleArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ int hist[256], ghist[256], sh[4], scan_ws[33], cnt_sh[4];
+  cg::cluster_group cluster = cg::this_cluster();
+  const unsigned cs = cluster.num_blocks(), rank = cluster.block_rank();
+  const int i = blockIdx.x / cs;
+  unsigned* keys = (unsigned*)smem_raw;                              // [slice] inverted key (larger = earlier), bit 0 cleared
+  signed char* lab = (signed char*)(smem_raw + (size_t)a.slice * 4);   // [slice] 1 positive, 0 negative, -1 ignore
+  const int a_lo = min((int)rank * a.slice, a.A), a_hi = min(a_lo + a.slice, a.A), n = a_hi - a_lo;
+  for (int t = threadIdx.x; t < n; t += blockDim.x) {
+    const size_t g = (size_t)i * a.A + a_lo + t;
+    unsigned k = ~glue_key(rnd[g]);
+    keys[t] = k == 0 ? 1u : k;
+    const float l = labels[g];
+    lab[t] = l >= 1.f ? 1 : (l == 0.f ? 0 : -1);
+  }
+  __syncthreads();
+  const int per = (n + (int)blockDim.x - 1) / (int)blockDim.x;
+  const int t_lo = min((int)threadIdx.x * per, n), t_hi = min(t_lo + per, n);
+  int64_t* pidx = pos_idx + (size_t)i * a.P;
+  unsigned char* pok = pos_ok + (size_t)i * a.P;
+  float4* preg = reg_t + (size_t)i * a.P;
+  const size_t S = (size_t)a.P + a.B;
+  int64_t* sidx = sel_idx + (size_t)i * S;
+  float* slab = sel_label + (size_t)i * S;
+  float* sw = sel_w + (size_t)i * S;
+  int n_pos_total = 0;
+  for (int phase = 0; phase < 2; ++phase) {
+    const signed char want_lab = phase == 0 ? 1 : 0;
+    const int cap = phase == 0 ? a.P : a.B;
+    int want = phase == 0 ? a.P : a.B - n_pos_total;
+    const bool none = want <= 0;
+    if (none) want = 1;
+    unsigned T;
+    int quota;
+    auto key_of = [&](int t, unsigned* k) { *k = keys[t]; return lab[t] == want_lab; };
+    radix_select(key_of, n, want, &T, &quota, hist, ghist, sh);
+    int my_ties = 0;
+    for (int t = t_lo; t < t_hi; ++t) my_ties += (lab[t] == want_lab && keys[t] == T);
+    int tie_tot;
+    int tr = block_excl_scan(my_ties, &tie_tot, scan_ws);
+    if (threadIdx.x == 0) cnt_sh[0] = tie_tot;
+    cluster.sync();
+    for (unsigned r = 0; r < rank; ++r) tr += cluster.map_shared_rank(cnt_sh, r)[0];
+    int my_sel = 0;
+    unsigned long long selbits = 0;             // per <= 64 (slice <= 64 * 1024, checked on the host)
+    for (int t = t_lo; t < t_hi; ++t) {
+      if (lab[t] != want_lab) continue;
+      const bool is_tie = keys[t] == T;
+      const bool sel = !none && (keys[t] > T || (is_tie && tr < quota));
+      tr += is_tie;
+      if (sel) {
+        ++my_sel;
+        selbits |= 1ull << (t - t_lo);
+      }
+    }
+    int sel_tot;
+    int pos = block_excl_scan(my_sel, &sel_tot, scan_ws);
+    if (threadIdx.x == 0) cnt_sh[1] = sel_tot;
+    cluster.sync();
+    int total = 0;
+    for (unsigned r = 0; r < cs; ++r) {
+      const int c = cluster.map_shared_rank(cnt_sh, r)[1];
+      if (r < rank) pos += c;
+      total += c;
+    }
+    for (int t = t_lo; t < t_hi; ++t)
+      if ((selbits >> (t - t_lo)) & 1ull) {
+        const int g = a_lo + t;
+        if (phase == 0 && pos < a.P) {
+          pidx[pos] = g;
+          pok[pos] = 1;
+          sidx[pos] = g;
+          slab[pos] = 1.f;
+          sw[pos] = 1.f;
+          // box_coder.py:22-50 with the RPN's weights
+          const float4 b = anchors[g];
+          const float4 q = gt[(size_t)i * a.gmax + matched[(size_t)i * a.A + g]];
+          const float ew = __fadd_rn(__fsub_rn(b.z, b.x), 1.f), eh = __fadd_rn(__fsub_rn(b.w, b.y), 1.f);
+          const float ex = __fadd_rn(b.x, __fmul_rn(0.5f, ew)), ey = __fadd_rn(b.y, __fmul_rn(0.5f, eh));
+          const float gw = __fadd_rn(__fsub_rn(q.z, q.x), 1.f), gh = __fadd_rn(__fsub_rn(q.w, q.y), 1.f);
+          const float gx = __fadd_rn(q.x, __fmul_rn(0.5f, gw)), gy = __fadd_rn(q.y, __fmul_rn(0.5f, gh));
+          float4 tt;
+          tt.x = __fdiv_rn(__fmul_rn(a.wx, __fsub_rn(gx, ex)), ew);
+          tt.y = __fdiv_rn(__fmul_rn(a.wy, __fsub_rn(gy, ey)), eh);
+          tt.z = __fmul_rn(a.ww, logf(__fdiv_rn(gw, ew)));
+          tt.w = __fmul_rn(a.wh, logf(__fdiv_rn(gh, eh)));
+          preg[pos] = tt;
+        } else if (phase == 1 && pos < a.B) {
+          sidx[a.P + pos] = g;
+          slab[a.P + pos] = 0.f;
+          sw[a.P + pos] = 1.f;
+        }
+        ++pos;
+      }
+    // padding of the list (rank 0): index 0, weight 0
+    if (rank == 0) {
+      const int filled = total < cap ? total : cap;
+      for (int t = filled + threadIdx.x; t < cap; t += blockDim.x) {
+        if (phase == 0) {
+          pidx[t] = 0;
+          pok[t] = 0;
+          preg[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+          sidx[t] = 0;
+          slab[t] = 1.f;
+          sw[t] = 0.f;
+        } else {
+          sidx[a.P + t] = 0;
+          slab[a.P + t] = 0.f;
+          sw[a.P + t] = 0.f;
+        }
+      }
+    }
+    if (phase == 0) n_pos_total = total < a.P ? total : a.P;
+    cluster.sync();        // cnt_sh is reused by the next phase; nobody leaves while its counters may still be read
+  }
+}
+
 }  // namespace mrb
 using namespace mrb;
 
@@ -1071,6 +1210,43 @@ MRB_API int mrb_box_post_select(const float* boxes, const float* scores, const i
   cfg.numAttrs = 1;
   MRB_CUDA_TRY(cudaLaunchKernelEx(&cfg, box_post_select_kernel, (const float4*)boxes, scores, keep, num_keep, (float4*)out_boxes,
                                   out_scores, out_labels, out_count, a));
+  return MRB_OK;
+}
+
+MRB_API int mrb_rpn_sample(const float* labels, const int32_t* matched_gt, const float* rand_keys, const float* anchors,
+                           const float* gt_boxes, int num_images, int num_anchors, int gmax, int batch_size_per_image,
+                           float positive_fraction, const float* weights_host, int64_t* pos_idx, uint8_t* pos_ok, float* reg_targets,
+                           int64_t* sel_idx, float* sel_label, float* sel_weight, mrb_stream_t stream) {
+  if (!labels || !matched_gt || !rand_keys || !anchors || !gt_boxes || !weights_host || !pos_idx || !pos_ok || !reg_targets ||
+      !sel_idx || !sel_label || !sel_weight || num_images <= 0 || num_anchors <= 0 || gmax <= 0 || batch_size_per_image <= 0)
+    return MRB_ERR_BAD_ARG;
+  if (((uintptr_t)anchors & 15) || ((uintptr_t)gt_boxes & 15) || ((uintptr_t)reg_targets & 15)) return MRB_ERR_BAD_ARG;
+  SampleArgs a;
+  a.N = num_images; a.A = num_anchors; a.gmax = gmax; a.B = batch_size_per_image;
+  a.P = (int)(batch_size_per_image * positive_fraction);
+  if (a.P < 1 || a.P > batch_size_per_image) return MRB_ERR_BAD_ARG;
+  a.wx = weights_host[0]; a.wy = weights_host[1]; a.ww = weights_host[2]; a.wh = weights_host[3];
+  int cs = 1;
+  while (cs < 8 && (num_anchors + cs - 1) / cs > 36 * 1024) cs <<= 1;
+  a.slice = (num_anchors + cs - 1) / cs;
+  if (a.slice > 40000) return MRB_ERR_UNSUPPORTED;   // 5 B of shared memory per anchor; 16-CTA clusters are not portable
+  const size_t smem = (size_t)a.slice * 5 + 16;
+  if (smem > 200 * 1024) return MRB_ERR_UNSUPPORTED;
+  MRB_CUDA_TRY(cudaFuncSetAttribute(rpn_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(num_images * cs);
+  cfg.blockDim = dim3(kGlueThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cs;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  MRB_CUDA_TRY(cudaLaunchKernelEx(&cfg, rpn_sample_kernel, labels, matched_gt, rand_keys, (const float4*)anchors, (const float4*)gt_boxes,
+                                  pos_idx, (unsigned char*)pos_ok, (float4*)reg_targets, sel_idx, sel_label, sel_weight, a));
   return MRB_OK;
 }
 

@@ -50,8 +50,40 @@ mask_targets_poly_kernel(const float2* __restrict__ polys, const int* __restrict
   }
 }
 
+// Rectangle instances (the synthetic benchmark's masks; also what a box-only dataset yields): cell (i, j) of ROI r is inside iff
+// its centre, in the M x M frame of the ROI, lies within the matched ground-truth box scaled into that frame -- the closed-form
+// special case of the rule above, in the operation order of the harness's PyTorch formulation (mrb_b200/model/roi_heads.py,
+// MaskHead.mask_targets), so the two agree bit for bit.
+__global__ void __launch_bounds__(256)
+mask_targets_rect_kernel(const float4* __restrict__ gt, const float* __restrict__ rois, int roi_stride, float* __restrict__ out, int R,
+                         int M) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)R * M * M) return;
+  const int r = (int)(t / (M * M)), cell = (int)(t - (long long)r * M * M), i = cell / M, j = cell - i * M;
+  const float* q = rois + (size_t)r * roi_stride;
+  const float x1 = q[0], y1 = q[1], x2 = q[2], y2 = q[3];
+  const float4 g = gt[r];
+  const float sx = __fdiv_rn((float)M, fmaxf(__fsub_rn(x2, x1), 1e-6f)), sy = __fdiv_rn((float)M, fmaxf(__fsub_rn(y2, y1), 1e-6f));
+  const float cx = (float)j + 0.5f, cy = (float)i + 0.5f;
+  const bool inx = cx >= __fmul_rn(__fsub_rn(g.x, x1), sx) && cx <= __fmul_rn(__fsub_rn(g.z, x1), sx);
+  const bool iny = cy >= __fmul_rn(__fsub_rn(g.y, y1), sy) && cy <= __fmul_rn(__fsub_rn(g.w, y1), sy);
+  out[t] = (inx && iny) ? 1.f : 0.f;
+}
+
 }  // namespace mrb
 using namespace mrb;
+
+MRB_API int mrb_mask_targets_rect(const float* gt_boxes, const float* rois, int roi_stride, float* out, int num_rois, int mask_size,
+                                  mrb_stream_t stream) {
+  if (num_rois < 0 || mask_size <= 0 || roi_stride < 4) return MRB_ERR_BAD_ARG;
+  if (num_rois == 0) return MRB_OK;
+  if (!gt_boxes || !rois || !out || ((uintptr_t)gt_boxes & 15)) return MRB_ERR_BAD_ARG;
+  const long long total = (long long)num_rois * mask_size * mask_size;
+  mask_targets_rect_kernel<<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>((const float4*)gt_boxes, rois, roi_stride, out, num_rois,
+                                                                                   mask_size);
+  MRB_LAUNCH_CHECK();
+  return MRB_OK;
+}
 
 MRB_API int mrb_mask_targets_polygons(const float* polys_xy, const int* poly_start, const int* inst_start, const float* rois,
                                       const int* inst_of_roi, float* out, int num_rois, int mask_size, mrb_stream_t stream) {

@@ -109,6 +109,9 @@ __device__ __forceinline__ bool suppresses(const float4 a, float a_area, const f
   const float xx2 = fminf(a.z, b.z), yy2 = fminf(a.w, b.w);
   const float w = fmaxf(0.f, __fadd_rn(__fsub_rn(xx2, xx1), 1.f));
   const float h = fmaxf(0.f, __fadd_rn(__fsub_rn(yy2, yy1), 1.f));
+  // disjoint boxes: inter == +0, so the quotient is +-0 or NaN and `>= thr` is false for every thr > 0 -- skip the division
+  // (most pairs of an RPN problem; the kernel is bound by the divisions otherwise)
+  if (thr > 0.f && (w == 0.f || h == 0.f)) return false;
   const float inter = __fmul_rn(w, h);
   const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(a_area, b_area), inter));
   return ovr >= thr;

@@ -247,6 +247,9 @@ roi_align_fpn_fwd_v2_kernel(FpnArgs a, const float* __restrict__ rois, __nv_bflo
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const RoiGeomF g = fpn_geom(rois + (size_t)n * 5, a);
   const int H = a.H[g.level], W = a.W[g.level], C = a.C, PP = a.P * a.P, PPS = PP | 1;
+  // gridDim.y CTAs share the bins of a ROI (few ROIs, many bins: the mask head's 256 x 14 x 14)
+  const int bins_per = (PP + (int)gridDim.y - 1) / (int)gridDim.y;
+  const int bin_lo = (int)blockIdx.y * bins_per, bin_hi = min(bin_lo + bins_per, PP);
   float* tile = reinterpret_cast<float*>(smem_raw);  // [256][PPS], NCHW-order output only
   __shared__ Axis2 s_ay[kMaxP], s_ax[kMaxP];
   if ((int)threadIdx.x < a.P)
@@ -259,7 +262,7 @@ roi_align_fpn_fwd_v2_kernel(FpnArgs a, const float* __restrict__ rois, __nv_bflo
     const int cl = c0 + lane * kV2Lane;
     const bool c_ok = cl < C;
     const __nv_bfloat16* __restrict__ src = base + (c_ok ? cl : 0);
-    for (int bin = warp; bin < PP; bin += kFpnThreads / 32) {
+    for (int bin = bin_lo + warp; bin < bin_hi; bin += kFpnThreads / 32) {
       const int ph = bin / a.P, pw = bin - ph * a.P;
       const Axis2 ay = s_ay[ph], ax = s_ax[pw];
       float acc[kV2Lane];
@@ -311,7 +314,7 @@ roi_align_fpn_fwd_v2_kernel(FpnArgs a, const float* __restrict__ rois, __nv_bflo
       const int cn = min(32 * kV2Lane, C - c0);
       __nv_bfloat16* __restrict__ dst = out + ((size_t)n * C + c0) * PP;
       for (int c = warp; c < cn; c += kFpnThreads / 32)
-        for (int bin = lane; bin < PP; bin += 32) dst[(size_t)c * PP + bin] = __float2bfloat16_rn(tile[c * PPS + bin]);
+        for (int bin = bin_lo + lane; bin < bin_hi; bin += 32) dst[(size_t)c * PP + bin] = __float2bfloat16_rn(tile[c * PPS + bin]);
       __syncthreads();
     }
   }
@@ -440,7 +443,11 @@ MRB_API int mrb_roi_align_fpn_fwd(const void* const* feats_host, const int* heig
   if (dtype == MRB_BF16 && !no_v2 && sampling_ratio == 2 && channels % kV2Lane == 0 && pooled <= kMaxP && smem2 <= 72 * 1024) {
     // (adaptive sampling grids, other channel counts and large NCHW tiles take the first form)
     if (smem2 > 48 * 1024) MRB_CUDA_TRY(cudaFuncSetAttribute(roi_align_fpn_fwd_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-    roi_align_fpn_fwd_v2_kernel<<<num_rois, kFpnThreads, smem2, (cudaStream_t)stream>>>(a, rois, (__nv_bfloat16*)output);
+    // at least ~4 CTAs per SM in total: split a ROI's bins over up to 8 CTAs when there are few ROIs
+    int split = (4 * kNumSMs + num_rois - 1) / num_rois;
+    split = split < 1 ? 1 : (split > 8 ? 8 : split);
+    if (split > pooled * pooled) split = pooled * pooled;
+    roi_align_fpn_fwd_v2_kernel<<<dim3(num_rois, split), kFpnThreads, smem2, (cudaStream_t)stream>>>(a, rois, (__nv_bfloat16*)output);
   } else if (dtype == MRB_BF16) {
     if (smem > 48 * 1024) MRB_CUDA_TRY(cudaFuncSetAttribute(roi_align_fpn_fwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     roi_align_fpn_fwd_kernel<__nv_bfloat16><<<grid, kFpnThreads, smem, (cudaStream_t)stream>>>(a, rois, (__nv_bfloat16*)output);

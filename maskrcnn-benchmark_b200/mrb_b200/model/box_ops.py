@@ -128,14 +128,15 @@ def _mask_of(idx, ok, n):
     return out[:n]
 
 
-def sample_pos_neg_idx(labels, batch_size, positive_fraction, generator=None):
+def sample_pos_neg_idx(labels, batch_size, positive_fraction, generator=None, key=None):
     """modeling/balanced_positive_negative_sampler.py:19-68 for one image, as fixed-size index lists:
     (pos_idx [P], pos_ok [P], neg_idx [B], neg_ok [B]) with P = int(batch_size * positive_fraction), B = batch_size:
     up to P random positives, the rest (up to batch_size in total) random negatives -- the distribution of
     randperm(...)[:num], without host synchronisation.  labels: -1 ignore, 0 negative, >0 positive."""
     n = labels.numel()
     num_pos_cap = min(int(batch_size * positive_fraction), n)
-    key = torch.rand(n, device=labels.device, generator=generator)
+    if key is None:
+        key = torch.rand(n, device=labels.device, generator=generator)
     pos_idx, pos_ok = _pick_random_idx(labels >= 1, key, num_pos_cap, num_pos_cap)
     neg_idx, neg_ok = _pick_random_idx(labels == 0, key, min(batch_size, n), batch_size - pos_ok.sum())
     return pos_idx, pos_ok, neg_idx, neg_ok

@@ -69,7 +69,8 @@ class GeneralizedRCNN(nn.Module):
                 tgt = ops.mask_targets_polygons(polyset, rois_sel[:, 1:], (mg + inst_off).reshape(-1), res)
             else:
                 gt_sel = torch.gather(gtp[0], 1, mg[..., None].expand(-1, -1, 4)).reshape(-1, 4)
-                tgt = mask.mask_targets(gt_sel, rois_sel[:, 1:], res)
+                from mrb_b200 import ops as _ops
+                tgt = _ops.mask_targets_rect(gt_sel, rois_sel, res)
             if getattr(be, "fused_losses", False):
                 from mrb_b200 import ops as _ops
                 return _ops.mask_head_loss(mask.run(be, feats, rois_sel, padded_logits=True), lab_sel, tgt, wsel)

@@ -262,7 +262,7 @@ class RPN(nn.Module):
 
     # ------------------------------------------------------------------ loss
     @torch.no_grad()
-    def loss_targets_fused(self, anchors_all, image_sizes, targets, gtp, generator=None, stacked=False):
+    def loss_targets_fused(self, anchors_all, image_sizes, targets, gtp, generator=None, stacked=False, keys=None):
         """loss_targets with the IoU / Matcher / labelling of all anchors of the batch as one launch pair
         (mrb_rpn_anchor_match); the sampling and the encoding of the sampled rows as in loss_targets."""
         from mrb_b200 import ops
@@ -270,10 +270,18 @@ class RPN(nn.Module):
         widths, heights = self._sizes(image_sizes, anchors_all.device)
         labels, matched = ops.rpn_anchor_match(anchors_all, gtp[0], gtp[2], widths, heights, cfg.rpn_fg_iou, cfg.rpn_bg_iou,
                                                float(self.anchor_generator.straddle_thresh))
+        if keys is None and labels.shape[1] <= 8 * 40000:
+            # sampling + encode of the batch as ONE cluster launch (the PyTorch formulation below thins, compacts and top-k's
+            # per image: ~30 launches each; it stays as the checker of the kernel, tests/test_glue_gpu.py)
+            keys = torch.rand(labels.shape, device=labels.device, generator=generator)
+            st = ops.rpn_sample(labels, matched, keys, anchors_all, gtp[0], cfg.rpn_batch_size, cfg.rpn_positive_fraction,
+                                self.box_coder.weights)
+            return st if stacked else [tuple(t[i] for t in st) for i in range(labels.shape[0])]
         out = []
         for i, t in enumerate(targets):
             pos_idx, pos_ok, neg_idx, neg_ok = box_ops.sample_pos_neg_idx(labels[i], cfg.rpn_batch_size,
-                                                                            cfg.rpn_positive_fraction, generator)
+                                                                            cfg.rpn_positive_fraction, generator,
+                                                                            key=None if keys is None else keys[i])
             gt = t["boxes"][matched[i][pos_idx].long()]
             reg_t = self.box_coder.encode(gt, anchors_all[pos_idx])
             sel = torch.cat([pos_idx, neg_idx])

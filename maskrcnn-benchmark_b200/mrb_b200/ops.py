@@ -492,6 +492,28 @@ def mask_targets_polygons(polyset, rois, inst_of_roi, m):
     return out
 
 
+def mask_targets_rect(gt_boxes, rois, m):
+    """[R, m, m] fp32 {0,1}: the matched ground-truth RECTANGLE gt_boxes[r] cropped to box rois[r] and sampled at the m x m cell
+    centres (project_masks_on_boxes for rectangle instances), one launch.  rois: [R, 4] or [R, 5] (image index first)."""
+    if not rois.is_cuda:
+        raise RuntimeError("mask_targets_rect: expected CUDA tensors (no CPU path)")
+    gt_boxes = gt_boxes.float().contiguous()
+    rois = rois.float().contiguous()
+    r, w = rois.shape
+    out = torch.empty((r, m, m), dtype=torch.float32, device=rois.device)
+    if r:
+        off = 1 if w == 5 else 0
+        with _c.on_device(rois.device):
+            _c.check(lib.mrb_mask_targets_rect(_c._ptr(gt_boxes), _c_void_p_offset(rois, off), w, _c._ptr(out), r, m, _c._stream()),
+                     "mrb_mask_targets_rect")
+        _count(1)
+    return out
+
+
+def _c_void_p_offset(t, elems):
+    return ctypes.c_void_p(t.data_ptr() + elems * t.element_size())
+
+
 # ------------------------------------------------------------------------- fused FPN ROIAlign
 class _RoiAlignFpn(torch.autograd.Function):
     @staticmethod
@@ -734,6 +756,31 @@ def rpn_decode_packed(head_out, apl, anchors, topk_idx, image_w, image_h, boxes_
                                            _c._ptr(image_h), _c._ptr(boxes_out), _c._ptr(scores_out), n, a, k, w,
                                            ctypes.c_float(clip), _c._stream()), "mrb_rpn_decode_packed")
     _count(1)
+
+
+def rpn_sample(labels, matched, rand_keys, anchors, gt_boxes, batch_size_per_image, positive_fraction, weights=(1.0, 1.0, 1.0, 1.0)):
+    """BalancedPositiveNegativeSampler over the labelled anchors of the batch + encode of the sampled positives, one launch.
+    labels [N, A] fp32 (1 / 0 / -1), matched [N, A] int32, rand_keys [N, A] iid uniform -> the six inputs of rpn_loss:
+    (pos_idx [N, P], pos_ok [N, P] bool, reg_targets [N, P, 4], sel_idx [N, P + B], sel_label, sel_weight)."""
+    labels, rand_keys, anchors, gt_boxes = (_f32c(t, "rpn_sample") for t in (labels, rand_keys, anchors, gt_boxes))
+    n, a = labels.shape
+    b = int(batch_size_per_image)
+    p = int(b * positive_fraction)
+    dev = labels.device
+    pos_idx = torch.empty((n, p), dtype=torch.int64, device=dev)
+    pos_ok = torch.empty((n, p), dtype=torch.bool, device=dev)
+    reg_t = torch.empty((n, p, 4), dtype=torch.float32, device=dev)
+    sel_idx = torch.empty((n, p + b), dtype=torch.int64, device=dev)
+    sel_lab = torch.empty((n, p + b), dtype=torch.float32, device=dev)
+    sel_w = torch.empty((n, p + b), dtype=torch.float32, device=dev)
+    w = (ctypes.c_float * 4)(*[float(x) for x in weights])
+    with _c.on_device(dev):
+        _c.check(lib.mrb_rpn_sample(_c._ptr(labels), _c._ptr(matched), _c._ptr(rand_keys), _c._ptr(anchors), _c._ptr(gt_boxes), n, a,
+                                    gt_boxes.shape[1], b, ctypes.c_float(positive_fraction), w, _c._ptr(pos_idx), _c._ptr(pos_ok),
+                                    _c._ptr(reg_t), _c._ptr(sel_idx), _c._ptr(sel_lab), _c._ptr(sel_w), _c._stream()),
+                 "mrb_rpn_sample")
+    _count(1)
+    return pos_idx, pos_ok, reg_t, sel_idx, sel_lab, sel_w
 
 
 def rpn_topk_decode(head_out, apl, anchors, k, image_w, image_h, boxes_out, scores_out, weights=(1.0, 1.0, 1.0, 1.0), xform_clip=None):

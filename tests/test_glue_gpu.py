@@ -708,3 +708,61 @@ def test_fused_reference_box_postprocessor(built_lib):
         if a.shape == b.shape:
             same = (np.abs(_canon(a) - _canon(b)).max(1) <= 1e-4).mean()
             assert same > 0.97, same
+
+
+@pytest.mark.parametrize("gcounts", [(9, 4), (60, 1)])
+def test_rpn_sample_equals_torch_formulation(built_lib, gcounts):
+    """mrb_rpn_sample (cluster radix select of the n smallest keys + encode) vs the harness's PyTorch sampling on the same keys:
+    the same sampled sets, the same regression targets"""
+    from mrb_b200 import ops
+    from mrb_b200.model.rpn import RPN
+    cfg = _cfg()
+    rpn = RPN(cfg, 256).to(DEV)
+    g = torch.Generator().manual_seed(51 + sum(gcounts))
+    grids = [(200, 336), (100, 168), (50, 84), (25, 42), (13, 21)]
+    anchors_all = torch.cat(rpn.anchor_generator.grid(grids, DEV), 0)
+    sizes = [(800, 1333), (768, 1216)]
+    targets = []
+    for gc, (h, w) in zip(gcounts, sizes):
+        targets.append({"boxes": _rand_boxes(g, gc, w, h, 20, 500).to(DEV), "labels": torch.ones(gc, dtype=torch.int64, device=DEV)})
+    gtp = ops.pad_targets(targets, DEV)
+    n, a = 2, anchors_all.shape[0]
+    keys = torch.rand((n, a), generator=g).to(DEV)
+    want = rpn.loss_targets_fused(anchors_all, sizes, targets, gtp, None, stacked=False, keys=keys)
+    widths, heights = rpn._sizes(sizes, torch.device(DEV))
+    labels, matched = ops.rpn_anchor_match(anchors_all, gtp[0], gtp[2], widths, heights, cfg.rpn_fg_iou, cfg.rpn_bg_iou,
+                                           float(cfg.straddle_thresh))
+    pos_idx, pos_ok, reg_t, sel_idx, sel_lab, sel_w = ops.rpn_sample(labels, matched, keys, anchors_all, gtp[0], cfg.rpn_batch_size,
+                                                                       cfg.rpn_positive_fraction)
+    P = int(cfg.rpn_batch_size * cfg.rpn_positive_fraction)
+    for i in range(n):
+        wp_idx, wp_ok, wreg, wsel, wlab, ww = want[i]
+        got_pos = pos_idx[i][pos_ok[i]]
+        ref_pos = wp_idx[wp_ok]
+        assert torch.equal(torch.sort(got_pos)[0], torch.sort(ref_pos)[0]), (i, got_pos.numel(), ref_pos.numel())
+        assert (got_pos[1:] > got_pos[:-1]).all()                      # emitted in anchor order
+        # regression targets of the same anchors
+        order_ref = torch.argsort(ref_pos)
+        torch.testing.assert_close(reg_t[i][pos_ok[i]], wreg[wp_ok][order_ref], rtol=1e-6, atol=1e-7)
+        got_neg = sel_idx[i, P:][sel_w[i, P:] > 0]
+        ref_neg = wsel[P:][ww[P:] > 0]
+        assert torch.equal(torch.sort(got_neg)[0], torch.sort(ref_neg)[0]), (i, got_neg.numel(), ref_neg.numel())
+        assert got_pos.numel() + got_neg.numel() == min(cfg.rpn_batch_size, int((labels[i] >= 1).sum().clamp(max=P)) + int((labels[i] == 0).sum()))
+        assert torch.equal(sel_idx[i, :P][pos_ok[i]], got_pos) and float(sel_lab[i, :P].min()) == 1.0 and float(sel_lab[i, P:].max()) == 0.0
+        assert torch.equal(sel_w[i, :P] > 0, pos_ok[i])
+
+
+def test_mask_targets_rect_equals_torch_formulation(built_lib):
+    from mrb_b200 import ops
+    from mrb_b200.model.roi_heads import MaskHead
+    g = torch.Generator().manual_seed(61)
+    r, m = 256, 28
+    gt = _rand_boxes(g, r, 1333, 800, 30, 400).to(DEV)
+    props = _rand_boxes(g, r, 1333, 800, 16, 300)
+    props[::3] = gt.cpu()[::3] + torch.randn(len(props[::3]), 4, generator=g) * 5
+    props[5] = torch.tensor([10.0, 10.0, 10.0, 50.0])                    # zero width
+    rois = torch.cat([torch.zeros(r, 1), props], 1).to(DEV)
+    got = ops.mask_targets_rect(gt, rois, m)
+    want = MaskHead.mask_targets(gt, rois[:, 1:], m)
+    assert torch.equal(got, want), (got != want).sum().item()
+    assert 0.02 < float(got.mean()) < 0.9
