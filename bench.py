@@ -630,7 +630,7 @@ def arm_reference_graph(args, cfg_name, device, rank, world, timer, aten=False):
     for i in range(args.warmup):
         r0 = step_dev(i)
         if first is None:
-            first = round(float(r0), 4)
+            first = round(float(r0.detach()), 4)
     ops.STATS["launches"] = 0
     ops.STATS["conv_calls"] = []
     for k in ("_seg", "_seg2"):

@@ -124,6 +124,11 @@ int mrb_nms_batched(const float* boxes, const float* scores, const int* offsets_
                     float threshold, int64_t* keep, int32_t* num_keep, void* workspace,
                     size_t workspace_bytes, mrb_stream_t stream);
 
+/* The same for problems whose rows are ALREADY in descending-score order (the RPN's sorted top-k, inference.py:91-95): the
+ * rank sort is skipped.  Same kept set as mrb_nms_batched on such input. */
+int mrb_nms_batched_presorted(const float* boxes, const int* offsets_host, int num_problems, float threshold, int64_t* keep,
+                              int32_t* num_keep, void* workspace, size_t workspace_bytes, mrb_stream_t stream);
+
 /* ----------------------------------------------------------- SigmoidFocalLoss
  * replaces SigmoidFocalLoss_forward / _backward (csrc/SigmoidFocalLoss.h:10-41;
  * csrc/cuda/SigmoidFocalLoss_cuda.cu:20-188).  logits [A,num_classes] fp32, targets [A]

@@ -138,6 +138,57 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
   return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
 
+// ---- CTA-pair (cta_group::2) variants: two SMs of a cluster cooperate on one 256-row MMA; each CTA stages its own 128-row A
+// tile and HALF of the B tile, the leader CTA (cluster rank 0) issues the MMAs and its commits are multicast to both CTAs.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {   // same offset in CTA `rank` of the cluster
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_2cta(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_2cta(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2cta(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2cta(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2cta(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2cta(uint32_t bar) {     // arrives on `bar` of BOTH CTAs of the pair
+  const uint16_t mask = 3;
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(mask) : "memory");
+}
+
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
@@ -169,7 +220,28 @@ struct ConvArgs {
   int tile_sets;                   // 2 or 3 buffer sets in a ring across tiles (store drain / input prefetch overlap)
   int tile_rows;                   // th * tw <= 128 rows of the M = 128 tile carry pixels (the rest is never stored)
   int grouped;                     // block-diagonal 64-channel super-groups: A channel offset = n_tile * 64, BN = 64
+  int tiles_m;                     // batch * tiles_h * tiles_w; with CTA pairs tiles_total counts PAIRS of M tiles x tiles_n
 };
+
+// CTA pairs: `tile` indexes (pair of M tiles, N tile); CTA `rank` of the pair owns M tile 2 * pair + rank.  An odd tail gets a
+// tile beyond the image: its loads are zero-filled and its stores dropped by the TMA unit / the validity test.
+template <bool TWO>
+__device__ __forceinline__ void tile_coords_t(const ConvArgs& a, int tile, int rank, int& n_tile, int& img, int& h0, int& w0) {
+  n_tile = tile % a.tiles_n;
+  int m = tile / a.tiles_n;
+  if (TWO) {
+    m = 2 * m + rank;
+    if (m >= a.tiles_m) {
+      img = 0; h0 = a.tiles_h * a.th; w0 = 0;
+      return;
+    }
+  }
+  const int wt = m % a.tiles_w; m /= a.tiles_w;
+  const int ht = m % a.tiles_h;
+  img = m / a.tiles_h;
+  h0 = ht * a.th;
+  w0 = wt * a.tw;
+}
 
 __device__ __forceinline__ void tile_coords(const ConvArgs& a, int tile, int& n_tile, int& img, int& h0, int& w0) {
   n_tile = tile % a.tiles_n;
@@ -252,13 +324,17 @@ __device__ __noinline__ void epilogue_chunk32_slow(const ConvArgs& a, uint32_t t
   }
 }
 
+template <bool TWO>
 __global__ void __launch_bounds__(kConvThreads, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+conv_tc_kernel_t(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_res,
                const __grid_constant__ CUtensorMap map_mask, const ConvArgs a) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t stage_bytes = kABytes + (uint32_t)a.bn * 128u;
+  const uint32_t rank = TWO ? cluster_ctarank() : 0u;            // CTA pair: 0 = leader (issues the MMAs)
+  const uint32_t b_rows = TWO ? (uint32_t)a.bn >> 1 : (uint32_t)a.bn;   // rows of the B tile this CTA stages
+  const uint32_t stage_bytes = kABytes + b_rows * 128u;
+  const int tile0 = TWO ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, tstep = TWO ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   // [ring: stages x (A 16 KB + B)] [tile buffers: tile_bufs x ceil(BN/64) x 16 KB (TMA epilogue only)] [barriers] ...
   const uint32_t tile_base = smem_base + (uint32_t)a.stages * stage_bytes;
   const uint32_t tile_buf_bytes = (uint32_t)((a.bn + 63) >> 6) * kABytes;
@@ -280,7 +356,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < a.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 32 * kEpiWarps); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), (TWO ? 2 : 1) * 32 * kEpiWarps); }
     for (int b = 0; b < 3; ++b) { mbar_init(tile_bar(b), 1); mbar_init(done_bar(b), 32 * kEpiWarps); }
     fence_barrier_init();
     tma_prefetch_desc(&map_a);
@@ -291,9 +367,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       if (a.relu_mask) tma_prefetch_desc(&map_mask);
     }
   }
-  if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+  if (warp == 1) {
+    if (TWO) tmem_alloc_2cta(tmem_slot, tmem_cols);
+    else tmem_alloc(tmem_slot, tmem_cols);
+  }
   tc_fence_before();
   __syncthreads();
+  if (TWO) cluster_sync_all();       // the peer's barriers are initialised before anything signals them
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
@@ -308,30 +388,39 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // ================================ TMA producer ================================
     if (lane == 0) {
       int s = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < a.tiles_total; tile += gridDim.x) {
+      for (int tile = tile0; tile < a.tiles_total; tile += tstep) {
         int n_tile, img, h0, w0;
-        tile_coords(a, tile, n_tile, img, h0, w0);
+        tile_coords_t<TWO>(a, tile, (int)rank, n_tile, img, h0, w0);
         for (int kb = 0; kb < k_blocks; ++kb) {
           const int tap = kb / a.cin_blocks, cb = kb - tap * a.cin_blocks;
           const int r = tap / a.kw, q = tap - r * a.kw;
           mbar_wait(empty_bar(s), phase ^ 1u);
-          mbar_expect_tx(full_bar(s), a_tx + (uint32_t)a.bn * 128u);
           const uint32_t sa = smem_base + (uint32_t)s * stage_bytes;
-          tma_load_4d(sa, &map_a, full_bar(s), (a.grouped ? n_tile * 64 : 0) + cb * kBlockK, w0 + q - a.pad_w, h0 + r - a.pad_h, img);
-          tma_load_3d(sa + kABytes, &map_b, full_bar(s), cb * kBlockK, tap, n_tile * a.bn);
+          if (TWO) {
+            // both CTAs' boxes complete on the LEADER's full barrier; the leader announces the bytes of the pair
+            if (rank == 0) mbar_expect_tx(full_bar(s), 2u * (a_tx + b_rows * 128u));
+            const uint32_t lead_bar = mapa_shared(full_bar(s), 0);
+            tma_load_4d_2cta(sa, &map_a, lead_bar, cb * kBlockK, w0 + q - a.pad_w, h0 + r - a.pad_h, img);
+            tma_load_3d_2cta(sa + kABytes, &map_b, lead_bar, cb * kBlockK, tap, n_tile * a.bn + (int)(rank * b_rows));
+          } else {
+            mbar_expect_tx(full_bar(s), a_tx + (uint32_t)a.bn * 128u);
+            tma_load_4d(sa, &map_a, full_bar(s), (a.grouped ? n_tile * 64 : 0) + cb * kBlockK, w0 + q - a.pad_w, h0 + r - a.pad_h, img);
+            tma_load_3d(sa + kABytes, &map_b, full_bar(s), cb * kBlockK, tap, n_tile * a.bn);
+          }
           if (++s == a.stages) { s = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
-    if (lane == 0) {
+    if (lane == 0 && rank == 0) {
       // instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6)=1, a=BF16 [7,10)=1, b=BF16 [10,13)=1,
-      // a,b K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29)
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.bn >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+      // a,b K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29) (M = 256 over the CTA pair)
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.bn >> 3) << 17) |
+                             ((uint32_t)((TWO ? 2 * kTileM : kTileM) >> 4) << 24);
       int s = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < a.tiles_total; tile += gridDim.x) {
+      for (int tile = tile0; tile < a.tiles_total; tile += tstep) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * a.bn);
@@ -341,10 +430,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           const uint32_t sa = smem_base + (uint32_t)s * stage_bytes;
           const uint64_t da = umma_desc_k_sw128(sa), db = umma_desc_k_sw128(sa + kABytes);
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k)  // +32 B per K=16 step inside the 128 B swizzle span
-            umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
-          umma_commit(empty_bar(s));
-          if (kb == k_blocks - 1) umma_commit(tfull_bar(acc));
+          for (int k = 0; k < kBlockK / 16; ++k) {  // +32 B per K=16 step inside the 128 B swizzle span
+            if (TWO) umma_bf16_2cta(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+            else umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+          }
+          if (TWO) {
+            umma_commit_2cta(empty_bar(s));                         // frees the slot in both CTAs
+            if (kb == k_blocks - 1) umma_commit_2cta(tfull_bar(acc));   // publishes both CTAs' accumulators
+          } else {
+            umma_commit(empty_bar(s));
+            if (kb == k_blocks - 1) umma_commit(tfull_bar(acc));
+          }
           if (++s == a.stages) { s = 0; phase ^= 1u; }
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
@@ -361,7 +457,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const uint32_t m_off = (has_res && has_mask) ? tile_buf_bytes : 0u;         // the mask shares T when it is alone
       auto arm = [&](int tile, int b) {  // stage the inputs of `tile` into set b (or just release it)
         int n_tile, img, h0, w0;
-        tile_coords(a, tile, n_tile, img, h0, w0);
+        tile_coords_t<TWO>(a, tile, (int)rank, n_tile, img, h0, w0);
         const int cols = min(a.bn, a.cout - n_tile * a.bn), nb = (cols + 63) >> 6;
         const uint32_t bt = tile_base + (uint32_t)b * set_bytes;
         if (has_res || has_mask) {
@@ -376,19 +472,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       };
       const int sets = a.tile_sets;
       {
-        int t = blockIdx.x;
-        for (int j = 0; j < sets && t < a.tiles_total; ++j, t += gridDim.x) arm(t, j);
+        int t = tile0;
+        for (int j = 0; j < sets && t < a.tiles_total; ++j, t += tstep) arm(t, j);
       }
       int sidx = 0; uint32_t dphase = 0;
-      for (int tile = blockIdx.x; tile < a.tiles_total; tile += gridDim.x) {
+      for (int tile = tile0; tile < a.tiles_total; tile += tstep) {
         int n_tile, img, h0, w0;
-        tile_coords(a, tile, n_tile, img, h0, w0);
+        tile_coords_t<TWO>(a, tile, (int)rank, n_tile, img, h0, w0);
         mbar_wait(done_bar(sidx), dphase);           // every epilogue thread wrote (and proxy-fenced) its row of set sidx
         const uint32_t buf_t = tile_base + (uint32_t)sidx * set_bytes;
         const int cols = min(a.bn, a.cout - n_tile * a.bn), nb = (cols + 63) >> 6;
         for (int x = 0; x < nb; ++x) tma_store_4d(&map_out, buf_t + (uint32_t)x * kABytes, n_tile * a.bn + x * 64, w0, h0, img);
         bulk_commit();
-        const long long nxt = (long long)tile + (long long)sets * gridDim.x;
+        const long long nxt = (long long)tile + (long long)sets * tstep;
         if (nxt < a.tiles_total) {
           bulk_wait_read0();                         // the set has been read out: refill / release it
           arm((int)nxt, sidx);
@@ -427,7 +523,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const uint32_t row_off = (uint32_t)row * 128u, row_sw = (uint32_t)(row & 7);
       const int sets = a.tile_sets;
       int sidx = 0; uint32_t sphase = 0;
-      for (int tile = blockIdx.x; tile < a.tiles_total; tile += gridDim.x) {
+      for (int tile = tile0; tile < a.tiles_total; tile += tstep) {
         const int n_tile = tile % a.tiles_n;
         const uint32_t buf_t = tile_base + (uint32_t)sidx * set_bytes, buf_m = buf_t + m_off;
         mbar_wait(tile_bar(sidx), sphase);
@@ -488,16 +584,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           }
         }
         tc_fence_before();
-        mbar_arrive(tempty_bar(acc));
+        if (TWO) mbar_arrive_cluster(mapa_shared(tempty_bar(acc), 0));     // the leader's MMA waits for both CTAs' epilogues
+        else mbar_arrive(tempty_bar(acc));
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         fence_proxy_async_smem();            // this thread's tile-buffer writes -> visible to the TMA (async proxy)
         mbar_arrive(done_bar(sidx));
         if (++sidx == sets) { sidx = 0; sphase ^= 1u; }
       }
     }
-    for (int tile = blockIdx.x; tile < a.tiles_total && !a.tma_epi; tile += gridDim.x) {
+    for (int tile = tile0; tile < a.tiles_total && !a.tma_epi; tile += tstep) {
       int n_tile, img, h0, w0;
-      tile_coords(a, tile, n_tile, img, h0, w0);
+      tile_coords_t<TWO>(a, tile, (int)rank, n_tile, img, h0, w0);
       const int h = h0 + hh, w = w0 + ww;
       const bool valid = (row < a.tile_rows) && (h < a.Ho) && (w < a.Wo);
       const long long pix = (long long)img * a.out_n + (long long)h * a.out_h + (long long)w * a.out_w;
@@ -609,15 +706,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         epilogue_chunk32_slow(a, t_row + (uint32_t)col, c0, valid, pix, rpix, sc + col, bi + col, has_scale || has_bias);
       }
       tc_fence_before();
-      mbar_arrive(tempty_bar(acc));
+      if (TWO) mbar_arrive_cluster(mapa_shared(tempty_bar(acc), 0));
+      else mbar_arrive(tempty_bar(acc));
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
   }
   tc_fence_before();
   __syncthreads();
+  if (TWO) cluster_sync_all();       // the leader's MMAs read the peer's shared memory: nobody leaves before both are done
   tc_fence_after();
-  if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+  if (warp == 1) {
+    if (TWO) tmem_dealloc_2cta(tmem_base, tmem_cols);
+    else tmem_dealloc(tmem_base, tmem_cols);
+  }
 }
+
+
 
 // ------------------------------------------------------------------------------- weight gradient
 // dW[co][tap][ci] = sum over pixels G[pixel, co] * X[pixel + tap, ci]      (fp32 result, split-K + red.add)
@@ -918,15 +1022,24 @@ static int encode_bf16(CUtensorMap* m, const void* base, int rank, const cuuint6
 // Launch with the programmatic-stream-serialization attribute (see pdl_wait in the kernels).  MRB_NO_PDL=1 in the
 // environment falls back to a plain launch (A/B switch for measurements).
 template <typename... KArgs, typename... Args>
-static cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t stream, Args... args) {
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t stream, int cluster, Args... args) {
   static const bool no_pdl = [] { const char* e = getenv("MRB_NO_PDL"); return e && e[0] == '1'; }();
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block);
   cfg.dynamicSmemBytes = smem; cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr; cfg.numAttrs = no_pdl ? 0 : 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (cluster > 1) {                 // thread-block cluster of `cluster` CTAs along x (the CTA pairs of conv_tc_kernel_t<true>)
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = (unsigned)cluster; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (!no_pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr; cfg.numAttrs = na;
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
@@ -1047,9 +1160,16 @@ static int conv_launch(const ConvPlan& pl, const void* x, const void* w, int cin
   ConvArgs a;
   a.th = th; a.tw = tw; a.Ho = pl.Ho; a.Wo = pl.Wo;
   a.tiles_h = ceil_div(pl.Ho, th); a.tiles_w = ceil_div(pl.Wo, tw); a.tiles_n = ceil_div(cout, bn);
-  const long long tiles = (long long)pl.batch * a.tiles_h * a.tiles_w * a.tiles_n;
+  const long long tiles_m = (long long)pl.batch * a.tiles_h * a.tiles_w;
+  const long long tiles = tiles_m * a.tiles_n;
   if (tiles <= 0 || tiles >= (1ll << 31)) return tiles == 0 ? MRB_OK : MRB_ERR_UNSUPPORTED;
   a.tiles_total = (int)tiles;
+  a.tiles_m = (int)tiles_m;
+  // CTA pairs (cta_group::2): two SMs share one B tile (each stages half of it) for a 256-row MMA: 2/3 of the L2 -> SM operand
+  // bytes per FLOP at BN = 256.  MRB_CONV_2CTA=1 enables it for every launch it supports, =0 disables it.
+  static const int two_mode = [] { const char* e = getenv("MRB_CONV_2CTA"); return e ? atoi(e) : 0; }();
+  const bool two = two_mode == 1 && !grouped && bn >= 32 && (bn % 16) == 0 && tiles_m >= 2;
+  if (two) a.tiles_total = (int)(((tiles_m + 1) / 2) * a.tiles_n);
   a.cin_blocks = grouped ? 1 : ceil_div(cin, kBlockK); a.kh = kh; a.kw = kw; a.pad_h = pad_h; a.pad_w = pad_w;
   a.cout = cout; a.bn = bn; a.relu = relu; a.out_f32 = out_f32;
   a.out_n = pl.out_n; a.out_h = pl.out_h; a.out_w = pl.out_w;
@@ -1062,7 +1182,7 @@ static int conv_launch(const ConvPlan& pl, const void* x, const void* w, int cin
   a.tile_sets = tile_sets;
   a.tile_rows = tile_rows;
   a.grouped = grouped ? 1 : 0;
-  const uint32_t stage_bytes = kABytes + bn * 128;
+  const uint32_t stage_bytes = kABytes + (two ? bn / 2 : bn) * 128;
   // fixed part: barriers + TMEM slot + scale/bias (4 KB) + alignment slack, plus either the tile buffers or the
   // per-warp staging blocks of the per-thread epilogue
   const size_t epi_bytes = tma_epi ? (size_t)tile_sets * tile_bufs * ceil_div(bn, 64) * kABytes : (size_t)2048 * kEpiWarps;
@@ -1099,14 +1219,20 @@ static int conv_launch(const ConvPlan& pl, const void* x, const void* w, int cin
     const int wk = grouped ? 64 : cin;          // K extent of one weight row
     cuuint64_t dims[3] = {(cuuint64_t)wk, (cuuint64_t)taps, (cuuint64_t)cout};
     cuuint64_t strides[2] = {(cuuint64_t)wk * 2, (cuuint64_t)taps * wk * 2};
-    cuuint32_t box[3] = {(cuuint32_t)kBlockK, 1, (cuuint32_t)bn};
+    cuuint32_t box[3] = {(cuuint32_t)kBlockK, 1, (cuuint32_t)(two ? bn / 2 : bn)};
     int rc = encode_bf16(&map_b, w, 3, dims, strides, box);
     if (rc) return rc;
   }
   // the attribute is per device: one process may drive several GPUs (cuda:0 then cuda:1)
-  MRB_CUDA_TRY(ensure_max_smem(conv_tc_kernel, 0));
+  if (two) {
+    MRB_CUDA_TRY(ensure_max_smem(conv_tc_kernel_t<true>, 2));
+    const int pairs = a.tiles_total < kNumSMs / 2 ? a.tiles_total : kNumSMs / 2;
+    MRB_CUDA_TRY(launch_pdl(conv_tc_kernel_t<true>, 2 * pairs, kConvThreads, smem, stream, 2, map_a, map_b, map_out, map_res, map_mask, a));
+    return MRB_OK;
+  }
+  MRB_CUDA_TRY(ensure_max_smem(conv_tc_kernel_t<false>, 0));
   const int grid = a.tiles_total < kNumSMs ? a.tiles_total : kNumSMs;
-  MRB_CUDA_TRY(launch_pdl(conv_tc_kernel, grid, kConvThreads, smem, stream, map_a, map_b, map_out, map_res, map_mask, a));
+  MRB_CUDA_TRY(launch_pdl(conv_tc_kernel_t<false>, grid, kConvThreads, smem, stream, 1, map_a, map_b, map_out, map_res, map_mask, a));
   return MRB_OK;
 }
 
@@ -1387,7 +1513,7 @@ static int conv_wgrad_impl(const mrb_conv_params* p, const void* input, const vo
   }
   MRB_CUDA_TRY(ensure_max_smem(conv_wgrad_tc_kernel, 1));
   const int grid = a.items_total < kNumSMs ? a.items_total : kNumSMs;
-  MRB_CUDA_TRY(launch_pdl(conv_wgrad_tc_kernel, grid, kWgradThreads, smem, stream, map_g, map_x, a));
+  MRB_CUDA_TRY(launch_pdl(conv_wgrad_tc_kernel, grid, kWgradThreads, smem, stream, 1, map_g, map_x, a));
   return MRB_OK;
 }
 

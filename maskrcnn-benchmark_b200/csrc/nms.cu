@@ -102,6 +102,21 @@ nms_rank_kernel(const float* __restrict__ boxes, const float* __restrict__ score
   }
 }
 
+// rows already in descending-score order (the RPN's sorted top-k): rank == index, the O(n^2) rank sort is a plain gather
+__global__ void __launch_bounds__(kRankThreads)
+nms_presorted_kernel(const float* __restrict__ boxes, NmsBatch nb, unsigned char* __restrict__ ws_base) {
+  const int p = blockIdx.y;
+  const int n = nb.off[p + 1] - nb.off[p];
+  const int i = blockIdx.x * kRankThreads + threadIdx.x;
+  if (i >= n) return;
+  const NmsWs w = nms_ws_carve(ws_base + nb.ws[p], n);
+  const float4 b = (reinterpret_cast<const float4*>(boxes) + nb.off[p])[i];
+  w.boxes[i] = b;
+  w.areas[i] = __fmul_rn(__fadd_rn(__fsub_rn(b.z, b.x), 1.f), __fadd_rn(__fsub_rn(b.w, b.y), 1.f));
+  w.order[i] = i;
+  w.flags[i] = 0;
+}
+
 // --- 2. upper-triangular suppression mask ----------------------------------------------------
 __device__ __forceinline__ bool suppresses(const float4 a, float a_area, const float4 b, float b_area, float thr) {
   // nms_cpu.cpp:49-60
@@ -256,7 +271,7 @@ nms_scan_kernel(NmsBatch nb, unsigned char* __restrict__ ws_base, long long* __r
 }
 
 static int nms_run(const float* boxes, const float* scores, const NmsBatch& nb, float thr, long long* keep,
-                   int* num_keep, void* ws, cudaStream_t stream) {
+                   int* num_keep, void* ws, cudaStream_t stream, bool presorted = false) {
   int max_n = 0;
   for (int p = 0; p < nb.num; ++p) max_n = max(max_n, nb.off[p + 1] - nb.off[p]);
   if (max_n == 0) {
@@ -266,7 +281,10 @@ static int nms_run(const float* boxes, const float* scores, const NmsBatch& nb, 
   if ((size_t)max_cb * 16 > 160 * 1024) return MRB_ERR_UNSUPPORTED;
   {
     dim3 grid(ceil_div(max_n, kRankThreads), nb.num);
-    nms_rank_kernel<<<grid, kRankThreads, 0, stream>>>(boxes, scores, nb, (unsigned char*)ws);
+    if (presorted)
+      nms_presorted_kernel<<<grid, kRankThreads, 0, stream>>>(boxes, nb, (unsigned char*)ws);
+    else
+      nms_rank_kernel<<<grid, kRankThreads, 0, stream>>>(boxes, scores, nb, (unsigned char*)ws);
     MRB_LAUNCH_CHECK();
   }
   {
@@ -296,9 +314,9 @@ MRB_API size_t mrb_nms_batched_workspace_bytes(const int* offsets_host, int num_
   return tot;
 }
 
-MRB_API int mrb_nms_batched(const float* boxes, const float* scores, const int* offsets_host, int num_problems,
+static int nms_batched_impl(const float* boxes, const float* scores, const int* offsets_host, int num_problems,
                             float threshold, int64_t* keep, int32_t* num_keep, void* workspace,
-                            size_t workspace_bytes, mrb_stream_t stream) {
+                            size_t workspace_bytes, mrb_stream_t stream, bool presorted) {
   if (num_problems < 0 || !offsets_host) return MRB_ERR_BAD_ARG;
   if (num_problems == 0) return MRB_OK;
   if (!num_keep) return MRB_ERR_BAD_ARG;
@@ -317,10 +335,22 @@ MRB_API int mrb_nms_batched(const float* boxes, const float* scores, const int* 
     nb.off[nb.num] = offsets_host[p0 + nb.num];
     if (off > workspace_bytes) return MRB_ERR_WORKSPACE;
     if (off > 0 && (!boxes || !scores || !keep || !workspace)) return MRB_ERR_BAD_ARG;
-    int rc = nms_run(boxes, scores, nb, threshold, (long long*)keep, num_keep + p0, workspace, (cudaStream_t)stream);
+    int rc = nms_run(boxes, scores, nb, threshold, (long long*)keep, num_keep + p0, workspace, (cudaStream_t)stream, presorted);
     if (rc) return rc;
   }
   return MRB_OK;
+}
+
+MRB_API int mrb_nms_batched(const float* boxes, const float* scores, const int* offsets_host, int num_problems,
+                            float threshold, int64_t* keep, int32_t* num_keep, void* workspace,
+                            size_t workspace_bytes, mrb_stream_t stream) {
+  return nms_batched_impl(boxes, scores, offsets_host, num_problems, threshold, keep, num_keep, workspace, workspace_bytes, stream, false);
+}
+
+MRB_API int mrb_nms_batched_presorted(const float* boxes, const int* offsets_host, int num_problems, float threshold, int64_t* keep,
+                                      int32_t* num_keep, void* workspace, size_t workspace_bytes, mrb_stream_t stream) {
+  return nms_batched_impl(boxes, boxes /* unused */, offsets_host, num_problems, threshold, keep, num_keep, workspace,
+                          workspace_bytes, stream, true);
 }
 
 MRB_API int mrb_nms(const float* boxes, const float* scores, int n, float threshold, int64_t* keep,

@@ -371,7 +371,8 @@ def _fuse_rpn_postprocessor(mod, be):
                 ops.rpn_decode(lgs[l], dls[l], anchors[0][l].bbox, idx, widths, heights, boxes[off:off + n * k],
                                scores[off:off + n * k], self.box_coder.weights, self.box_coder.bbox_xform_clip)
                 off += n * k
-            keep, counts = ops.nms_batched(boxes, scores, [k for k in ks for _ in range(n)], float(self.nms_thresh))
+            # rows of every problem are in descending-score order (sorted top-k): the NMS skips its rank sort
+            keep, counts = ops.nms_batched(boxes, scores, [k for k in ks for _ in range(n)], float(self.nms_thresh), presorted=True)
             gb = gc = None
             gs = [0] * n
             if self.training and targets is not None:                                                          # add_gt_proposals

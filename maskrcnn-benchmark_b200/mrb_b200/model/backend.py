@@ -663,6 +663,6 @@ class B200Backend(Backend):
         from mrb_b200 import ops
         return ops.roi_align_fpn(list(feats), rois, scales, pooled, sampling_ratio, out_nhwc=nhwc)
 
-    def nms_batched(self, boxes, scores, sizes, thr):
+    def nms_batched(self, boxes, scores, sizes, thr, presorted=False):
         from mrb_b200 import ops
-        return ops.nms_batched(boxes, scores, sizes, thr)
+        return ops.nms_batched(boxes, scores, sizes, thr, presorted=presorted)

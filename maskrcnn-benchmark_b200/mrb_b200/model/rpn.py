@@ -163,7 +163,11 @@ class RPN(nn.Module):
         for h in handles:
             be.join(h)
         sizes = [k for k in ks for _ in range(n)]
-        keep, counts = be.nms_batched(boxes, scores, sizes, cfg.rpn_nms_thresh)
+        # every problem's rows come out of a sorted top-k (descending logit == descending sigmoid, ties in anchor order)
+        try:
+            keep, counts = be.nms_batched(boxes, scores, sizes, cfg.rpn_nms_thresh, presorted=True)
+        except TypeError:            # a backend without the presorted form
+            keep, counts = be.nms_batched(boxes, scores, sizes, cfg.rpn_nms_thresh)
         per_batch = bool(training and cfg.fpn_post_nms_per_batch)
         add_gt = training and gtp is not None
         return ops.rpn_collect(boxes, scores, keep, counts, ks, n, post_n, fpn_post_n, per_batch,

@@ -581,7 +581,7 @@ def roi_align_fpn(feats, rois, scales, pooled, sampling_ratio, out_nhwc=False, k
 
 
 # --------------------------------------------------------------------------------- batched NMS
-def nms_batched(boxes, scores, sizes, threshold):
+def nms_batched(boxes, scores, sizes, threshold, presorted=False):
     """Independent NMS problems stored back to back (sizes[p] rows each).
     -> (keep int64 [sum sizes]: per problem, kept indices relative to the problem, ascending, first
     counts[p] entries valid; counts int32 [len(sizes)] on device).  No host synchronisation."""
@@ -601,9 +601,14 @@ def nms_batched(boxes, scores, sizes, threshold):
     with _c.on_device(boxes.device):
         nbytes = lib.mrb_nms_batched_workspace_bytes(offs_c, p)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=boxes.device)
-        _c.check(lib.mrb_nms_batched(_c._ptr(boxes), _c._ptr(scores), offs_c, p, ctypes.c_float(threshold), _c._ptr(keep),
-                                     _c._ptr(counts), _c._ptr(ws), ctypes.c_size_t(nbytes), _c._stream()),
-                 "mrb_nms_batched")
+        if presorted:    # rows of every problem already in descending-score order: no rank sort
+            _c.check(lib.mrb_nms_batched_presorted(_c._ptr(boxes), offs_c, p, ctypes.c_float(threshold), _c._ptr(keep),
+                                                   _c._ptr(counts), _c._ptr(ws), ctypes.c_size_t(nbytes), _c._stream()),
+                     "mrb_nms_batched_presorted")
+        else:
+            _c.check(lib.mrb_nms_batched(_c._ptr(boxes), _c._ptr(scores), offs_c, p, ctypes.c_float(threshold), _c._ptr(keep),
+                                         _c._ptr(counts), _c._ptr(ws), ctypes.c_size_t(nbytes), _c._stream()),
+                     "mrb_nms_batched")
     _count(3)
     return keep[:offs[-1]], counts[:p]
 

@@ -766,3 +766,19 @@ def test_mask_targets_rect_equals_torch_formulation(built_lib):
     want = MaskHead.mask_targets(gt, rois[:, 1:], m)
     assert torch.equal(got, want), (got != want).sum().item()
     assert 0.02 < float(got.mean()) < 0.9
+
+
+def test_nms_batched_presorted_equals_sorting_form(built_lib):
+    from mrb_b200 import ops
+    g = torch.Generator().manual_seed(71)
+    n, ks = 2, [2000, 1200, 819, 64]
+    boxes, scores, sizes = _nms_problem_set(g, n, ks, quantise=128)          # sorted per problem, with equal scores
+    boxes[:300] = boxes[:300] * 0.2 + 100                                    # heavy overlap in the first problem
+    k1, c1 = ops.nms_batched(boxes, scores, sizes, 0.7)
+    k2, c2 = ops.nms_batched(boxes, scores, sizes, 0.7, presorted=True)
+    assert torch.equal(c1, c2)
+    off = 0
+    for sz, c in zip(sizes, c1.tolist()):
+        assert torch.equal(k1[off:off + c], k2[off:off + c])
+        off += sz
+    assert int(c1[0]) < 1900
