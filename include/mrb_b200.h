@@ -272,7 +272,8 @@ int mrb_roi_assign_sample(const float* boxes, const uint8_t* valid, const float*
                           int batch_size_per_image, float positive_fraction, float fg_iou, float bg_iou,
                           const float* weights_host, int mask_rois_per_image, float* out_rois, int64_t* out_labels,
                           float* out_reg_targets, int64_t* out_gt_index, float* mask_rois, int64_t* mask_labels,
-                          float* mask_weight, int64_t* mask_gt_index, mrb_stream_t stream);
+                          float* mask_weight, int64_t* mask_gt_index, int64_t* out_proposal_index /* [N*S] or NULL */,
+                          mrb_stream_t stream);
 /* Box-head post-processing (PostProcessor.forward, modeling/roi_heads/box_head/inference.py:45-149), fixed shapes, no host
  * synchronisation.  mrb_box_post_decode: softmax over the C class logits of `outputs` [N*P, ld] (C logits, then 4C regression
  * outputs per row), per-class BoxCoder.decode of `proposals` [N*P, 4] + clip_to_image, score threshold -> one NMS problem per

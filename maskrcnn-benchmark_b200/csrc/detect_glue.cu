@@ -457,7 +457,7 @@ roi_assign_sample_kernel(const float4* __restrict__ boxes, const unsigned char* 
                          const float4* __restrict__ gt, const int64_t* __restrict__ gt_labels, const int32_t* __restrict__ gt_count,
                          float* __restrict__ out_rois, int64_t* __restrict__ out_labels, float4* __restrict__ out_reg,
                          int64_t* __restrict__ out_gidx, float* __restrict__ m_rois, int64_t* __restrict__ m_labels,
-                         float* __restrict__ m_w, int64_t* __restrict__ m_gidx, AssignArgs a) {
+                         float* __restrict__ m_w, int64_t* __restrict__ m_gidx, int64_t* __restrict__ out_index, AssignArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int hist[256], ghist[256], sh[4], scan_ws[33];
   unsigned* keys = (unsigned*)smem_raw;          // [P] inverted random key (larger = earlier in the permutation)
@@ -573,6 +573,7 @@ roi_assign_sample_kernel(const float4* __restrict__ boxes, const unsigned char* 
     out_rois[o * 5 + 4] = b.w;
     out_labels[o] = ok ? (int64_t)lab[p] : (int64_t)-1;
     out_gidx[o] = g;
+    if (out_index) out_index[o] = p;
     // box_coder.py:22-50
     float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
     if (G > 0) q = gb[g];
@@ -1119,7 +1120,7 @@ MRB_API int mrb_roi_assign_sample(const float* boxes, const uint8_t* valid, cons
                                   int batch_size_per_image, float positive_fraction, float fg_iou, float bg_iou,
                                   const float* weights_host, int mask_rois_per_image, float* out_rois, int64_t* out_labels,
                                   float* out_reg_targets, int64_t* out_gt_index, float* mask_rois, int64_t* mask_labels,
-                                  float* mask_weight, int64_t* mask_gt_index, mrb_stream_t stream) {
+                                  float* mask_weight, int64_t* mask_gt_index, int64_t* out_proposal_index, mrb_stream_t stream) {
   if (num_images <= 0 || num_proposals <= 0 || gmax <= 0 || batch_size_per_image <= 0 || !weights_host) return MRB_ERR_BAD_ARG;
   if (!boxes || !valid || !rand_keys || !gt_boxes || !gt_labels || !gt_count || !out_rois || !out_labels || !out_reg_targets ||
       !out_gt_index)
@@ -1159,7 +1160,7 @@ MRB_API int mrb_roi_assign_sample(const float* boxes, const uint8_t* valid, cons
   cfg.numAttrs = 1;
   MRB_CUDA_TRY(cudaLaunchKernelEx(&cfg, roi_assign_sample_kernel, (const float4*)boxes, (const unsigned char*)valid, rand_keys,
                                   (const float4*)gt_boxes, gt_labels, gt_count, out_rois, out_labels, (float4*)out_reg_targets,
-                                  out_gt_index, mask_rois, mask_labels, mask_weight, mask_gt_index, a));
+                                  out_gt_index, mask_rois, mask_labels, mask_weight, mask_gt_index, out_proposal_index, a));
   return MRB_OK;
 }
 

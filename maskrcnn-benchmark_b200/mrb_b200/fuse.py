@@ -33,7 +33,11 @@ of the modules whose bodies are chains the conv engine fuses into one launch eac
   PostProcessor.forward      per (image, class): nonzero, decode, NMS      softmax+decode+threshold launch, ONE batched NMS
     (box_head/inference.py:45-149)  (sync), cat, kthvalue on the host         over images x classes, top-k launch, one sync
   project_masks_on_boxes     host loop: crop, resize, rasterise, upload    one launch on the polygon vertices
-    (mask_head/loss.py:11-42)                                               (the last three only with backend.fused_glue)
+    (mask_head/loss.py:11-42)
+  RPNLossComputation.__call__  per image: IoU 268k x G, Matcher, dense     anchor labelling (2 launches) + sampling/encode
+    target side (rpn/loss.py:56-110)  encode, nonzero, randperm            (1 cluster launch) for the batch; loss arithmetic kept
+  FastRCNNLossComputation.subsample  per image: IoU, Matcher, encode,      one launch for the batch, one sync
+    (box_head/loss.py:82-118)          sampler, nonzero                    (the last five only with backend.fused_glue)
 
 Nothing else changes: module classes, parameters, buffers and state_dict keys are the reference's; the anchor
 generator, matcher/sampler, box coder and all losses are the reference's own Python.
@@ -465,6 +469,137 @@ def _fuse_box_postprocessor(mod, be):
     return True
 
 
+class _FusedRPNLoss:
+    """RPNLossComputation.__call__ (rpn/loss.py:92-131) with the target side as three launches: anchor labelling
+    (mrb_rpn_anchor_match: IoU, Matcher with low-quality matches, between-threshold discards) + the anchors' own visibility
+    field, BalancedPositiveNegativeSampler + BoxCoder.encode of the sampled positives (mrb_rpn_sample; the sample is "the n
+    smallest of iid keys", the distribution of the reference's randperm[:n]).  The loss arithmetic on the ~2 x 384 sampled rows
+    is the reference's (same ops, same normalisation), gathered from its own concat_box_prediction_layers layout."""
+
+    def __init__(self, orig):
+        import sys
+        self.orig = orig
+        self.concat = getattr(sys.modules.get(type(orig).__module__), "concat_box_prediction_layers")
+        for n in ("proposal_matcher", "fg_bg_sampler", "box_coder", "copied_fields", "generate_labels_func", "discard_cases"):
+            setattr(self, n, getattr(orig, n))
+
+    def __getattr__(self, name):              # anything else (match_targets_to_anchors, prepare_targets ...) is the reference's
+        return getattr(self.orig, name)
+
+    def __call__(self, anchors, objectness, box_regression, targets):
+        import torch.nn.functional as F
+        from mrb_b200 import ops
+        o = self.orig
+        dev = objectness[0].device
+        n = len(anchors)
+        gs = [len(t) for t in targets]
+        if dev.type != "cuda" or min(gs) == 0 or n > 64:
+            return o(anchors, objectness, box_regression, targets)
+        with torch.no_grad():
+            anc = torch.cat([a.bbox for a in anchors[0]], 0).float()               # the grid is the same for every image
+            vis = torch.stack([torch.cat([a.get_field("visibility") for a in per], 0) for per in anchors]).bool()
+            gmax = max(gs)
+            gb = torch.zeros((n, gmax, 4), dtype=torch.float32, device=dev)
+            gc = torch.zeros((n,), dtype=torch.int32, device=dev)
+            for i, t in enumerate(targets):
+                gb[i, :gs[i]] = t.convert("xyxy").bbox
+                gc[i:i + 1].fill_(gs[i])
+            m = self.proposal_matcher
+            labels, matched = ops.rpn_anchor_match(anc, gb, gc, gc, gc, float(m.high_threshold), float(m.low_threshold), -1.0)
+            labels = torch.where(vis, labels, torch.full((), -1.0, device=dev))    # discard_cases: not_visibility
+            keys = torch.rand(labels.shape, device=dev)
+            sp = self.fg_bg_sampler
+            pos_idx, pos_ok, reg_t, sel_idx, sel_lab, sel_w = ops.rpn_sample(
+                labels, matched, keys, anc, gb, int(sp.batch_size_per_image), float(sp.positive_fraction), self.box_coder.weights)
+        obj, reg = self.concat(objectness, box_regression)                        # [N * A, 1], [N * A, 4], image-major
+        a_tot = anc.shape[0]
+        obj = obj.reshape(n, a_tot)
+        reg = reg.reshape(n, a_tot, 4)
+        num = sel_w.sum().clamp(min=1)
+        zero = torch.zeros((), dtype=torch.float32, device=dev)
+        diff = torch.abs(torch.where(pos_ok[..., None], torch.gather(reg, 1, pos_idx[..., None].expand(-1, -1, 4)).float() - reg_t, zero))
+        beta = 1.0 / 9
+        l1 = torch.where(diff < beta, 0.5 * diff * diff / beta, diff - 0.5 * beta)
+        box_loss = torch.where(pos_ok[..., None], l1, zero).sum() / num           # smooth_l1_loss(size_average=False) / #sampled
+        bce = F.binary_cross_entropy_with_logits(torch.gather(obj, 1, sel_idx).float(), sel_lab, reduction="none")
+        objectness_loss = torch.where(sel_w > 0, bce, zero).sum() / num           # mean over the sampled anchors
+        return objectness_loss, box_loss
+
+
+def _fuse_rpn_loss(parent, be):
+    ev = getattr(parent, "loss_evaluator", None)
+    if type(ev).__name__ != "RPNLossComputation":
+        return False
+    need = ("proposal_matcher", "fg_bg_sampler", "box_coder", "discard_cases", "generate_labels_func")
+    if not all(hasattr(ev, n) for n in need):
+        return False
+    m = ev.proposal_matcher
+    if not getattr(m, "allow_low_quality_matches", False) or sorted(ev.discard_cases) != ["between_thresholds", "not_visibility"] or \
+            getattr(ev.generate_labels_func, "__name__", "") != "generate_rpn_labels":
+        return False
+    parent.loss_evaluator = _FusedRPNLoss(ev)
+    return True
+
+
+def _fuse_box_subsample(ev, be):
+    """FastRCNNLossComputation.subsample (roi_heads/box_head/loss.py:82-118): boxlist_iou + Matcher + labels + regression
+    targets + BalancedPositiveNegativeSampler for the batch as ONE launch (mrb_roi_assign_sample), one host synchronisation to
+    size the returned BoxLists (the reference synchronises in every `nonzero`).  Returned BoxLists carry the same fields
+    (objectness, labels, regression_targets) for the sampled proposals in proposal order."""
+    import types
+    need = ("proposal_matcher", "fg_bg_sampler", "box_coder", "cls_agnostic_bbox_reg", "subsample")
+    if type(ev).__name__ != "FastRCNNLossComputation" or not all(hasattr(ev, n) for n in need):
+        return False
+    if getattr(ev.proposal_matcher, "allow_low_quality_matches", True) or getattr(ev, "_mrb_fused", False):
+        return False
+    orig = ev.subsample
+    ev._mrb_fused = True
+
+    def subsample(self, proposals, targets):
+        from mrb_b200 import ops
+        n = len(proposals)
+        dev = proposals[0].bbox.device
+        counts = [len(p) for p in proposals]
+        gs = [len(t) for t in targets]
+        pm = max(counts)
+        if dev.type != "cuda" or min(gs) == 0 or pm == 0 or pm > 8192 or not all(t.has_field("labels") for t in targets):
+            return orig(proposals, targets)
+        with torch.no_grad():
+            boxes = torch.zeros((n, pm, 4), dtype=torch.float32, device=dev)
+            valid = torch.zeros((n, pm), dtype=torch.bool, device=dev)
+            gmax = max(gs)
+            gb = torch.zeros((n, gmax, 4), dtype=torch.float32, device=dev)
+            gl = torch.zeros((n, gmax), dtype=torch.int64, device=dev)
+            gc = torch.zeros((n,), dtype=torch.int32, device=dev)
+            for i, (p, t) in enumerate(zip(proposals, targets)):
+                boxes[i, :counts[i]] = p.convert("xyxy").bbox
+                valid[i, :counts[i]] = True
+                gb[i, :gs[i]] = t.convert("xyxy").bbox
+                gl[i, :gs[i]] = t.get_field("labels")
+                gc[i:i + 1].fill_(gs[i])
+            keys = torch.rand((n, pm), device=dev)
+            m, sp = self.proposal_matcher, self.fg_bg_sampler
+            s = int(sp.batch_size_per_image)
+            out = ops.roi_assign_sample(boxes, valid, keys, gb, gl, gc, s, float(sp.positive_fraction), float(m.high_threshold),
+                                        float(m.low_threshold), self.box_coder.weights, 0, with_index=True)
+            ks = (out["labels"] >= 0).sum(1).tolist()               # the one host synchronisation of the sampling
+            rois = out["rois"].view(n, s, 5)
+            res = []
+            for i, p in enumerate(proposals):
+                k = ks[i]
+                bl = type(p)(rois[i, :k, 1:], p.size, mode="xyxy")
+                idx = out["index"][i, :k]
+                for f in p.fields():
+                    bl.add_field(f, p.get_field(f)[idx])
+                bl.add_field("labels", out["labels"][i, :k])
+                bl.add_field("regression_targets", out["reg_targets"][i, :k])
+                res.append(bl)
+        self._proposals = res
+        return res
+    ev.subsample = types.MethodType(subsample, ev)
+    return True
+
+
 def _fuse_mask_targets(be, rep):
     """project_masks_on_boxes (roi_heads/mask_head/loss.py:11-42): the per-proposal crop / resize / rasterise loop on the
     HOST (flagged as a bottleneck at loss.py:31-32) becomes one launch on the polygons' vertices (csrc/mask_targets.cu).
@@ -506,9 +641,12 @@ def _fuse_mask_targets(be, rep):
     return True
 
 
-def fuse_model(model, backend=None, channels_last_weights=True):
+def fuse_model(model, backend=None, channels_last_weights=True, sampling=True):
     """Rebind the forwards listed in the module docstring, in place.  Returns a report
-    {"fused": {kind: count}, "skipped": [reasons]}.  Idempotent."""
+    {"fused": {kind: count}, "skipped": [reasons]}.  Idempotent.
+    sampling=False leaves the two stages that DRAW RANDOM SAMPLES (RPN loss targets, box-head subsample) to the reference's
+    own Python: their fused forms sample with iid keys instead of torch.randperm -- the same distribution, not the same
+    sample -- so comparisons that pin the reference's random stream (tests/refgraph) keep the reference's sampler."""
     if backend is None:
         from mrb_b200 import engine
         backend = engine.default_backend()
@@ -569,6 +707,13 @@ def fuse_model(model, backend=None, channels_last_weights=True):
                 bump("rpn_postprocessor")
             elif not getattr(mod, "_mrb_fused", False) and _fuse_box_postprocessor(mod, be):
                 bump("box_postprocessor")
+            if not sampling:
+                continue
+            if type(getattr(mod, "loss_evaluator", None)).__name__ == "RPNLossComputation" and _fuse_rpn_loss(mod, be):
+                bump("rpn_loss_targets")
+            elif type(getattr(mod, "loss_evaluator", None)).__name__ == "FastRCNNLossComputation" and \
+                    _fuse_box_subsample(mod.loss_evaluator, be):
+                bump("box_subsample")
         _fuse_mask_targets(be, rep)
     _wire_resnet(model, be)
     model._mrb_backend = be

@@ -690,7 +690,7 @@ def pad_targets(targets, device):
 
 
 def roi_assign_sample(boxes, valid, rand_keys, gt_boxes, gt_labels, gt_count, batch_size_per_image, positive_fraction, fg_iou,
-                      bg_iou, weights, mask_rois_per_image=0):
+                      bg_iou, weights, mask_rois_per_image=0, with_index=False):
     """FastRCNNLossComputation.subsample (box_head/loss.py:41-118) + the mask branch's positives-first list, one launch.
     -> dict(rois [N*S, 5], labels [N, S], reg_targets [N, S, 4], gt_index [N, S]) (+ mask_rois [N*M, 5], mask_labels [N*M],
     mask_weight [N*M], mask_gt_index [N, M] when mask_rois_per_image = M > 0)."""
@@ -709,6 +709,8 @@ def roi_assign_sample(boxes, valid, rand_keys, gt_boxes, gt_labels, gt_count, ba
                     "mask_labels": torch.empty((n * m,), dtype=torch.int64, device=dev),
                     "mask_weight": torch.empty((n * m,), dtype=torch.float32, device=dev),
                     "mask_gt_index": torch.empty((n, m), dtype=torch.int64, device=dev)})
+    if with_index:
+        out["index"] = torch.empty((n, s), dtype=torch.int64, device=dev)      # proposal index of every output row
     w = (ctypes.c_float * 4)(*[float(x) for x in weights])
     with _c.on_device(dev):
         _c.check(lib.mrb_roi_assign_sample(
@@ -716,7 +718,7 @@ def roi_assign_sample(boxes, valid, rand_keys, gt_boxes, gt_labels, gt_count, ba
             gt_boxes.shape[1], s, ctypes.c_float(positive_fraction), ctypes.c_float(fg_iou), ctypes.c_float(bg_iou), w, m,
             _c._ptr(out["rois"]), _c._ptr(out["labels"]), _c._ptr(out["reg_targets"]), _c._ptr(out["gt_index"]),
             _c._ptr(out.get("mask_rois")), _c._ptr(out.get("mask_labels")), _c._ptr(out.get("mask_weight")),
-            _c._ptr(out.get("mask_gt_index")), _c._stream()), "mrb_roi_assign_sample")
+            _c._ptr(out.get("mask_gt_index")), _c._ptr(out.get("index")), _c._stream()), "mrb_roi_assign_sample")
     _count(1)
     return out
 

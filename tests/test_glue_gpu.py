@@ -782,3 +782,85 @@ def test_nms_batched_presorted_equals_sorting_form(built_lib):
         assert torch.equal(k1[off:off + c], k2[off:off + c])
         off += sz
     assert int(c1[0]) < 1900
+
+
+def test_fused_reference_rpn_loss_targets_and_box_subsample(built_lib):
+    """mrb_b200.fuse binds the target side of RPNLossComputation.__call__ and FastRCNNLossComputation.subsample of the UNMODIFIED
+    reference to the glue launches: the sampling-independent parts equal the reference's Python"""
+    from mrb_b200 import fuse, refenv
+    if refenv.activate() is None:
+        pytest.skip("reference checkout absent")
+    from maskrcnn_benchmark.modeling.balanced_positive_negative_sampler import BalancedPositiveNegativeSampler
+    from maskrcnn_benchmark.modeling.box_coder import BoxCoder
+    from maskrcnn_benchmark.modeling.matcher import Matcher
+    from maskrcnn_benchmark.modeling.roi_heads.box_head.loss import FastRCNNLossComputation
+    from maskrcnn_benchmark.modeling.rpn.loss import RPNLossComputation, generate_rpn_labels
+    from maskrcnn_benchmark.structures.bounding_box import BoxList
+    from mrb_b200.model.backend import B200Backend
+    from mrb_b200.model.rpn import RPN
+    cfg = _cfg()
+    rpn = RPN(cfg, 256).to(DEV)
+    be = B200Backend()
+    g = torch.Generator().manual_seed(81)
+    n, A = 2, 3
+    grids = [(100, 168), (50, 84), (25, 42), (13, 21), (7, 11)]
+    anchors = rpn.anchor_generator.grid(grids, DEV)
+    sizes = [(800, 1333), (768, 1216)]
+    targets = [BoxList(_rand_boxes(g, 3, 1333, 800, 90, 400).to(DEV), (1333, 800), mode="xyxy"),
+               BoxList(_rand_boxes(g, 2, 1216, 768, 90, 400).to(DEV), (1216, 768), mode="xyxy")]
+    for t in targets:
+        t.add_field("labels", torch.randint(1, 81, (len(t),), generator=g).to(DEV))
+    anchor_lists = []
+    for (h, w) in sizes:
+        per = []
+        for a in anchors:
+            bl = BoxList(a, (w, h), mode="xyxy")
+            bl.add_field("visibility", (a[:, 0] >= 0) & (a[:, 1] >= 0) & (a[:, 2] < w) & (a[:, 3] < h))
+            per.append(bl)
+        anchor_lists.append(per)
+    obj = [torch.full((n, A, h, w), 0.3, device=DEV) for h, w in grids]                 # equal logits: the loss depends on the
+    reg = [(torch.randn(n, 4 * A, h, w, generator=g) * 0.3).to(DEV) for h, w in grids]  # sample only through its counts
+
+    class Parent:
+        pass
+    par = Parent()
+    par.loss_evaluator = RPNLossComputation(Matcher(0.7, 0.3, allow_low_quality_matches=True), BalancedPositiveNegativeSampler(256, 0.5),
+                                            BoxCoder((1.0, 1.0, 1.0, 1.0)), generate_rpn_labels)
+    ref_ev = par.loss_evaluator
+    assert fuse._fuse_rpn_loss(par, be)
+    want = ref_ev(anchor_lists, obj, reg, targets)
+    got = par.loss_evaluator(anchor_lists, obj, reg, targets)
+    torch.testing.assert_close(got[0], want[0], rtol=1e-5, atol=1e-6)
+    from maskrcnn_benchmark.structures.boxlist_ops import cat_boxlist
+    lab_dense, _ = ref_ev.prepare_targets([cat_boxlist(per) for per in anchor_lists], targets)
+    npos = [int((l >= 1).sum()) for l in lab_dense]
+    assert min(npos) > 0
+    if max(npos) <= 128:          # every positive is sampled by both: the box loss does not depend on the sample
+        torch.testing.assert_close(got[1], want[1], rtol=1e-4, atol=1e-6)
+    else:                         # the samples differ: same scale only
+        assert 0.3 < float(got[1]) / float(want[1]) < 3.0, (float(got[1]), float(want[1]), npos)
+    # box-head subsample
+    p = 1500
+    props = []
+    for i, (h, w) in enumerate(sizes):
+        b, _, _ = _proposal_case(g, p - 100 * i, len(targets[i]), 0.4, 0)
+        b[:len(targets[i]) * 20] = targets[i].bbox.cpu().repeat_interleave(20, 0) + torch.randn(len(targets[i]) * 20, 4, generator=g) * 4
+        bl = BoxList(b.to(DEV), (w, h), mode="xyxy")
+        bl.add_field("objectness", torch.rand(len(b), generator=g).to(DEV))
+        props.append(bl)
+    ev = FastRCNNLossComputation(Matcher(0.5, 0.5, allow_low_quality_matches=False), BalancedPositiveNegativeSampler(512, 0.25),
+                                 BoxCoder((10.0, 10.0, 5.0, 5.0)))
+    lab_ref, reg_ref = ev.prepare_targets(props, targets)                  # the reference's dense labels / regression targets
+    assert fuse._fuse_box_subsample(ev, be)
+    out = ev.subsample([bl.copy_with_fields(["objectness"]) for bl in props], targets)
+    assert ev._proposals is out
+    for i, bl in enumerate(out):
+        d = (bl.bbox[:, None, :] - props[i].bbox[None, :, :]).abs().sum(-1)
+        src = d.argmin(1)
+        assert float(d.min(1)[0].max()) == 0.0 and (src[1:] > src[:-1]).all()           # proposal order, no duplicates
+        assert torch.equal(bl.get_field("labels"), lab_ref[i][src])
+        assert torch.equal(bl.get_field("objectness"), props[i].get_field("objectness")[src])
+        pos = bl.get_field("labels") > 0
+        torch.testing.assert_close(bl.get_field("regression_targets")[pos], reg_ref[i][src][pos], rtol=1e-5, atol=1e-6)
+        npos_all = int((lab_ref[i] > 0).sum())
+        assert int(pos.sum()) == min(npos_all, 128) and len(bl) == min(512, int(pos.sum()) + int((lab_ref[i] == 0).sum()))
