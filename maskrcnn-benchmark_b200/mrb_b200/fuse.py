@@ -600,6 +600,70 @@ def _fuse_box_subsample(ev, be):
     return True
 
 
+def _fuse_mask_prepare_targets(ev, be):
+    """MaskRCNNLossComputation.prepare_targets (roi_heads/mask_head/loss.py:68-98): the reference indexes the targets' BoxList and
+    SegmentationMask by the matched indices (Python loops over the positives, twice) before the host-side rasterisation.  Here the
+    matching is three small tensor ops, the polygons of ALL instances of the image are packed once (cached per SegmentationMask
+    object) and the rasteriser takes the matched instance index of every positive proposal on the device: no per-proposal
+    Python, one `nonzero` as in the reference."""
+    import types
+    import weakref
+    if type(ev).__name__ != "MaskRCNNLossComputation" or not all(hasattr(ev, n) for n in ("proposal_matcher", "discretization_size")) \
+            or getattr(ev, "_mrb_fused", False):
+        return False
+    pm = ev.proposal_matcher
+    if getattr(pm, "allow_low_quality_matches", True) or float(pm.low_threshold) != float(pm.high_threshold):
+        return False
+    orig = ev.prepare_targets
+    cache = {}
+
+    def polyset_of(seg, dev):
+        from mrb_b200 import ops
+        key = id(seg)
+        hit = cache.get(key)
+        if hit is not None and hit[0]() is seg and hit[1].xy.device == dev:
+            return hit[1]
+        ps = ops.PolygonSet([[p.tolist() for p in pi.polygons] for pi in seg.instances.polygons], dev)
+        try:
+            cache[key] = (weakref.ref(seg, lambda _r, k=key: cache.pop(k, None)), ps)
+        except TypeError:
+            pass
+        return ps
+
+    def prepare_targets(self, proposals, targets):
+        from mrb_b200 import ops
+        from mrb_b200.model import box_ops
+        labels, masks = [], []
+        for p, t in zip(proposals, targets):
+            dev = p.bbox.device
+            seg = t.get_field("masks") if t.has_field("masks") else None
+            if dev.type != "cuda" or len(t) == 0 or getattr(seg, "mode", None) != "poly" or getattr(seg.instances, "polygons", None) is None \
+                    or t.mode != "xyxy" or p.mode != "xyxy":
+                return orig(proposals, targets)
+            with torch.no_grad():
+                m = self.proposal_matcher
+                q = box_ops.box_iou(t.bbox.float(), p.bbox.float())                 # boxlist_iou, [G, P]
+                vals, midx = q.max(dim=0)                                           # matcher.py:60-81, no low-quality pass
+                lab = t.get_field("labels").to(torch.int64)[midx]
+                lab = torch.where(vals < float(m.low_threshold), torch.zeros_like(lab), lab)
+                pos = torch.nonzero(lab > 0).squeeze(1)                             # as the reference (mask_head/loss.py:86)
+                bx = p.bbox.float()[pos]
+                w, h = seg.size
+                x1 = bx[:, 0].clamp(min=0, max=w - 1)                               # PolygonInstance.crop: clamped, at least 1 x 1
+                y1 = bx[:, 1].clamp(min=0, max=h - 1)
+                x2 = torch.maximum(bx[:, 2].clamp(min=0, max=w), x1 + 1)
+                y2 = torch.maximum(bx[:, 3].clamp(min=0, max=h), y1 + 1)
+                mk = ops.mask_targets_polygons(polyset_of(seg, dev), torch.stack([x1, y1, x2, y2], 1), midx[pos].to(torch.int32),
+                                               int(self.discretization_size)) if pos.numel() else \
+                    torch.empty(0, dtype=torch.float32, device=dev)
+            labels.append(lab)
+            masks.append(mk)
+        return labels, masks
+    ev.prepare_targets = types.MethodType(prepare_targets, ev)
+    ev._mrb_fused = True
+    return True
+
+
 def _fuse_mask_targets(be, rep):
     """project_masks_on_boxes (roi_heads/mask_head/loss.py:11-42): the per-proposal crop / resize / rasterise loop on the
     HOST (flagged as a bottleneck at loss.py:31-32) becomes one launch on the polygons' vertices (csrc/mask_targets.cu).
@@ -707,6 +771,9 @@ def fuse_model(model, backend=None, channels_last_weights=True, sampling=True):
                 bump("rpn_postprocessor")
             elif not getattr(mod, "_mrb_fused", False) and _fuse_box_postprocessor(mod, be):
                 bump("box_postprocessor")
+            if type(getattr(mod, "loss_evaluator", None)).__name__ == "MaskRCNNLossComputation" and \
+                    _fuse_mask_prepare_targets(mod.loss_evaluator, be):
+                bump("mask_prepare_targets")
             if not sampling:
                 continue
             if type(getattr(mod, "loss_evaluator", None)).__name__ == "RPNLossComputation" and _fuse_rpn_loss(mod, be):

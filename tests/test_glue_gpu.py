@@ -864,3 +864,42 @@ def test_fused_reference_rpn_loss_targets_and_box_subsample(built_lib):
         torch.testing.assert_close(bl.get_field("regression_targets")[pos], reg_ref[i][src][pos], rtol=1e-5, atol=1e-6)
         npos_all = int((lab_ref[i] > 0).sum())
         assert int(pos.sum()) == min(npos_all, 128) and len(bl) == min(512, int(pos.sum()) + int((lab_ref[i] == 0).sum()))
+
+
+def test_fused_reference_mask_prepare_targets(built_lib):
+    """MaskRCNNLossComputation.prepare_targets of the unmodified reference, fused (device-side matching + one rasterisation launch
+    on cached polygon sets) vs the reference's Python (its BoxList / SegmentationMask indexing + host rasterisation)"""
+    from mrb_b200 import fuse, refenv
+    if refenv.activate() is None:
+        pytest.skip("reference checkout absent")
+    from maskrcnn_benchmark.modeling.matcher import Matcher
+    from maskrcnn_benchmark.modeling.roi_heads.mask_head.loss import MaskRCNNLossComputation
+    from maskrcnn_benchmark.structures.bounding_box import BoxList
+    from maskrcnn_benchmark.structures.segmentation_mask import SegmentationMask
+    from mrb_b200.model.backend import B200Backend
+    g = torch.Generator().manual_seed(91)
+    props, targets = [], []
+    for (w, h), gc in (((1333, 800), 6), ((1216, 768), 3)):
+        gt = _rand_boxes(g, gc, w, h, 60, 400)
+        polys = []
+        for j, b in enumerate(gt.tolist()):
+            x1, y1, x2, y2 = b
+            polys.append([[x1, y1, x2, y1, x2, y2, x1, y2]] if j % 2 == 0 else [[x1, y1, x2, (y1 + y2) / 2, x1, y2]])
+        t = BoxList(gt.to(DEV), (w, h), mode="xyxy")
+        t.add_field("labels", torch.randint(1, 81, (gc,), generator=g).to(DEV))
+        t.add_field("masks", SegmentationMask(polys, (w, h), mode="poly"))
+        targets.append(t)
+        pb = gt.repeat_interleave(7, 0) + torch.randn(gc * 7, 4, generator=g) * 6          # positives around every instance
+        pb[:, 0::2] = pb[:, 0::2].clamp(0, w - 1)
+        pb[:, 1::2] = pb[:, 1::2].clamp(0, h - 1)
+        props.append(BoxList(pb.to(DEV), (w, h), mode="xyxy"))
+    ref = MaskRCNNLossComputation(Matcher(0.5, 0.5, allow_low_quality_matches=False), 28)
+    fus = MaskRCNNLossComputation(Matcher(0.5, 0.5, allow_low_quality_matches=False), 28)
+    assert fuse._fuse_mask_prepare_targets(fus, B200Backend())
+    lw, mw = ref.prepare_targets(props, targets)
+    lg, mg = fus.prepare_targets(props, targets)
+    lg2, mg2 = fus.prepare_targets(props, targets)                       # second call: cached polygon sets
+    for a, b, c, d, e in zip(lw, lg, mw, mg, mg2):
+        assert torch.equal(a, b)
+        assert c.shape == d.shape and float((c != d).float().mean()) < 2e-3 and torch.equal(d, e)
+        assert float(d.mean()) > 0.05
