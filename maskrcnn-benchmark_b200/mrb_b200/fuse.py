@@ -505,7 +505,8 @@ class _FusedRPNLoss:
                 gb[i, :gs[i]] = t.convert("xyxy").bbox
                 gc[i:i + 1].fill_(gs[i])
             m = self.proposal_matcher
-            labels, matched = ops.rpn_anchor_match(anc, gb, gc, gc, gc, float(m.high_threshold), float(m.low_threshold), -1.0)
+            wh = torch.zeros((n,), dtype=torch.float32, device=dev)     # image sizes: unused, the visibility test is off (-1)
+            labels, matched = ops.rpn_anchor_match(anc, gb, gc, wh, wh, float(m.high_threshold), float(m.low_threshold), -1.0)
             labels = torch.where(vis, labels, torch.full((), -1.0, device=dev))    # discard_cases: not_visibility
             keys = torch.rand(labels.shape, device=dev)
             sp = self.fg_bg_sampler

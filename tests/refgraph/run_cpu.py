@@ -10,7 +10,9 @@ common.route_cpu_C_to_oracle()
 reseed = common.deterministic_randperm()
 import torch  # noqa: E402
 
-cfgname = sys.argv[1] if len(sys.argv) > 1 else "e2e_mask_rcnn_R_50_FPN_1x.yaml"
+args = [a for a in sys.argv[1:] if not a.startswith("--")]
+glue_bindings = "--glue-bindings" in sys.argv      # also install the detection-glue bindings (they must fall back on CPU tensors)
+cfgname = args[0] if args else "e2e_mask_rcnn_R_50_FPN_1x.yaml"
 model, cfg = common.build(cfgname)
 model.train()
 il, targets = common.inputs()
@@ -21,7 +23,10 @@ with torch.no_grad():
 model.train()
 from oracle.cpu_backend import CpuCheckerBackend  # noqa: E402
 from mrb_b200.fuse import fuse_model  # noqa: E402
-rep = fuse_model(model, CpuCheckerBackend())
+be = CpuCheckerBackend()
+if glue_bindings:
+    be.fused_glue = True
+rep = fuse_model(model, be)
 l1, g1 = common.train_step(model, il, targets, reseed)
 worst = 0.0
 for k in l0:
