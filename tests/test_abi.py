@@ -197,3 +197,30 @@ def test_flat_sgd_matches_torch_sgd_and_bumps_versions():
     for a, b in zip(m.parameters(), m2.parameters()):
         torch.testing.assert_close(a, b, rtol=1e-6, atol=1e-7)
     assert all(p._version > v for p, v in zip(m.parameters(), versions))
+
+
+def test_glue_wrappers_refuse_cpu_tensors(built_lib):
+    """the detection-glue / loss wrappers of mrb_b200.ops have no CPU path: CPU tensors raise instead of falling back"""
+    import pytest
+    import torch
+    from mrb_b200 import ops
+    b = torch.zeros(2, 10, 4)
+    with pytest.raises(RuntimeError):
+        ops.rpn_collect(torch.zeros(20, 4), torch.zeros(20), torch.zeros(20, dtype=torch.int64), torch.zeros(2, dtype=torch.int32),
+                        [10], 2, 10, 10, True)
+    with pytest.raises(RuntimeError):
+        ops.roi_assign_sample(b, torch.ones(2, 10, dtype=torch.bool), torch.rand(2, 10), torch.zeros(2, 1, 4),
+                              torch.ones(2, 1, dtype=torch.int64), torch.ones(2, dtype=torch.int32), 8, 0.25, 0.5, 0.5, (10, 10, 5, 5))
+    with pytest.raises(RuntimeError):
+        ops.rpn_anchor_match(torch.zeros(16, 4), torch.zeros(2, 1, 4), torch.ones(2, dtype=torch.int32), torch.ones(2), torch.ones(2),
+                             0.7, 0.3, 0.0)
+    with pytest.raises(RuntimeError):
+        ops.box_head_loss(torch.zeros(4, 408), torch.zeros(4, dtype=torch.int64), torch.zeros(4, 4), 81)
+    with pytest.raises(RuntimeError):
+        ops.rpn_topk_decode(torch.zeros(1, 2, 2, 16), 3, torch.zeros(12, 4), 4, torch.ones(1), torch.ones(1), torch.zeros(1, 4, 4),
+                            torch.zeros(1, 4))
+    with pytest.raises(RuntimeError):
+        ops.box_postprocess(torch.zeros(20, 408), 81, b, torch.ones(2, 10, dtype=torch.bool), torch.ones(2), torch.ones(2), 0.05,
+                            (10, 10, 5, 5), 0.5, 100)
+    with pytest.raises(RuntimeError):
+        ops.mask_targets_rect(torch.zeros(3, 4), torch.zeros(3, 5), 28)
