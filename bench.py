@@ -672,7 +672,9 @@ def arm_reference_graph(args, cfg_name, device, rank, world, timer, aten=False):
             "model_path": ("reference GeneralizedRCNN (baseline/_ref mirror, unmodified) on ATen/cuDNN: bf16 autocast, channels_last, "
                            "torch.optim.SGD; ROIAlign/NMS from this repo's _C (the reference's CUDA sources need THC)") if aten else
                           "reference GeneralizedRCNN (baseline/_ref mirror, unmodified) over maskrcnn_benchmark.layers/_C of this "
-                          "repo + mrb_b200.fuse.fuse_model; eager; ParamArena fused SGD",
+                          "repo + mrb_b200.fuse.fuse_model (conv chains, poolers, heads; RPN / box post-processors, loss-target stages "
+                          "and mask targets bound to the glue launches) + CUDA-graph replay of the static segments "
+                          "(mrb_b200.graphed); the rest eager; ParamArena fused SGD",
             "value": round(imgs / t_dev, 3), "ms_per_step": round(t_dev / args.steps * 1e3, 2),
             "e2e": {"value": round(imgs / t_e2e, 3), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "mode": "images of step i+1 copied host -> device on a copy stream during step i (pinned memory); targets' boxes / "
